@@ -1,0 +1,113 @@
+"""ctypes binding of include/babelb200.h.  There is no CPU fallback: if libbabelb200.so is missing
+or a call fails, an exception is raised."""
+import ctypes
+import os
+import numpy as np
+
+_HERE = os.path.dirname(os.path.abspath(__file__))
+LIB_PATH = os.path.join(_HERE, 'libbabelb200.so')
+
+MAP_NAMES = ['ALLV', 'Vx', 'Vy', 'Vz', 'Sigmaxx', 'Sigmayy', 'Sigmazz', 'Sigmaxy', 'Sigmaxz', 'Sigmayz', 'Pressure']
+MAP_ID = {n: i for i, n in enumerate(MAP_NAMES)}
+NCOEF = 8
+
+
+class BabelB200Error(RuntimeError):
+    pass
+
+
+class FdtdDesc(ctypes.Structure):
+    _fields_ = [('n1', ctypes.c_int32), ('n2', ctypes.c_int32), ('n3', ctypes.c_int32),
+                ('i0', ctypes.c_int32), ('i1', ctypes.c_int32), ('pml', ctypes.c_int32),
+                ('nmat', ctypes.c_int32), ('nsrc', ctypes.c_int32), ('nt_src', ctypes.c_int32),
+                ('steps', ctypes.c_int32), ('type_source', ctypes.c_int32), ('sel_rms_peak', ctypes.c_int32),
+                ('sel_maps_rms', ctypes.c_uint32), ('sel_maps_sensor', ctypes.c_uint32),
+                ('sensor_subsampling', ctypes.c_int32), ('sensor_start', ctypes.c_int32),
+                ('device', ctypes.c_int32), ('rank', ctypes.c_int32), ('nranks', ctypes.c_int32),
+                ('kernel_variant', ctypes.c_int32), ('reserved', ctypes.c_int32), ('dt', ctypes.c_double)]
+
+
+class FdtdStats(ctypes.Structure):
+    _fields_ = [('run_ms', ctypes.c_double), ('stress_ms', ctypes.c_double), ('particle_ms', ctypes.c_double),
+                ('pml_ms', ctypes.c_double), ('other_ms', ctypes.c_double),
+                ('stress_launches', ctypes.c_int64), ('particle_launches', ctypes.c_int64),
+                ('pml_launches', ctypes.c_int64), ('other_launches', ctypes.c_int64),
+                ('steps_done', ctypes.c_int64), ('cells_local', ctypes.c_int64),
+                ('device_bytes', ctypes.c_int64), ('nsamples', ctypes.c_int64)]
+
+
+# every symbol include/babelb200.h declares (checked by tests/test_capi.py)
+SYMBOLS = ['bb_last_error', 'bb_version', 'bb_device_count', 'bb_device_name', 'bb_fdtd_create',
+           'bb_fdtd_destroy', 'bb_fdtd_set_stream', 'bb_fdtd_set_materials', 'bb_fdtd_set_maps',
+           'bb_fdtd_set_source_cells', 'bb_fdtd_set_source_functions', 'bb_fdtd_set_sensors',
+           'bb_nccl_unique_id', 'bb_fdtd_comm_init', 'bb_fdtd_run', 'bb_fdtd_reset', 'bb_fdtd_get_map',
+           'bb_fdtd_get_sensors', 'bb_fdtd_get_stats', 'bb_rayleigh_forward']
+
+_lib = None
+
+
+def lib():
+    global _lib
+    if _lib is None:
+        if not os.path.exists(LIB_PATH):
+            raise BabelB200Error(
+                'libbabelb200.so is not built (%s). Run `python -m babelbrain_b200.build`; '
+                'there is no CPU fallback.' % LIB_PATH)
+        L = ctypes.CDLL(LIB_PATH)
+        L.bb_last_error.restype = ctypes.c_char_p
+        L.bb_version.restype = ctypes.c_char_p
+        vp, i64, i32 = ctypes.c_void_p, ctypes.c_int64, ctypes.c_int
+        L.bb_device_name.argtypes = [i32, ctypes.c_char_p, i32]
+        L.bb_fdtd_create.argtypes = [ctypes.POINTER(FdtdDesc), ctypes.POINTER(vp)]
+        L.bb_fdtd_destroy.argtypes = [vp]
+        L.bb_fdtd_destroy.restype = None
+        L.bb_fdtd_set_stream.argtypes = [vp, vp]
+        L.bb_fdtd_set_materials.argtypes = [vp, vp, vp]
+        L.bb_fdtd_set_maps.argtypes = [vp, vp, vp]
+        L.bb_fdtd_set_source_cells.argtypes = [vp, i64, vp, vp, vp, vp, vp]
+        L.bb_fdtd_set_source_functions.argtypes = [vp, vp, i32, i64]
+        L.bb_fdtd_set_sensors.argtypes = [vp, i64, vp]
+        L.bb_nccl_unique_id.argtypes = [ctypes.c_char_p]
+        L.bb_fdtd_comm_init.argtypes = [vp, ctypes.c_char_p]
+        L.bb_fdtd_run.argtypes = [vp, i64, i32]
+        L.bb_fdtd_reset.argtypes = [vp]
+        L.bb_fdtd_get_map.argtypes = [vp, i32, i32, vp]
+        L.bb_fdtd_get_sensors.argtypes = [vp, i32, vp]
+        L.bb_fdtd_get_stats.argtypes = [vp, ctypes.POINTER(FdtdStats)]
+        L.bb_rayleigh_forward.argtypes = [ctypes.c_float, ctypes.c_float, i64, vp, vp, vp, i64, vp, vp,
+                                          ctypes.c_float, i64, i32, ctypes.POINTER(ctypes.c_double)]
+        _lib = L
+    return _lib
+
+
+def check(rc):
+    if rc != 0:
+        msg = lib().bb_last_error().decode('utf-8', 'replace')
+        if rc == 1:
+            raise ValueError('babelb200: ' + msg)
+        raise BabelB200Error('babelb200 error %d: %s' % (rc, msg))
+
+
+def ptr(a):
+    return None if a is None else a.ctypes.data_as(ctypes.c_void_p)
+
+
+def device_count():
+    n = lib().bb_device_count()
+    if n < 0:
+        raise BabelB200Error(lib().bb_last_error().decode())
+    return n
+
+
+def device_names():
+    out = []
+    for d in range(device_count()):
+        buf = ctypes.create_string_buffer(256)
+        check(lib().bb_device_name(d, buf, 256))
+        out.append(buf.value.decode())
+    return out
+
+
+def require_gpu():
+    if device_count() == 0:
+        raise BabelB200Error('no CUDA device visible: babelbrain_b200 has no CPU fallback')

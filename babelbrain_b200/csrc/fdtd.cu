@@ -1,0 +1,595 @@
+// Host side of the FDTD path: opaque handle, device memory, time loop, C ABI.
+// Replaces the body of PModel.StaggeredFDTD_3D_with_relaxation
+// (TranscranialModeling/BabelIntegrationBASE.py:2338-2365) below the Python boundary.
+#include <stdarg.h>
+#include <string.h>
+#include <vector>
+#include <algorithm>
+#include "common.h"
+#include "fdtd_kernels.cuh"
+#include "fdtd_tiled.cuh"
+#include "nccl_dyn.h"
+
+static thread_local char g_err[1024] = "";
+void bb_set_error(const char *fmt, ...) {
+    va_list ap;
+    va_start(ap, fmt);
+    vsnprintf(g_err, sizeof(g_err), fmt, ap);
+    va_end(ap);
+}
+extern "C" const char *bb_last_error(void) { return g_err; }
+extern "C" const char *bb_version(void) { return "babelb200 0.1 (sm_100a)"; }
+
+extern "C" int bb_device_count(void) {
+    int n = 0;
+    cudaError_t e = cudaGetDeviceCount(&n);
+    if (e != cudaSuccess) { bb_set_error("cudaGetDeviceCount: %s", cudaGetErrorString(e)); return -1; }
+    return n;
+}
+extern "C" int bb_device_name(int device, char *out, int out_len) {
+    cudaDeviceProp prop;
+    BB_CUDA(cudaGetDeviceProperties(&prop, device));
+    snprintf(out, out_len, "%s", prop.name);
+    return BB_OK;
+}
+
+// ------------------------------------------------------------------------------------------
+enum { CAT_STRESS = 0, CAT_PARTICLE, CAT_PML, CAT_OTHER, CAT_COUNT };
+
+struct bb_fdtd {
+    bb_fdtd_desc d;
+    DevParams p;
+    int label_bytes = 1;
+    int nown = 0;
+    cudaStream_t stream = nullptr, comm_stream = nullptr;
+    bool own_stream = false;
+    std::vector<void *> allocs;
+    int64_t device_bytes = 0;
+    // sources
+    int64_t nsrc_cells = 0, nsrc_boundary = 0;
+    long long *src_cell = nullptr;
+    int *src_row = nullptr;
+    float *src_o[3] = {nullptr, nullptr, nullptr};
+    float *srcfun = nullptr;  // [nt_src][nsrc]
+    // sensors
+    int64_t nsensors = 0, nsamples = 0;
+    long long *sensor_cell = nullptr;
+    float *sensor_out = nullptr;  // [map][sample][sensor]
+    int n_sensor_maps = 0, n_acc_maps = 0;
+    int64_t step = 0;
+    long long sp_total = 0;
+    bool materials_set = false, maps_set = false;
+    // NCCL
+    ncclComm_t comm = nullptr;
+    cudaEvent_t ev_boundary = nullptr, ev_halo = nullptr;
+    // timing
+    cudaEvent_t ev_run0 = nullptr, ev_run1 = nullptr;
+    std::vector<cudaEvent_t> ev_pool;
+    std::vector<int> ev_cat;
+    size_t ev_used = 0;
+    bb_fdtd_stats stats;
+};
+
+static int dev_alloc(bb_fdtd *h, void **ptr, size_t bytes, bool zero = true) {
+    if (bytes == 0) bytes = 16;
+    BB_CUDA(cudaMalloc(ptr, bytes));
+    h->allocs.push_back(*ptr);
+    h->device_bytes += (int64_t)bytes;
+    if (zero) BB_CUDA(cudaMemsetAsync(*ptr, 0, bytes, h->stream));
+    return BB_OK;
+}
+
+static int popcount32(uint32_t v) { return __builtin_popcount(v); }
+
+extern "C" int bb_fdtd_create(const bb_fdtd_desc *d, bb_fdtd **out) {
+    BB_REQUIRE(d && out, "null argument");
+    BB_REQUIRE(d->n1 > 0 && d->n2 > 0 && d->n3 > 0, "bad grid %d %d %d", d->n1, d->n2, d->n3);
+    BB_REQUIRE(d->pml >= 2 && 2 * d->pml < d->n1 && 2 * d->pml < d->n2 && 2 * d->pml < d->n3,
+               "PML thickness %d must be >= 2 and leave an interior", d->pml);
+    BB_REQUIRE(d->i0 >= 0 && d->i1 <= d->n1 && d->i1 - d->i0 >= (d->nranks > 1 ? 4 : 1), "bad slab [%d,%d)", d->i0, d->i1);
+    BB_REQUIRE(d->nmat >= 1 && d->nmat <= 32767, "nmat %d out of range", d->nmat);
+    BB_REQUIRE(d->steps >= 0 && d->sensor_subsampling >= 1 && d->sensor_start >= 0, "bad time parameters");
+    BB_REQUIRE(d->type_source >= 0 && d->type_source <= 3, "TypeSource %d not supported", d->type_source);
+    BB_REQUIRE(d->sel_rms_peak >= 0 && d->sel_rms_peak <= 3, "SelRMSorPeak %d", d->sel_rms_peak);
+    BB_REQUIRE((d->sel_maps_rms >> BB_MAP_COUNT) == 0 && (d->sel_maps_sensor >> BB_MAP_COUNT) == 0, "bad map mask");
+    int ndev = bb_device_count();
+    if (ndev <= 0) { if (ndev == 0) bb_set_error("no CUDA device (this library has no CPU fallback)"); return BB_ERR_CUDA; }
+    BB_REQUIRE(d->device >= 0 && d->device < ndev, "device %d of %d", d->device, ndev);
+    BB_CUDA(cudaSetDevice(d->device));
+    bb_fdtd *h = new bb_fdtd();
+    h->d = *d;
+    memset(&h->stats, 0, sizeof(h->stats));
+    BB_CUDA(cudaStreamCreateWithFlags(&h->stream, cudaStreamNonBlocking));
+    BB_CUDA(cudaStreamCreateWithFlags(&h->comm_stream, cudaStreamNonBlocking));
+    h->own_stream = true;
+    BB_CUDA(cudaEventCreate(&h->ev_run0));
+    BB_CUDA(cudaEventCreate(&h->ev_run1));
+    BB_CUDA(cudaEventCreateWithFlags(&h->ev_boundary, cudaEventDisableTiming));
+    BB_CUDA(cudaEventCreateWithFlags(&h->ev_halo, cudaEventDisableTiming));
+
+    DevParams &p = h->p;
+    memset(&p, 0, sizeof(p));
+    p.n1 = d->n1; p.n2 = d->n2; p.n3 = d->n3; p.i0 = d->i0; p.i1 = d->i1; p.P = d->pml;
+    p.pitch = (d->n3 + 31) / 32 * 32;
+    h->nown = d->i1 - d->i0;
+    p.nloc = h->nown + 4;
+    p.plane = (long long)p.n2 * p.pitch;
+    p.dt = (float)d->dt;
+    h->label_bytes = d->nmat <= 127 ? 1 : 2;
+    const size_t vol = (size_t)p.nloc * p.plane;
+    int rc;
+    for (int c = 0; c < 3; c++) if ((rc = dev_alloc(h, (void **)&p.V[c], vol * 4))) return rc;
+    for (int c = 0; c < 6; c++) if ((rc = dev_alloc(h, (void **)&p.S[c], vol * 4))) return rc;
+    for (int c = 0; c < 6; c++) if ((rc = dev_alloc(h, (void **)&p.R[c], vol * 4))) return rc;
+    if ((rc = dev_alloc(h, (void **)&p.Pr, vol * 4))) return rc;
+    // label planes carry one extra zero plane so that (i+1) lookups of the last halo plane stay in bounds
+    if ((rc = dev_alloc(h, (void **)&p.lab, (vol + p.plane) * h->label_bytes))) return rc;
+    if ((rc = dev_alloc(h, (void **)&p.mat, sizeof(MatRow) * d->nmat))) return rc;
+    if ((rc = dev_alloc(h, (void **)&p.pml, sizeof(float) * 4 * (d->pml + 1)))) return rc;
+    // PML shell of this slab
+    const int P = d->pml;
+    p.ilo_end = d->i0 < P ? std::min(P, d->i1) : d->i0;
+    p.ihi_begin = d->i1 > d->n1 - P ? std::max(d->n1 - P, d->i0) : d->i1;
+    if (p.ihi_begin < p.ilo_end) p.ihi_begin = p.ilo_end;
+    const long long nmid = p.ihi_begin - p.ilo_end;
+    long long sizes[6] = { (long long)(p.ilo_end - d->i0) * p.n2 * p.n3, (long long)(d->i1 - p.ihi_begin) * p.n2 * p.n3,
+                           nmid * P * p.n3, nmid * P * p.n3, nmid * (p.n2 - 2 * P) * P, nmid * (p.n2 - 2 * P) * P };
+    long long tot = 0;
+    for (int b = 0; b < 6; b++) { p.off[b] = tot; tot += sizes[b]; }
+    h->sp_total = tot;
+    for (int c = 0; c < SP_COUNT; c++) if ((rc = dev_alloc(h, (void **)&p.sp[c], (size_t)tot * 4))) return rc;
+    // accumulators
+    h->n_acc_maps = popcount32(d->sel_maps_rms);
+    h->n_sensor_maps = popcount32(d->sel_maps_sensor);
+    p.sel_maps = d->sel_maps_rms;
+    p.sel_rms_peak = d->sel_rms_peak;
+    p.acc_stride = (long long)h->nown * p.plane;
+    if ((d->sel_rms_peak & 1) && h->n_acc_maps)
+        if ((rc = dev_alloc(h, (void **)&p.acc_rms, (size_t)h->n_acc_maps * p.acc_stride * 4))) return rc;
+    if ((d->sel_rms_peak & 2) && h->n_acc_maps)
+        if ((rc = dev_alloc(h, (void **)&p.acc_peak, (size_t)h->n_acc_maps * p.acc_stride * 4))) return rc;
+    for (int n = 0; n < d->steps; n++)
+        if (n % d->sensor_subsampling == 0 && n / d->sensor_subsampling >= d->sensor_start) h->nsamples++;
+    BB_CUDA(cudaStreamSynchronize(h->stream));
+    *out = h;
+    return BB_OK;
+}
+
+extern "C" void bb_fdtd_destroy(bb_fdtd *h) {
+    if (!h) return;
+    cudaSetDevice(h->d.device);
+    cudaDeviceSynchronize();
+    if (h->comm) nccl_api().CommDestroy(h->comm);
+    for (void *a : h->allocs) cudaFree(a);
+    for (cudaEvent_t e : h->ev_pool) cudaEventDestroy(e);
+    if (h->ev_run0) cudaEventDestroy(h->ev_run0);
+    if (h->ev_run1) cudaEventDestroy(h->ev_run1);
+    if (h->ev_boundary) cudaEventDestroy(h->ev_boundary);
+    if (h->ev_halo) cudaEventDestroy(h->ev_halo);
+    if (h->own_stream && h->stream) cudaStreamDestroy(h->stream);
+    if (h->comm_stream) cudaStreamDestroy(h->comm_stream);
+    delete h;
+}
+
+extern "C" int bb_fdtd_set_stream(bb_fdtd *h, void *s) {
+    BB_REQUIRE(h, "null handle");
+    BB_CUDA(cudaSetDevice(h->d.device));
+    BB_CUDA(cudaStreamSynchronize(h->stream));
+    if (h->own_stream) { cudaStreamDestroy(h->stream); h->own_stream = false; }
+    if (s) h->stream = (cudaStream_t)s;
+    else { BB_CUDA(cudaStreamCreateWithFlags(&h->stream, cudaStreamNonBlocking)); h->own_stream = true; }
+    return BB_OK;
+}
+
+extern "C" int bb_fdtd_set_materials(bb_fdtd *h, const float *table, const float *pml_table) {
+    BB_REQUIRE(h && table && pml_table, "null argument");
+    BB_CUDA(cudaSetDevice(h->d.device));
+    BB_CUDA(cudaMemcpyAsync((void *)h->p.mat, table, sizeof(MatRow) * h->d.nmat, cudaMemcpyHostToDevice, h->stream));
+    BB_CUDA(cudaMemcpyAsync((void *)h->p.pml, pml_table, sizeof(float) * 4 * (h->d.pml + 1), cudaMemcpyHostToDevice, h->stream));
+    BB_CUDA(cudaStreamSynchronize(h->stream));
+    h->materials_set = true;
+    return BB_OK;
+}
+
+extern "C" int bb_fdtd_set_maps(bb_fdtd *h, const uint32_t *material, const uint32_t *reflector) {
+    BB_REQUIRE(h && material, "null argument");
+    BB_CUDA(cudaSetDevice(h->d.device));
+    const DevParams &p = h->p;
+    const int glo = std::max(p.i0 - 2, 0), ghi = std::min(p.i1 + 2, p.n1);  // planes the host passes
+    const long long nrows = (long long)(ghi - glo) * p.n2;
+    const size_t bytes = (size_t)nrows * p.n3 * 4;
+    uint32_t *tmp = nullptr, *tmpr = nullptr;
+    int *bad = nullptr;
+    BB_CUDA(cudaMalloc(&tmp, bytes));
+    BB_CUDA(cudaMalloc(&bad, 4));
+    BB_CUDA(cudaMemsetAsync(bad, 0, 4, h->stream));
+    BB_CUDA(cudaMemcpyAsync(tmp, material, bytes, cudaMemcpyHostToDevice, h->stream));
+    if (reflector) {
+        BB_CUDA(cudaMalloc(&tmpr, bytes));
+        BB_CUDA(cudaMemcpyAsync(tmpr, reflector, bytes, cudaMemcpyHostToDevice, h->stream));
+    }
+    const long long first_row = (long long)(glo - (p.i0 - 2)) * p.n2;  // local row where the host data starts
+    const long long total = nrows * p.pitch;
+    const int bs = 256;
+    const unsigned grid = (unsigned)((total + bs - 1) / bs);
+    if (h->label_bytes == 1)
+        label_convert_kernel<uint8_t><<<grid, bs, 0, h->stream>>>(tmp, tmpr, (uint8_t *)p.lab + first_row * p.pitch, nrows, p.n3, p.pitch, h->d.nmat, bad);
+    else
+        label_convert_kernel<uint16_t><<<grid, bs, 0, h->stream>>>(tmp, tmpr, (uint16_t *)p.lab + first_row * p.pitch, nrows, p.n3, p.pitch, h->d.nmat, bad);
+    BB_CUDA(cudaGetLastError());
+    int hbad = 0;
+    BB_CUDA(cudaMemcpyAsync(&hbad, bad, 4, cudaMemcpyDeviceToHost, h->stream));
+    BB_CUDA(cudaStreamSynchronize(h->stream));
+    cudaFree(tmp); cudaFree(bad);
+    if (tmpr) cudaFree(tmpr);
+    BB_REQUIRE(!hbad, "MaterialMap holds a label >= number of materials (%d)", h->d.nmat);
+    h->maps_set = true;
+    return BB_OK;
+}
+
+// global C-order cell index -> padded local index; returns -1 when the cell is not owned
+static long long to_local(const DevParams &p, int64_t g) {
+    const int64_t n23 = (int64_t)p.n2 * p.n3;
+    const int i = (int)(g / n23);
+    const int64_t r = g - (int64_t)i * n23;
+    const int j = (int)(r / p.n3), k = (int)(r - (int64_t)j * p.n3);
+    if (i < p.i0 || i >= p.i1) return -1;
+    return ((long long)(i - p.i0 + 2) * p.n2 + j) * p.pitch + k;
+}
+
+extern "C" int bb_fdtd_set_source_cells(bb_fdtd *h, int64_t ncells, const int64_t *cell, const int32_t *row,
+                                        const float *ox, const float *oy, const float *oz) {
+    BB_REQUIRE(h && ncells >= 0, "bad argument");
+    BB_REQUIRE(ncells == 0 || (cell && row && ox && oy && oz), "null source arrays");
+    BB_CUDA(cudaSetDevice(h->d.device));
+    const DevParams &p = h->p;
+    // boundary-plane cells first (they are injected before the halo send), then interior cells
+    std::vector<int64_t> order;
+    order.reserve(ncells);
+    std::vector<long long> loc(ncells);
+    const bool multi = h->d.nranks > 1;
+    int64_t nb = 0;
+    for (int pass = 0; pass < 2; pass++)
+        for (int64_t s = 0; s < ncells; s++) {
+            if (pass == 0) {
+                loc[s] = to_local(p, cell[s]);
+                BB_REQUIRE(loc[s] >= 0, "source cell %lld is outside the slab [%d,%d)", (long long)cell[s], p.i0, p.i1);
+                BB_REQUIRE(row[s] >= 0 && row[s] < h->d.nsrc, "source row %d out of range", row[s]);
+            }
+            const int ip = (int)(loc[s] / p.plane) - 2;
+            const bool boundary = multi && (ip < 2 || ip >= h->nown - 2);
+            if ((pass == 0) == boundary) order.push_back(s);
+            if (pass == 0 && boundary) nb++;
+        }
+    std::vector<long long> c2(ncells);
+    std::vector<int> r2(ncells);
+    std::vector<float> o2[3];
+    for (int a = 0; a < 3; a++) o2[a].resize(ncells);
+    for (int64_t t = 0; t < ncells; t++) {
+        const int64_t s = order[t];
+        c2[t] = loc[s]; r2[t] = row[s]; o2[0][t] = ox[s]; o2[1][t] = oy[s]; o2[2][t] = oz[s];
+    }
+    int rc;
+    if ((rc = dev_alloc(h, (void **)&h->src_cell, ncells * 8, false))) return rc;
+    if ((rc = dev_alloc(h, (void **)&h->src_row, ncells * 4, false))) return rc;
+    for (int a = 0; a < 3; a++) if ((rc = dev_alloc(h, (void **)&h->src_o[a], ncells * 4, false))) return rc;
+    if (ncells) {
+        BB_CUDA(cudaMemcpy(h->src_cell, c2.data(), ncells * 8, cudaMemcpyHostToDevice));
+        BB_CUDA(cudaMemcpy(h->src_row, r2.data(), ncells * 4, cudaMemcpyHostToDevice));
+        for (int a = 0; a < 3; a++) BB_CUDA(cudaMemcpy(h->src_o[a], o2[a].data(), ncells * 4, cudaMemcpyHostToDevice));
+    }
+    h->nsrc_cells = ncells;
+    h->nsrc_boundary = nb;
+    return BB_OK;
+}
+
+extern "C" int bb_fdtd_set_source_functions(bb_fdtd *h, const void *data, int is_f64, int64_t row_stride) {
+    BB_REQUIRE(h && data, "null argument");
+    BB_CUDA(cudaSetDevice(h->d.device));
+    const int nsrc = h->d.nsrc, nt = h->d.nt_src;
+    BB_REQUIRE(nsrc > 0 && nt > 0 && row_stride >= nt, "bad SourceFunctions shape");
+    int rc;
+    if (!h->srcfun) if ((rc = dev_alloc(h, (void **)&h->srcfun, (size_t)nsrc * nt * 4, false))) return rc;
+    const size_t esz = is_f64 ? 8 : 4;
+    const dim3 blk(32, 8);
+    // stream the host matrix through a bounded staging buffer (rows of 32-multiples)
+    const int64_t max_stage_bytes = 1ll << 30;
+    int64_t rows_per = std::max<int64_t>(32, (max_stage_bytes / (row_stride * (int64_t)esz)) / 32 * 32);
+    rows_per = std::min<int64_t>(rows_per, (nsrc + 31) / 32 * 32);
+    void *stage = nullptr;
+    BB_CUDA(cudaMalloc(&stage, (size_t)rows_per * row_stride * esz));
+    for (int64_t s0 = 0; s0 < nsrc; s0 += rows_per) {
+        const int64_t ns = std::min<int64_t>(rows_per, nsrc - s0);
+        const size_t nbytes = ((size_t)(ns - 1) * row_stride + nt) * esz;
+        BB_CUDA(cudaMemcpyAsync(stage, (const char *)data + (size_t)s0 * row_stride * esz, nbytes, cudaMemcpyHostToDevice, h->stream));
+        const dim3 grid((nt + 31) / 32, (unsigned)((ns + 31) / 32));
+        // out rows are full length nsrc: offset columns by s0
+        if (is_f64) srcfun_transpose_kernel<double><<<grid, blk, 0, h->stream>>>((const double *)stage, row_stride, h->srcfun + s0, (int)ns, nt);
+        else srcfun_transpose_kernel<float><<<grid, blk, 0, h->stream>>>((const float *)stage, row_stride, h->srcfun + s0, (int)ns, nt);
+        BB_CUDA(cudaGetLastError());
+        BB_CUDA(cudaStreamSynchronize(h->stream));
+    }
+    cudaFree(stage);
+    return BB_OK;
+}
+
+extern "C" int bb_fdtd_set_sensors(bb_fdtd *h, int64_t nsensors, const int64_t *cell) {
+    BB_REQUIRE(h && nsensors >= 0 && (nsensors == 0 || cell), "bad argument");
+    BB_CUDA(cudaSetDevice(h->d.device));
+    std::vector<long long> loc(nsensors);
+    for (int64_t s = 0; s < nsensors; s++) {
+        loc[s] = to_local(h->p, cell[s]);
+        BB_REQUIRE(loc[s] >= 0, "sensor cell %lld is outside the slab", (long long)cell[s]);
+    }
+    int rc;
+    if ((rc = dev_alloc(h, (void **)&h->sensor_cell, nsensors * 8, false))) return rc;
+    if (nsensors) BB_CUDA(cudaMemcpy(h->sensor_cell, loc.data(), nsensors * 8, cudaMemcpyHostToDevice));
+    if ((rc = dev_alloc(h, (void **)&h->sensor_out, (size_t)h->n_sensor_maps * h->nsamples * nsensors * 4))) return rc;
+    BB_CUDA(cudaStreamSynchronize(h->stream));
+    h->nsensors = nsensors;
+    return BB_OK;
+}
+
+extern "C" int bb_nccl_unique_id(char *out128) {
+    BB_REQUIRE(out128, "null argument");
+    if (!nccl_api().ok) { bb_set_error("NCCL not available: %s", nccl_api().err.c_str()); return BB_ERR_NCCL; }
+    ncclUniqueId id;
+    ncclResult_t r = nccl_api().GetUniqueId(&id);
+    if (r != ncclSuccess) { bb_set_error("ncclGetUniqueId: %s", nccl_api().GetErrorString(r)); return BB_ERR_NCCL; }
+    memcpy(out128, &id, 128);
+    return BB_OK;
+}
+
+extern "C" int bb_fdtd_comm_init(bb_fdtd *h, const char *id128) {
+    BB_REQUIRE(h && id128, "null argument");
+    BB_REQUIRE(h->d.nranks > 1, "comm_init needs nranks > 1");
+    if (!nccl_api().ok) { bb_set_error("NCCL not available: %s", nccl_api().err.c_str()); return BB_ERR_NCCL; }
+    BB_CUDA(cudaSetDevice(h->d.device));
+    ncclUniqueId id;
+    memcpy(&id, id128, 128);
+    ncclResult_t r = nccl_api().CommInitRank(&h->comm, h->d.nranks, id, h->d.rank);
+    if (r != ncclSuccess) { bb_set_error("ncclCommInitRank: %s", nccl_api().GetErrorString(r)); return BB_ERR_NCCL; }
+    return BB_OK;
+}
+
+// ------------------------------------------------------------------------------------------
+// time loop
+// ------------------------------------------------------------------------------------------
+struct Timer {
+    bb_fdtd *h; bool on;
+    void begin(int cat) {
+        if (!on) return;
+        if (h->ev_used + 2 > h->ev_pool.size()) {
+            for (int n = 0; n < 2; n++) { cudaEvent_t e; cudaEventCreate(&e); h->ev_pool.push_back(e); }
+        }
+        h->ev_cat.push_back(cat);
+        cudaEventRecord(h->ev_pool[h->ev_used], h->stream);
+    }
+    void end() {
+        if (!on) return;
+        cudaEventRecord(h->ev_pool[h->ev_used + 1], h->stream);
+        h->ev_used += 2;
+    }
+};
+
+template <typename LT>
+static int launch_half_step(bb_fdtd *h, bool stress, bool acc, int ib, int ie, Timer &tm) {
+    if (ie <= ib) return BB_OK;
+    const DevParams &p = h->p;
+    if (h->d.kernel_variant == 1) {
+        const dim3 blk(64, 4, 1), grid((p.n3 + 63) / 64, (p.n2 + 3) / 4, ie - ib);
+        tm.begin(stress ? CAT_STRESS : CAT_PARTICLE);
+        if (stress) {
+            if (acc) stress_direct<LT, true><<<grid, blk, 0, h->stream>>>(p, ib);
+            else stress_direct<LT, false><<<grid, blk, 0, h->stream>>>(p, ib);
+        } else {
+            if (acc) particle_direct<LT, true><<<grid, blk, 0, h->stream>>>(p, ib);
+            else particle_direct<LT, false><<<grid, blk, 0, h->stream>>>(p, ib);
+        }
+        tm.end();
+        BB_CUDA(cudaGetLastError());
+        return BB_OK;
+    }
+    return launch_tiled<LT>(h->p, stress, acc, ib, ie, h->stream, [&](int cat) { tm.begin(cat == 0 ? (stress ? CAT_STRESS : CAT_PARTICLE) : CAT_PML); }, [&]() { tm.end(); });
+}
+
+static int launch_sources(bb_fdtd *h, int n, int64_t first, int64_t count, Timer &tm) {
+    if (count <= 0 || n >= h->d.nt_src || !h->srcfun) return BB_OK;
+    tm.begin(CAT_OTHER);
+    source_kernel<<<(unsigned)((count + 127) / 128), 128, 0, h->stream>>>(h->p, h->d.type_source, count, h->src_cell + first, h->src_row + first,
+                                                                         h->src_o[0] + first, h->src_o[1] + first, h->src_o[2] + first,
+                                                                         h->srcfun + (size_t)n * h->d.nsrc);
+    tm.end();
+    BB_CUDA(cudaGetLastError());
+    return BB_OK;
+}
+
+// exchange two planes of three fields with both slab neighbours (NCCL send/recv on comm_stream)
+static int halo_exchange(bb_fdtd *h, float *const f[3]) {
+    const DevParams &p = h->p;
+    const size_t cnt = (size_t)2 * p.plane;
+    const int r = h->d.rank, nr = h->d.nranks;
+    NcclApi &api = nccl_api();
+    ncclResult_t rc = api.GroupStart();
+    for (int c = 0; c < 3 && rc == ncclSuccess; c++) {
+        if (r > 0) {
+            rc = api.Send(f[c] + 2 * p.plane, cnt, ncclFloat, r - 1, h->comm, h->comm_stream);
+            if (rc == ncclSuccess) rc = api.Recv(f[c], cnt, ncclFloat, r - 1, h->comm, h->comm_stream);
+        }
+        if (r < nr - 1 && rc == ncclSuccess) {
+            rc = api.Send(f[c] + (size_t)h->nown * p.plane, cnt, ncclFloat, r + 1, h->comm, h->comm_stream);
+            if (rc == ncclSuccess) rc = api.Recv(f[c] + (size_t)(h->nown + 2) * p.plane, cnt, ncclFloat, r + 1, h->comm, h->comm_stream);
+        }
+    }
+    ncclResult_t rc2 = api.GroupEnd();
+    if (rc == ncclSuccess) rc = rc2;
+    if (rc != ncclSuccess) { bb_set_error("NCCL halo exchange: %s", api.GetErrorString(rc)); return BB_ERR_NCCL; }
+    return BB_OK;
+}
+
+template <typename LT>
+static int half_step(bb_fdtd *h, bool stress, int n, bool acc, Timer &tm) {
+    const DevParams &p = h->p;
+    const bool src_here = stress ? (h->d.type_source >= 2) : (h->d.type_source < 2);
+    int rc;
+    if (h->d.nranks > 1) {
+        // inputs of this half-step: halos sent during the previous half-step
+        BB_CUDA(cudaStreamWaitEvent(h->stream, h->ev_halo, 0));
+        if ((rc = launch_half_step<LT>(h, stress, acc, p.i0, p.i0 + 2, tm))) return rc;
+        if ((rc = launch_half_step<LT>(h, stress, acc, p.i1 - 2, p.i1, tm))) return rc;
+        if (src_here && (rc = launch_sources(h, n, 0, h->nsrc_boundary, tm))) return rc;
+        BB_CUDA(cudaEventRecord(h->ev_boundary, h->stream));
+        BB_CUDA(cudaStreamWaitEvent(h->comm_stream, h->ev_boundary, 0));
+        float *sf[3] = { p.S[0], p.S[3], p.S[4] };
+        float *vf[3] = { p.V[0], p.V[1], p.V[2] };
+        if ((rc = halo_exchange(h, stress ? sf : vf))) return rc;
+        BB_CUDA(cudaEventRecord(h->ev_halo, h->comm_stream));
+        if ((rc = launch_half_step<LT>(h, stress, acc, p.i0 + 2, p.i1 - 2, tm))) return rc;
+        if (src_here && (rc = launch_sources(h, n, h->nsrc_boundary, h->nsrc_cells - h->nsrc_boundary, tm))) return rc;
+    } else {
+        if ((rc = launch_half_step<LT>(h, stress, acc, p.i0, p.i1, tm))) return rc;
+        if (src_here && (rc = launch_sources(h, n, 0, h->nsrc_cells, tm))) return rc;
+    }
+    return BB_OK;
+}
+
+template <typename LT>
+static int run_steps(bb_fdtd *h, int64_t nsteps, Timer &tm) {
+    const bb_fdtd_desc &d = h->d;
+    const int n0 = d.sensor_start * d.sensor_subsampling;
+    const unsigned stress_maps = d.sel_maps_rms & 0x7F0u, part_maps = d.sel_maps_rms & 0xFu;
+    int rc;
+    for (int64_t t = 0; t < nsteps; t++) {
+        const int n = (int)h->step;
+        const bool window = d.sel_rms_peak != 0 && n >= n0;
+        if ((rc = half_step<LT>(h, true, n, window && stress_maps, tm))) return rc;
+        if ((rc = half_step<LT>(h, false, n, window && part_maps, tm))) return rc;
+        if (h->nsensors && h->n_sensor_maps && n % d.sensor_subsampling == 0 && n / d.sensor_subsampling >= d.sensor_start) {
+            const long long sample = n / d.sensor_subsampling - d.sensor_start;
+            tm.begin(CAT_OTHER);
+            sensor_kernel<LT><<<(unsigned)((h->nsensors + 255) / 256), 256, 0, h->stream>>>(h->p, d.sel_maps_sensor, h->nsensors, h->sensor_cell,
+                                                                                           h->sensor_out, h->nsamples, sample);
+            tm.end();
+            BB_CUDA(cudaGetLastError());
+        }
+        h->step++;
+    }
+    return BB_OK;
+}
+
+extern "C" int bb_fdtd_run(bb_fdtd *h, int64_t nsteps, int profile) {
+    BB_REQUIRE(h, "null handle");
+    if (!h->materials_set || !h->maps_set) { bb_set_error("set_materials / set_maps must be called before run"); return BB_ERR_STATE; }
+    if (h->d.nranks > 1 && !h->comm) { bb_set_error("multi-rank handle without comm_init"); return BB_ERR_STATE; }
+    BB_CUDA(cudaSetDevice(h->d.device));
+    if (nsteps < 0 || h->step + nsteps > h->d.steps) nsteps = h->d.steps - h->step;
+    Timer tm{h, profile != 0};
+    h->ev_used = 0;
+    h->ev_cat.clear();
+    if (h->d.nranks > 1) BB_CUDA(cudaEventRecord(h->ev_halo, h->comm_stream));
+    BB_CUDA(cudaEventRecord(h->ev_run0, h->stream));
+    int rc = h->label_bytes == 1 ? run_steps<uint8_t>(h, nsteps, tm) : run_steps<uint16_t>(h, nsteps, tm);
+    if (rc) return rc;
+    if (h->d.nranks > 1) BB_CUDA(cudaStreamWaitEvent(h->stream, h->ev_halo, 0));
+    BB_CUDA(cudaEventRecord(h->ev_run1, h->stream));
+    BB_CUDA(cudaStreamSynchronize(h->stream));
+    BB_CUDA(cudaGetLastError());
+    float ms = 0;
+    BB_CUDA(cudaEventElapsedTime(&ms, h->ev_run0, h->ev_run1));
+    bb_fdtd_stats &st = h->stats;
+    st.run_ms = ms;
+    st.stress_ms = st.particle_ms = st.pml_ms = st.other_ms = 0;
+    st.stress_launches = st.particle_launches = st.pml_launches = st.other_launches = 0;
+    for (size_t e = 0; e < h->ev_cat.size(); e++) {
+        float t = 0;
+        cudaEventElapsedTime(&t, h->ev_pool[2 * e], h->ev_pool[2 * e + 1]);
+        switch (h->ev_cat[e]) {
+        case CAT_STRESS: st.stress_ms += t; st.stress_launches++; break;
+        case CAT_PARTICLE: st.particle_ms += t; st.particle_launches++; break;
+        case CAT_PML: st.pml_ms += t; st.pml_launches++; break;
+        default: st.other_ms += t; st.other_launches++; break;
+        }
+    }
+    st.steps_done = h->step;
+    return BB_OK;
+}
+
+extern "C" int bb_fdtd_reset(bb_fdtd *h) {
+    BB_REQUIRE(h, "null handle");
+    BB_CUDA(cudaSetDevice(h->d.device));
+    const DevParams &p = h->p;
+    const size_t vol = (size_t)p.nloc * p.plane * 4;
+    for (int c = 0; c < 3; c++) BB_CUDA(cudaMemsetAsync(p.V[c], 0, vol, h->stream));
+    for (int c = 0; c < 6; c++) { BB_CUDA(cudaMemsetAsync(p.S[c], 0, vol, h->stream)); BB_CUDA(cudaMemsetAsync(p.R[c], 0, vol, h->stream)); }
+    BB_CUDA(cudaMemsetAsync(p.Pr, 0, vol, h->stream));
+    const size_t tot = (size_t)h->sp_total * 4;
+    for (int c = 0; c < SP_COUNT; c++) BB_CUDA(cudaMemsetAsync(p.sp[c], 0, tot, h->stream));
+    if (p.acc_rms) BB_CUDA(cudaMemsetAsync(p.acc_rms, 0, (size_t)h->n_acc_maps * p.acc_stride * 4, h->stream));
+    if (p.acc_peak) BB_CUDA(cudaMemsetAsync(p.acc_peak, 0, (size_t)h->n_acc_maps * p.acc_stride * 4, h->stream));
+    if (h->sensor_out) BB_CUDA(cudaMemsetAsync(h->sensor_out, 0, (size_t)h->n_sensor_maps * h->nsamples * h->nsensors * 4, h->stream));
+    BB_CUDA(cudaStreamSynchronize(h->stream));
+    h->step = 0;
+    return BB_OK;
+}
+
+extern "C" int bb_fdtd_get_map(bb_fdtd *h, int which, int map_id, float *out) {
+    BB_REQUIRE(h && out, "null argument");
+    BB_REQUIRE(map_id >= 0 && map_id < BB_MAP_COUNT && which >= 0 && which <= 2, "bad map selector");
+    BB_CUDA(cudaSetDevice(h->d.device));
+    const DevParams &p = h->p;
+    const long long nrows = (long long)h->nown * p.n2;
+    const long long total = nrows * p.n3;
+    float *tmp = nullptr;
+    BB_CUDA(cudaMalloc(&tmp, (size_t)total * 4));
+    const unsigned grid = (unsigned)((total + 255) / 256);
+    if (which == 2) {
+        BB_REQUIRE(map_id != BB_MAP_ALLV, "no last map for ALLV");
+        if (map_id == BB_MAP_PRESSURE) {
+            if (h->label_bytes == 1) finalize_pressure_kernel<uint8_t><<<grid, 256, 0, h->stream>>>(p, tmp, nrows);
+            else finalize_pressure_kernel<uint16_t><<<grid, 256, 0, h->stream>>>(p, tmp, nrows);
+        } else {
+            const float *src = map_id <= BB_MAP_VZ ? p.V[map_id - BB_MAP_VX] : p.S[map_id - BB_MAP_SXX];
+            finalize_map_kernel<<<grid, 256, 0, h->stream>>>(src + 2 * p.plane, tmp, nrows, p.n3, p.pitch, 0, 0.f);
+        }
+    } else {
+        const float *base = which == 0 ? p.acc_rms : p.acc_peak;
+        if (!base || !(h->d.sel_maps_rms & (1u << map_id))) { cudaFree(tmp); bb_set_error("map %d was not selected", map_id); return BB_ERR_ARG; }
+        const int slot = popcount32(h->d.sel_maps_rms & ((1u << map_id) - 1u));
+        const int n0 = h->d.sensor_start * h->d.sensor_subsampling;
+        const long long nacc = std::max<long long>(1, h->d.steps - n0);
+        const int mode = which == 0 ? 1 : (map_id == BB_MAP_ALLV ? 2 : 0);
+        finalize_map_kernel<<<grid, 256, 0, h->stream>>>(base + (size_t)slot * p.acc_stride, tmp, nrows, p.n3, p.pitch, mode, 1.0f / (float)nacc);
+    }
+    BB_CUDA(cudaGetLastError());
+    BB_CUDA(cudaMemcpyAsync(out, tmp, (size_t)total * 4, cudaMemcpyDeviceToHost, h->stream));
+    BB_CUDA(cudaStreamSynchronize(h->stream));
+    cudaFree(tmp);
+    return BB_OK;
+}
+
+extern "C" int bb_fdtd_get_sensors(bb_fdtd *h, int map_id, float *out) {
+    BB_REQUIRE(h && out, "null argument");
+    BB_REQUIRE(map_id >= 0 && map_id < BB_MAP_COUNT && (h->d.sel_maps_sensor & (1u << map_id)), "sensor map %d not selected", map_id);
+    BB_CUDA(cudaSetDevice(h->d.device));
+    if (h->nsensors == 0 || h->nsamples == 0) return BB_OK;
+    const int slot = popcount32(h->d.sel_maps_sensor & ((1u << map_id) - 1u));
+    const size_t n = (size_t)h->nsensors * h->nsamples;
+    float *tmp = nullptr;
+    BB_CUDA(cudaMalloc(&tmp, n * 4));
+    sensor_transpose_kernel<<<(unsigned)((h->nsensors + 255) / 256), 256, 0, h->stream>>>(h->sensor_out + (size_t)slot * n, tmp, h->nsensors, (int)h->nsamples);
+    BB_CUDA(cudaGetLastError());
+    BB_CUDA(cudaMemcpyAsync(out, tmp, n * 4, cudaMemcpyDeviceToHost, h->stream));
+    BB_CUDA(cudaStreamSynchronize(h->stream));
+    cudaFree(tmp);
+    return BB_OK;
+}
+
+extern "C" int bb_fdtd_get_stats(bb_fdtd *h, bb_fdtd_stats *out) {
+    BB_REQUIRE(h && out, "null argument");
+    *out = h->stats;
+    out->cells_local = (int64_t)h->nown * h->p.n2 * h->p.n3;
+    out->device_bytes = h->device_bytes;
+    out->nsamples = h->nsamples;
+    out->steps_done = h->step;
+    return BB_OK;
+}

@@ -1,0 +1,145 @@
+// Global kernels of the FDTD path.
+#pragma once
+#include "fdtd_cell.cuh"
+
+// ------------------------------------------------------------------------------------------
+// variant 1 ("direct"): one thread per cell, operands straight from global memory through L1/L2.
+// Kept as the simple reference kernel (kernel_variant = 1) and used for the PML shell.
+// ------------------------------------------------------------------------------------------
+template <typename LT, bool ACC>
+__global__ void __launch_bounds__(256) stress_direct(const DevParams p, int ib) {
+    const int k = blockIdx.x * blockDim.x + threadIdx.x;
+    const int j = blockIdx.y * blockDim.y + threadIdx.y;
+    const int i = ib + blockIdx.z;
+    if (k >= p.n3 || j >= p.n2) return;
+    const long long q = ((long long)(i - p.i0 + 2) * p.n2 + j) * p.pitch + k;
+    if (in_pml1(i, p.n1, p.P) || in_pml1(j, p.n2, p.P) || in_pml1(k, p.n3, p.P)) stress_cell_pml<LT>(p, i, j, k, q);
+    else stress_cell_interior<LT, ACC>(p, i, j, k, q);
+}
+
+template <typename LT, bool ACC>
+__global__ void __launch_bounds__(256) particle_direct(const DevParams p, int ib) {
+    const int k = blockIdx.x * blockDim.x + threadIdx.x;
+    const int j = blockIdx.y * blockDim.y + threadIdx.y;
+    const int i = ib + blockIdx.z;
+    if (k >= p.n3 || j >= p.n2) return;
+    const long long q = ((long long)(i - p.i0 + 2) * p.n2 + j) * p.pitch + k;
+    if (in_pml1(i, p.n1, p.P) || in_pml1(j, p.n2, p.P) || in_pml1(k, p.n3, p.P)) particle_cell_pml<LT>(p, i, j, k, q);
+    else particle_cell_interior<LT, ACC>(p, i, j, k, q);
+}
+
+// ------------------------------------------------------------------------------------------
+// sources, sensors, bookkeeping
+// ------------------------------------------------------------------------------------------
+// one thread per source cell; sf is [nt_src][nsrc] (row n contiguous)
+__global__ void source_kernel(const DevParams p, int type_source, long long ncells, const long long *__restrict__ cell,
+                              const int *__restrict__ row, const float *__restrict__ ox,
+                              const float *__restrict__ oy, const float *__restrict__ oz,
+                              const float *__restrict__ sf_row) {
+    const long long s = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    if (s >= ncells) return;
+    const float v = sf_row[row[s]];
+    const long long q = cell[s];
+    if (type_source >= 2) {
+        const float w = v * ox[s];
+        if (type_source == 2) { p.S[0][q] += w; p.S[1][q] += w; p.S[2][q] += w; }
+        else { p.S[0][q] = w; p.S[1][q] = w; p.S[2][q] = w; }
+    } else {
+        if (type_source == 0) { p.V[0][q] += v * ox[s]; p.V[1][q] += v * oy[s]; p.V[2][q] += v * oz[s]; }
+        else { p.V[0][q] = v * ox[s]; p.V[1][q] = v * oy[s]; p.V[2][q] = v * oz[s]; }
+    }
+}
+
+template <typename LT>
+__device__ __forceinline__ float field_value(const DevParams &p, int map, long long q) {
+    switch (map) {
+    case BB_MAP_ALLV: {
+        const float a = p.V[0][q], b = p.V[1][q], c = p.V[2][q];
+        return sqrtf(a * a + b * b + c * c);
+    }
+    case BB_MAP_VX: case BB_MAP_VY: case BB_MAP_VZ: return p.V[map - BB_MAP_VX][q];
+    case BB_MAP_PRESSURE: {
+        const unsigned m = reinterpret_cast<const LT *>(p.lab)[q] & LabelTraits<LT>::MASK;
+        return -__ldg(&p.mat[m].K) * p.Pr[q];
+    }
+    default: return p.S[map - BB_MAP_SXX][q];
+    }
+}
+
+// out layout on the device: [selected map][sample][sensor]
+template <typename LT>
+__global__ void sensor_kernel(const DevParams p, unsigned sel_maps, long long nsensors, const long long *__restrict__ cell,
+                              float *__restrict__ out, long long nsamples, long long sample) {
+    const long long s = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    if (s >= nsensors) return;
+    const long long q = cell[s];
+    int slot = 0;
+    for (int m = 0; m < BB_MAP_COUNT; m++) {
+        if (!(sel_maps & (1u << m))) continue;
+        out[((long long)slot * nsamples + sample) * nsensors + s] = field_value<LT>(p, m, q);
+        slot++;
+    }
+}
+
+// (sample, sensor) -> (sensor, sample)
+__global__ void sensor_transpose_kernel(const float *__restrict__ in, float *__restrict__ out, long long nsensors, int nsamples) {
+    const long long s = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    if (s >= nsensors) return;
+    for (int t = 0; t < nsamples; t++) out[s * nsamples + t] = in[(long long)t * nsensors + s];
+}
+
+// uint32 host labels (dense rows of n3) -> LT labels (pitched rows), reflector -> top bit
+template <typename LT>
+__global__ void label_convert_kernel(const uint32_t *__restrict__ in, const uint32_t *__restrict__ refl, LT *__restrict__ out,
+                                     long long nrows, int n3, int pitch, int nmat, int *__restrict__ bad) {
+    const long long t = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    const long long r = t / pitch;
+    const int k = (int)(t - r * pitch);
+    if (r >= nrows) return;
+    unsigned v = 0;
+    if (k < n3) {
+        v = in[r * n3 + k];
+        if (v >= (unsigned)nmat) { atomicExch(bad, 1); v = 0; }
+        if (refl && refl[r * n3 + k]) v |= LabelTraits<LT>::REFL;
+    }
+    out[r * pitch + k] = (LT)v;
+}
+
+// SourceFunctions (nsrc, nt) with row stride -> float32 [nt][nsrc]; 32x32 smem tile transpose
+template <typename T>
+__global__ void srcfun_transpose_kernel(const T *__restrict__ in, long long row_stride, float *__restrict__ out, int nsrc, int nt) {
+    __shared__ float tile[32][33];
+    const int t0 = blockIdx.x * 32, s0 = blockIdx.y * 32;
+    for (int r = threadIdx.y; r < 32; r += blockDim.y) {
+        const int s = s0 + r, t = t0 + threadIdx.x;
+        tile[r][threadIdx.x] = (s < nsrc && t < nt) ? (float)in[(long long)s * row_stride + t] : 0.0f;
+    }
+    __syncthreads();
+    for (int r = threadIdx.y; r < 32; r += blockDim.y) {
+        const int t = t0 + r, s = s0 + threadIdx.x;
+        if (t < nt && s < nsrc) out[(long long)t * nsrc + s] = tile[threadIdx.x][r];
+    }
+}
+
+// dense (nown, n2, n3) result from a pitched owned-planes array; mode 0 copy, 1 sqrt(x/nacc), 2 sqrt(x)
+__global__ void finalize_map_kernel(const float *__restrict__ in, float *__restrict__ out, long long nrows, int n3, int pitch,
+                                    int mode, float inv_nacc) {
+    const long long t = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    const long long r = t / n3;
+    const int k = (int)(t - r * n3);
+    if (r >= nrows) return;
+    float v = in[r * pitch + k];
+    if (mode == 1) v = sqrtf(v * inv_nacc);
+    else if (mode == 2) v = sqrtf(v);
+    out[t] = v;
+}
+
+template <typename LT>
+__global__ void finalize_pressure_kernel(const DevParams p, float *__restrict__ out, long long nrows) {
+    const long long t = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    const long long r = t / p.n3;
+    const int k = (int)(t - r * p.n3);
+    if (r >= nrows) return;
+    const long long q = 2 * p.plane + r * p.pitch + k;
+    out[t] = field_value<LT>(p, BB_MAP_PRESSURE, q);
+}

@@ -1,0 +1,111 @@
+// Rayleigh-Sommerfeld forward integral on the GPU; replaces ForwardSimple(cwvnb, center, ds, u0, rf)
+// (TranscranialModeling/BabelIntegrationSingle.py:295, BabelIntegrationANNULAR_ARRAY.py:383,411).
+//   out[p] = j k/(2 pi) * sum_s ds[s] exp(Im(k) R)/R * u0[s] exp(-j Re(k) R),  R = |rf[p]-center[s]|
+// Compute bound (FP32 + MUFU): sources are staged through shared memory as float4 + float2 records
+// and every thread accumulates PPT field points so each staged source is reused PPT*blockDim times.
+#include "common.h"
+
+namespace {
+constexpr int RB = 256;      // threads per CTA
+constexpr int PPT = 2;       // field points per thread
+constexpr int STILE = 512;   // sources per shared-memory tile
+
+template <bool ATT, bool MAXD, bool PERPOINT>
+__global__ void __launch_bounds__(RB) rayleigh_kernel(float k_re, float k_im, long long nsrc, const float *__restrict__ center,
+                                                       const float *__restrict__ ds, const float2 *__restrict__ u0,
+                                                       long long npts, const float *__restrict__ rf, float2 *__restrict__ out,
+                                                       float max_distance) {
+    __shared__ float4 s_pos[STILE];  // x, y, z, ds
+    __shared__ float2 s_u[STILE];
+    float px[PPT], py[PPT], pz[PPT], ar[PPT], ai[PPT];
+    long long pidx[PPT];
+#pragma unroll
+    for (int t = 0; t < PPT; t++) {
+        pidx[t] = ((long long)blockIdx.x * PPT + t) * RB + threadIdx.x;
+        const long long pp = pidx[t] < npts ? pidx[t] : npts - 1;
+        px[t] = rf[3 * pp]; py[t] = rf[3 * pp + 1]; pz[t] = rf[3 * pp + 2];
+        ar[t] = 0.f; ai[t] = 0.f;
+    }
+    for (long long s0 = 0; s0 < nsrc; s0 += STILE) {
+        const int ns = (int)min((long long)STILE, nsrc - s0);
+        __syncthreads();
+        for (int s = threadIdx.x; s < ns; s += RB) {
+            const long long g = s0 + s;
+            s_pos[s] = make_float4(center[3 * g], center[3 * g + 1], center[3 * g + 2], ds[g]);
+            if (!PERPOINT) s_u[s] = u0[g];
+        }
+        __syncthreads();
+#pragma unroll 4
+        for (int s = 0; s < ns; s++) {
+            const float4 c = s_pos[s];
+            float2 u;
+            if (!PERPOINT) u = s_u[s];
+#pragma unroll
+            for (int t = 0; t < PPT; t++) {
+                const float dx = c.x - px[t], dy = c.y - py[t], dz = c.z - pz[t];
+                const float R = sqrtf(dx * dx + dy * dy + dz * dz);
+                if (MAXD && R > max_distance) continue;
+                if (PERPOINT) u = u0[(pidx[t] < npts ? pidx[t] : npts - 1) * nsrc + s0 + s];
+                float amp = c.w / R;
+                if (ATT) amp *= expf(R * k_im);
+                float sn, cs;
+                sincosf(R * k_re, &sn, &cs);
+                ar[t] += amp * (u.x * cs + u.y * sn);
+                ai[t] += amp * (u.y * cs - u.x * sn);
+            }
+        }
+    }
+    const float inv2pi = 0.15915494309189535f;
+#pragma unroll
+    for (int t = 0; t < PPT; t++) {
+        if (pidx[t] < npts)
+            out[pidx[t]] = make_float2((-ar[t] * k_im - ai[t] * k_re) * inv2pi, (ar[t] * k_re - ai[t] * k_im) * inv2pi);
+    }
+}
+}  // namespace
+
+extern "C" int bb_rayleigh_forward(float k_re, float k_im, int64_t nsrc, const float *center, const float *ds,
+                                   const float *u0_reim, int64_t npts, const float *rf, float *out_reim,
+                                   float max_distance, int64_t u0_step, int device, double *kernel_ms) {
+    BB_REQUIRE(nsrc > 0 && npts > 0 && center && ds && u0_reim && rf && out_reim, "bad Rayleigh arguments");
+    BB_REQUIRE(u0_step == 0 || u0_step == nsrc, "u0step must equal the number of sources");
+    int ndev = bb_device_count();
+    if (ndev <= 0) { if (ndev == 0) bb_set_error("no CUDA device (this library has no CPU fallback)"); return BB_ERR_CUDA; }
+    BB_REQUIRE(device >= 0 && device < ndev, "device %d of %d", device, ndev);
+    BB_CUDA(cudaSetDevice(device));
+    float *d_center = nullptr, *d_ds = nullptr, *d_rf = nullptr;
+    float2 *d_u0 = nullptr, *d_out = nullptr;
+    const size_t nu = u0_step ? (size_t)npts * nsrc : (size_t)nsrc;
+    cudaStream_t st;
+    BB_CUDA(cudaStreamCreateWithFlags(&st, cudaStreamNonBlocking));
+    BB_CUDA(cudaMalloc(&d_center, (size_t)nsrc * 12));
+    BB_CUDA(cudaMalloc(&d_ds, (size_t)nsrc * 4));
+    BB_CUDA(cudaMalloc(&d_u0, nu * 8));
+    BB_CUDA(cudaMalloc(&d_rf, (size_t)npts * 12));
+    BB_CUDA(cudaMalloc(&d_out, (size_t)npts * 8));
+    BB_CUDA(cudaMemcpyAsync(d_center, center, (size_t)nsrc * 12, cudaMemcpyHostToDevice, st));
+    BB_CUDA(cudaMemcpyAsync(d_ds, ds, (size_t)nsrc * 4, cudaMemcpyHostToDevice, st));
+    BB_CUDA(cudaMemcpyAsync(d_u0, u0_reim, nu * 8, cudaMemcpyHostToDevice, st));
+    BB_CUDA(cudaMemcpyAsync(d_rf, rf, (size_t)npts * 12, cudaMemcpyHostToDevice, st));
+    cudaEvent_t e0, e1;
+    BB_CUDA(cudaEventCreate(&e0));
+    BB_CUDA(cudaEventCreate(&e1));
+    const unsigned grid = (unsigned)((npts + (long long)RB * PPT - 1) / ((long long)RB * PPT));
+    const bool att = k_im != 0.f, maxd = max_distance > 0.f, pp = u0_step != 0;
+    BB_CUDA(cudaEventRecord(e0, st));
+#define BB_RL(A, M, Q) rayleigh_kernel<A, M, Q><<<grid, RB, 0, st>>>(k_re, k_im, nsrc, d_center, d_ds, d_u0, npts, d_rf, d_out, max_distance)
+    if (pp) { if (att) { if (maxd) BB_RL(true, true, true); else BB_RL(true, false, true); } else { if (maxd) BB_RL(false, true, true); else BB_RL(false, false, true); } }
+    else { if (att) { if (maxd) BB_RL(true, true, false); else BB_RL(true, false, false); } else { if (maxd) BB_RL(false, true, false); else BB_RL(false, false, false); } }
+#undef BB_RL
+    BB_CUDA(cudaGetLastError());
+    BB_CUDA(cudaEventRecord(e1, st));
+    BB_CUDA(cudaMemcpyAsync(out_reim, d_out, (size_t)npts * 8, cudaMemcpyDeviceToHost, st));
+    BB_CUDA(cudaStreamSynchronize(st));
+    float ms = 0;
+    cudaEventElapsedTime(&ms, e0, e1);
+    if (kernel_ms) *kernel_ms = ms;
+    cudaEventDestroy(e0); cudaEventDestroy(e1);
+    cudaFree(d_center); cudaFree(d_ds); cudaFree(d_u0); cudaFree(d_rf); cudaFree(d_out);
+    cudaStreamDestroy(st);
+    return BB_OK;
+}

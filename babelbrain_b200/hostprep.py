@@ -1,0 +1,108 @@
+"""
+Host-side (float64) preparation shared by every run: per-material coefficient tables, the stable
+time step, the PML damping tables and the step/sample bookkeeping.  This is the part of
+``PropagationModel.CalculateMatricesForPropagation`` / ``StaggeredFDTD_3D_with_relaxation`` that runs
+before the time loop (callers: TranscranialModeling/BabelIntegrationBASE.py:1799,1801,2338).
+
+The arithmetic of BabelViscoFDTD is not available in the reference tree (un-vendored pip package,
+environment_linux.yml:44); the formulas below restate the published scheme and are cross-checked
+against the independent restatement in oracle/fdtd_numpy.py by tests/test_hostprep.py.
+"""
+import numpy as np
+
+MAP_NAMES = ['ALLV', 'Vx', 'Vy', 'Vz', 'Sigmaxx', 'Sigmayy', 'Sigmazz', 'Sigmaxy', 'Sigmaxz', 'Sigmayz', 'Pressure']
+
+
+def maps_mask(names):
+    m = 0
+    for n in names:
+        if n not in MAP_NAMES:
+            raise ValueError('unknown map name %r (valid: %s)' % (n, MAP_NAMES))
+        m |= 1 << MAP_NAMES.index(n)
+    return m
+
+
+def quality_factors(MaterialProperties, Frequency, QCorrection=1.0):
+    """Low-loss Q = omega/(2 c alpha) per mode, times the per-material QCorrection
+    (BabelIntegrationBASE.py:1249-1272 passes 1 for fluids, 3 for bone)."""
+    MP = np.atleast_2d(np.asarray(MaterialProperties, dtype=np.float64))
+    w = 2.0 * np.pi * float(Frequency)
+    qc = np.broadcast_to(np.asarray(QCorrection, dtype=np.float64), (MP.shape[0],))
+    with np.errstate(divide='ignore', invalid='ignore'):
+        QL = np.where((MP[:, 3] > 0) & (MP[:, 1] > 0), w / (2.0 * MP[:, 1] * MP[:, 3]), 0.0) * qc
+        QS = np.where((MP[:, 4] > 0) & (MP[:, 2] > 0), w / (2.0 * MP[:, 2] * MP[:, 4]), 0.0) * qc
+    return QL, QS
+
+
+def relaxation_fit(Frequency, QL, QS):
+    """Single standard-linear-solid (tau-method): common tau_sigma per material from the L mode
+    (S mode when only shear attenuates); per-mode tau so that Q(omega) is met exactly."""
+    w = 2.0 * np.pi * float(Frequency)
+    qref = np.where(QL > 0, QL, QS)
+    on = qref > 0
+    iq = np.where(on, 1.0 / np.where(on, qref, 1.0), 0.0)
+    x = np.where(on, np.sqrt(1.0 + iq * iq) - iq, 1.0)   # omega * tau_sigma
+    ots = np.where(on, w / x, 0.0)
+
+    def tau_of(Q):
+        has = on & (Q > 0)
+        iqm = np.where(has, 1.0 / np.where(has, Q, 1.0), 0.0)
+        y = (x + iqm) / (1.0 - x * iqm)                   # omega * tau_epsilon
+        return np.where(has, y / x - 1.0, 0.0)
+    return tau_of(QL), tau_of(QS), ots
+
+
+def dispersion_factor(Frequency, tau, ots):
+    """relaxed speed / phase speed at omega for the SLS (QfactorCorrection)."""
+    w = 2.0 * np.pi * float(Frequency)
+    on = ots > 0
+    x = np.where(on, w / np.where(on, ots, 1.0), 0.0)
+    y = x * (1.0 + tau)
+    F = (1.0 + 1j * y) / (1.0 + 1j * x)
+    return np.where(on, np.real(1.0 / np.sqrt(F)), 1.0)
+
+
+def material_table(MaterialProperties, Frequency, QfactorCorrection, SpatialStep, QCorrection=1.0):
+    """(nmat, 8) float64 rows [M, G, L, B, tauL, tauS, 1/tau_sigma, K], moduli divided by h."""
+    MP = np.atleast_2d(np.asarray(MaterialProperties, dtype=np.float64))
+    if MP.shape[1] != 5:
+        raise ValueError('MaterialProperties must be (N,5): rho, cL, cS, attL, attS')
+    h = float(SpatialStep)
+    QL, QS = quality_factors(MP, Frequency, QCorrection)
+    tauL, tauS, ots = relaxation_fit(Frequency, QL, QS)
+    rho, cL, cS = MP[:, 0], MP[:, 1], MP[:, 2]
+    cLr, cSr = cL, cS
+    if QfactorCorrection:
+        cLr = cL * dispersion_factor(Frequency, tauL, ots)
+        cSr = cS * dispersion_factor(Frequency, tauS, ots)
+    M = rho * cLr * cLr / h
+    G = rho * cSr * cSr / h
+    T = np.stack([M, G, M - 2.0 * G, 1.0 / (rho * h), tauL, tauS, ots, rho * cL * cL / h], axis=1)
+    return T, dict(QL=QL, QS=QS, cLr=cLr, cSr=cSr)
+
+
+def stable_dt(MaterialProperties, SpatialStep, AlphaCFL):
+    MP = np.atleast_2d(np.asarray(MaterialProperties, dtype=np.float64))
+    return float(AlphaCFL) * np.sqrt(3.0) / 3.0 * float(SpatialStep) / MP[:, 1].max()
+
+
+def pml_table(NDelta, SpatialStep, dt, Vmax, ReflectionLimit):
+    """(4, NDelta+1) float64: InvDXDT, DXDT, InvDXDThp, DXDThp."""
+    P = int(NDelta)
+    d0 = np.log(1.0 / float(ReflectionLimit)) * 3.0 * float(Vmax) / (2.0 * P * float(SpatialStep))
+    xi = np.arange(P + 1, dtype=np.float64)
+    d = d0 * (xi / P) ** 2
+    dh = d0 * ((xi + 0.5) / P) ** 2
+    return np.stack([1.0 / (1.0 / dt + d / 2), 1.0 / dt - d / 2, 1.0 / (1.0 / dt + dh / 2), 1.0 / dt - dh / 2])
+
+
+def number_of_steps(DurationSimulation, dt):
+    r = float(DurationSimulation) / float(dt)
+    if abs(r - round(r)) < 1e-6 * max(1.0, r):
+        return int(round(r))
+    return int(np.ceil(r))
+
+
+def sample_steps(steps, SensorSubSampling, SensorStart):
+    n = np.arange(0, steps, int(SensorSubSampling))
+    return n[n // int(SensorSubSampling) >= int(SensorStart)]

@@ -1,0 +1,311 @@
+"""
+Host-side mirror of ``BabelViscoFDTD.PropagationModel.PropagationModel`` for the path BabelBrain
+drives (TranscranialModeling/BabelIntegrationBASE.py:43 ``PModel=PropagationModel()``;
+:1799/:1801 ``CalculateMatricesForPropagation``; :2338/:2374/:2401
+``StaggeredFDTD_3D_with_relaxation``).  Same names, argument meaning, return tuples and error
+behaviour; the time loop runs in libbabelb200.so (CUDA, sm_100a) through the C ABI of
+include/babelb200.h.  No CPU fallback: without the library or a GPU the call raises.
+"""
+import collections.abc
+import ctypes
+import weakref
+import numpy as np
+
+from . import _capi, hostprep
+from .slab import SlabPlan
+
+_live_lastmaps = []
+
+
+class FdtdSlab:
+    """One slab [i0,i1) of a simulation on one GPU (the whole domain when nranks == 1)."""
+
+    def __init__(self, MaterialMap, MaterialProperties, Frequency, SourceMap, SourceFunctions, SpatialStep,
+                 DurationSimulation, SensorMap, Ox=np.array([1]), Oy=np.array([1]), Oz=np.array([1]),
+                 AlphaCFL=0.99, NDelta=12, ReflectionLimit=1.0e-5, DT=None, QfactorCorrection=True,
+                 QCorrection=1.0, TypeSource=0, SelRMSorPeak=1, SelMapsRMSPeakList=('ALLV',),
+                 SelMapsSensorsList=('Vx', 'Vy', 'Vz'), SensorSubSampling=2, SensorStart=0,
+                 ReflectorMask=None, device=0, rank=0, nranks=1, kernel_variant=0, steps=None,
+                 origin=None, n1_global=None):
+        self._h = None
+        if not isinstance(MaterialMap, np.ndarray) or MaterialMap.ndim != 3:
+            raise ValueError('MaterialMap must be a 3-D numpy array')
+        for name, arr in (('MaterialMap', MaterialMap), ('SourceMap', SourceMap), ('SensorMap', SensorMap)):
+            if not isinstance(arr, np.ndarray) or arr.dtype != np.uint32:
+                raise TypeError('%s must be a numpy array of dtype uint32' % name)
+            if arr.shape != MaterialMap.shape:
+                raise ValueError('%s must have the shape of MaterialMap' % name)
+        MP = np.atleast_2d(np.asarray(MaterialProperties, dtype=np.float64))
+        # the volumes either cover the whole grid (origin None) or only this rank's planes
+        # [origin, origin + shape[0]) = SlabPlan.with_halo(rank) of a grid with n1_global planes
+        N1 = int(MaterialMap.shape[0] if origin is None else n1_global)
+        N2, N3 = MaterialMap.shape[1:]
+        org = 0 if origin is None else int(origin)
+        self.shape = (N1, N2, N3)
+        if MaterialMap.max() >= MP.shape[0]:
+            raise ValueError('MaterialMap holds label %d but MaterialProperties has %d rows' % (MaterialMap.max(), MP.shape[0]))
+        h = float(SpatialStep)
+        table, self.analysis = hostprep.material_table(MP, Frequency, QfactorCorrection, h, QCorrection)
+        dt_ideal = hostprep.stable_dt(MP, h, AlphaCFL)
+        if DT is None:
+            dt = dt_ideal
+        else:
+            dt = float(DT)
+            if dt > dt_ideal * (1.0 + 1e-9):
+                raise ValueError('Staggered:DT_INVALID: DT %g is larger than the stable step %g' % (dt, dt_ideal))
+        self.dt = dt
+        self.steps = hostprep.number_of_steps(DurationSimulation, dt) if steps is None else int(steps)
+        self.sub = int(SensorSubSampling)
+        self.sensor_start = int(SensorStart)
+        self.sample_steps = hostprep.sample_steps(self.steps, self.sub, self.sensor_start)
+        self.rms_names = [n for n in hostprep.MAP_NAMES if n in SelMapsRMSPeakList]
+        self.sensor_names = [n for n in hostprep.MAP_NAMES if n in SelMapsSensorsList]
+        hostprep.maps_mask(SelMapsRMSPeakList), hostprep.maps_mask(SelMapsSensorsList)
+        self.sel_rms_peak = int(SelRMSorPeak)
+        if self.sel_rms_peak not in (1, 2, 3):
+            raise ValueError('SelRMSorPeak must be 1 (RMS), 2 (peak) or 3 (both)')
+        SF = np.asarray(SourceFunctions)
+        if SF.ndim != 2:
+            raise ValueError('SourceFunctions must be (Nsources, Ntime)')
+        if SF.dtype not in (np.float64, np.float32) or SF.strides[1] != SF.itemsize:
+            SF = np.ascontiguousarray(SF, dtype=np.float64)
+        self.plan = SlabPlan(N1, nranks, NDelta)
+        self.rank, self.nranks = int(rank), int(nranks)
+        i0, i1 = self.plan.owned(rank)
+        self.i0, self.i1 = i0, i1
+        glo, ghi = self.plan.with_halo(rank)
+        if origin is not None and (org != glo or MaterialMap.shape[0] != ghi - glo):
+            raise ValueError('local volumes must cover planes [%d,%d) of the global grid' % (glo, ghi))
+
+        # ---- sources owned by this slab (global C-order cell index; ids are 1-based rows)
+        sm_slab = SourceMap[i0 - org:i1 - org]
+        flat = np.flatnonzero(sm_slab.reshape(-1))
+        rows = sm_slab.reshape(-1)[flat].astype(np.int64) - 1
+        if flat.size and rows.max() >= SF.shape[0]:
+            raise ValueError('SourceMap refers to source %d but SourceFunctions has %d rows' % (rows.max() + 1, SF.shape[0]))
+        cells = flat.astype(np.int64) + np.int64(i0) * N2 * N3
+
+        def weights(O):
+            O = np.asarray(O)
+            if O.size == 1:
+                return np.full(cells.shape, float(O.reshape(-1)[0]), np.float32)
+            if O.shape != MaterialMap.shape:
+                raise ValueError('Ox/Oy/Oz must be single values or volumes of the MaterialMap shape')
+            return np.ascontiguousarray(O[i0 - org:i1 - org].reshape(-1)[flat], dtype=np.float32)
+        ox, oy, oz = weights(Ox), weights(Oy), weights(Oz)
+
+        # ---- sensors: IndexSensorMap is the 1-based Fortran-order linear index (BASE.py:2503-2511)
+        # (with local volumes only this slab's part of the global table is known)
+        sl, sj, sk = np.nonzero(SensorMap[i0 - org:i1 - org])
+        findex = (sl.astype(np.int64) + i0) + sj.astype(np.int64) * N1 + sk.astype(np.int64) * N1 * N2
+        order = np.argsort(findex, kind='stable')
+        findex = findex[order]
+        scell = (((sl[order].astype(np.int64) + i0) * N2 + sj[order]) * N3 + sk[order]).astype(np.int64)
+        idx_dtype = np.uint32 if N1 * N2 * N3 < 2 ** 32 else np.uint64
+        self.IndexSensorMapLocal = (findex + 1).astype(idx_dtype)
+        if origin is None and self.nranks > 1:
+            fl = np.flatnonzero(SensorMap.reshape(-1, order='F'))
+            self.IndexSensorMap = (fl + 1).astype(idx_dtype)
+            self.sensor_rows = np.searchsorted(fl, findex)
+        else:
+            self.IndexSensorMap = self.IndexSensorMapLocal
+            self.sensor_rows = np.arange(findex.size)
+        self.nsensors_total = self.IndexSensorMap.size
+
+        _capi.require_gpu()
+        L = _capi.lib()
+        self._L = L
+        d = _capi.FdtdDesc(n1=N1, n2=N2, n3=N3, i0=i0, i1=i1, pml=int(NDelta), nmat=MP.shape[0],
+                           nsrc=SF.shape[0], nt_src=SF.shape[1], steps=self.steps, type_source=int(TypeSource),
+                           sel_rms_peak=self.sel_rms_peak, sel_maps_rms=hostprep.maps_mask(self.rms_names),
+                           sel_maps_sensor=hostprep.maps_mask(self.sensor_names),
+                           sensor_subsampling=self.sub, sensor_start=self.sensor_start, device=int(device),
+                           rank=self.rank, nranks=self.nranks, kernel_variant=int(kernel_variant), reserved=0,
+                           dt=dt)
+        hp = ctypes.c_void_p()
+        _capi.check(L.bb_fdtd_create(ctypes.byref(d), ctypes.byref(hp)))
+        self._h = hp
+        self._finalizer = weakref.finalize(self, L.bb_fdtd_destroy, hp)
+        t32 = np.ascontiguousarray(table, dtype=np.float32)
+        pml = np.ascontiguousarray(hostprep.pml_table(NDelta, h, dt, MP[:, 1].max(), ReflectionLimit), dtype=np.float32)
+        _capi.check(L.bb_fdtd_set_materials(hp, _capi.ptr(t32), _capi.ptr(pml)))
+        mm = np.ascontiguousarray(MaterialMap[glo - org:ghi - org])
+        refl = None
+        if ReflectorMask is not None:
+            RM = np.asarray(ReflectorMask)
+            if RM.shape != MaterialMap.shape:
+                raise ValueError('ReflectorMask must have the shape of MaterialMap')
+            refl = np.ascontiguousarray(RM[glo - org:ghi - org], dtype=np.uint32)
+        _capi.check(L.bb_fdtd_set_maps(hp, _capi.ptr(mm), _capi.ptr(refl)))
+        rows32 = np.ascontiguousarray(rows, dtype=np.int32)
+        _capi.check(L.bb_fdtd_set_source_cells(hp, cells.size, _capi.ptr(cells), _capi.ptr(rows32),
+                                               _capi.ptr(ox), _capi.ptr(oy), _capi.ptr(oz)))
+        if cells.size:
+            _capi.check(L.bb_fdtd_set_source_functions(hp, _capi.ptr(SF), int(SF.dtype == np.float64),
+                                                       SF.strides[0] // SF.itemsize))
+        _capi.check(L.bb_fdtd_set_sensors(hp, scell.size, _capi.ptr(scell)))
+        self.h2d_bytes = int(mm.nbytes + (refl.nbytes if refl is not None else 0) + SF.nbytes * (cells.size > 0)
+                             + cells.nbytes + rows32.nbytes + 3 * ox.nbytes + scell.nbytes + t32.nbytes + pml.nbytes)
+        self.d2h_bytes = 0
+
+    # ------------------------------------------------------------------
+    def comm_init(self, unique_id):
+        _capi.check(self._L.bb_fdtd_comm_init(self._h, unique_id))
+
+    @staticmethod
+    def nccl_unique_id():
+        buf = ctypes.create_string_buffer(128)
+        _capi.check(_capi.lib().bb_nccl_unique_id(buf))
+        return buf.raw
+
+    def set_stream(self, cuda_stream_ptr):
+        _capi.check(self._L.bb_fdtd_set_stream(self._h, ctypes.c_void_p(cuda_stream_ptr)))
+
+    def run(self, nsteps=-1, profile=False):
+        _capi.check(self._L.bb_fdtd_run(self._h, int(nsteps), int(bool(profile))))
+        return self.stats()
+
+    def reset(self):
+        _capi.check(self._L.bb_fdtd_reset(self._h))
+
+    def stats(self):
+        st = _capi.FdtdStats()
+        _capi.check(self._L.bb_fdtd_get_stats(self._h, ctypes.byref(st)))
+        return {k: getattr(st, k) for k, _ in _capi.FdtdStats._fields_}
+
+    def get_map(self, which, name, out=None):
+        """which: 0 RMS, 1 peak, 2 last field.  Returns / fills the (i1-i0, N2, N3) float32 slab."""
+        N1, N2, N3 = self.shape
+        if out is None:
+            out = np.empty((self.i1 - self.i0, N2, N3), np.float32)
+        assert out.flags.c_contiguous and out.dtype == np.float32
+        _capi.check(self._L.bb_fdtd_get_map(self._h, int(which), _capi.MAP_ID[name], _capi.ptr(out)))
+        self.d2h_bytes += out.nbytes
+        return out
+
+    def get_sensors(self, name):
+        out = np.empty((self.sensor_rows.size, self.sample_steps.size), np.float32)
+        _capi.check(self._L.bb_fdtd_get_sensors(self._h, _capi.MAP_ID[name], _capi.ptr(out)))
+        self.d2h_bytes += out.nbytes
+        return out
+
+    def close(self):
+        if self._h is not None:
+            self._finalizer()
+            self._h = None
+
+
+class _LastMap(collections.abc.Mapping):
+    """LastMap of the reference call, fetched from the device on first access of a key.  The caller
+    discards it (BabelIntegrationBASE.py:2338 binds it to a throw-away local), so nothing is copied
+    unless it is read.  Only the most recent simulation keeps its device state."""
+    _keys = hostprep.MAP_NAMES[1:]
+
+    def __init__(self, slab):
+        self._slab = slab
+        self._cache = {}
+
+    def __getitem__(self, k):
+        if k not in self._keys:
+            raise KeyError(k)
+        if k not in self._cache:
+            if self._slab is None:
+                raise RuntimeError('LastMap of an earlier simulation was released when a newer one started')
+            self._cache[k] = self._slab.get_map(2, k)
+        return self._cache[k]
+
+    def __iter__(self):
+        return iter(self._keys)
+
+    def __len__(self):
+        return len(self._keys)
+
+    def _release(self):
+        if self._slab is not None:
+            self._slab.close()
+            self._slab = None
+
+
+def collect_results(slab):
+    """Assemble the reference's return values from a finished single-slab run."""
+    N1, N2, N3 = slab.shape
+    Sensor = {'time': slab.sample_steps.astype(np.float64) * slab.dt}
+    for name in slab.sensor_names:
+        Sensor[name] = slab.get_sensors(name)
+    RMS, Peak = {}, {}
+    for name in slab.rms_names:
+        if slab.sel_rms_peak & 1:
+            RMS[name] = slab.get_map(0, name)
+        if slab.sel_rms_peak & 2:
+            Peak[name] = slab.get_map(1, name)
+    InputParam = {'IndexSensorMap': slab.IndexSensorMap, 'DT': slab.dt, 'N1': N1, 'N2': N2, 'N3': N3,
+                  'TimeSteps': slab.steps, 'SensorSubSampling': slab.sub, 'SensorStart': slab.sensor_start}
+    return Sensor, RMS, Peak, InputParam
+
+
+class PropagationModel:
+    """Drop-in for BabelViscoFDTD.PropagationModel.PropagationModel (the two methods BabelBrain uses)."""
+
+    def CalculateMatricesForPropagation(self, MaterialMap, MaterialProperties, Frequency, QfactorCorrection, h,
+                                        AlphaCFL, QCorrection=1.0):
+        """Returns the 10-tuple whose element 0 is the stable time step -- the only element the
+        caller reads (BabelIntegrationBASE.py:1799,1801).  The others are the per-material arrays
+        (rho, mu, lambda+2mu, lambda, tau_long, tau_shear, tau_sigma, Q_long, Q_shear)."""
+        MP = np.atleast_2d(np.asarray(MaterialProperties, dtype=np.float64))
+        T, A = hostprep.material_table(MP, Frequency, QfactorCorrection, h, QCorrection)
+        dt = hostprep.stable_dt(MP, h, AlphaCFL)
+        with np.errstate(divide='ignore'):
+            tau_sigma = np.where(T[:, 6] > 0, 1.0 / np.where(T[:, 6] > 0, T[:, 6], 1.0), 0.0)
+        return (dt, MP[:, 0].copy(), T[:, 1] * h, T[:, 0] * h, T[:, 2] * h, T[:, 4].copy(), T[:, 5].copy(),
+                tau_sigma, A['QL'], A['QS'])
+
+    def StaggeredFDTD_3D_with_relaxation(self, MaterialMap, MaterialProperties, Frequency, SourceMap,
+                                         SourceFunctions, SpatialStep, DurationSimulation, SensorMap,
+                                         Ox=np.array([1]), Oy=np.array([1]), Oz=np.array([1]),
+                                         AlphaCFL=0.99, NDelta=12, ReflectionLimit=1.0000e-05,
+                                         IntervalSnapshots=-1, COMPUTING_BACKEND=1, USE_SINGLE=True,
+                                         SPP_ZONES=1, SPP_VolumeFraction=None, DT=None,
+                                         QfactorCorrection=True, QCorrection=1.0, CheckOnlyParams=False,
+                                         TypeSource=0, SelRMSorPeak=1, SelMapsRMSPeakList=['ALLV'],
+                                         SelMapsSensorsList=['Vx', 'Vy', 'Vz'], SensorSubSampling=2,
+                                         SensorStart=0, DefaultGPUDeviceName='B200', DefaultGPUDeviceNumber=0,
+                                         ReflectorMask=None, SILENT=0, ManualGroupSize=None, ManualLocalSize=None,
+                                         **_ignored):
+        """Same call as the reference.  COMPUTING_BACKEND, DefaultGPUDeviceName, USE_SINGLE and the
+        manual work-group sizes are accepted for compatibility; every backend value runs the
+        sm_100a CUDA path in float32 (there is no multi-backend dispatch)."""
+        if IntervalSnapshots > 0:
+            raise NotImplementedError('IntervalSnapshots is not supported (BabelBrain never passes it)')
+        if SPP_ZONES != 1:
+            raise NotImplementedError('superposition zones (SPP_ZONES>1) are not supported')
+        for v in _live_lastmaps:
+            v._release()
+        del _live_lastmaps[:]
+        slab = FdtdSlab(MaterialMap, MaterialProperties, Frequency, SourceMap, SourceFunctions, SpatialStep,
+                        DurationSimulation, SensorMap, Ox=Ox, Oy=Oy, Oz=Oz, AlphaCFL=AlphaCFL, NDelta=NDelta,
+                        ReflectionLimit=ReflectionLimit, DT=DT, QfactorCorrection=QfactorCorrection,
+                        QCorrection=QCorrection, TypeSource=TypeSource, SelRMSorPeak=SelRMSorPeak,
+                        SelMapsRMSPeakList=SelMapsRMSPeakList, SelMapsSensorsList=SelMapsSensorsList,
+                        SensorSubSampling=SensorSubSampling, SensorStart=SensorStart, ReflectorMask=ReflectorMask,
+                        device=_select_device(DefaultGPUDeviceName, DefaultGPUDeviceNumber))
+        if CheckOnlyParams:
+            slab.close()
+            return None
+        slab.run()
+        self.last_stats = slab.stats()
+        Sensor, RMS, Peak, InputParam = collect_results(slab)
+        last = _LastMap(slab)
+        _live_lastmaps.append(last)
+        if SelRMSorPeak == 3:
+            return Sensor, last, RMS, Peak, InputParam
+        return Sensor, last, (RMS if SelRMSorPeak == 1 else Peak), InputParam
+
+
+def _select_device(name, number=0):
+    """Device-name substring selection like the reference's InitCuda; falls back to ordinal
+    `number` (or 0) when nothing matches -- the name is advisory on a B200 box."""
+    names = _capi.device_names()
+    hits = [n for n, s in enumerate(names) if isinstance(name, str) and name and name in s]
+    if hits:
+        return hits[min(int(number), len(hits) - 1)]
+    return min(int(number), len(names) - 1) if names else 0

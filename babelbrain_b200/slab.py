@@ -1,0 +1,64 @@
+"""
+Slab decomposition of the FDTD domain along axis 0 (the slowest-varying axis of the caller's
+C-order volumes, so every halo is a set of contiguous planes).  Pure host logic: used by the CUDA
+path (one process per GPU, halos exchanged inside libbabelb200.so with NCCL send/recv) and
+exercised on CPU with world_size-2 gloo tests.  The reference has no distributed layer at all
+(SURVEY.md section 2b); the single-GPU result is the parity oracle of the multi-GPU one.
+"""
+import numpy as np
+
+HALO = 2  # planes: the 4th-order staggered stencil reaches 2 cells one way and 1 the other
+
+
+class SlabPlan:
+    def __init__(self, n1, nranks, pml=12, min_planes=4):
+        n1, nranks = int(n1), int(nranks)
+        if nranks < 1:
+            raise ValueError('nranks must be >= 1')
+        if nranks > 1 and n1 // nranks < min_planes:
+            raise ValueError('too many ranks: %d planes over %d ranks (need >= %d each)' % (n1, nranks, min_planes))
+        self.n1, self.nranks, self.pml = n1, nranks, int(pml)
+        base, rem = divmod(n1, nranks)
+        sizes = [base + (1 if r < rem else 0) for r in range(nranks)]
+        self.bounds = np.concatenate([[0], np.cumsum(sizes)]).astype(int)
+
+    def owned(self, rank):
+        return int(self.bounds[rank]), int(self.bounds[rank + 1])
+
+    def with_halo(self, rank):
+        i0, i1 = self.owned(rank)
+        return max(i0 - HALO, 0), min(i1 + HALO, self.n1)
+
+    def neighbours(self, rank):
+        return (rank - 1 if rank > 0 else None), (rank + 1 if rank < self.nranks - 1 else None)
+
+    def rank_of_plane(self, i):
+        return int(np.searchsorted(self.bounds, i, side='right') - 1)
+
+    def halo_bytes_per_half_step(self, n2, pitch):
+        """bytes one interior rank sends per half-step: 3 fields x 2 planes x 2 neighbours, fp32."""
+        return 3 * HALO * 2 * n2 * pitch * 4
+
+
+def sensor_rows_of_slab(index_sensor_map, shape, i0, i1):
+    """Rows of the global sensor table (IndexSensorMap order: 1-based Fortran linear index,
+    BabelIntegrationBASE.py:2503-2511) whose voxel lies in planes [i0,i1)."""
+    n1 = shape[0]
+    i = (np.asarray(index_sensor_map).astype(np.int64) - 1) % n1
+    return np.flatnonzero((i >= i0) & (i < i1))
+
+
+def assemble_maps(shape, plan, slabs):
+    """slabs: list over ranks of (i1-i0, N2, N3) arrays -> full (N1,N2,N3) volume."""
+    out = np.empty(shape, np.float32)
+    for r, a in enumerate(slabs):
+        i0, i1 = plan.owned(r)
+        out[i0:i1] = a
+    return out
+
+
+def assemble_sensors(nsensors, nsamples, rows_per_rank, data_per_rank):
+    out = np.zeros((nsensors, nsamples), np.float32)
+    for rows, data in zip(rows_per_rank, data_per_rank):
+        out[rows] = data
+    return out

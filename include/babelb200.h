@@ -1,0 +1,134 @@
+/*
+ * babelb200.h -- C ABI of libbabelb200.so: the B200 (sm_100a) replacement for the solver calls
+ * BabelBrain makes into the BabelViscoFDTD package.
+ *
+ * The reference binds this path from Python, so the binding a maintainer adds is a ctypes stub
+ * (babelbrain_b200/_capi.py; INTEGRATION.md shows it).  Every entry point below replaces one
+ * piece of a reference call:
+ *
+ *   bb_fdtd_*            PModel.StaggeredFDTD_3D_with_relaxation(...)
+ *                        TranscranialModeling/BabelIntegrationBASE.py:2338-2365 (forward),
+ *                        :2374-2398 (back-propagation), :2401-2428 (refocus)
+ *   bb_rayleigh_forward  ForwardSimple(cwvnb, center, ds, u0, rf)
+ *                        TranscranialModeling/BabelIntegrationSingle.py:295,
+ *                        BabelIntegrationANNULAR_ARRAY.py:383,411,
+ *                        BabelIntegrationCONCAVE_PHASEDARRAY.py:307,328,425,446
+ *   bb_device_count/name InitCuda(deviceName) (BabelIntegrationBASE.py:918-925) and
+ *                        StaggeredFDTD_3D_With_Relaxation_CUDA.ListDevices()
+ *                        (BabelBrain/SelFiles/SelFiles.py:254-258)
+ *
+ * Conventions: plain pointers and sizes only; the caller owns every host buffer, the library
+ * owns all device memory inside the opaque handle; every function returns 0 on success and a
+ * non-zero code otherwise, with a thread-local message in bb_last_error().  There is no CPU
+ * fallback: without a CUDA device every compute entry point fails with BB_ERR_CUDA.
+ *
+ * Volumes are (N1,N2,N3) C-order (k fastest), exactly the caller's numpy arrays
+ * (BabelIntegrationBASE.py:2111 MaterialMap uint32, :2283 SensorMap uint32).  A handle owns the
+ * slab of planes i in [i0,i1) of the global grid (i0=0,i1=N1 on one GPU); host volume pointers
+ * passed to a handle cover the planes [max(i0-2,0), min(i1+2,N1)) -- the slab plus its halo.
+ */
+#ifndef BABELB200_H
+#define BABELB200_H
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define BB_OK 0
+#define BB_ERR_ARG 1
+#define BB_ERR_CUDA 2
+#define BB_ERR_NCCL 3
+#define BB_ERR_STATE 4
+
+/* map ids = bit positions of the SelMaps masks (order of the reference's map names) */
+enum bb_map {
+    BB_MAP_ALLV = 0, BB_MAP_VX, BB_MAP_VY, BB_MAP_VZ, BB_MAP_SXX, BB_MAP_SYY, BB_MAP_SZZ,
+    BB_MAP_SXY, BB_MAP_SXZ, BB_MAP_SYZ, BB_MAP_PRESSURE, BB_MAP_COUNT
+};
+#define BB_NCOEF 8 /* per-material row: M, G, L, B, tauL, tauS, 1/tau_sigma, K  (all / h) */
+
+typedef struct bb_fdtd bb_fdtd;
+
+typedef struct bb_fdtd_desc {
+    int32_t n1, n2, n3;          /* global grid (MaterialMap.shape) */
+    int32_t i0, i1;              /* planes owned by this handle */
+    int32_t pml;                 /* NDelta (BabelIntegrationBASE.py:2350) */
+    int32_t nmat;                /* rows of MaterialList */
+    int32_t nsrc;                /* rows of SourceFunctions */
+    int32_t nt_src;              /* columns of SourceFunctions (LengthSource) */
+    int32_t steps;               /* time steps of the run */
+    int32_t type_source;         /* TypeSource: 0/1 particle soft/hard, 2/3 stress soft/hard */
+    int32_t sel_rms_peak;        /* SelRMSorPeak: 1 RMS, 2 peak, 3 both */
+    uint32_t sel_maps_rms;       /* SelMapsRMSPeakList as a bit mask of bb_map */
+    uint32_t sel_maps_sensor;    /* SelMapsSensorsList as a bit mask of bb_map */
+    int32_t sensor_subsampling;  /* SensorSubSampling */
+    int32_t sensor_start;        /* SensorStart */
+    int32_t device;              /* CUDA ordinal */
+    int32_t rank, nranks;        /* slab rank (0,1 on one GPU) */
+    int32_t kernel_variant;      /* 0 = default (fastest); other values select debug variants */
+    int32_t reserved;
+    double dt;                   /* DT */
+} bb_fdtd_desc;
+
+typedef struct bb_fdtd_stats {
+    double run_ms;               /* device time of the last bb_fdtd_run (CUDA events) */
+    double stress_ms;            /* sum over launches of the stress kernel (profile mode) */
+    double particle_ms;          /* sum over launches of the particle kernel (profile mode) */
+    double pml_ms;               /* sum over launches of the PML kernels (profile mode) */
+    double other_ms;             /* sources + sensors + halo (profile mode) */
+    int64_t stress_launches, particle_launches, pml_launches, other_launches;
+    int64_t steps_done;
+    int64_t cells_local;         /* (i1-i0)*N2*N3 */
+    int64_t device_bytes;        /* device memory held by the handle */
+    int64_t nsamples;            /* sensor samples per sensor */
+} bb_fdtd_stats;
+
+/* ---- library / device ---- */
+const char *bb_last_error(void);
+const char *bb_version(void);
+int bb_device_count(void);                                   /* <0 on error */
+int bb_device_name(int device, char *out, int out_len);
+
+/* ---- FDTD handle ---- */
+int bb_fdtd_create(const bb_fdtd_desc *desc, bb_fdtd **out);
+void bb_fdtd_destroy(bb_fdtd *h);
+/* optional: run on the caller's CUDA stream (cudaStream_t as void*); NULL = library stream */
+int bb_fdtd_set_stream(bb_fdtd *h, void *cuda_stream);
+/* nmat x BB_NCOEF float table and the 4 x (pml+1) PML table (InvDXDT, DXDT, InvDXDThp, DXDThp) */
+int bb_fdtd_set_materials(bb_fdtd *h, const float *table, const float *pml_table);
+/* uint32 label planes [max(i0-2,0), min(i1+2,n1)) ; reflector may be NULL (ReflectorMask=None) */
+int bb_fdtd_set_maps(bb_fdtd *h, const uint32_t *material, const uint32_t *reflector);
+/* source cells owned by this slab: global C-order linear cell index, 0-based source row, and the
+ * Ox/Oy/Oz weights at those cells (BabelIntegrationBASE.py:2328-2335) */
+int bb_fdtd_set_source_cells(bb_fdtd *h, int64_t ncells, const int64_t *cell, const int32_t *row,
+                             const float *ox, const float *oy, const float *oz);
+/* SourceFunctions as the caller holds it: (nsrc, nt_src), float64 or float32, row stride in
+ * elements (BabelIntegrationSingle.py:335).  Converted and transposed on the device. */
+int bb_fdtd_set_source_functions(bb_fdtd *h, const void *data, int is_f64, int64_t row_stride);
+/* sensors owned by this slab: global C-order linear cell index, in IndexSensorMap order */
+int bb_fdtd_set_sensors(bb_fdtd *h, int64_t nsensors, const int64_t *cell);
+/* slab neighbours exchange halos with NCCL send/recv; id = 128-byte ncclUniqueId from rank 0 */
+int bb_nccl_unique_id(char *out128);
+int bb_fdtd_comm_init(bb_fdtd *h, const char *id128);
+/* advance nsteps (<0: all remaining).  profile != 0 brackets each kernel with CUDA events. */
+int bb_fdtd_run(bb_fdtd *h, int64_t nsteps, int profile);
+int bb_fdtd_reset(bb_fdtd *h);                               /* zero state, step counter = 0 */
+/* results: which = 0 RMS, 1 peak, 2 last field; out = (i1-i0, N2, N3) float32 */
+int bb_fdtd_get_map(bb_fdtd *h, int which, int map_id, float *out);
+/* out = (nsensors, nsamples) float32 for one selected sensor map */
+int bb_fdtd_get_sensors(bb_fdtd *h, int map_id, float *out);
+int bb_fdtd_get_stats(bb_fdtd *h, bb_fdtd_stats *out);
+
+/* ---- Rayleigh integral ---- */
+/* out[p] = j k /(2 pi) * sum_s ds[s] exp(Im(k) R)/R u0[s] exp(-j Re(k) R); host pointers;
+ * center (nsrc,3), u0_reim (nsrc,2), rf (npts,3), out_reim (npts,2); max_distance<=0: no skip.
+ * u0_step != 0: per-point source amplitudes, u0_reim is (npts*nsrc, 2). */
+int bb_rayleigh_forward(float k_re, float k_im, int64_t nsrc, const float *center, const float *ds,
+                        const float *u0_reim, int64_t npts, const float *rf, float *out_reim,
+                        float max_distance, int64_t u0_step, int device, double *kernel_ms);
+
+#ifdef __cplusplus
+}
+#endif
+#endif

@@ -375,6 +375,13 @@ def run(MaterialMap, MaterialProperties, Frequency, SourceMap, SourceFunctions, 
             pb = split(nb_, cb, rig, Db)
             S[...] = np.where(on, Sint, np.where(upd, pa + pb, S))
             R[...] = np.where(ta, NextR, R)
+        if refl is not None:
+            for S in (Sxx, Syy, Szz, Sxy, Sxz, Syz, Pr):
+                S[refl] = 0
+        pscaled = -tab['K'][mm] * Pr
+        if n >= n0:  # RMS/peak are taken inside the half-step, before this step's source is added
+            accumulate({'Sigmaxx': Sxx, 'Sigmayy': Syy, 'Sigmazz': Szz, 'Sigmaxy': Sxy, 'Sigmaxz': Sxz,
+                        'Sigmayz': Syz, 'Pressure': pscaled})
         if TypeSource >= 2 and n < nt_src and len(src_id):
             val = SF[src_id, n].astype(dtype) * ox
             for S in (Sxx, Syy, Szz):
@@ -382,13 +389,6 @@ def run(MaterialMap, MaterialProperties, Frequency, SourceMap, SourceFunctions, 
                     S[src_idx] += val
                 else:
                     S[src_idx] = val
-        if refl is not None:
-            for S in (Sxx, Syy, Szz, Sxy, Sxz, Syz):
-                S[refl] = 0
-        pscaled = -tab['K'][mm] * Pr
-        if n >= n0:
-            accumulate({'Sigmaxx': Sxx, 'Sigmayy': Syy, 'Sigmazz': Szz, 'Sigmaxy': Sxy, 'Sigmaxz': Sxz,
-                        'Sigmayz': Syz, 'Pressure': pscaled})
         # ---------------- particle half-step
         for V, Bv, nm, (f1, k1, a1, c1), (f2, k2, a2, c2), (f3, k3, a3, c3) in (
                 (Vx, Bx, 'Vx', (Sxx, 'f', 0, hI), (Sxy, 'b', 1, cJ), (Sxz, 'b', 2, cK)),
@@ -402,13 +402,6 @@ def run(MaterialMap, MaterialProperties, Frequency, SourceMap, SourceFunctions, 
             p2 = split(nm + '_y', c2, Bv, D2)
             p3 = split(nm + '_z', c3, Bv, D3)
             V[...] = np.where(interior, Vint, np.where(upd, p1 + p2 + p3, V))
-        if TypeSource < 2 and n < nt_src and len(src_id):
-            val = SF[src_id, n].astype(dtype)
-            for V, o in ((Vx, ox), (Vy, oy), (Vz, oz)):
-                if TypeSource == 0:
-                    V[src_idx] += val * o
-                else:
-                    V[src_idx] = val * o
         if refl is not None:
             for V in (Vx, Vy, Vz):
                 V[refl] = 0
@@ -418,6 +411,13 @@ def run(MaterialMap, MaterialProperties, Frequency, SourceMap, SourceFunctions, 
                 acc['ALLV'] += np.where(interior, Vx * Vx + Vy * Vy + Vz * Vz, 0)
             if 'ALLV' in peak:
                 peak['ALLV'] = np.where(interior, np.maximum(peak['ALLV'], Vx * Vx + Vy * Vy + Vz * Vz), peak['ALLV'])
+        if TypeSource < 2 and n < nt_src and len(src_id):
+            val = SF[src_id, n].astype(dtype)
+            for V, o in ((Vx, ox), (Vy, oy), (Vz, oz)):
+                if TypeSource == 0:
+                    V[src_idx] += val * o
+                else:
+                    V[src_idx] = val * o
         # ---------------- sensors
         if n in sample_steps:
             q = sample_steps.index(n)

@@ -275,36 +275,21 @@ int oracle_fdtd_run(const oracle_params *prm, const uint32_t *matmap, const real
         for (int i = 0; i < n1; i++)
             for (int j = 0; j < n2; j++)
                 for (int k = 0; k < n3; k++) stress_cell(&c, i, j, k, 0);
-        if (prm->type_source >= 2 && n < prm->nt_src) {
-            for (int64_t s = 0; s < prm->nsrc_cells; s++) {
-                const real v = srcfun[(int64_t)n * prm->nsrc + src_id[s]] * ox[s];
-                const int64_t p = src_cell[s];
-                if (prm->type_source == 2) { c.S[0][p] += v; c.S[1][p] += v; c.S[2][p] += v; }
-                else { c.S[0][p] = v; c.S[1][p] = v; c.S[2][p] = v; }
-            }
-        }
-        if (reflector) {
-#pragma omp parallel for
-            for (int64_t p = 0; p < N; p++) if (reflector[p]) for (int a = 0; a < 6; a++) c.S[a][p] = 0;
-        }
         for (int pass = 0; pass < 2; pass++) {
-            /* pass 0: stress-kernel maps right after the stress half-step; pass 1: particle maps */
+            /* pass 0: stress half-step already done above; pass 1: particle half-step.
+               Order inside a half-step: update -> reflector -> RMS/peak -> source. */
             if (pass == 1) {
 #pragma omp parallel for collapse(2) schedule(static)
                 for (int i = 0; i < n1; i++)
                     for (int j = 0; j < n2; j++)
                         for (int k = 0; k < n3; k++) particle_cell(&c, i, j, k);
-                if (prm->type_source < 2 && n < prm->nt_src) {
-                    for (int64_t s = 0; s < prm->nsrc_cells; s++) {
-                        const real v = srcfun[(int64_t)n * prm->nsrc + src_id[s]];
-                        const int64_t p = src_cell[s];
-                        if (prm->type_source == 0) { c.V[0][p] += v * ox[s]; c.V[1][p] += v * oy[s]; c.V[2][p] += v * oz[s]; }
-                        else { c.V[0][p] = v * ox[s]; c.V[1][p] = v * oy[s]; c.V[2][p] = v * oz[s]; }
-                    }
-                }
-                if (reflector) {
+            }
+            if (reflector) {
 #pragma omp parallel for
-                    for (int64_t p = 0; p < N; p++) if (reflector[p]) for (int a = 0; a < 3; a++) c.V[a][p] = 0;
+                for (int64_t p = 0; p < N; p++) {
+                    if (!reflector[p]) continue;
+                    if (pass == 0) { for (int a = 0; a < 6; a++) c.S[a][p] = 0; c.Pr[p] = 0; }
+                    else for (int a = 0; a < 3; a++) c.V[a][p] = 0;
                 }
             }
             const uint32_t maps = pass == 0 ? stress_maps : part_maps;
@@ -322,6 +307,20 @@ int oracle_fdtd_run(const oracle_params *prm, const uint32_t *matmap, const real
                                 if ((prm->sel_rms_peak & 2) && v > out_peak[o]) out_peak[o] = v;
                             }
                         }
+            }
+            if (n < prm->nt_src) {
+                for (int64_t s = 0; s < prm->nsrc_cells; s++) {
+                    const real v = srcfun[(int64_t)n * prm->nsrc + src_id[s]];
+                    const int64_t p = src_cell[s];
+                    if (pass == 0 && prm->type_source >= 2) {
+                        const real w = v * ox[s];
+                        if (prm->type_source == 2) { c.S[0][p] += w; c.S[1][p] += w; c.S[2][p] += w; }
+                        else { c.S[0][p] = w; c.S[1][p] = w; c.S[2][p] = w; }
+                    } else if (pass == 1 && prm->type_source < 2) {
+                        if (prm->type_source == 0) { c.V[0][p] += v * ox[s]; c.V[1][p] += v * oy[s]; c.V[2][p] += v * oz[s]; }
+                        else { c.V[0][p] = v * ox[s]; c.V[1][p] = v * oy[s]; c.V[2][p] = v * oz[s]; }
+                    }
+                }
             }
         }
         if (n % sub == 0 && n / sub >= prm->sensor_start) {

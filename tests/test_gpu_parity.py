@@ -1,0 +1,156 @@
+"""GPU parity tests proper: the CUDA path (through the reference-shaped Python API -> C ABI) against
+the C oracle on the same seeded inputs.  Tolerance (north_star): float32 pressure-amplitude map
+relative L2 <= 1e-4 with an identical peak voxel; index maps bit-exact."""
+import numpy as np
+import pytest
+
+import oracle
+from babelbrain_b200 import workloads
+from babelbrain_b200.propagation import FdtdSlab, collect_results, PropagationModel
+
+pytestmark = pytest.mark.gpu
+TOL = 1e-4
+DROP = ('COMPUTING_BACKEND', 'USE_SINGLE', 'DefaultGPUDeviceName')
+
+
+def rl2(a, b):
+    a = np.asarray(a, np.float64)
+    b = np.asarray(b, np.float64)
+    nb = float(np.linalg.norm(b))
+    d = float(np.linalg.norm(a - b))
+    return d / nb if nb > 0 else d
+
+
+def run_cuda(w, variant=0, **over):
+    kw = {k: v for k, v in w['kwargs'].items() if k not in DROP}
+    kw.update(over)
+    s = FdtdSlab(*w['args'], kernel_variant=variant, **kw)
+    s.run()
+    out = collect_results(s)
+    last = {k: s.get_map(2, k) for k in ('Vx', 'Vy', 'Vz', 'Sigmaxx', 'Sigmaxy', 'Pressure')}
+    s.close()
+    return out, last
+
+
+def run_oracle(w, **over):
+    kw = {k: v for k, v in w['kwargs'].items() if k not in DROP}
+    kw.update(over)
+    return oracle.run_c(*w['args'], want_last=True, **kw)
+
+
+CASES = [('single_water', (40, 44, 56), 5, 8), ('ctx500_skull', (56, 48, 72), 6, 8),
+         ('ctx500_skull', (40, 70, 45), 4, 6), ('h317_skull', (48, 48, 48), 3, 6),
+         ('dome_stress', (64, 64, 48), 4, 8), ('hires_1mhz', (44, 40, 70), 3, 12)]
+
+
+@pytest.mark.parametrize('variant', [0, 1])
+@pytest.mark.parametrize('name,shape,periods,pml', CASES)
+def test_parity_small(name, shape, periods, pml, variant):
+    w = workloads.make_workload(name, shape=shape, periods=periods, pml=pml)
+    (Sensor, RMS, Peak, IP), last = run_cuda(w, variant)
+    ref = run_oracle(w)
+    assert np.array_equal(IP['IndexSensorMap'], ref['IndexSensorMap'])
+    assert np.allclose(Sensor['time'], ref['Sensor']['time'], rtol=1e-12)
+    for k in ref['RMS']:
+        assert rl2(RMS[k], ref['RMS'][k]) <= TOL, (k, rl2(RMS[k], ref['RMS'][k]))
+    for k in ref['Peak']:
+        assert rl2(Peak[k], ref['Peak'][k]) <= TOL, k
+    main = RMS if 'Pressure' in RMS else Peak
+    refm = ref['RMS'] if 'Pressure' in ref['RMS'] else ref['Peak']
+    assert np.argmax(main['Pressure']) == np.argmax(refm['Pressure'])
+    assert rl2(Sensor['Pressure'], ref['Sensor']['Pressure']) <= TOL
+    for k, v in last.items():
+        assert rl2(v, ref['LastMap'][k]) <= 5 * TOL, (k, rl2(v, ref['LastMap'][k]))
+
+
+def test_all_maps_and_peak():
+    w = workloads.make_workload('ctx500_skull', shape=(48, 44, 52), periods=4, pml=6)
+    maps = ['ALLV', 'Vx', 'Vy', 'Vz', 'Sigmaxx', 'Sigmayy', 'Sigmazz', 'Sigmaxy', 'Sigmaxz', 'Sigmayz', 'Pressure']
+    over = dict(SelMapsRMSPeakList=maps, SelMapsSensorsList=maps, SelRMSorPeak=3)
+    (Sensor, RMS, Peak, IP), _ = run_cuda(w, 0, **over)
+    ref = run_oracle(w, **over)
+    for k in maps:
+        assert rl2(RMS[k], ref['RMS'][k]) <= TOL, ('rms', k, rl2(RMS[k], ref['RMS'][k]))
+        assert rl2(Peak[k], ref['Peak'][k]) <= TOL, ('peak', k, rl2(Peak[k], ref['Peak'][k]))
+        assert rl2(Sensor[k], ref['Sensor'][k]) <= TOL, ('sensor', k)
+
+
+def test_reflector_and_hard_source():
+    w = workloads.make_workload('ctx500_skull', shape=(44, 44, 56), periods=4, pml=6)
+    refl = np.zeros(w['args'][0].shape, np.uint32)
+    refl[18:24, 10:30, 30:34] = 1
+    for ts in (0, 1):
+        over = dict(ReflectorMask=refl, TypeSource=ts)
+        (Sensor, RMS, Peak, IP), _ = run_cuda(w, 0, **over)
+        ref = run_oracle(w, **over)
+        assert rl2(RMS['Pressure'], ref['RMS']['Pressure']) <= TOL
+        assert np.all(RMS['Pressure'][18:24, 10:30, 30:34] == 0)
+
+
+def test_many_materials_uint16_labels():
+    """CT-style maps: > 127 materials switch the device labels to uint16 (BabelIntegrationBASE.py:1268)."""
+    w = workloads.make_workload('ctx500_skull', shape=(40, 40, 48), periods=3, pml=6)
+    MM, ML = w['args'][0], w['args'][1]
+    rng = np.random.default_rng(3)
+    nb = 300
+    bone = np.tile(ML[2], (nb, 1)) * (1 + 0.1 * rng.random((nb, 5)))
+    ML2 = np.vstack([ML, bone])
+    MM2 = MM.copy()
+    sel = MM == 2
+    MM2[sel] = 5 + rng.integers(0, nb, sel.sum()).astype(np.uint32)
+    args = (MM2, ML2) + w['args'][2:]
+    w2 = dict(args=args, kwargs=dict(w['kwargs'], QCorrection=np.concatenate([w['kwargs']['QCorrection'], np.full(nb, 3.0)])), meta=w['meta'])
+    (Sensor, RMS, Peak, IP), _ = run_cuda(w2, 0)
+    ref = run_oracle(w2)
+    assert rl2(RMS['Pressure'], ref['RMS']['Pressure']) <= TOL
+
+
+def test_public_api_tuple_and_errors():
+    w = workloads.make_workload('single_water', shape=(40, 40, 48), periods=3, pml=8)
+    PM = PropagationModel()
+    r = PM.StaggeredFDTD_3D_with_relaxation(*w['args'], **w['kwargs'])
+    assert len(r) == 4
+    Sensor, LastMap, RMS, IP = r
+    assert RMS['Pressure'].dtype == np.float32 and RMS['Pressure'].flags.writeable
+    RMS['Pressure'] *= 2.0
+    assert Sensor['Pressure'].shape == (IP['IndexSensorMap'].size, Sensor['time'].size)
+    assert Sensor['time'].size % (w['meta']['ppp'] // w['meta']['sub']) == 0
+    assert LastMap['Vz'].shape == w['args'][0].shape
+    r5 = PM.StaggeredFDTD_3D_with_relaxation(*w['args'], **dict(w['kwargs'], SelRMSorPeak=3))
+    assert len(r5) == 5
+    bad = list(w['args'])
+    bad[0] = bad[0].astype(np.int32)
+    with pytest.raises(TypeError):
+        PM.StaggeredFDTD_3D_with_relaxation(*bad, **w['kwargs'])
+    bad = list(w['args'])
+    bad[0] = bad[0] + 7
+    with pytest.raises(ValueError):
+        PM.StaggeredFDTD_3D_with_relaxation(*bad, **w['kwargs'])
+    with pytest.raises(ValueError):
+        PM.StaggeredFDTD_3D_with_relaxation(*w['args'], **dict(w['kwargs'], DT=w['kwargs']['DT'] * 10))
+
+
+def test_full_size_config1_against_oracle():
+    """BASELINE config 1 (250 kHz water, 120x120x160, 720 steps) at full size."""
+    w = workloads.make_workload('single_water')
+    (Sensor, RMS, Peak, IP), _ = run_cuda(w, 0)
+    ref = run_oracle(w)
+    assert rl2(RMS['Pressure'], ref['RMS']['Pressure']) <= TOL
+    assert np.argmax(RMS['Pressure']) == np.argmax(ref['RMS']['Pressure'])
+    assert rl2(Sensor['Pressure'], ref['Sensor']['Pressure']) <= TOL
+
+
+def test_properties_linearity_and_variants_large():
+    """Size-independent properties on a larger domain: linear in source amplitude; the tiled and the
+    direct kernels agree; a homogeneous lossless medium has p == -Sigmaxx."""
+    w = workloads.make_workload('ctx500_skull', shape=(120, 112, 160), periods=10)
+    (S1, R1, _, _), l1 = run_cuda(w, 0)
+    (S2, R2, _, _), l2 = run_cuda(w, 1)
+    assert rl2(R1['Pressure'], R2['Pressure']) <= 1e-5
+    args = list(w['args'])
+    args[4] = args[4] * 3.0
+    (S3, R3, _, _), _ = run_cuda(dict(args=tuple(args), kwargs=w['kwargs']), 0)
+    assert rl2(R3['Pressure'], 3.0 * R1['Pressure'].astype(np.float64)) <= 1e-5
+    ww = workloads.make_workload('single_water', shape=(96, 96, 128), periods=8)
+    (S4, R4, _, _), l4 = run_cuda(ww, 0, SelMapsRMSPeakList=['Pressure', 'Sigmaxx'])
+    assert rl2(R4['Pressure'], R4['Sigmaxx']) <= 1e-5
