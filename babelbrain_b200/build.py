@@ -8,7 +8,7 @@ HERE = os.path.dirname(os.path.abspath(__file__))
 CSRC = os.path.join(HERE, 'csrc')
 LIB = os.path.join(HERE, 'libbabelb200.so')
 SOURCES = ['fdtd.cu', 'rayleigh.cu']
-HEADERS = ['common.h', 'fdtd_cell.cuh', 'fdtd_kernels.cuh', 'fdtd_tiled.cuh', 'nccl_dyn.h',
+HEADERS = ['common.h', 'fdtd_cell.cuh', 'fdtd_kernels.cuh', 'fdtd_direct.cuh', 'fdtd_tma.cuh', 'nccl_dyn.h',
            os.path.join('..', '..', 'include', 'babelb200.h')]
 
 

@@ -1,6 +1,7 @@
 // Shared host/device definitions for libbabelb200 (sm_100a only).
 #pragma once
 #include <cuda_runtime.h>
+#include <cuda.h>      // CUtensorMap (types only: the driver entry point is resolved at run time)
 #include <stdint.h>
 #include <stdio.h>
 #include <string>
@@ -26,15 +27,39 @@ void bb_set_error(const char *fmt, ...);
         }                                                                                   \
     } while (0)
 
-// One row of the per-material coefficient table (32 B = one sector per lookup).
-struct __align__(16) MatRow {
-    float M, G, L, B;        // (lambda+2mu)/h, mu/h, lambda/h, 1/(rho h)   (relaxed moduli)
-    float tauL, tauS, ots, K; // tau_L, tau_S, 1/tau_sigma, rho cL^2/h (pressure scaling)
+// Derived per-material coefficients (computed once, in double, from the host's BB_NCOEF-float row
+// and dt) so that the per-cell update has no divisions:
+//   normal:  R' = a R - LMCb th + MCb oth ;  S += dt (LM th - Mi2 oth + (R+R')/2)
+//   edge  :  rig = 4/(sum invG) (0 when any neighbour is fluid: invG = +inf), te = mean tauS,
+//            R' = a R - cs rig te D ;  S += dt (rig (1+te) D + (R+R')/2)
+struct __align__(16) MatCoef {
+    float LM, Mi2, LMCb, MCb;   // M(1+tauL), 2G(1+tauS), dt M tauL ots/den, dt 2G tauS ots/den
+    float a, cs, K, invG;       // num/den, dt ots/den, rho cL^2/h, 1/G (+inf for fluids)
+    float tauS, B, M, L;        // tau_S, 1/(rho h), relaxed (lambda+2mu)/h and lambda/h (PML)
+};
+constexpr int BB_MAX_SMEM_MAT = 128;   // uint8 labels hold at most 127 materials -> table in smem
+
+// Per-index coefficients of one grid axis (built on the host from the PML table):
+//   damping of a split part  f_a' = aI f_a + bI C D   at integer nodes, (aH, bH) at half nodes;
+//   outside the PML of that axis aI = aH = 1, bI = bH = dt (plain explicit update);
+//   staggered differences  D- = cab (f0 - f-1) - cbb (f+1 - f-2),  D+ = caf (f+1 - f0) - cbf (f+2 - f-1)
+//   with the domain-edge rules folded into the coefficients (9/8,1/24 | 1,0 | 0,0).
+struct __align__(16) AxisCoef {
+    float aI, bI, aH, bH;
+    float cab, cbb, caf, cbf;
 };
 
-enum { SP_VX_X = 0, SP_VX_Y, SP_VX_Z, SP_VY_X, SP_VY_Y, SP_VY_Z, SP_VZ_X, SP_VZ_Y, SP_VZ_Z,
-       SP_SXX_X, SP_SXX_Y, SP_SXX_Z, SP_SYY_X, SP_SYY_Y, SP_SYY_Z, SP_SZZ_X, SP_SZZ_Y, SP_SZZ_Z,
-       SP_SXY_X, SP_SXY_Y, SP_SXZ_X, SP_SXZ_Z, SP_SYZ_Y, SP_SYZ_Z, SP_COUNT };
+// split-field parts kept per damping axis (8 fields each), only where that axis is damped:
+//   X parts: Sxx Syy Szz Sxy Sxz | Vx Vy Vz     (planes with i in the PML)
+//   Y parts: Sxx Syy Szz Sxy Syz | Vx Vy Vz     (rows with j in the PML)
+//   Z parts: Sxx Syy Szz Sxz Syz | Vx Vy Vz     (columns with k in the PML)
+constexpr int BB_NPART = 8;
+
+// tile flags, one byte per (local plane, tile row, tile column) of the 8x32 (j,k) tiling
+enum { TF_ATT = 1,      // a non-PML cell of the tile attenuates -> normal memory variables move
+       TF_SOLID = 2,    // a cell of the tile (+1 in j,k, planes i and i+1) has G != 0 -> shear stresses / memory variables move
+       TF_SHEAR = 4,    // a cell of the tile (+-2 in j,k) on this plane has G != 0 -> its shear stresses can be non-zero
+       TF_INT = 8 };    // the tile holds non-PML cells on this plane
 
 // Device-side view of one slab.  Local plane ip <-> global i = i0 - 2 + ip (two halo planes on
 // each side are always allocated); element (ip, j, k) lives at (ip*n2 + j)*pitch + k.
@@ -48,14 +73,35 @@ struct DevParams {
     float dt;
     float *V[3], *S[6], *R[6], *Pr;
     const void *lab;     // uint8_t or uint16_t labels, same layout; top bit = reflector
-    const MatRow *mat;
-    const float *pml;    // InvDXDT, DXDT, InvDXDThp, DXDThp, each P+1
-    float *sp[SP_COUNT]; // split-field parts, compact over the PML shell of this slab
-    int ilo_end, ihi_begin;
-    long long off[6];
+    const MatCoef *coef; // derived rows indexed by label
+    int nmat;
+    const unsigned char *flags; // [nloc][ntj][ntk]
+    int ntj, ntk;
+    const AxisCoef *axI, *axJ, *axK;   // [n1], [n2], [n3]
+    // damped parts: XP [(ipx*n2 + j)*pitch + k] over this slab's i-PML planes,
+    // YP [((i-i0)*2P + jp)*pitch + k], ZP [((i-i0)*n2 + j)*zpw + kp] over the owned planes
+    float *XP[BB_NPART], *YP[BB_NPART], *ZP[BB_NPART];
+    int nxlo;            // owned planes inside the low-i PML: global i in [i0, i0+nxlo)
+    int xhi_begin;       // first owned plane inside the high-i PML (== i1 when none)
+    int zpw;             // row length of the Z parts (2P rounded up to 8)
     // RMS / peak accumulators: [slot][(i-i0)*plane + j*pitch + k]
     float *acc_rms, *acc_peak;
     long long acc_stride;
     unsigned sel_maps;   // maps being accumulated
     int sel_rms_peak;
+};
+
+// TMA descriptors of one half-step kernel (passed as a __grid_constant__ parameter)
+struct StressMaps {
+    CUtensorMap v[3];    // Vx Vy Vz, box (TX+4, TY+4, 1)
+    CUtensorMap lab;     // labels, box (LW, TY+1, 1)
+    CUtensorMap s[6];    // stresses, box (TX, TY, 1)
+    CUtensorMap r[6];    // memory variables
+    CUtensorMap pr;      // pressure accumulator
+};
+struct ParticleMaps {
+    CUtensorMap sxx;     // box (TX, TY, 1): only the i-stencil
+    CUtensorMap sh[5];   // Syy Szz Sxy Sxz Syz, box (TX+4, TY+4, 1)
+    CUtensorMap lab;
+    CUtensorMap v[3];    // box (TX, TY, 1)
 };

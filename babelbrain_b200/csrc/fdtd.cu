@@ -7,7 +7,8 @@
 #include <algorithm>
 #include "common.h"
 #include "fdtd_kernels.cuh"
-#include "fdtd_tiled.cuh"
+#include "fdtd_direct.cuh"
+#include "fdtd_tma.cuh"
 #include "nccl_dyn.h"
 
 static thread_local char g_err[1024] = "";
@@ -57,8 +58,11 @@ struct bb_fdtd {
     float *sensor_out = nullptr;  // [map][sample][sensor]
     int n_sensor_maps = 0, n_acc_maps = 0;
     int64_t step = 0;
-    long long sp_total = 0;
-    bool materials_set = false, maps_set = false;
+    size_t xp_floats = 0, yp_floats = 0, zp_floats = 0;   // per part array
+    bool materials_set = false, maps_set = false, prepared = false;
+    StressMaps smaps;
+    ParticleMaps pmaps;
+    int chunk_override = 0;
     // NCCL
     ncclComm_t comm = nullptr;
     cudaEvent_t ev_boundary = nullptr, ev_halo = nullptr;
@@ -80,6 +84,62 @@ static int dev_alloc(bb_fdtd *h, void **ptr, size_t bytes, bool zero = true) {
 }
 
 static int popcount32(uint32_t v) { return __builtin_popcount(v); }
+
+// ------------------------------------------------------------------------------------------
+// TMA descriptors (driver entry point resolved at run time: the library links only cudart)
+// ------------------------------------------------------------------------------------------
+typedef CUresult (*EncodeTiledFn)(CUtensorMap *, CUtensorMapDataType, cuuint32_t, void *, const cuuint64_t *, const cuuint64_t *,
+                                  const cuuint32_t *, const cuuint32_t *, CUtensorMapInterleave, CUtensorMapSwizzle,
+                                  CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+
+static EncodeTiledFn encode_tiled_fn() {
+    static EncodeTiledFn fn = nullptr;
+    if (!fn) {
+        void *f = nullptr;
+        cudaDriverEntryPointQueryResult qres;
+        if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &f, cudaEnableDefault, &qres) == cudaSuccess && qres == cudaDriverEntryPointSuccess)
+            fn = reinterpret_cast<EncodeTiledFn>(f);
+    }
+    return fn;
+}
+
+// 3-D map over a pitched (planes, n2, n3) volume of `esz`-byte elements; box (bw, bh, 1); out-of-volume taps read zero
+static int make_map(CUtensorMap *m, const void *base, CUtensorMapDataType dt, int esz, const DevParams &p, int planes, int bw, int bh) {
+    EncodeTiledFn enc = encode_tiled_fn();
+    if (!enc) { bb_set_error("cuTensorMapEncodeTiled is not available from this driver"); return BB_ERR_CUDA; }
+    const cuuint64_t dims[3] = { (cuuint64_t)p.n3, (cuuint64_t)p.n2, (cuuint64_t)planes };
+    const cuuint64_t strides[2] = { (cuuint64_t)p.pitch * esz, (cuuint64_t)p.plane * esz };
+    const cuuint32_t box[3] = { (cuuint32_t)bw, (cuuint32_t)bh, 1 };
+    const cuuint32_t estr[3] = { 1, 1, 1 };
+    CUresult r = enc(m, dt, 3, const_cast<void *>(base), dims, strides, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_NONE,
+                     CU_TENSOR_MAP_L2_PROMOTION_L2_128B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+    if (r != CUDA_SUCCESS) { bb_set_error("cuTensorMapEncodeTiled failed (%d) for box %dx%d", (int)r, bw, bh); return BB_ERR_CUDA; }
+    return BB_OK;
+}
+
+static int make_tensor_maps(bb_fdtd *h) {
+    using namespace tma;
+    const DevParams &p = h->p;
+    const CUtensorMapDataType F = CU_TENSOR_MAP_DATA_TYPE_FLOAT32;
+    int rc;
+    for (int c = 0; c < 3; c++) {
+        if ((rc = make_map(&h->smaps.v[c], p.V[c], F, 4, p, p.nloc, SW, SH))) return rc;
+        if ((rc = make_map(&h->pmaps.v[c], p.V[c], F, 4, p, p.nloc, TX, TY))) return rc;
+    }
+    for (int c = 0; c < 6; c++) {
+        if ((rc = make_map(&h->smaps.s[c], p.S[c], F, 4, p, p.nloc, TX, TY))) return rc;
+        if ((rc = make_map(&h->smaps.r[c], p.R[c], F, 4, p, p.nloc, TX, TY))) return rc;
+    }
+    if ((rc = make_map(&h->smaps.pr, p.Pr, F, 4, p, p.nloc, TX, TY))) return rc;
+    if ((rc = make_map(&h->pmaps.sxx, p.S[0], F, 4, p, p.nloc, TX, TY))) return rc;
+    const int order[5] = { 1, 2, 3, 4, 5 };   // Syy Szz Sxy Sxz Syz
+    for (int c = 0; c < 5; c++) if ((rc = make_map(&h->pmaps.sh[c], p.S[order[c]], F, 4, p, p.nloc, SW, SH))) return rc;
+    const bool u8 = h->label_bytes == 1;
+    const int lw = u8 ? LabBox<uint8_t>::W : LabBox<uint16_t>::W;
+    if ((rc = make_map(&h->smaps.lab, p.lab, u8 ? CU_TENSOR_MAP_DATA_TYPE_UINT8 : CU_TENSOR_MAP_DATA_TYPE_UINT16, h->label_bytes, p, p.nloc + 1, lw, LH))) return rc;
+    h->pmaps.lab = h->smaps.lab;
+    return BB_OK;
+}
 
 extern "C" int bb_fdtd_create(const bb_fdtd_desc *d, bb_fdtd **out) {
     BB_REQUIRE(d && out, "null argument");
@@ -115,7 +175,9 @@ extern "C" int bb_fdtd_create(const bb_fdtd_desc *d, bb_fdtd **out) {
     p.nloc = h->nown + 4;
     p.plane = (long long)p.n2 * p.pitch;
     p.dt = (float)d->dt;
+    p.nmat = d->nmat;
     h->label_bytes = d->nmat <= 127 ? 1 : 2;
+    if (const char *e = getenv("BB_CHUNK")) h->chunk_override = atoi(e);
     const size_t vol = (size_t)p.nloc * p.plane;
     int rc;
     for (int c = 0; c < 3; c++) if ((rc = dev_alloc(h, (void **)&p.V[c], vol * 4))) return rc;
@@ -124,20 +186,26 @@ extern "C" int bb_fdtd_create(const bb_fdtd_desc *d, bb_fdtd **out) {
     if ((rc = dev_alloc(h, (void **)&p.Pr, vol * 4))) return rc;
     // label planes carry one extra zero plane so that (i+1) lookups of the last halo plane stay in bounds
     if ((rc = dev_alloc(h, (void **)&p.lab, (vol + p.plane) * h->label_bytes))) return rc;
-    if ((rc = dev_alloc(h, (void **)&p.mat, sizeof(MatRow) * d->nmat))) return rc;
-    if ((rc = dev_alloc(h, (void **)&p.pml, sizeof(float) * 4 * (d->pml + 1)))) return rc;
-    // PML shell of this slab
+    if ((rc = dev_alloc(h, (void **)&p.coef, sizeof(MatCoef) * d->nmat))) return rc;
+    if ((rc = dev_alloc(h, (void **)&p.axI, sizeof(AxisCoef) * d->n1))) return rc;
+    if ((rc = dev_alloc(h, (void **)&p.axJ, sizeof(AxisCoef) * d->n2))) return rc;
+    if ((rc = dev_alloc(h, (void **)&p.axK, sizeof(AxisCoef) * d->n3))) return rc;
+    p.ntk = p.pitch / tma::TX;
+    p.ntj = (p.n2 + tma::TY - 1) / tma::TY;
+    if ((rc = dev_alloc(h, (void **)&p.flags, (size_t)p.nloc * p.ntj * p.ntk))) return rc;
+    // damped split parts of the PML shell of this slab
     const int P = d->pml;
-    p.ilo_end = d->i0 < P ? std::min(P, d->i1) : d->i0;
-    p.ihi_begin = d->i1 > d->n1 - P ? std::max(d->n1 - P, d->i0) : d->i1;
-    if (p.ihi_begin < p.ilo_end) p.ihi_begin = p.ilo_end;
-    const long long nmid = p.ihi_begin - p.ilo_end;
-    long long sizes[6] = { (long long)(p.ilo_end - d->i0) * p.n2 * p.n3, (long long)(d->i1 - p.ihi_begin) * p.n2 * p.n3,
-                           nmid * P * p.n3, nmid * P * p.n3, nmid * (p.n2 - 2 * P) * P, nmid * (p.n2 - 2 * P) * P };
-    long long tot = 0;
-    for (int b = 0; b < 6; b++) { p.off[b] = tot; tot += sizes[b]; }
-    h->sp_total = tot;
-    for (int c = 0; c < SP_COUNT; c++) if ((rc = dev_alloc(h, (void **)&p.sp[c], (size_t)tot * 4))) return rc;
+    p.nxlo = std::max(0, std::min(P, d->i1) - d->i0);
+    p.xhi_begin = std::min(std::max(d->n1 - P, d->i0), d->i1);
+    p.zpw = (2 * P + 7) / 8 * 8;
+    h->xp_floats = (size_t)(p.nxlo + (d->i1 - p.xhi_begin)) * p.plane;
+    h->yp_floats = (size_t)h->nown * 2 * P * p.pitch;
+    h->zp_floats = (size_t)h->nown * p.n2 * p.zpw;
+    for (int c = 0; c < BB_NPART; c++) {
+        if ((rc = dev_alloc(h, (void **)&p.XP[c], h->xp_floats * 4))) return rc;
+        if ((rc = dev_alloc(h, (void **)&p.YP[c], h->yp_floats * 4))) return rc;
+        if ((rc = dev_alloc(h, (void **)&p.ZP[c], h->zp_floats * 4))) return rc;
+    }
     // accumulators
     h->n_acc_maps = popcount32(d->sel_maps_rms);
     h->n_sensor_maps = popcount32(d->sel_maps_sensor);
@@ -150,6 +218,7 @@ extern "C" int bb_fdtd_create(const bb_fdtd_desc *d, bb_fdtd **out) {
         if ((rc = dev_alloc(h, (void **)&p.acc_peak, (size_t)h->n_acc_maps * p.acc_stride * 4))) return rc;
     for (int n = 0; n < d->steps; n++)
         if (n % d->sensor_subsampling == 0 && n / d->sensor_subsampling >= d->sensor_start) h->nsamples++;
+    if (d->kernel_variant == 0 && (rc = make_tensor_maps(h))) return rc;
     BB_CUDA(cudaStreamSynchronize(h->stream));
     *out = h;
     return BB_OK;
@@ -181,13 +250,51 @@ extern "C" int bb_fdtd_set_stream(bb_fdtd *h, void *s) {
     return BB_OK;
 }
 
+static void fill_axis(std::vector<AxisCoef> &t, int N, int P, const float *pml, double dt) {
+    const float *Inv = pml, *DX = pml + (P + 1), *InvH = pml + 2 * (P + 1), *DXH = pml + 3 * (P + 1);
+    t.resize(N);
+    for (int n = 0; n < N; n++) {
+        AxisCoef &c = t[n];
+        c.aI = c.aH = 1.0f; c.bI = c.bH = (float)dt;
+        int d = 0, dh = -1;
+        if (n < P) { d = P - n; dh = P - 1 - n; }
+        else if (n >= N - P) { d = n - (N - P - 1); dh = d; }
+        if (d > 0) { c.aI = (float)((double)Inv[d] * (double)DX[d]); c.bI = Inv[d]; }
+        if (dh >= 0) { c.aH = (float)((double)InvH[dh] * (double)DXH[dh]); c.bH = InvH[dh]; }
+        // backward difference landing on n, forward difference landing on n + 1/2
+        if (n > 1 && n < N - 1) { c.cab = 1.125f; c.cbb = 1.0f / 24.0f; } else if (n > 0) { c.cab = 1.0f; c.cbb = 0.0f; } else { c.cab = c.cbb = 0.0f; }
+        if (n > 0 && n < N - 2) { c.caf = 1.125f; c.cbf = 1.0f / 24.0f; } else if (n < N - 1) { c.caf = 1.0f; c.cbf = 0.0f; } else { c.caf = c.cbf = 0.0f; }
+    }
+}
+
 extern "C" int bb_fdtd_set_materials(bb_fdtd *h, const float *table, const float *pml_table) {
     BB_REQUIRE(h && table && pml_table, "null argument");
     BB_CUDA(cudaSetDevice(h->d.device));
-    BB_CUDA(cudaMemcpyAsync((void *)h->p.mat, table, sizeof(MatRow) * h->d.nmat, cudaMemcpyHostToDevice, h->stream));
-    BB_CUDA(cudaMemcpyAsync((void *)h->p.pml, pml_table, sizeof(float) * 4 * (h->d.pml + 1), cudaMemcpyHostToDevice, h->stream));
+    // derived rows (double precision on the host, see MatCoef)
+    std::vector<MatCoef> co(h->d.nmat);
+    const double dt = h->d.dt;
+    for (int m = 0; m < h->d.nmat; m++) {
+        const float *r = table + (size_t)m * BB_NCOEF;
+        const double M = r[0], G = r[1], L = r[2], B = r[3], tL = r[4], tS = r[5], ots = r[6], K = r[7];
+        const double den = 1.0 + dt * 0.5 * ots, num = 1.0 - dt * 0.5 * ots;
+        MatCoef &c = co[m];
+        c.LM = (float)(M * (1.0 + tL)); c.Mi2 = (float)(2.0 * G * (1.0 + tS));
+        c.LMCb = (float)(dt * M * tL * ots / den); c.MCb = (float)(dt * 2.0 * G * tS * ots / den);
+        c.a = (float)(num / den); c.cs = (float)(dt * ots / den); c.K = (float)K;
+        c.invG = G != 0.0 ? (float)(1.0 / G) : INFINITY;
+        c.tauS = (float)tS; c.B = (float)B; c.M = (float)M; c.L = (float)L;
+    }
+    BB_CUDA(cudaMemcpyAsync((void *)h->p.coef, co.data(), sizeof(MatCoef) * h->d.nmat, cudaMemcpyHostToDevice, h->stream));
+    std::vector<AxisCoef> ax[3];
+    const int N[3] = { h->d.n1, h->d.n2, h->d.n3 };
+    const AxisCoef *dst[3] = { h->p.axI, h->p.axJ, h->p.axK };
+    for (int a = 0; a < 3; a++) {
+        fill_axis(ax[a], N[a], h->d.pml, pml_table, dt);
+        BB_CUDA(cudaMemcpyAsync((void *)dst[a], ax[a].data(), sizeof(AxisCoef) * N[a], cudaMemcpyHostToDevice, h->stream));
+    }
     BB_CUDA(cudaStreamSynchronize(h->stream));
     h->materials_set = true;
+    h->prepared = false;
     return BB_OK;
 }
 
@@ -224,6 +331,7 @@ extern "C" int bb_fdtd_set_maps(bb_fdtd *h, const uint32_t *material, const uint
     if (tmpr) cudaFree(tmpr);
     BB_REQUIRE(!hbad, "MaterialMap holds a label >= number of materials (%d)", h->d.nmat);
     h->maps_set = true;
+    h->prepared = false;
     return BB_OK;
 }
 
@@ -372,25 +480,65 @@ struct Timer {
     }
 };
 
+static int pick_chunk(const bb_fdtd *h, int nplanes) {
+    // enough CTAs for ~4 full waves of 2 CTAs on each of the 148 SMs, chunks of 8..64 planes
+    if (h->chunk_override > 0) return std::min(std::min(h->chunk_override, (int)tma::MAXCHUNK), nplanes);
+    const int tiles = h->p.ntk * h->p.ntj;
+    int nch = std::max(1, (4 * 296 + tiles - 1) / tiles);
+    int chunk = (nplanes + nch - 1) / nch;
+    chunk = std::max(chunk, std::min(nplanes, 8));
+    return std::min(chunk, (int)tma::MAXCHUNK);
+}
+
+template <typename K>
+static int set_smem(K kernel, int bytes) {
+    BB_CUDA(cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, bytes));
+    return BB_OK;
+}
+
 template <typename LT>
-static int launch_half_step(bb_fdtd *h, bool stress, bool acc, int ib, int ie, Timer &tm) {
+static int prepare_kernels() {
+    int rc;
+    if ((rc = set_smem(tma::stress_tma<LT, 0>, tma::StressSmem::BYTES))) return rc;
+    if ((rc = set_smem(tma::stress_tma<LT, 1>, tma::StressSmem::BYTES))) return rc;
+    if ((rc = set_smem(tma::stress_tma<LT, 2>, tma::StressSmem::BYTES))) return rc;
+    if ((rc = set_smem(tma::particle_tma<LT, 0>, tma::ParticleSmem::BYTES))) return rc;
+    if ((rc = set_smem(tma::particle_tma<LT, 2>, tma::ParticleSmem::BYTES))) return rc;
+    return BB_OK;
+}
+
+// one half-step over the owned planes [ib, ie): a single fused launch (interior + PML shell)
+template <typename LT>
+static int launch_half_step(bb_fdtd *h, bool stress, int acc_mode, int ib, int ie, Timer &tm) {
     if (ie <= ib) return BB_OK;
     const DevParams &p = h->p;
+    tm.begin(stress ? CAT_STRESS : CAT_PARTICLE);
     if (h->d.kernel_variant == 1) {
         const dim3 blk(64, 4, 1), grid((p.n3 + 63) / 64, (p.n2 + 3) / 4, ie - ib);
-        tm.begin(stress ? CAT_STRESS : CAT_PARTICLE);
         if (stress) {
-            if (acc) stress_direct<LT, true><<<grid, blk, 0, h->stream>>>(p, ib);
-            else stress_direct<LT, false><<<grid, blk, 0, h->stream>>>(p, ib);
+            if (acc_mode) direct::stress_direct<LT, true><<<grid, blk, 0, h->stream>>>(p, ib);
+            else direct::stress_direct<LT, false><<<grid, blk, 0, h->stream>>>(p, ib);
         } else {
-            if (acc) particle_direct<LT, true><<<grid, blk, 0, h->stream>>>(p, ib);
-            else particle_direct<LT, false><<<grid, blk, 0, h->stream>>>(p, ib);
+            if (acc_mode) direct::particle_direct<LT, true><<<grid, blk, 0, h->stream>>>(p, ib);
+            else direct::particle_direct<LT, false><<<grid, blk, 0, h->stream>>>(p, ib);
         }
-        tm.end();
-        BB_CUDA(cudaGetLastError());
-        return BB_OK;
+    } else {
+        const int chunk = pick_chunk(h, ie - ib);
+        const dim3 blk(tma::TX, tma::TY, 1), grid(p.ntk, p.ntj, (ie - ib + chunk - 1) / chunk);
+        if (stress) {
+            const int sm = tma::StressSmem::BYTES;
+            if (acc_mode == 1) tma::stress_tma<LT, 1><<<grid, blk, sm, h->stream>>>(h->smaps, p, ib, ie, chunk);
+            else if (acc_mode == 2) tma::stress_tma<LT, 2><<<grid, blk, sm, h->stream>>>(h->smaps, p, ib, ie, chunk);
+            else tma::stress_tma<LT, 0><<<grid, blk, sm, h->stream>>>(h->smaps, p, ib, ie, chunk);
+        } else {
+            const int sm = tma::ParticleSmem::BYTES;
+            if (acc_mode) tma::particle_tma<LT, 2><<<grid, blk, sm, h->stream>>>(h->pmaps, p, ib, ie, chunk);
+            else tma::particle_tma<LT, 0><<<grid, blk, sm, h->stream>>>(h->pmaps, p, ib, ie, chunk);
+        }
     }
-    return launch_tiled<LT>(h->p, stress, acc, ib, ie, h->stream, [&](int cat) { tm.begin(cat == 0 ? (stress ? CAT_STRESS : CAT_PARTICLE) : CAT_PML); }, [&]() { tm.end(); });
+    tm.end();
+    BB_CUDA(cudaGetLastError());
+    return BB_OK;
 }
 
 static int launch_sources(bb_fdtd *h, int n, int64_t first, int64_t count, Timer &tm) {
@@ -428,7 +576,7 @@ static int halo_exchange(bb_fdtd *h, float *const f[3]) {
 }
 
 template <typename LT>
-static int half_step(bb_fdtd *h, bool stress, int n, bool acc, Timer &tm) {
+static int half_step(bb_fdtd *h, bool stress, int n, int acc, Timer &tm) {
     const DevParams &p = h->p;
     const bool src_here = stress ? (h->d.type_source >= 2) : (h->d.type_source < 2);
     int rc;
@@ -462,8 +610,9 @@ static int run_steps(bb_fdtd *h, int64_t nsteps, Timer &tm) {
     for (int64_t t = 0; t < nsteps; t++) {
         const int n = (int)h->step;
         const bool window = d.sel_rms_peak != 0 && n >= n0;
-        if ((rc = half_step<LT>(h, true, n, window && stress_maps, tm))) return rc;
-        if ((rc = half_step<LT>(h, false, n, window && part_maps, tm))) return rc;
+        const bool only_p_rms = d.sel_rms_peak == 1 && d.sel_maps_rms == (1u << BB_MAP_PRESSURE);
+        if ((rc = half_step<LT>(h, true, n, (window && stress_maps) ? (only_p_rms ? 1 : 2) : 0, tm))) return rc;
+        if ((rc = half_step<LT>(h, false, n, (window && part_maps) ? 2 : 0, tm))) return rc;
         if (h->nsensors && h->n_sensor_maps && n % d.sensor_subsampling == 0 && n / d.sensor_subsampling >= d.sensor_start) {
             const long long sample = n / d.sensor_subsampling - d.sensor_start;
             tm.begin(CAT_OTHER);
@@ -483,6 +632,15 @@ extern "C" int bb_fdtd_run(bb_fdtd *h, int64_t nsteps, int profile) {
     if (h->d.nranks > 1 && !h->comm) { bb_set_error("multi-rank handle without comm_init"); return BB_ERR_STATE; }
     BB_CUDA(cudaSetDevice(h->d.device));
     if (nsteps < 0 || h->step + nsteps > h->d.steps) nsteps = h->d.steps - h->step;
+    if (!h->prepared) {
+        const dim3 blk(tma::TX, tma::TY, 1), grid(h->p.ntk, h->p.ntj, h->p.nloc);
+        int rcp;
+        if (h->label_bytes == 1) { tma::flags_kernel<uint8_t><<<grid, blk, 0, h->stream>>>(h->p, (unsigned char *)h->p.flags); rcp = prepare_kernels<uint8_t>(); }
+        else { tma::flags_kernel<uint16_t><<<grid, blk, 0, h->stream>>>(h->p, (unsigned char *)h->p.flags); rcp = prepare_kernels<uint16_t>(); }
+        BB_CUDA(cudaGetLastError());
+        if (rcp) return rcp;
+        h->prepared = true;
+    }
     Timer tm{h, profile != 0};
     h->ev_used = 0;
     h->ev_cat.clear();
@@ -522,8 +680,11 @@ extern "C" int bb_fdtd_reset(bb_fdtd *h) {
     for (int c = 0; c < 3; c++) BB_CUDA(cudaMemsetAsync(p.V[c], 0, vol, h->stream));
     for (int c = 0; c < 6; c++) { BB_CUDA(cudaMemsetAsync(p.S[c], 0, vol, h->stream)); BB_CUDA(cudaMemsetAsync(p.R[c], 0, vol, h->stream)); }
     BB_CUDA(cudaMemsetAsync(p.Pr, 0, vol, h->stream));
-    const size_t tot = (size_t)h->sp_total * 4;
-    for (int c = 0; c < SP_COUNT; c++) BB_CUDA(cudaMemsetAsync(p.sp[c], 0, tot, h->stream));
+    for (int c = 0; c < BB_NPART; c++) {
+        BB_CUDA(cudaMemsetAsync(p.XP[c], 0, std::max<size_t>(h->xp_floats * 4, 16), h->stream));
+        BB_CUDA(cudaMemsetAsync(p.YP[c], 0, std::max<size_t>(h->yp_floats * 4, 16), h->stream));
+        BB_CUDA(cudaMemsetAsync(p.ZP[c], 0, std::max<size_t>(h->zp_floats * 4, 16), h->stream));
+    }
     if (p.acc_rms) BB_CUDA(cudaMemsetAsync(p.acc_rms, 0, (size_t)h->n_acc_maps * p.acc_stride * 4, h->stream));
     if (p.acc_peak) BB_CUDA(cudaMemsetAsync(p.acc_peak, 0, (size_t)h->n_acc_maps * p.acc_stride * 4, h->stream));
     if (h->sensor_out) BB_CUDA(cudaMemsetAsync(h->sensor_out, 0, (size_t)h->n_sensor_maps * h->nsamples * h->nsensors * 4, h->stream));

@@ -1,32 +1,6 @@
-// Global kernels of the FDTD path.
+// Auxiliary kernels of the FDTD path: source injection, sensor sampling, format conversion.
 #pragma once
 #include "fdtd_cell.cuh"
-
-// ------------------------------------------------------------------------------------------
-// variant 1 ("direct"): one thread per cell, operands straight from global memory through L1/L2.
-// Kept as the simple reference kernel (kernel_variant = 1) and used for the PML shell.
-// ------------------------------------------------------------------------------------------
-template <typename LT, bool ACC>
-__global__ void __launch_bounds__(256) stress_direct(const DevParams p, int ib) {
-    const int k = blockIdx.x * blockDim.x + threadIdx.x;
-    const int j = blockIdx.y * blockDim.y + threadIdx.y;
-    const int i = ib + blockIdx.z;
-    if (k >= p.n3 || j >= p.n2) return;
-    const long long q = ((long long)(i - p.i0 + 2) * p.n2 + j) * p.pitch + k;
-    if (in_pml1(i, p.n1, p.P) || in_pml1(j, p.n2, p.P) || in_pml1(k, p.n3, p.P)) stress_cell_pml<LT>(p, i, j, k, q);
-    else stress_cell_interior<LT, ACC>(p, i, j, k, q);
-}
-
-template <typename LT, bool ACC>
-__global__ void __launch_bounds__(256) particle_direct(const DevParams p, int ib) {
-    const int k = blockIdx.x * blockDim.x + threadIdx.x;
-    const int j = blockIdx.y * blockDim.y + threadIdx.y;
-    const int i = ib + blockIdx.z;
-    if (k >= p.n3 || j >= p.n2) return;
-    const long long q = ((long long)(i - p.i0 + 2) * p.n2 + j) * p.pitch + k;
-    if (in_pml1(i, p.n1, p.P) || in_pml1(j, p.n2, p.P) || in_pml1(k, p.n3, p.P)) particle_cell_pml<LT>(p, i, j, k, q);
-    else particle_cell_interior<LT, ACC>(p, i, j, k, q);
-}
 
 // ------------------------------------------------------------------------------------------
 // sources, sensors, bookkeeping
@@ -60,7 +34,7 @@ __device__ __forceinline__ float field_value(const DevParams &p, int map, long l
     case BB_MAP_VX: case BB_MAP_VY: case BB_MAP_VZ: return p.V[map - BB_MAP_VX][q];
     case BB_MAP_PRESSURE: {
         const unsigned m = reinterpret_cast<const LT *>(p.lab)[q] & LabelTraits<LT>::MASK;
-        return -__ldg(&p.mat[m].K) * p.Pr[q];
+        return -__ldg(&p.coef[m].K) * p.Pr[q];
     }
     default: return p.S[map - BB_MAP_SXX][q];
     }

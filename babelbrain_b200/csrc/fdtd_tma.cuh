@@ -1,0 +1,544 @@
+// kernel_variant = 0: the production half-step kernels.
+//
+// One CTA owns an 8 x 32 (j,k) tile of the plane (k = the contiguous axis of the caller's C-order
+// volumes) and marches `chunk` planes along the slab axis i.  Every operand of a plane reaches
+// shared memory through TMA (cp.async.bulk.tensor, 3-D descriptors over the pitched volumes) into
+// two mbarrier-tracked rings that run several planes ahead of the arithmetic:
+//   * the "halo ring" holds the stencil inputs of the half-step (V for the stress kernel, the
+//     stresses for the particle kernel) as (8+4) x (32+8) boxes plus the label box; out-of-volume
+//     taps are zero-filled by the TMA unit, so the kernels carry no boundary branches for loads;
+//   * the "point ring" holds the read-modify-write fields of the cell itself (stresses, memory
+//     variables and pressure for the stress kernel, V for the particle kernel) as 8 x 32 boxes.
+// The i-direction stencil lives in a register queue fed from the halo ring; the in-plane stencil
+// reads the ring directly (row pitch 40 floats: conflict-free).  Results go straight from registers
+// to global memory (one 128-byte row segment per warp and field).
+//
+// Which fields move at all is decided per (plane, tile) from the flag byte computed once per
+// simulation (flags_kernel): memory variables only where something attenuates, shear stresses only
+// where something is solid, nothing but the split parts inside the PML.  The PML shell is handled
+// in the same launch: a cell whose axis is damped updates the stored damped part of that axis and
+// adds the increment to the total field (fdtd_cell.cuh).
+#pragma once
+#include "fdtd_cell.cuh"
+
+namespace tma {
+constexpr int TX = 32, TY = 8, HALO = 2;
+// the innermost TMA coordinate must be a multiple of 16 bytes (measured: a box starting at k0-2
+// raises an illegal-instruction fault), so halo boxes start at k0-4 and are TX+8 floats wide
+constexpr int HK = 4;
+constexpr int SW = TX + 2 * HK;          // 40
+constexpr int SH = TY + 2 * HALO;        // 12
+constexpr int NT = TX * TY;              // 256 threads
+constexpr int HBOX = SW * SH * 4;        // 1920 bytes landed per halo box
+constexpr int HBOX_STRIDE = 1920;        // 128-byte aligned slot
+constexpr int PBOX = TX * TY * 4;        // 1024 bytes per point box
+constexpr int LH = TY + 1;               // label rows j0 .. j0+TY
+constexpr int LBOX_STRIDE = 768;         // >= LW*LH*sizeof(LT), 128-byte aligned
+template <typename LT> struct LabBox { static constexpr int W = 16 * 3 / sizeof(LT) < TX + 8 ? TX + 8 : 16 * 3 / sizeof(LT); };
+// uint8: 48 labels = 48 bytes per row; uint16: 40 labels = 80 bytes per row (both multiples of 16 bytes, >= TX+1)
+constexpr int MAXCHUNK = 64;
+
+// ---------------------------------------------------------------- PTX wrappers
+__device__ __forceinline__ uint32_t smem_u32(const void *p) { return (uint32_t)__cvta_generic_to_shared(p); }
+__device__ __forceinline__ void mbar_init(uint64_t *bar, int count) {
+    asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(bar)), "r"(count) : "memory");
+}
+__device__ __forceinline__ void mbar_expect_tx(uint64_t *bar, uint32_t bytes) {
+    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_u32(bar)), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ bool mbar_try_wait(uint64_t *bar, uint32_t parity) {
+    uint32_t ok;
+    asm volatile("{\n\t.reg .pred p;\n\tmbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\tselp.u32 %0, 1, 0, p;\n\t}"
+                 : "=r"(ok) : "r"(smem_u32(bar)), "r"(parity) : "memory");
+    return ok != 0;
+}
+// a TMA that never lands (bad descriptor, wrong byte count) must not hang the GPU: trap after ~seconds
+__device__ __forceinline__ void mbar_wait(uint64_t *bar, uint32_t parity) {
+    unsigned spins = 0;
+    while (!mbar_try_wait(bar, parity)) { if (++spins > (1u << 26)) __trap(); }
+}
+__device__ __forceinline__ void tma_load_3d(void *dst, const CUtensorMap *map, uint64_t *bar, int c0, int c1, int c2) {
+    asm volatile("cp.async.bulk.tensor.3d.shared::cluster.global.tile.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4, %5}], [%2];"
+                 ::"r"(smem_u32(dst)), "l"(reinterpret_cast<uint64_t>(map)), "r"(smem_u32(bar)), "r"(c0), "r"(c1), "r"(c2) : "memory");
+}
+__device__ __forceinline__ void fence_barrier_init() { asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory"); }
+
+// ---------------------------------------------------------------- tile flags
+template <typename LT>
+__global__ void __launch_bounds__(NT) flags_kernel(const DevParams p, unsigned char *__restrict__ flags) {
+    __shared__ unsigned sflag;
+    const int tx = threadIdx.x, ty = threadIdx.y, tid = ty * TX + tx;
+    const int k0 = blockIdx.x * TX, j0 = blockIdx.y * TY, ip = blockIdx.z;
+    const int i = p.i0 - 2 + ip;
+    if (tid == 0) sflag = 0;
+    __syncthreads();
+    const LT *lab = reinterpret_cast<const LT *>(p.lab);
+    const unsigned MSK = LabelTraits<LT>::MASK;
+    unsigned f = 0;
+    const bool xd = in_pml1(i, p.n1, p.P);
+    for (int t = tid; t < SH * SW; t += NT) {
+        const int r = t / SW, c = t - r * SW;
+        const int jj = j0 - HALO + r, kk = k0 - HK + c;
+        if (jj < 0 || jj >= p.n2 || kk < 0 || kk >= p.n3 || c < HK - HALO || c >= HK + TX + HALO) continue;
+        const long long q = ((long long)ip * p.n2 + jj) * p.pitch + kk;
+        const unsigned m = lab[q] & MSK;
+        const bool solid = __ldg(&p.coef[m].invG) < 3.0e38f;
+        const bool inner = r >= HALO && r < HALO + TY && c >= HK && c < HK + TX;
+        const bool ext1 = r >= HALO && r <= HALO + TY && c >= HK && c <= HK + TX;
+        if (solid) f |= TF_SHEAR | (ext1 ? TF_SOLID : 0);
+        if (ext1 && ip + 1 < p.nloc) {   // plane i+1 feeds the xy / xz edges of plane i
+            const unsigned m1 = lab[q + p.plane] & MSK;
+            if (__ldg(&p.coef[m1].invG) < 3.0e38f) f |= TF_SOLID;
+        }
+        if (inner && !xd && !in_pml1(jj, p.n2, p.P) && !in_pml1(kk, p.n3, p.P)) {
+            f |= TF_INT;
+            if (__ldg(&p.coef[m].tauS) != 0.0f || __ldg(&p.coef[m].LMCb) != 0.0f) f |= TF_ATT;
+        }
+    }
+    if (f) atomicOr(&sflag, f);
+    __syncthreads();
+    if (tid == 0) flags[((long long)ip * p.ntj + blockIdx.y) * p.ntk + blockIdx.x] = (unsigned char)sflag;
+}
+
+// ---------------------------------------------------------------- shared-memory layout
+template <int NSH, int NSP, int NHF, int NPF>
+struct Smem {
+    // NHF halo boxes + 1 label box per halo stage; NPF point boxes per point stage
+    static constexpr int HSTAGE = NHF * HBOX_STRIDE + LBOX_STRIDE;
+    static constexpr int PSTAGE = NPF * PBOX;
+    static constexpr int OFF_H = 0;
+    static constexpr int OFF_P = OFF_H + NSH * HSTAGE;
+    static constexpr int OFF_COEF = OFF_P + NSP * PSTAGE;                          // MatCoef[128] (uint8 labels)
+    static constexpr int OFF_AXJ = OFF_COEF + BB_MAX_SMEM_MAT * (int)sizeof(MatCoef);
+    static constexpr int OFF_AXK = OFF_AXJ + TY * (int)sizeof(AxisCoef);
+    static constexpr int OFF_FLAGS = OFF_AXK + TX * (int)sizeof(AxisCoef);
+    static constexpr int OFF_BAR = OFF_FLAGS + ((MAXCHUNK + 8 + 15) / 16) * 16;
+    static constexpr int BYTES = OFF_BAR + (NSH + NSP) * 8 + 128;                  // + alignment slack
+};
+
+// =========================================================================================
+// stress half-step
+// =========================================================================================
+constexpr int ST_NSH = 5, ST_NSP = 3;
+using StressSmem = Smem<ST_NSH, ST_NSP, 3, 13>;
+// point-box order inside a stage
+enum { PB_SXX = 0, PB_SYY, PB_SZZ, PB_SXY, PB_SXZ, PB_SYZ, PB_RXX, PB_RYY, PB_RZZ, PB_RXY, PB_RXZ, PB_RYZ, PB_PR };
+
+template <typename LT, int ACC>
+__global__ void __launch_bounds__(NT, 2) stress_tma(const __grid_constant__ StressMaps tm, const DevParams p, int ia, int ie, int chunk) {
+    constexpr bool SMC = sizeof(LT) == 1;
+    constexpr int LW = LabBox<LT>::W;
+    using L = StressSmem;
+    extern __shared__ unsigned char smem_raw[];
+    unsigned char *sm = reinterpret_cast<unsigned char *>((reinterpret_cast<uintptr_t>(smem_raw) + 127) & ~(uintptr_t)127);
+    MatCoef *sC = reinterpret_cast<MatCoef *>(sm + L::OFF_COEF);
+    AxisCoef *sJ = reinterpret_cast<AxisCoef *>(sm + L::OFF_AXJ);
+    AxisCoef *sK = reinterpret_cast<AxisCoef *>(sm + L::OFF_AXK);
+    unsigned char *sF = sm + L::OFF_FLAGS;
+    uint64_t *barH = reinterpret_cast<uint64_t *>(sm + L::OFF_BAR);
+    uint64_t *barP = barH + ST_NSH;
+
+    const int tx = threadIdx.x, ty = threadIdx.y, tid = ty * TX + tx;
+    const int k0 = blockIdx.x * TX, j0 = blockIdx.y * TY;
+    const int ic0 = ia + blockIdx.z * chunk, ic1 = min(ic0 + chunk, ie);
+    const int np = ic1 - ic0;                 // planes of this CTA
+    const int k = k0 + tx, j = j0 + ty;
+    const bool active = k < p.n3 && j < p.n2;
+    const bool jkd = in_pml1(j, p.n2, p.P) || in_pml1(k, p.n3, p.P);
+    const bool jkupd = j < p.n2 - 1 && k < p.n3 - 1;
+    const bool jkedge = j <= 1 || j >= p.n2 - 2 || k <= 1 || k >= p.n3 - 2;
+    const long long s1 = p.plane;
+    const int ipl0 = ic0 - p.i0 + 2;          // local plane of ic0
+
+    // ---- per-CTA tables
+    if (SMC) for (int t = tid; t < p.nmat * (int)(sizeof(MatCoef) / 4); t += NT) reinterpret_cast<float *>(sC)[t] = reinterpret_cast<const float *>(p.coef)[t];
+    if (tid < TY * 8) { const int r = tid >> 3, e = tid & 7; reinterpret_cast<float *>(sJ)[tid] = reinterpret_cast<const float *>(p.axJ + min(j0 + r, p.n2 - 1))[e]; }
+    { const int r = tid >> 3, e = tid & 7; reinterpret_cast<float *>(sK)[tid] = reinterpret_cast<const float *>(p.axK + min(k0 + r, p.n3 - 1))[e]; }
+    if (tid < np + 2) {
+        const int ipl = ipl0 + tid;
+        sF[tid] = ipl < p.nloc ? p.flags[((long long)ipl * p.ntj + blockIdx.y) * p.ntk + blockIdx.x] : 0;
+    }
+    if (tid == 0) {
+        for (int s = 0; s < ST_NSH + ST_NSP; s++) mbar_init(barH + s, 1);
+        fence_barrier_init();
+    }
+    __syncthreads();
+
+    // ---- producer (thread 0): issue the TMA loads of one ring slot
+    auto issue_h = [&](int r) {     // halo plane ic0 + r, r in [0, np+2)
+        unsigned char *st = sm + L::OFF_H + (r % ST_NSH) * L::HSTAGE;
+        uint64_t *bar = barH + (r % ST_NSH);
+        mbar_expect_tx(bar, 3 * HBOX + LW * LH * (int)sizeof(LT));
+        const int ipl = ipl0 + r;
+#pragma unroll
+        for (int c = 0; c < 3; c++) tma_load_3d(st + c * HBOX_STRIDE, &tm.v[c], bar, k0 - HK, j0 - HALO, ipl);
+        tma_load_3d(st + 3 * HBOX_STRIDE, &tm.lab, bar, k0, j0, ipl);
+    };
+    auto issue_p = [&](int r) {     // point plane ic0 + r, r in [0, np)
+        unsigned char *st = sm + L::OFF_P + (r % ST_NSP) * L::PSTAGE;
+        uint64_t *bar = barP + (r % ST_NSP);
+        const unsigned f = sF[r];
+        const bool fint = f & TF_INT, fatt = f & TF_ATT, fsol = f & TF_SOLID;
+        const int nbox = 3 + (fint ? 1 : 0) + (fatt ? 3 : 0) + (fsol ? 3 : 0) + (fsol && fint ? 3 : 0);
+        mbar_expect_tx(bar, nbox * PBOX);
+        const int ipl = ipl0 + r;
+#pragma unroll
+        for (int c = 0; c < 3; c++) tma_load_3d(st + (PB_SXX + c) * PBOX, &tm.s[c], bar, k0, j0, ipl);
+        if (fint) tma_load_3d(st + PB_PR * PBOX, &tm.pr, bar, k0, j0, ipl);
+        if (fatt) {
+#pragma unroll
+            for (int c = 0; c < 3; c++) tma_load_3d(st + (PB_RXX + c) * PBOX, &tm.r[c], bar, k0, j0, ipl);
+        }
+        if (fsol) {
+#pragma unroll
+            for (int c = 3; c < 6; c++) tma_load_3d(st + (PB_SXX + c) * PBOX, &tm.s[c], bar, k0, j0, ipl);
+            if (fint) {
+#pragma unroll
+                for (int c = 3; c < 6; c++) tma_load_3d(st + (PB_RXX + c) * PBOX, &tm.r[c], bar, k0, j0, ipl);
+            }
+        }
+    };
+    if (tid == 0) {
+        for (int r = 0; r < ST_NSH && r < np + 2; r++) issue_h(r);
+        for (int r = 0; r < ST_NSP && r < np; r++) issue_p(r);
+    }
+
+    // ---- register queue along i (state before the shift of plane ic0)
+    const float *__restrict__ Vx = p.V[0], *__restrict__ Vy = p.V[1], *__restrict__ Vz = p.V[2];
+    const long long col = (long long)min(j, p.n2 - 1) * p.pitch + min(k, p.pitch - 1);
+    long long q = (long long)ipl0 * s1 + col;
+    float vx_m2, vx_m1 = Vx[q - 2 * s1], vx_0 = Vx[q - s1], vx_p1 = 0.f;
+    float vy_m1, vy_0 = Vy[q - s1], vy_p1 = 0.f, vy_p2 = 0.f;
+    float vz_m1, vz_0 = Vz[q - s1], vz_p1 = 0.f, vz_p2 = 0.f;
+    const int sc = (ty + HALO) * SW + tx + HK;     // this thread's cell in a halo box
+    const int lc = ty * LW + tx;                     // ... in a label box
+    const int pc = ty * TX + tx;                     // ... in a point box
+    const float dt = p.dt;
+    float *__restrict__ Pr = p.Pr;
+    const unsigned MSK = LabelTraits<LT>::MASK;
+
+    auto hbox = [&](int r, int c) { return reinterpret_cast<const float *>(sm + L::OFF_H + (r % ST_NSH) * L::HSTAGE + c * HBOX_STRIDE); };
+    auto lbox = [&](int r) { return reinterpret_cast<const LT *>(sm + L::OFF_H + (r % ST_NSH) * L::HSTAGE + 3 * HBOX_STRIDE); };
+    auto wait_h = [&](int r) { mbar_wait(barH + (r % ST_NSH), (r / ST_NSH) & 1); };
+
+    // planes ic0 and ic0+1 feed the queue before the loop
+    wait_h(0);
+    vx_p1 = hbox(0, 0)[sc]; vy_p1 = hbox(0, 1)[sc]; vz_p1 = hbox(0, 2)[sc];
+    wait_h(1);
+    vy_p2 = hbox(1, 1)[sc]; vz_p2 = hbox(1, 2)[sc];
+
+    for (int it = 0; it < np; it++, q += s1) {
+        const int i = ic0 + it;
+        const unsigned f = sF[it];
+        wait_h(it + 2);
+        // ---------------- shift the queue: plane i becomes the centre
+        vx_m2 = vx_m1; vx_m1 = vx_0; vx_0 = vx_p1; vx_p1 = hbox(it + 1, 0)[sc];
+        vy_m1 = vy_0; vy_0 = vy_p1; vy_p1 = vy_p2; vy_p2 = hbox(it + 2, 1)[sc];
+        vz_m1 = vz_0; vz_0 = vz_p1; vz_p1 = vz_p2; vz_p2 = hbox(it + 2, 2)[sc];
+        mbar_wait(barP + (it % ST_NSP), (it / ST_NSP) & 1);
+        const bool xd = in_pml1(i, p.n1, p.P);
+        const bool cellpml = xd || jkd;
+        if (active && (!cellpml || (jkupd && i < p.n1 - 1))) {
+            const float *bx = hbox(it, 0), *by = hbox(it, 1), *bz = hbox(it, 2);
+            const LT *l0p = lbox(it), *l1p = lbox(it + 1);
+            const float *pb = reinterpret_cast<const float *>(sm + L::OFF_P + (it % ST_NSP) * L::PSTAGE);
+            const unsigned l0 = l0p[lc];
+            const bool refl = (l0 & LabelTraits<LT>::REFL) != 0;
+            MatCoef c;
+            if (SMC) c = sC[l0 & MSK]; else c = load_coef_global(p.coef, l0 & MSK);
+            // ---------------- the nine staggered differences
+            float D[9];
+            if (!(jkedge || i <= 1 || i >= p.n1 - 2)) {
+                D[0] = D4(vx_0, vx_m1, vx_p1, vx_m2);
+                D[1] = D4(by[sc], by[sc - SW], by[sc + SW], by[sc - 2 * SW]);
+                D[2] = D4(bz[sc], bz[sc - 1], bz[sc + 1], bz[sc - 2]);
+                if (f & TF_SOLID) {
+                    D[3] = D4(vy_p1, vy_0, vy_p2, vy_m1);
+                    D[4] = D4(bx[sc + SW], bx[sc], bx[sc + 2 * SW], bx[sc - SW]);
+                    D[5] = D4(vz_p1, vz_0, vz_p2, vz_m1);
+                    D[6] = D4(bx[sc + 1], bx[sc], bx[sc + 2], bx[sc - 1]);
+                    D[7] = D4(bz[sc + SW], bz[sc], bz[sc + 2 * SW], bz[sc - SW]);
+                    D[8] = D4(by[sc + 1], by[sc], by[sc + 2], by[sc - 1]);
+                }
+            } else {   // cells next to a face of the domain: edge-aware coefficients
+                const AxisCoef ci = load_axis(p.axI, i), cj = sJ[ty], ck = sK[tx];
+                D[0] = D4C(ci.cab, ci.cbb, vx_0, vx_m1, vx_p1, vx_m2);
+                D[1] = D4C(cj.cab, cj.cbb, by[sc], by[sc - SW], by[sc + SW], by[sc - 2 * SW]);
+                D[2] = D4C(ck.cab, ck.cbb, bz[sc], bz[sc - 1], bz[sc + 1], bz[sc - 2]);
+                D[3] = D4C(ci.caf, ci.cbf, vy_p1, vy_0, vy_p2, vy_m1);
+                D[4] = D4C(cj.caf, cj.cbf, bx[sc + SW], bx[sc], bx[sc + 2 * SW], bx[sc - SW]);
+                D[5] = D4C(ci.caf, ci.cbf, vz_p1, vz_0, vz_p2, vz_m1);
+                D[6] = D4C(ck.caf, ck.cbf, bx[sc + 1], bx[sc], bx[sc + 2], bx[sc - 1]);
+                D[7] = D4C(cj.caf, cj.cbf, bz[sc + SW], bz[sc], bz[sc + 2 * SW], bz[sc - SW]);
+                D[8] = D4C(ck.caf, ck.cbf, by[sc + 1], by[sc], by[sc + 2], by[sc - 1]);
+            }
+            // ---------------- edge rigidities (only where something is solid)
+            float rigxy = 0.f, rigxz = 0.f, rigyz = 0.f, texy = 0.f, texz = 0.f, teyz = 0.f;
+            if (f & TF_SOLID) {
+                const unsigned mi = l1p[lc] & MSK, mj = l0p[lc + LW] & MSK, mk = l0p[lc + 1] & MSK;
+                const unsigned mij = l1p[lc + LW] & MSK, mik = l1p[lc + 1] & MSK, mjk = l0p[lc + LW + 1] & MSK;
+                float igi, igj, igk, igij, igik, igjk, ti, tj, tk, tij, tik, tjk;
+                if (SMC) {
+                    igi = sC[mi].invG; igj = sC[mj].invG; igk = sC[mk].invG; igij = sC[mij].invG; igik = sC[mik].invG; igjk = sC[mjk].invG;
+                    ti = sC[mi].tauS; tj = sC[mj].tauS; tk = sC[mk].tauS; tij = sC[mij].tauS; tik = sC[mik].tauS; tjk = sC[mjk].tauS;
+                } else {
+                    igi = __ldg(&p.coef[mi].invG); igj = __ldg(&p.coef[mj].invG); igk = __ldg(&p.coef[mk].invG);
+                    igij = __ldg(&p.coef[mij].invG); igik = __ldg(&p.coef[mik].invG); igjk = __ldg(&p.coef[mjk].invG);
+                    ti = __ldg(&p.coef[mi].tauS); tj = __ldg(&p.coef[mj].tauS); tk = __ldg(&p.coef[mk].tauS);
+                    tij = __ldg(&p.coef[mij].tauS); tik = __ldg(&p.coef[mik].tauS); tjk = __ldg(&p.coef[mjk].tauS);
+                }
+                rigxy = rigidity4(c.invG, igi, igj, igij);
+                rigxz = rigidity4(c.invG, igi, igk, igik);
+                rigyz = rigidity4(c.invG, igj, igk, igjk);
+                texy = 0.25f * (c.tauS + ti + tj + tij);
+                texz = 0.25f * (c.tauS + ti + tk + tik);
+                teyz = 0.25f * (c.tauS + tj + tk + tjk);
+            }
+            float s[6];
+            s[0] = pb[PB_SXX * TX * TY + pc]; s[1] = pb[PB_SYY * TX * TY + pc]; s[2] = pb[PB_SZZ * TX * TY + pc];
+            if (f & TF_SOLID) { s[3] = pb[PB_SXY * TX * TY + pc]; s[4] = pb[PB_SXZ * TX * TY + pc]; s[5] = pb[PB_SYZ * TX * TY + pc]; }
+            else { s[3] = s[4] = s[5] = 0.f; }
+            if (cellpml) {
+                // ---------------- PML shell: damped split parts
+                const PmlCell pcell = make_pml_cell(p, i, j, k, load_axis(p.axI, i), sJ[ty], sK[tx]);
+                if (!(f & TF_SOLID)) { D[3] = D[4] = D[5] = D[6] = D[7] = D[8] = 0.f; }
+                stress_pml(p, pcell, c.M, c.L, rigxy, rigxz, rigyz, D, s);
+                if (refl) { s[0] = s[1] = s[2] = s[3] = s[4] = s[5] = 0.f; }
+                p.S[0][q] = s[0]; p.S[1][q] = s[1]; p.S[2][q] = s[2];
+                if (f & TF_SOLID) { p.S[3][q] = s[3]; p.S[4][q] = s[4]; p.S[5][q] = s[5]; }
+            } else {
+                // ---------------- interior: viscoelastic update
+                const bool att = attenuates(c);
+                float pr = pb[PB_PR * TX * TY + pc];
+                float r0 = 0.f, r1 = 0.f, r2 = 0.f;
+                if (att) { r0 = pb[PB_RXX * TX * TY + pc]; r1 = pb[PB_RYY * TX * TY + pc]; r2 = pb[PB_RZZ * TX * TY + pc]; }
+                stress_normal_interior(c, dt, att, D[0], D[1], D[2], s[0], s[1], s[2], r0, r1, r2, pr);
+                if (refl) { s[0] = s[1] = s[2] = 0.f; pr = 0.f; }
+                p.S[0][q] = s[0]; p.S[1][q] = s[1]; p.S[2][q] = s[2]; Pr[q] = pr;
+                if (att) { p.R[0][q] = r0; p.R[1][q] = r1; p.R[2][q] = r2; }
+                if (f & TF_SOLID) {
+                    if (rigxy != 0.f) {
+                        float r = pb[PB_RXY * TX * TY + pc];
+                        stress_shear_interior(c, dt, rigxy, texy, D[3] + D[4], s[3], r);
+                        if (refl) s[3] = 0.f;
+                        p.S[3][q] = s[3];
+                        if (texy != 0.f) p.R[3][q] = r;
+                    }
+                    if (rigxz != 0.f) {
+                        float r = pb[PB_RXZ * TX * TY + pc];
+                        stress_shear_interior(c, dt, rigxz, texz, D[5] + D[6], s[4], r);
+                        if (refl) s[4] = 0.f;
+                        p.S[4][q] = s[4];
+                        if (texz != 0.f) p.R[4][q] = r;
+                    }
+                    if (rigyz != 0.f) {
+                        float r = pb[PB_RYZ * TX * TY + pc];
+                        stress_shear_interior(c, dt, rigyz, teyz, D[7] + D[8], s[5], r);
+                        if (refl) s[5] = 0.f;
+                        p.S[5][q] = s[5];
+                        if (teyz != 0.f) p.R[5][q] = r;
+                    }
+                }
+                if (ACC == 1) {
+                    const float v = -c.K * pr;
+                    p.acc_rms[q - 2 * s1] += v * v;
+                } else if (ACC == 2) {
+                    const long long qa = q - 2 * s1;
+#pragma unroll
+                    for (int n = 0; n < 6; n++) accumulate(p, BB_MAP_SXX + n, qa, s[n], false);
+                    accumulate(p, BB_MAP_PRESSURE, qa, -c.K * pr, false);
+                }
+            }
+        }
+        __syncthreads();   // every warp is done with the slots of plane i
+        if (tid == 0) {
+            if (it + ST_NSH < np + 2) issue_h(it + ST_NSH);
+            if (it + ST_NSP < np) issue_p(it + ST_NSP);
+        }
+    }
+}
+
+// =========================================================================================
+// particle half-step
+// =========================================================================================
+constexpr int PT_NSH = 5, PT_NSP = 3;
+// halo-stage boxes: Syy Szz Sxy Sxz Syz (halo boxes) then Sxx (point box, i-stencil only) then labels
+struct ParticleSmem {
+    static constexpr int HSTAGE = 5 * HBOX_STRIDE + PBOX + LBOX_STRIDE;
+    static constexpr int PSTAGE = 3 * PBOX;
+    static constexpr int OFF_H = 0;
+    static constexpr int OFF_P = OFF_H + PT_NSH * HSTAGE;
+    static constexpr int OFF_B = OFF_P + PT_NSP * PSTAGE;                           // float B[128]
+    static constexpr int OFF_AXJ = OFF_B + BB_MAX_SMEM_MAT * 4;
+    static constexpr int OFF_AXK = OFF_AXJ + TY * (int)sizeof(AxisCoef);
+    static constexpr int OFF_FLAGS = OFF_AXK + TX * (int)sizeof(AxisCoef);
+    static constexpr int OFF_BAR = OFF_FLAGS + ((MAXCHUNK + 8 + 15) / 16) * 16;
+    static constexpr int BYTES = OFF_BAR + (PT_NSH + PT_NSP) * 8 + 128;
+};
+enum { HB_SYY = 0, HB_SZZ, HB_SXY, HB_SXZ, HB_SYZ };
+
+template <typename LT, int ACC>
+__global__ void __launch_bounds__(NT, 2) particle_tma(const __grid_constant__ ParticleMaps tm, const DevParams p, int ia, int ie, int chunk) {
+    constexpr bool SMC = sizeof(LT) == 1;
+    constexpr int LW = LabBox<LT>::W;
+    using L = ParticleSmem;
+    extern __shared__ unsigned char smem_raw[];
+    unsigned char *sm = reinterpret_cast<unsigned char *>((reinterpret_cast<uintptr_t>(smem_raw) + 127) & ~(uintptr_t)127);
+    float *sB = reinterpret_cast<float *>(sm + L::OFF_B);
+    AxisCoef *sJ = reinterpret_cast<AxisCoef *>(sm + L::OFF_AXJ);
+    AxisCoef *sK = reinterpret_cast<AxisCoef *>(sm + L::OFF_AXK);
+    unsigned char *sF = sm + L::OFF_FLAGS;
+    uint64_t *barH = reinterpret_cast<uint64_t *>(sm + L::OFF_BAR);
+    uint64_t *barP = barH + PT_NSH;
+
+    const int tx = threadIdx.x, ty = threadIdx.y, tid = ty * TX + tx;
+    const int k0 = blockIdx.x * TX, j0 = blockIdx.y * TY;
+    const int ic0 = ia + blockIdx.z * chunk, ic1 = min(ic0 + chunk, ie);
+    const int np = ic1 - ic0;
+    const int k = k0 + tx, j = j0 + ty;
+    const bool active = k < p.n3 && j < p.n2;
+    const bool jkd = in_pml1(j, p.n2, p.P) || in_pml1(k, p.n3, p.P);
+    const bool jkupd = j < p.n2 - 1 && k < p.n3 - 1;
+    const bool jkedge = j <= 1 || j >= p.n2 - 2 || k <= 1 || k >= p.n3 - 2;
+    const long long s1 = p.plane;
+    const int ipl0 = ic0 - p.i0 + 2;
+
+    if (SMC) for (int t = tid; t < p.nmat; t += NT) sB[t] = p.coef[t].B;
+    if (tid < TY * 8) { const int r = tid >> 3, e = tid & 7; reinterpret_cast<float *>(sJ)[tid] = reinterpret_cast<const float *>(p.axJ + min(j0 + r, p.n2 - 1))[e]; }
+    { const int r = tid >> 3, e = tid & 7; reinterpret_cast<float *>(sK)[tid] = reinterpret_cast<const float *>(p.axK + min(k0 + r, p.n3 - 1))[e]; }
+    if (tid < np + 2) {
+        const int ipl = ipl0 + tid;
+        sF[tid] = ipl < p.nloc ? p.flags[((long long)ipl * p.ntj + blockIdx.y) * p.ntk + blockIdx.x] : 0;
+    }
+    if (tid == 0) {
+        for (int s = 0; s < PT_NSH + PT_NSP; s++) mbar_init(barH + s, 1);
+        fence_barrier_init();
+    }
+    __syncthreads();
+
+    auto issue_h = [&](int r) {
+        unsigned char *st = sm + L::OFF_H + (r % PT_NSH) * L::HSTAGE;
+        uint64_t *bar = barH + (r % PT_NSH);
+        const bool fsh = sF[r] & TF_SHEAR;
+        mbar_expect_tx(bar, (fsh ? 5 : 2) * HBOX + PBOX + LW * LH * (int)sizeof(LT));
+        const int ipl = ipl0 + r;
+        const int nb = fsh ? 5 : 2;
+        for (int c = 0; c < nb; c++) tma_load_3d(st + c * HBOX_STRIDE, &tm.sh[c], bar, k0 - HK, j0 - HALO, ipl);
+        tma_load_3d(st + 5 * HBOX_STRIDE, &tm.sxx, bar, k0, j0, ipl);
+        tma_load_3d(st + 5 * HBOX_STRIDE + PBOX, &tm.lab, bar, k0, j0, ipl);
+    };
+    auto issue_p = [&](int r) {
+        unsigned char *st = sm + L::OFF_P + (r % PT_NSP) * L::PSTAGE;
+        uint64_t *bar = barP + (r % PT_NSP);
+        mbar_expect_tx(bar, 3 * PBOX);
+        const int ipl = ipl0 + r;
+#pragma unroll
+        for (int c = 0; c < 3; c++) tma_load_3d(st + c * PBOX, &tm.v[c], bar, k0, j0, ipl);
+    };
+    if (tid == 0) {
+        for (int r = 0; r < PT_NSH && r < np + 2; r++) issue_h(r);
+        for (int r = 0; r < PT_NSP && r < np; r++) issue_p(r);
+    }
+
+    // queues: Sxx holds i-1..i+2 ; Sxy, Sxz hold i-2..i+1 (state before the shift of plane ic0)
+    const float *__restrict__ Sxx = p.S[0], *__restrict__ Sxy = p.S[3], *__restrict__ Sxz = p.S[4];
+    const long long col = (long long)min(j, p.n2 - 1) * p.pitch + min(k, p.pitch - 1);
+    long long q = (long long)ipl0 * s1 + col;
+    float xx_m1, xx_0 = Sxx[q - s1], xx_p1 = 0.f, xx_p2 = 0.f;
+    float xy_m2, xy_m1 = Sxy[q - 2 * s1], xy_0 = Sxy[q - s1], xy_p1 = 0.f;
+    float xz_m2, xz_m1 = Sxz[q - 2 * s1], xz_0 = Sxz[q - s1], xz_p1 = 0.f;
+    const int sc = (ty + HALO) * SW + tx + HK;
+    const int lc = ty * LW + tx;
+    const int pc = ty * TX + tx;
+    const float dt = p.dt;
+    const unsigned MSK = LabelTraits<LT>::MASK;
+
+    auto hbox = [&](int r, int c) { return reinterpret_cast<const float *>(sm + L::OFF_H + (r % PT_NSH) * L::HSTAGE + c * HBOX_STRIDE); };
+    auto xxbox = [&](int r) { return reinterpret_cast<const float *>(sm + L::OFF_H + (r % PT_NSH) * L::HSTAGE + 5 * HBOX_STRIDE); };
+    auto lbox = [&](int r) { return reinterpret_cast<const LT *>(sm + L::OFF_H + (r % PT_NSH) * L::HSTAGE + 5 * HBOX_STRIDE + PBOX); };
+    auto wait_h = [&](int r) { mbar_wait(barH + (r % PT_NSH), (r / PT_NSH) & 1); };
+
+    wait_h(0);
+    xx_p1 = xxbox(0)[pc];
+    if (sF[0] & TF_SHEAR) { xy_p1 = hbox(0, HB_SXY)[sc]; xz_p1 = hbox(0, HB_SXZ)[sc]; }
+    wait_h(1);
+    xx_p2 = xxbox(1)[pc];
+
+    for (int it = 0; it < np; it++, q += s1) {
+        const int i = ic0 + it;
+        const unsigned f = sF[it];
+        const bool fsh = f & TF_SHEAR;
+        wait_h(it + 2);
+        xx_m1 = xx_0; xx_0 = xx_p1; xx_p1 = xx_p2; xx_p2 = xxbox(it + 2)[pc];
+        xy_m2 = xy_m1; xy_m1 = xy_0; xy_0 = xy_p1;
+        xz_m2 = xz_m1; xz_m1 = xz_0; xz_0 = xz_p1;
+        if (sF[it + 1] & TF_SHEAR) { xy_p1 = hbox(it + 1, HB_SXY)[sc]; xz_p1 = hbox(it + 1, HB_SXZ)[sc]; }
+        else { xy_p1 = 0.f; xz_p1 = 0.f; }
+        mbar_wait(barP + (it % PT_NSP), (it / PT_NSP) & 1);
+        const bool xd = in_pml1(i, p.n1, p.P);
+        const bool cellpml = xd || jkd;
+        if (active && (!cellpml || (jkupd && i < p.n1 - 1))) {
+            const float *byy = hbox(it, HB_SYY), *bzz = hbox(it, HB_SZZ);
+            const float *bxy = hbox(it, HB_SXY), *bxz = hbox(it, HB_SXZ), *byz = hbox(it, HB_SYZ);
+            const LT *l0p = lbox(it), *l1p = lbox(it + 1);
+            const float *pb = reinterpret_cast<const float *>(sm + L::OFF_P + (it % PT_NSP) * L::PSTAGE);
+            const unsigned l0 = l0p[lc];
+            const unsigned mi = l1p[lc] & MSK, mj = l0p[lc + LW] & MSK, mk = l0p[lc + 1] & MSK;
+            float b0, bi, bj, bk;
+            if (SMC) { b0 = sB[l0 & MSK]; bi = sB[mi]; bj = sB[mj]; bk = sB[mk]; }
+            else { b0 = __ldg(&p.coef[l0 & MSK].B); bi = __ldg(&p.coef[mi].B); bj = __ldg(&p.coef[mj].B); bk = __ldg(&p.coef[mk].B); }
+            const float bx = 0.5f * (b0 + bi), by = 0.5f * (b0 + bj), bz = 0.5f * (b0 + bk);
+            float X[9];
+            if (!(jkedge || i <= 1 || i >= p.n1 - 2)) {
+                X[0] = D4(xx_p1, xx_0, xx_p2, xx_m1);
+                X[3] = D4(xy_0, xy_m1, xy_p1, xy_m2);
+                X[6] = D4(xz_0, xz_m1, xz_p1, xz_m2);
+                X[4] = D4(byy[sc + SW], byy[sc], byy[sc + 2 * SW], byy[sc - SW]);
+                X[8] = D4(bzz[sc + 1], bzz[sc], bzz[sc + 2], bzz[sc - 1]);
+                if (fsh) {
+                    X[1] = D4(bxy[sc], bxy[sc - SW], bxy[sc + SW], bxy[sc - 2 * SW]);
+                    X[2] = D4(bxz[sc], bxz[sc - 1], bxz[sc + 1], bxz[sc - 2]);
+                    X[5] = D4(byz[sc], byz[sc - 1], byz[sc + 1], byz[sc - 2]);
+                    X[7] = D4(byz[sc], byz[sc - SW], byz[sc + SW], byz[sc - 2 * SW]);
+                } else { X[1] = X[2] = X[5] = X[7] = 0.f; }
+            } else {
+                const AxisCoef ci = load_axis(p.axI, i), cj = sJ[ty], ck = sK[tx];
+                X[0] = D4C(ci.caf, ci.cbf, xx_p1, xx_0, xx_p2, xx_m1);
+                X[3] = D4C(ci.cab, ci.cbb, xy_0, xy_m1, xy_p1, xy_m2);
+                X[6] = D4C(ci.cab, ci.cbb, xz_0, xz_m1, xz_p1, xz_m2);
+                X[4] = D4C(cj.caf, cj.cbf, byy[sc + SW], byy[sc], byy[sc + 2 * SW], byy[sc - SW]);
+                X[8] = D4C(ck.caf, ck.cbf, bzz[sc + 1], bzz[sc], bzz[sc + 2], bzz[sc - 1]);
+                if (fsh) {
+                    X[1] = D4C(cj.cab, cj.cbb, bxy[sc], bxy[sc - SW], bxy[sc + SW], bxy[sc - 2 * SW]);
+                    X[2] = D4C(ck.cab, ck.cbb, bxz[sc], bxz[sc - 1], bxz[sc + 1], bxz[sc - 2]);
+                    X[5] = D4C(ck.cab, ck.cbb, byz[sc], byz[sc - 1], byz[sc + 1], byz[sc - 2]);
+                    X[7] = D4C(cj.cab, cj.cbb, byz[sc], byz[sc - SW], byz[sc + SW], byz[sc - 2 * SW]);
+                } else { X[1] = X[2] = X[5] = X[7] = 0.f; }
+            }
+            float v[3] = { pb[pc], pb[TX * TY + pc], pb[2 * TX * TY + pc] };
+            if (cellpml) {
+                const PmlCell pcell = make_pml_cell(p, i, j, k, load_axis(p.axI, i), sJ[ty], sK[tx]);
+                particle_pml(p, pcell, bx, by, bz, X, v);
+            } else {
+                v[0] += dt * bx * (X[0] + X[1] + X[2]);
+                v[1] += dt * by * (X[3] + X[4] + X[5]);
+                v[2] += dt * bz * (X[6] + X[7] + X[8]);
+            }
+            if (l0 & LabelTraits<LT>::REFL) { v[0] = v[1] = v[2] = 0.f; }
+            p.V[0][q] = v[0]; p.V[1][q] = v[1]; p.V[2][q] = v[2];
+            if (ACC && !cellpml) {
+                const long long qa = q - 2 * s1;
+                accumulate(p, BB_MAP_VX, qa, v[0], false);
+                accumulate(p, BB_MAP_VY, qa, v[1], false);
+                accumulate(p, BB_MAP_VZ, qa, v[2], false);
+                accumulate(p, BB_MAP_ALLV, qa, v[0] * v[0] + v[1] * v[1] + v[2] * v[2], true);
+            }
+        }
+        __syncthreads();
+        if (tid == 0) {
+            if (it + PT_NSH < np + 2) issue_h(it + PT_NSH);
+            if (it + PT_NSP < np) issue_p(it + PT_NSP);
+        }
+    }
+}
+}  // namespace tma

@@ -21,6 +21,16 @@ def rl2(a, b):
     return d / nb if nb > 0 else d
 
 
+def same_peak(a, b, tie=1e-5):
+    """Identical peak voxel; a mirror-symmetric workload has twin maxima that differ by rounding
+    only, so a voxel where the oracle itself is within `tie` (relative) of its maximum also counts."""
+    ia, ib = int(np.argmax(a)), int(np.argmax(b))
+    if ia == ib:
+        return True
+    fa, fb = a.reshape(-1), b.reshape(-1)
+    return abs(float(fb[ia]) - float(fb[ib])) <= tie * float(fb[ib]) and abs(float(fa[ia]) - float(fa[ib])) <= tie * float(fa[ia])
+
+
 def run_cuda(w, variant=0, **over):
     kw = {k: v for k, v in w['kwargs'].items() if k not in DROP}
     kw.update(over)
@@ -57,7 +67,7 @@ def test_parity_small(name, shape, periods, pml, variant):
         assert rl2(Peak[k], ref['Peak'][k]) <= TOL, k
     main = RMS if 'Pressure' in RMS else Peak
     refm = ref['RMS'] if 'Pressure' in ref['RMS'] else ref['Peak']
-    assert np.argmax(main['Pressure']) == np.argmax(refm['Pressure'])
+    assert same_peak(main['Pressure'], refm['Pressure'])
     assert rl2(Sensor['Pressure'], ref['Sensor']['Pressure']) <= TOL
     for k, v in last.items():
         assert rl2(v, ref['LastMap'][k]) <= 5 * TOL, (k, rl2(v, ref['LastMap'][k]))
@@ -136,7 +146,7 @@ def test_full_size_config1_against_oracle():
     (Sensor, RMS, Peak, IP), _ = run_cuda(w, 0)
     ref = run_oracle(w)
     assert rl2(RMS['Pressure'], ref['RMS']['Pressure']) <= TOL
-    assert np.argmax(RMS['Pressure']) == np.argmax(ref['RMS']['Pressure'])
+    assert same_peak(RMS['Pressure'], ref['RMS']['Pressure'])
     assert rl2(Sensor['Pressure'], ref['Sensor']['Pressure']) <= TOL
 
 
