@@ -78,12 +78,16 @@ struct DevParams {
     const unsigned char *flags; // [nloc][ntj][ntk]
     int ntj, ntk;
     const AxisCoef *axI, *axJ, *axK;   // [n1], [n2], [n3]
-    // damped parts: XP [(ipx*n2 + j)*pitch + k] over this slab's i-PML planes,
-    // YP [((i-i0)*2P + jp)*pitch + k], ZP [((i-i0)*n2 + j)*zpw + kp] over the owned planes
+    // damped parts, stored tile-aligned so that a TMA box of a part maps 1:1 onto a tile:
+    //   XP [(ipx*n2 + j)*pitch + k]              over this slab's i-PML planes,
+    //   YP [((i-i0)*nyrows + jp)*pitch + k]      jp = ytile(j/8)*8 + j%8 over the tile rows that hold j-PML cells,
+    //   ZP [((i-i0)*n2 + j)*zpw + kp]            kp = ztile(k/32)*32 + k%32 over the tile columns that hold k-PML cells
+    // with ytile(t) = t < nylo ? t : t - tjhi0 + nylo (same for z).
     float *XP[BB_NPART], *YP[BB_NPART], *ZP[BB_NPART];
     int nxlo;            // owned planes inside the low-i PML: global i in [i0, i0+nxlo)
     int xhi_begin;       // first owned plane inside the high-i PML (== i1 when none)
-    int zpw;             // row length of the Z parts (2P rounded up to 8)
+    int nylo, tjhi0, nyrows;   // j tiles [0,nylo) and [tjhi0,ntj) hold PML rows; nyrows = stored rows
+    int nzlo, tkhi0, zpw;      // k tiles [0,nzlo) and [tkhi0,ntk) hold PML columns; zpw = stored columns
     // RMS / peak accumulators: [slot][(i-i0)*plane + j*pitch + k]
     float *acc_rms, *acc_peak;
     long long acc_stride;
@@ -93,15 +97,18 @@ struct DevParams {
 
 // TMA descriptors of one half-step kernel (passed as a __grid_constant__ parameter)
 struct StressMaps {
-    CUtensorMap v[3];    // Vx Vy Vz, box (TX+4, TY+4, 1)
+    CUtensorMap v[3];    // Vx Vy Vz, box (TX+8, TY+4, 1)
     CUtensorMap lab;     // labels, box (LW, TY+1, 1)
     CUtensorMap s[6];    // stresses, box (TX, TY, 1)
     CUtensorMap r[6];    // memory variables
     CUtensorMap pr;      // pressure accumulator
+    CUtensorMap xp[5], yp[5], zp[5];   // damped stress parts, box (TX, TY, 1)
+    CUtensorMap acc;     // pressure RMS accumulator (slot 0), box (TX, TY, 1)
 };
 struct ParticleMaps {
     CUtensorMap sxx;     // box (TX, TY, 1): only the i-stencil
-    CUtensorMap sh[5];   // Syy Szz Sxy Sxz Syz, box (TX+4, TY+4, 1)
+    CUtensorMap sh[5];   // Syy Szz Sxy Sxz Syz, box (TX+8, TY+4, 1)
     CUtensorMap lab;
     CUtensorMap v[3];    // box (TX, TY, 1)
+    CUtensorMap xp[3], yp[3], zp[3];   // damped velocity parts, box (TX, TY, 1)
 };

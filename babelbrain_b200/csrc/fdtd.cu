@@ -59,6 +59,7 @@ struct bb_fdtd {
     int n_sensor_maps = 0, n_acc_maps = 0;
     int64_t step = 0;
     size_t xp_floats = 0, yp_floats = 0, zp_floats = 0;   // per part array
+    int nxp = 0;                                          // planes of this slab inside the i-PML
     bool materials_set = false, maps_set = false, prepared = false;
     StressMaps smaps;
     ParticleMaps pmaps;
@@ -103,18 +104,24 @@ static EncodeTiledFn encode_tiled_fn() {
     return fn;
 }
 
-// 3-D map over a pitched (planes, n2, n3) volume of `esz`-byte elements; box (bw, bh, 1); out-of-volume taps read zero
-static int make_map(CUtensorMap *m, const void *base, CUtensorMapDataType dt, int esz, const DevParams &p, int planes, int bw, int bh) {
+// 3-D map over a row-major (d2, d1, d0) volume of `esz`-byte elements with row pitch `rowpitch` elements and
+// plane pitch `planepitch` elements; box (bw, bh, 1); out-of-volume taps read zero
+static int make_map3(CUtensorMap *m, const void *base, CUtensorMapDataType dt, int esz, long long d0, long long d1, long long d2,
+                     long long rowpitch, long long planepitch, int bw, int bh) {
     EncodeTiledFn enc = encode_tiled_fn();
     if (!enc) { bb_set_error("cuTensorMapEncodeTiled is not available from this driver"); return BB_ERR_CUDA; }
-    const cuuint64_t dims[3] = { (cuuint64_t)p.n3, (cuuint64_t)p.n2, (cuuint64_t)planes };
-    const cuuint64_t strides[2] = { (cuuint64_t)p.pitch * esz, (cuuint64_t)p.plane * esz };
+    const cuuint64_t dims[3] = { (cuuint64_t)std::max<long long>(d0, 1), (cuuint64_t)std::max<long long>(d1, 1), (cuuint64_t)std::max<long long>(d2, 1) };
+    const cuuint64_t strides[2] = { (cuuint64_t)rowpitch * esz, (cuuint64_t)planepitch * esz };
     const cuuint32_t box[3] = { (cuuint32_t)bw, (cuuint32_t)bh, 1 };
     const cuuint32_t estr[3] = { 1, 1, 1 };
     CUresult r = enc(m, dt, 3, const_cast<void *>(base), dims, strides, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_NONE,
                      CU_TENSOR_MAP_L2_PROMOTION_L2_128B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
     if (r != CUDA_SUCCESS) { bb_set_error("cuTensorMapEncodeTiled failed (%d) for box %dx%d", (int)r, bw, bh); return BB_ERR_CUDA; }
     return BB_OK;
+}
+// the pitched (planes, n2, n3) field volumes
+static int make_map(CUtensorMap *m, const void *base, CUtensorMapDataType dt, int esz, const DevParams &p, int planes, int bw, int bh) {
+    return make_map3(m, base, dt, esz, p.n3, p.n2, planes, p.pitch, p.plane, bw, bh);
 }
 
 static int make_tensor_maps(bb_fdtd *h) {
@@ -138,6 +145,17 @@ static int make_tensor_maps(bb_fdtd *h) {
     const int lw = u8 ? LabBox<uint8_t>::W : LabBox<uint16_t>::W;
     if ((rc = make_map(&h->smaps.lab, p.lab, u8 ? CU_TENSOR_MAP_DATA_TYPE_UINT8 : CU_TENSOR_MAP_DATA_TYPE_UINT16, h->label_bytes, p, p.nloc + 1, lw, LH))) return rc;
     h->pmaps.lab = h->smaps.lab;
+    // damped parts: stress kernel uses parts 0..4, particle kernel parts 5..7
+    for (int c = 0; c < BB_NPART; c++) {
+        CUtensorMap *mx = c < 5 ? &h->smaps.xp[c] : &h->pmaps.xp[c - 5];
+        CUtensorMap *my = c < 5 ? &h->smaps.yp[c] : &h->pmaps.yp[c - 5];
+        CUtensorMap *mz = c < 5 ? &h->smaps.zp[c] : &h->pmaps.zp[c - 5];
+        if ((rc = make_map3(mx, p.XP[c], F, 4, p.n3, p.n2, h->nxp, p.pitch, p.plane, TX, TY))) return rc;
+        if ((rc = make_map3(my, p.YP[c], F, 4, p.n3, p.nyrows, h->nown, p.pitch, (long long)p.nyrows * p.pitch, TX, TY))) return rc;
+        if ((rc = make_map3(mz, p.ZP[c], F, 4, p.zpw, p.n2, h->nown, p.zpw, (long long)p.n2 * p.zpw, TX, TY))) return rc;
+    }
+    if (p.acc_rms) { if ((rc = make_map3(&h->smaps.acc, p.acc_rms, F, 4, p.n3, p.n2, h->nown, p.pitch, p.plane, TX, TY))) return rc; }
+    else h->smaps.acc = h->smaps.pr;
     return BB_OK;
 }
 
@@ -197,9 +215,16 @@ extern "C" int bb_fdtd_create(const bb_fdtd_desc *d, bb_fdtd **out) {
     const int P = d->pml;
     p.nxlo = std::max(0, std::min(P, d->i1) - d->i0);
     p.xhi_begin = std::min(std::max(d->n1 - P, d->i0), d->i1);
-    p.zpw = (2 * P + 7) / 8 * 8;
-    h->xp_floats = (size_t)(p.nxlo + (d->i1 - p.xhi_begin)) * p.plane;
-    h->yp_floats = (size_t)h->nown * 2 * P * p.pitch;
+    // Y / Z parts are stored for whole tile rows / tile columns so that a TMA box maps 1:1 onto a tile
+    p.nylo = (P + tma::TY - 1) / tma::TY; p.tjhi0 = (d->n2 - P) / tma::TY;
+    if (p.tjhi0 < p.nylo) { p.nylo = p.ntj; p.tjhi0 = p.ntj; }   // tiny grids: every tile row is stored
+    p.nyrows = (p.nylo + (p.ntj - p.tjhi0)) * tma::TY;
+    p.nzlo = (P + tma::TX - 1) / tma::TX; p.tkhi0 = (d->n3 - P) / tma::TX;
+    if (p.tkhi0 < p.nzlo) { p.nzlo = p.ntk; p.tkhi0 = p.ntk; }
+    p.zpw = (p.nzlo + (p.ntk - p.tkhi0)) * tma::TX;
+    h->nxp = p.nxlo + (d->i1 - p.xhi_begin);
+    h->xp_floats = (size_t)h->nxp * p.plane;
+    h->yp_floats = (size_t)h->nown * p.nyrows * p.pitch;
     h->zp_floats = (size_t)h->nown * p.n2 * p.zpw;
     for (int c = 0; c < BB_NPART; c++) {
         if ((rc = dev_alloc(h, (void **)&p.XP[c], h->xp_floats * 4))) return rc;
@@ -524,7 +549,7 @@ static int launch_half_step(bb_fdtd *h, bool stress, int acc_mode, int ib, int i
         }
     } else {
         const int chunk = pick_chunk(h, ie - ib);
-        const dim3 blk(tma::TX, tma::TY, 1), grid(p.ntk, p.ntj, (ie - ib + chunk - 1) / chunk);
+        const dim3 blk(tma::TX, tma::NCW + 1, 1), grid(p.ntk, p.ntj, (ie - ib + chunk - 1) / chunk);
         if (stress) {
             const int sm = tma::StressSmem::BYTES;
             if (acc_mode == 1) tma::stress_tma<LT, 1><<<grid, blk, sm, h->stream>>>(h->smaps, p, ib, ie, chunk);

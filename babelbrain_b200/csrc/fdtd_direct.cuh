@@ -62,7 +62,7 @@ __global__ void __launch_bounds__(256) stress_direct(const DevParams p, int ib) 
     for (int n = 0; n < 6; n++) s[n] = p.S[n][q];
     if (pml) {
         const PmlCell pc = make_pml_cell(p, i, j, k, ci, cj, ck);
-        stress_pml(p, pc, c.M, c.L, rigxy, rigxz, rigyz, D, s);
+        stress_pml<false>(p, pc, c.M, c.L, rigxy, rigxz, rigyz, D, s);
         if (refl) { s[0] = s[1] = s[2] = s[3] = s[4] = s[5] = 0.0f; }
 #pragma unroll
         for (int n = 0; n < 6; n++) p.S[n][q] = s[n];
@@ -141,7 +141,7 @@ __global__ void __launch_bounds__(256) particle_direct(const DevParams p, int ib
     float v[3] = { p.V[0][q], p.V[1][q], p.V[2][q] };
     if (pml) {
         const PmlCell pc = make_pml_cell(p, i, j, k, ci, cj, ck);
-        particle_pml(p, pc, bx, by, bz, X, v);
+        particle_pml<false>(p, pc, bx, by, bz, X, v);
     } else {
         v[0] += p.dt * bx * (X[0] + X[1] + X[2]);
         v[1] += p.dt * by * (X[3] + X[4] + X[5]);

@@ -8,7 +8,12 @@
 //     stresses for the particle kernel) as (8+4) x (32+8) boxes plus the label box; out-of-volume
 //     taps are zero-filled by the TMA unit, so the kernels carry no boundary branches for loads;
 //   * the "point ring" holds the read-modify-write fields of the cell itself (stresses, memory
-//     variables and pressure for the stress kernel, V for the particle kernel) as 8 x 32 boxes.
+//     variables, pressure and the damped PML parts for the stress kernel; V and its damped parts
+//     for the particle kernel) as 8 x 32 boxes.
+// Warp 8 of the CTA is the producer: one lane waits on the slot's "empty" mbarrier and issues the
+// TMA loads of the next plane against the slot's "full" mbarrier.  Warps 0-7 are consumers (one tile
+// row each): they wait on "full", compute, store, and release the slot with one arrive per warp.
+// There is no CTA-wide barrier inside the plane loop, so warps drift apart by up to the ring depth.
 // The i-direction stencil lives in a register queue fed from the halo ring; the in-plane stencil
 // reads the ring directly (row pitch 40 floats: conflict-free).  Results go straight from registers
 // to global memory (one 128-byte row segment per warp and field).
@@ -28,7 +33,9 @@ constexpr int TX = 32, TY = 8, HALO = 2;
 constexpr int HK = 4;
 constexpr int SW = TX + 2 * HK;          // 40
 constexpr int SH = TY + 2 * HALO;        // 12
-constexpr int NT = TX * TY;              // 256 threads
+constexpr int NCW = TY;                  // consumer warps (one tile row each)
+constexpr int NT = TX * TY;              // 256 consumer threads
+constexpr int NTB = NT + 32;             // + the producer warp
 constexpr int HBOX = SW * SH * 4;        // 1920 bytes landed per halo box
 constexpr int HBOX_STRIDE = 1920;        // 128-byte aligned slot
 constexpr int PBOX = TX * TY * 4;        // 1024 bytes per point box
@@ -60,6 +67,9 @@ __device__ __forceinline__ void mbar_wait(uint64_t *bar, uint32_t parity) {
 __device__ __forceinline__ void tma_load_3d(void *dst, const CUtensorMap *map, uint64_t *bar, int c0, int c1, int c2) {
     asm volatile("cp.async.bulk.tensor.3d.shared::cluster.global.tile.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4, %5}], [%2];"
                  ::"r"(smem_u32(dst)), "l"(reinterpret_cast<uint64_t>(map)), "r"(smem_u32(bar)), "r"(c0), "r"(c1), "r"(c2) : "memory");
+}
+__device__ __forceinline__ void mbar_arrive(uint64_t *bar) {
+    asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(smem_u32(bar)) : "memory");
 }
 __device__ __forceinline__ void fence_barrier_init() { asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory"); }
 
@@ -100,108 +110,146 @@ __global__ void __launch_bounds__(NT) flags_kernel(const DevParams p, unsigned c
     if (tid == 0) flags[((long long)ip * p.ntj + blockIdx.y) * p.ntk + blockIdx.x] = (unsigned char)sflag;
 }
 
-// ---------------------------------------------------------------- shared-memory layout
-template <int NSH, int NSP, int NHF, int NPF>
-struct Smem {
-    // NHF halo boxes + 1 label box per halo stage; NPF point boxes per point stage
-    static constexpr int HSTAGE = NHF * HBOX_STRIDE + LBOX_STRIDE;
-    static constexpr int PSTAGE = NPF * PBOX;
-    static constexpr int OFF_H = 0;
-    static constexpr int OFF_P = OFF_H + NSH * HSTAGE;
-    static constexpr int OFF_COEF = OFF_P + NSP * PSTAGE;                          // MatCoef[128] (uint8 labels)
-    static constexpr int OFF_AXJ = OFF_COEF + BB_MAX_SMEM_MAT * (int)sizeof(MatCoef);
-    static constexpr int OFF_AXK = OFF_AXJ + TY * (int)sizeof(AxisCoef);
-    static constexpr int OFF_FLAGS = OFF_AXK + TX * (int)sizeof(AxisCoef);
-    static constexpr int OFF_BAR = OFF_FLAGS + ((MAXCHUNK + 8 + 15) / 16) * 16;
-    static constexpr int BYTES = OFF_BAR + (NSH + NSP) * 8 + 128;                  // + alignment slack
+// ---------------------------------------------------------------- ring bookkeeping
+// slot s of a ring: bit s of `ph` is the parity the next wait on that slot must observe
+template <int NS> struct Ring {
+    int slot = 0;
+    unsigned ph;
+    __device__ explicit Ring(unsigned initial_parity) : ph(initial_parity ? 0xFFFFFFFFu : 0u) {}
+    __device__ static int next(int s) { return s + 1 == NS ? 0 : s + 1; }
+    __device__ void wait(uint64_t *bars, int s) { mbar_wait(bars + s, (ph >> s) & 1u); ph ^= 1u << s; }
+    __device__ void advance() { slot = next(slot); }
 };
 
 // =========================================================================================
 // stress half-step
 // =========================================================================================
-constexpr int ST_NSH = 5, ST_NSP = 3;
-using StressSmem = Smem<ST_NSH, ST_NSP, 3, 13>;
-// point-box order inside a stage
-enum { PB_SXX = 0, PB_SYY, PB_SZZ, PB_SXY, PB_SXZ, PB_SYZ, PB_RXX, PB_RYY, PB_RZZ, PB_RXY, PB_RXZ, PB_RYZ, PB_PR };
+constexpr int ST_NSH = 4, ST_NSP = 3;
+// point-box order inside a stage; on a plane inside the i-PML the X parts use the R boxes (no
+// interior cell exists on such a plane, so memory variables are not needed there)
+enum { PB_SXX = 0, PB_SYY, PB_SZZ, PB_SXY, PB_SXZ, PB_SYZ, PB_RXX, PB_RYY, PB_RZZ, PB_RXY, PB_RXZ, PB_RYZ, PB_PR,
+       PB_Y0, PB_Z0 = PB_Y0 + 5, PB_ACC = PB_Z0 + 5, PB_COUNT };
+struct StressSmem {
+    static constexpr int HSTAGE = 3 * HBOX_STRIDE + LBOX_STRIDE;
+    static constexpr int PSTAGE = PB_COUNT * PBOX;
+    static constexpr int OFF_H = 0;
+    static constexpr int OFF_P = OFF_H + ST_NSH * HSTAGE;
+    static constexpr int OFF_COEF = OFF_P + ST_NSP * PSTAGE;                         // MatCoef[128] (uint8 labels)
+    static constexpr int OFF_AXJ = OFF_COEF + BB_MAX_SMEM_MAT * (int)sizeof(MatCoef);
+    static constexpr int OFF_AXK = OFF_AXJ + TY * (int)sizeof(AxisCoef);
+    static constexpr int OFF_FLAGS = OFF_AXK + TX * (int)sizeof(AxisCoef);
+    static constexpr int OFF_BAR = OFF_FLAGS + ((MAXCHUNK + 8 + 15) / 16) * 16;
+    static constexpr int BYTES = OFF_BAR + 2 * (ST_NSH + ST_NSP) * 8;
+};
 
 template <typename LT, int ACC>
-__global__ void __launch_bounds__(NT, 2) stress_tma(const __grid_constant__ StressMaps tm, const DevParams p, int ia, int ie, int chunk) {
+__global__ void __launch_bounds__(NTB, 2) stress_tma(const __grid_constant__ StressMaps tm, const DevParams p, int ia, int ie, int chunk) {
     constexpr bool SMC = sizeof(LT) == 1;
     constexpr int LW = LabBox<LT>::W;
     using L = StressSmem;
-    extern __shared__ unsigned char smem_raw[];
-    unsigned char *sm = reinterpret_cast<unsigned char *>((reinterpret_cast<uintptr_t>(smem_raw) + 127) & ~(uintptr_t)127);
+    extern __shared__ __align__(1024) unsigned char sm[];   // TMA destinations need 128-byte alignment
     MatCoef *sC = reinterpret_cast<MatCoef *>(sm + L::OFF_COEF);
     AxisCoef *sJ = reinterpret_cast<AxisCoef *>(sm + L::OFF_AXJ);
     AxisCoef *sK = reinterpret_cast<AxisCoef *>(sm + L::OFF_AXK);
     unsigned char *sF = sm + L::OFF_FLAGS;
-    uint64_t *barH = reinterpret_cast<uint64_t *>(sm + L::OFF_BAR);
-    uint64_t *barP = barH + ST_NSH;
+    uint64_t *fullH = reinterpret_cast<uint64_t *>(sm + L::OFF_BAR);
+    uint64_t *emptyH = fullH + ST_NSH, *fullP = emptyH + ST_NSH, *emptyP = fullP + ST_NSP;
 
     const int tx = threadIdx.x, ty = threadIdx.y, tid = ty * TX + tx;
     const int k0 = blockIdx.x * TX, j0 = blockIdx.y * TY;
     const int ic0 = ia + blockIdx.z * chunk, ic1 = min(ic0 + chunk, ie);
     const int np = ic1 - ic0;                 // planes of this CTA
-    const int k = k0 + tx, j = j0 + ty;
-    const bool active = k < p.n3 && j < p.n2;
-    const bool jkd = in_pml1(j, p.n2, p.P) || in_pml1(k, p.n3, p.P);
-    const bool jkupd = j < p.n2 - 1 && k < p.n3 - 1;
-    const bool jkedge = j <= 1 || j >= p.n2 - 2 || k <= 1 || k >= p.n3 - 2;
-    const long long s1 = p.plane;
     const int ipl0 = ic0 - p.i0 + 2;          // local plane of ic0
+    // which damped parts this tile can need (CTA-uniform)
+    const bool tile_jd = (int)blockIdx.y < p.nylo || (int)blockIdx.y >= p.tjhi0;
+    const bool tile_kd = (int)blockIdx.x < p.nzlo || (int)blockIdx.x >= p.tkhi0;
+    const int yt = ((int)blockIdx.y < p.nylo ? (int)blockIdx.y : (int)blockIdx.y - p.tjhi0 + p.nylo) * TY;
+    const int zt = ((int)blockIdx.x < p.nzlo ? (int)blockIdx.x : (int)blockIdx.x - p.tkhi0 + p.nzlo) * TX;
 
     // ---- per-CTA tables
-    if (SMC) for (int t = tid; t < p.nmat * (int)(sizeof(MatCoef) / 4); t += NT) reinterpret_cast<float *>(sC)[t] = reinterpret_cast<const float *>(p.coef)[t];
+    if (SMC) for (int t = tid; t < p.nmat * (int)(sizeof(MatCoef) / 4); t += NTB) reinterpret_cast<float *>(sC)[t] = reinterpret_cast<const float *>(p.coef)[t];
     if (tid < TY * 8) { const int r = tid >> 3, e = tid & 7; reinterpret_cast<float *>(sJ)[tid] = reinterpret_cast<const float *>(p.axJ + min(j0 + r, p.n2 - 1))[e]; }
-    { const int r = tid >> 3, e = tid & 7; reinterpret_cast<float *>(sK)[tid] = reinterpret_cast<const float *>(p.axK + min(k0 + r, p.n3 - 1))[e]; }
+    if (tid < TX * 8) { const int r = tid >> 3, e = tid & 7; reinterpret_cast<float *>(sK)[tid] = reinterpret_cast<const float *>(p.axK + min(k0 + r, p.n3 - 1))[e]; }
     if (tid < np + 2) {
         const int ipl = ipl0 + tid;
         sF[tid] = ipl < p.nloc ? p.flags[((long long)ipl * p.ntj + blockIdx.y) * p.ntk + blockIdx.x] : 0;
     }
     if (tid == 0) {
-        for (int s = 0; s < ST_NSH + ST_NSP; s++) mbar_init(barH + s, 1);
+        for (int s = 0; s < ST_NSH; s++) { mbar_init(fullH + s, 1); mbar_init(emptyH + s, NCW); }
+        for (int s = 0; s < ST_NSP; s++) { mbar_init(fullP + s, 1); mbar_init(emptyP + s, NCW); }
         fence_barrier_init();
     }
     __syncthreads();
 
-    // ---- producer (thread 0): issue the TMA loads of one ring slot
-    auto issue_h = [&](int r) {     // halo plane ic0 + r, r in [0, np+2)
-        unsigned char *st = sm + L::OFF_H + (r % ST_NSH) * L::HSTAGE;
-        uint64_t *bar = barH + (r % ST_NSH);
-        mbar_expect_tx(bar, 3 * HBOX + LW * LH * (int)sizeof(LT));
-        const int ipl = ipl0 + r;
+    // =============================== producer warp ===============================
+    if (ty == NCW) {
+        if (tx != 0) return;
+        Ring<ST_NSH> rh(1);
+        Ring<ST_NSP> rp(1);
+        for (int r = 0; r < np + 2; r++) {
+            {   // halo plane ic0 + r: V boxes + labels
+                const int slot = rh.slot;
+                rh.wait(emptyH, slot);
+                unsigned char *st = sm + L::OFF_H + slot * L::HSTAGE;
+                uint64_t *bar = fullH + slot;
+                mbar_expect_tx(bar, 3 * HBOX + LW * LH * (int)sizeof(LT));
+                const int ipl = ipl0 + r;
 #pragma unroll
-        for (int c = 0; c < 3; c++) tma_load_3d(st + c * HBOX_STRIDE, &tm.v[c], bar, k0 - HK, j0 - HALO, ipl);
-        tma_load_3d(st + 3 * HBOX_STRIDE, &tm.lab, bar, k0, j0, ipl);
-    };
-    auto issue_p = [&](int r) {     // point plane ic0 + r, r in [0, np)
-        unsigned char *st = sm + L::OFF_P + (r % ST_NSP) * L::PSTAGE;
-        uint64_t *bar = barP + (r % ST_NSP);
-        const unsigned f = sF[r];
-        const bool fint = f & TF_INT, fatt = f & TF_ATT, fsol = f & TF_SOLID;
-        const int nbox = 3 + (fint ? 1 : 0) + (fatt ? 3 : 0) + (fsol ? 3 : 0) + (fsol && fint ? 3 : 0);
-        mbar_expect_tx(bar, nbox * PBOX);
-        const int ipl = ipl0 + r;
+                for (int c = 0; c < 3; c++) tma_load_3d(st + c * HBOX_STRIDE, &tm.v[c], bar, k0 - HK, j0 - HALO, ipl);
+                tma_load_3d(st + 3 * HBOX_STRIDE, &tm.lab, bar, k0, j0, ipl);
+                rh.advance();
+            }
+            if (r < np) {   // point plane ic0 + r
+                const int slot = rp.slot;
+                rp.wait(emptyP, slot);
+                unsigned char *st = sm + L::OFF_P + slot * L::PSTAGE;
+                uint64_t *bar = fullP + slot;
+                const unsigned f = sF[r];
+                const int i = ic0 + r, ipl = ipl0 + r;
+                const bool xd = in_pml1(i, p.n1, p.P);
+                const bool fint = f & TF_INT, fatt = f & TF_ATT, fsol = f & TF_SOLID;
+                const int npart = fsol ? 5 : 3;
+                const bool acc = ACC == 1 && fint;
+                const int nbox = 3 + (fsol ? 3 : 0) + (xd ? npart : (fint ? 1 : 0) + (fatt ? 3 : 0) + (fsol && fint ? 3 : 0))
+                               + (tile_jd ? npart : 0) + (tile_kd ? npart : 0) + (acc ? 1 : 0);
+                mbar_expect_tx(bar, nbox * PBOX);
 #pragma unroll
-        for (int c = 0; c < 3; c++) tma_load_3d(st + (PB_SXX + c) * PBOX, &tm.s[c], bar, k0, j0, ipl);
-        if (fint) tma_load_3d(st + PB_PR * PBOX, &tm.pr, bar, k0, j0, ipl);
-        if (fatt) {
+                for (int c = 0; c < 3; c++) tma_load_3d(st + (PB_SXX + c) * PBOX, &tm.s[c], bar, k0, j0, ipl);
+                if (fsol) {
 #pragma unroll
-            for (int c = 0; c < 3; c++) tma_load_3d(st + (PB_RXX + c) * PBOX, &tm.r[c], bar, k0, j0, ipl);
-        }
-        if (fsol) {
+                    for (int c = 3; c < 6; c++) tma_load_3d(st + (PB_SXX + c) * PBOX, &tm.s[c], bar, k0, j0, ipl);
+                }
+                if (xd) {
+                    const int ipx = i < p.P ? i - p.i0 : p.nxlo + (i - p.xhi_begin);
+                    for (int c = 0; c < npart; c++) tma_load_3d(st + (PB_RXX + c) * PBOX, &tm.xp[c], bar, k0, j0, ipx);
+                } else {
+                    if (fint) tma_load_3d(st + PB_PR * PBOX, &tm.pr, bar, k0, j0, ipl);
+                    if (fatt) {
 #pragma unroll
-            for (int c = 3; c < 6; c++) tma_load_3d(st + (PB_SXX + c) * PBOX, &tm.s[c], bar, k0, j0, ipl);
-            if (fint) {
+                        for (int c = 0; c < 3; c++) tma_load_3d(st + (PB_RXX + c) * PBOX, &tm.r[c], bar, k0, j0, ipl);
+                    }
+                    if (fsol && fint) {
 #pragma unroll
-                for (int c = 3; c < 6; c++) tma_load_3d(st + (PB_RXX + c) * PBOX, &tm.r[c], bar, k0, j0, ipl);
+                        for (int c = 3; c < 6; c++) tma_load_3d(st + (PB_RXX + c) * PBOX, &tm.r[c], bar, k0, j0, ipl);
+                    }
+                }
+                if (tile_jd) for (int c = 0; c < npart; c++) tma_load_3d(st + (PB_Y0 + c) * PBOX, &tm.yp[c], bar, k0, yt, i - p.i0);
+                if (tile_kd) for (int c = 0; c < npart; c++) tma_load_3d(st + (PB_Z0 + c) * PBOX, &tm.zp[c], bar, zt, j0, i - p.i0);
+                if (acc) tma_load_3d(st + PB_ACC * PBOX, &tm.acc, bar, k0, j0, i - p.i0);
+                rp.advance();
             }
         }
-    };
-    if (tid == 0) {
-        for (int r = 0; r < ST_NSH && r < np + 2; r++) issue_h(r);
-        for (int r = 0; r < ST_NSP && r < np; r++) issue_p(r);
+        return;
     }
+
+    // =============================== consumer warps ===============================
+    const int k = k0 + tx, j = j0 + ty;
+    const bool active = k < p.n3 && j < p.n2;
+    const bool jd = in_pml1(j, p.n2, p.P), kd = in_pml1(k, p.n3, p.P);
+    const bool jkd = jd || kd;
+    const bool jkupd = j < p.n2 - 1 && k < p.n3 - 1;
+    const bool jkedge = j <= 1 || j >= p.n2 - 2 || k <= 1 || k >= p.n3 - 2;
+    const long long s1 = p.plane;
 
     // ---- register queue along i (state before the shift of plane ic0)
     const float *__restrict__ Vx = p.V[0], *__restrict__ Vy = p.V[1], *__restrict__ Vz = p.V[2];
@@ -214,34 +262,40 @@ __global__ void __launch_bounds__(NT, 2) stress_tma(const __grid_constant__ Stre
     const int lc = ty * LW + tx;                     // ... in a label box
     const int pc = ty * TX + tx;                     // ... in a point box
     const float dt = p.dt;
-    float *__restrict__ Pr = p.Pr;
     const unsigned MSK = LabelTraits<LT>::MASK;
+    // part arrays: index of this cell on plane ic0 and the per-plane strides
+    const long long qy_stride = (long long)p.nyrows * p.pitch, qz_stride = (long long)p.n2 * p.zpw;
+    long long qy = ((long long)(ic0 - p.i0) * p.nyrows + yt + ty) * p.pitch + k;
+    long long qz = ((long long)(ic0 - p.i0) * p.n2 + min(j, p.n2 - 1)) * p.zpw + zt + tx;
 
-    auto hbox = [&](int r, int c) { return reinterpret_cast<const float *>(sm + L::OFF_H + (r % ST_NSH) * L::HSTAGE + c * HBOX_STRIDE); };
-    auto lbox = [&](int r) { return reinterpret_cast<const LT *>(sm + L::OFF_H + (r % ST_NSH) * L::HSTAGE + 3 * HBOX_STRIDE); };
-    auto wait_h = [&](int r) { mbar_wait(barH + (r % ST_NSH), (r / ST_NSH) & 1); };
+    auto hbox = [&](int slot, int c) { return reinterpret_cast<const float *>(sm + L::OFF_H + slot * L::HSTAGE + c * HBOX_STRIDE); };
+    auto lbox = [&](int slot) { return reinterpret_cast<const LT *>(sm + L::OFF_H + slot * L::HSTAGE + 3 * HBOX_STRIDE); };
+    Ring<ST_NSH> rh(0);
+    Ring<ST_NSP> rp(0);
 
     // planes ic0 and ic0+1 feed the queue before the loop
-    wait_h(0);
+    rh.wait(fullH, 0);
     vx_p1 = hbox(0, 0)[sc]; vy_p1 = hbox(0, 1)[sc]; vz_p1 = hbox(0, 2)[sc];
-    wait_h(1);
+    rh.wait(fullH, 1);
     vy_p2 = hbox(1, 1)[sc]; vz_p2 = hbox(1, 2)[sc];
 
-    for (int it = 0; it < np; it++, q += s1) {
+    for (int it = 0; it < np; it++, q += s1, qy += qy_stride, qz += qz_stride) {
         const int i = ic0 + it;
         const unsigned f = sF[it];
-        wait_h(it + 2);
+        const int hs = rh.slot, hs1 = Ring<ST_NSH>::next(hs), hs2 = Ring<ST_NSH>::next(hs1);
+        const int ps = rp.slot;
+        rh.wait(fullH, hs2);
         // ---------------- shift the queue: plane i becomes the centre
-        vx_m2 = vx_m1; vx_m1 = vx_0; vx_0 = vx_p1; vx_p1 = hbox(it + 1, 0)[sc];
-        vy_m1 = vy_0; vy_0 = vy_p1; vy_p1 = vy_p2; vy_p2 = hbox(it + 2, 1)[sc];
-        vz_m1 = vz_0; vz_0 = vz_p1; vz_p1 = vz_p2; vz_p2 = hbox(it + 2, 2)[sc];
-        mbar_wait(barP + (it % ST_NSP), (it / ST_NSP) & 1);
+        vx_m2 = vx_m1; vx_m1 = vx_0; vx_0 = vx_p1; vx_p1 = hbox(hs1, 0)[sc];
+        vy_m1 = vy_0; vy_0 = vy_p1; vy_p1 = vy_p2; vy_p2 = hbox(hs2, 1)[sc];
+        vz_m1 = vz_0; vz_0 = vz_p1; vz_p1 = vz_p2; vz_p2 = hbox(hs2, 2)[sc];
+        rp.wait(fullP, ps);
         const bool xd = in_pml1(i, p.n1, p.P);
         const bool cellpml = xd || jkd;
         if (active && (!cellpml || (jkupd && i < p.n1 - 1))) {
-            const float *bx = hbox(it, 0), *by = hbox(it, 1), *bz = hbox(it, 2);
-            const LT *l0p = lbox(it), *l1p = lbox(it + 1);
-            const float *pb = reinterpret_cast<const float *>(sm + L::OFF_P + (it % ST_NSP) * L::PSTAGE);
+            const float *bx = hbox(hs, 0), *by = hbox(hs, 1), *bz = hbox(hs, 2);
+            const LT *l0p = lbox(hs), *l1p = lbox(hs1);
+            const float *pb = reinterpret_cast<const float *>(sm + L::OFF_P + ps * L::PSTAGE) + pc;
             const unsigned l0 = l0p[lc];
             const bool refl = (l0 & LabelTraits<LT>::REFL) != 0;
             MatCoef c;
@@ -259,7 +313,7 @@ __global__ void __launch_bounds__(NT, 2) stress_tma(const __grid_constant__ Stre
                     D[6] = D4(bx[sc + 1], bx[sc], bx[sc + 2], bx[sc - 1]);
                     D[7] = D4(bz[sc + SW], bz[sc], bz[sc + 2 * SW], bz[sc - SW]);
                     D[8] = D4(by[sc + 1], by[sc], by[sc + 2], by[sc - 1]);
-                }
+                } else { D[3] = D[4] = D[5] = D[6] = D[7] = D[8] = 0.f; }
             } else {   // cells next to a face of the domain: edge-aware coefficients
                 const AxisCoef ci = load_axis(p.axI, i), cj = sJ[ty], ck = sK[tx];
                 D[0] = D4C(ci.cab, ci.cbb, vx_0, vx_m1, vx_p1, vx_m2);
@@ -295,44 +349,50 @@ __global__ void __launch_bounds__(NT, 2) stress_tma(const __grid_constant__ Stre
                 teyz = 0.25f * (c.tauS + tj + tk + tjk);
             }
             float s[6];
-            s[0] = pb[PB_SXX * TX * TY + pc]; s[1] = pb[PB_SYY * TX * TY + pc]; s[2] = pb[PB_SZZ * TX * TY + pc];
-            if (f & TF_SOLID) { s[3] = pb[PB_SXY * TX * TY + pc]; s[4] = pb[PB_SXZ * TX * TY + pc]; s[5] = pb[PB_SYZ * TX * TY + pc]; }
+            s[0] = pb[PB_SXX * NT]; s[1] = pb[PB_SYY * NT]; s[2] = pb[PB_SZZ * NT];
+            if (f & TF_SOLID) { s[3] = pb[PB_SXY * NT]; s[4] = pb[PB_SXZ * NT]; s[5] = pb[PB_SYZ * NT]; }
             else { s[3] = s[4] = s[5] = 0.f; }
             if (cellpml) {
-                // ---------------- PML shell: damped split parts
-                const PmlCell pcell = make_pml_cell(p, i, j, k, load_axis(p.axI, i), sJ[ty], sK[tx]);
-                if (!(f & TF_SOLID)) { D[3] = D[4] = D[5] = D[6] = D[7] = D[8] = 0.f; }
-                stress_pml(p, pcell, c.M, c.L, rigxy, rigxz, rigyz, D, s);
+                // ---------------- PML shell: damped split parts (old values staged by TMA)
+                PmlCell pcell;
+                pcell.xd = xd; pcell.jd = jd; pcell.kd = kd;
+                const int ipx = i < p.P ? i - p.i0 : p.nxlo + (i - p.xhi_begin);
+                pcell.qx = (long long)ipx * s1 + col; pcell.qy = qy; pcell.qz = qz;
+                const AxisCoef ci = load_axis(p.axI, i), cj = sJ[ty], ck = sK[tx];
+                pcell.aI = ci.aI; pcell.bI = ci.bI; pcell.aIh = ci.aH; pcell.bIh = ci.bH;
+                pcell.aJ = cj.aI; pcell.bJ = cj.bI; pcell.aJh = cj.aH; pcell.bJh = cj.bH;
+                pcell.aK = ck.aI; pcell.bK = ck.bI; pcell.aKh = ck.aH; pcell.bKh = ck.bH;
+                stress_pml<true>(p, pcell, c.M, c.L, rigxy, rigxz, rigyz, D, s, pb + PB_RXX * NT, pb + PB_Y0 * NT, pb + PB_Z0 * NT);
                 if (refl) { s[0] = s[1] = s[2] = s[3] = s[4] = s[5] = 0.f; }
                 p.S[0][q] = s[0]; p.S[1][q] = s[1]; p.S[2][q] = s[2];
                 if (f & TF_SOLID) { p.S[3][q] = s[3]; p.S[4][q] = s[4]; p.S[5][q] = s[5]; }
             } else {
                 // ---------------- interior: viscoelastic update
                 const bool att = attenuates(c);
-                float pr = pb[PB_PR * TX * TY + pc];
+                float pr = pb[PB_PR * NT];
                 float r0 = 0.f, r1 = 0.f, r2 = 0.f;
-                if (att) { r0 = pb[PB_RXX * TX * TY + pc]; r1 = pb[PB_RYY * TX * TY + pc]; r2 = pb[PB_RZZ * TX * TY + pc]; }
+                if (att) { r0 = pb[PB_RXX * NT]; r1 = pb[PB_RYY * NT]; r2 = pb[PB_RZZ * NT]; }
                 stress_normal_interior(c, dt, att, D[0], D[1], D[2], s[0], s[1], s[2], r0, r1, r2, pr);
                 if (refl) { s[0] = s[1] = s[2] = 0.f; pr = 0.f; }
-                p.S[0][q] = s[0]; p.S[1][q] = s[1]; p.S[2][q] = s[2]; Pr[q] = pr;
+                p.S[0][q] = s[0]; p.S[1][q] = s[1]; p.S[2][q] = s[2]; p.Pr[q] = pr;
                 if (att) { p.R[0][q] = r0; p.R[1][q] = r1; p.R[2][q] = r2; }
                 if (f & TF_SOLID) {
                     if (rigxy != 0.f) {
-                        float r = pb[PB_RXY * TX * TY + pc];
+                        float r = pb[PB_RXY * NT];
                         stress_shear_interior(c, dt, rigxy, texy, D[3] + D[4], s[3], r);
                         if (refl) s[3] = 0.f;
                         p.S[3][q] = s[3];
                         if (texy != 0.f) p.R[3][q] = r;
                     }
                     if (rigxz != 0.f) {
-                        float r = pb[PB_RXZ * TX * TY + pc];
+                        float r = pb[PB_RXZ * NT];
                         stress_shear_interior(c, dt, rigxz, texz, D[5] + D[6], s[4], r);
                         if (refl) s[4] = 0.f;
                         p.S[4][q] = s[4];
                         if (texz != 0.f) p.R[4][q] = r;
                     }
                     if (rigyz != 0.f) {
-                        float r = pb[PB_RYZ * TX * TY + pc];
+                        float r = pb[PB_RYZ * NT];
                         stress_shear_interior(c, dt, rigyz, teyz, D[7] + D[8], s[5], r);
                         if (refl) s[5] = 0.f;
                         p.S[5][q] = s[5];
@@ -341,7 +401,7 @@ __global__ void __launch_bounds__(NT, 2) stress_tma(const __grid_constant__ Stre
                 }
                 if (ACC == 1) {
                     const float v = -c.K * pr;
-                    p.acc_rms[q - 2 * s1] += v * v;
+                    p.acc_rms[q - 2 * s1] = pb[PB_ACC * NT] + v * v;
                 } else if (ACC == 2) {
                     const long long qa = q - 2 * s1;
 #pragma unroll
@@ -350,22 +410,25 @@ __global__ void __launch_bounds__(NT, 2) stress_tma(const __grid_constant__ Stre
                 }
             }
         }
-        __syncthreads();   // every warp is done with the slots of plane i
-        if (tid == 0) {
-            if (it + ST_NSH < np + 2) issue_h(it + ST_NSH);
-            if (it + ST_NSP < np) issue_p(it + ST_NSP);
-        }
+        // ---------------- this warp is done with the slots of plane i
+        __syncwarp();
+        if (tx == 0) { mbar_arrive(emptyH + hs); mbar_arrive(emptyP + ps); }
+        rh.advance();
+        rp.advance();
     }
 }
 
 // =========================================================================================
 // particle half-step
 // =========================================================================================
-constexpr int PT_NSH = 5, PT_NSP = 3;
-// halo-stage boxes: Syy Szz Sxy Sxz Syz (halo boxes) then Sxx (point box, i-stencil only) then labels
+constexpr int PT_NSH = 4, PT_NSP = 3;
+// halo-stage boxes: Syy Szz Sxy Sxz Syz (halo boxes) then Sxx (point box, i-stencil only) then labels;
+// point-stage boxes: V (3), X parts (3), Y parts (3), Z parts (3)
+enum { HB_SYY = 0, HB_SZZ, HB_SXY, HB_SXZ, HB_SYZ };
+enum { QB_V = 0, QB_X = 3, QB_Y = 6, QB_Z = 9, QB_COUNT = 12 };
 struct ParticleSmem {
     static constexpr int HSTAGE = 5 * HBOX_STRIDE + PBOX + LBOX_STRIDE;
-    static constexpr int PSTAGE = 3 * PBOX;
+    static constexpr int PSTAGE = QB_COUNT * PBOX;
     static constexpr int OFF_H = 0;
     static constexpr int OFF_P = OFF_H + PT_NSH * HSTAGE;
     static constexpr int OFF_B = OFF_P + PT_NSP * PSTAGE;                           // float B[128]
@@ -373,72 +436,102 @@ struct ParticleSmem {
     static constexpr int OFF_AXK = OFF_AXJ + TY * (int)sizeof(AxisCoef);
     static constexpr int OFF_FLAGS = OFF_AXK + TX * (int)sizeof(AxisCoef);
     static constexpr int OFF_BAR = OFF_FLAGS + ((MAXCHUNK + 8 + 15) / 16) * 16;
-    static constexpr int BYTES = OFF_BAR + (PT_NSH + PT_NSP) * 8 + 128;
+    static constexpr int BYTES = OFF_BAR + 2 * (PT_NSH + PT_NSP) * 8;
 };
-enum { HB_SYY = 0, HB_SZZ, HB_SXY, HB_SXZ, HB_SYZ };
 
 template <typename LT, int ACC>
-__global__ void __launch_bounds__(NT, 2) particle_tma(const __grid_constant__ ParticleMaps tm, const DevParams p, int ia, int ie, int chunk) {
+__global__ void __launch_bounds__(NTB, 2) particle_tma(const __grid_constant__ ParticleMaps tm, const DevParams p, int ia, int ie, int chunk) {
     constexpr bool SMC = sizeof(LT) == 1;
     constexpr int LW = LabBox<LT>::W;
     using L = ParticleSmem;
-    extern __shared__ unsigned char smem_raw[];
-    unsigned char *sm = reinterpret_cast<unsigned char *>((reinterpret_cast<uintptr_t>(smem_raw) + 127) & ~(uintptr_t)127);
+    extern __shared__ __align__(1024) unsigned char sm[];
     float *sB = reinterpret_cast<float *>(sm + L::OFF_B);
     AxisCoef *sJ = reinterpret_cast<AxisCoef *>(sm + L::OFF_AXJ);
     AxisCoef *sK = reinterpret_cast<AxisCoef *>(sm + L::OFF_AXK);
     unsigned char *sF = sm + L::OFF_FLAGS;
-    uint64_t *barH = reinterpret_cast<uint64_t *>(sm + L::OFF_BAR);
-    uint64_t *barP = barH + PT_NSH;
+    uint64_t *fullH = reinterpret_cast<uint64_t *>(sm + L::OFF_BAR);
+    uint64_t *emptyH = fullH + PT_NSH, *fullP = emptyH + PT_NSH, *emptyP = fullP + PT_NSP;
 
     const int tx = threadIdx.x, ty = threadIdx.y, tid = ty * TX + tx;
     const int k0 = blockIdx.x * TX, j0 = blockIdx.y * TY;
     const int ic0 = ia + blockIdx.z * chunk, ic1 = min(ic0 + chunk, ie);
     const int np = ic1 - ic0;
-    const int k = k0 + tx, j = j0 + ty;
-    const bool active = k < p.n3 && j < p.n2;
-    const bool jkd = in_pml1(j, p.n2, p.P) || in_pml1(k, p.n3, p.P);
-    const bool jkupd = j < p.n2 - 1 && k < p.n3 - 1;
-    const bool jkedge = j <= 1 || j >= p.n2 - 2 || k <= 1 || k >= p.n3 - 2;
-    const long long s1 = p.plane;
     const int ipl0 = ic0 - p.i0 + 2;
+    const bool tile_jd = (int)blockIdx.y < p.nylo || (int)blockIdx.y >= p.tjhi0;
+    const bool tile_kd = (int)blockIdx.x < p.nzlo || (int)blockIdx.x >= p.tkhi0;
+    const int yt = ((int)blockIdx.y < p.nylo ? (int)blockIdx.y : (int)blockIdx.y - p.tjhi0 + p.nylo) * TY;
+    const int zt = ((int)blockIdx.x < p.nzlo ? (int)blockIdx.x : (int)blockIdx.x - p.tkhi0 + p.nzlo) * TX;
 
-    if (SMC) for (int t = tid; t < p.nmat; t += NT) sB[t] = p.coef[t].B;
+    if (SMC) for (int t = tid; t < p.nmat; t += NTB) sB[t] = p.coef[t].B;
     if (tid < TY * 8) { const int r = tid >> 3, e = tid & 7; reinterpret_cast<float *>(sJ)[tid] = reinterpret_cast<const float *>(p.axJ + min(j0 + r, p.n2 - 1))[e]; }
-    { const int r = tid >> 3, e = tid & 7; reinterpret_cast<float *>(sK)[tid] = reinterpret_cast<const float *>(p.axK + min(k0 + r, p.n3 - 1))[e]; }
+    if (tid < TX * 8) { const int r = tid >> 3, e = tid & 7; reinterpret_cast<float *>(sK)[tid] = reinterpret_cast<const float *>(p.axK + min(k0 + r, p.n3 - 1))[e]; }
     if (tid < np + 2) {
         const int ipl = ipl0 + tid;
         sF[tid] = ipl < p.nloc ? p.flags[((long long)ipl * p.ntj + blockIdx.y) * p.ntk + blockIdx.x] : 0;
     }
     if (tid == 0) {
-        for (int s = 0; s < PT_NSH + PT_NSP; s++) mbar_init(barH + s, 1);
+        for (int s = 0; s < PT_NSH; s++) { mbar_init(fullH + s, 1); mbar_init(emptyH + s, NCW); }
+        for (int s = 0; s < PT_NSP; s++) { mbar_init(fullP + s, 1); mbar_init(emptyP + s, NCW); }
         fence_barrier_init();
     }
     __syncthreads();
 
-    auto issue_h = [&](int r) {
-        unsigned char *st = sm + L::OFF_H + (r % PT_NSH) * L::HSTAGE;
-        uint64_t *bar = barH + (r % PT_NSH);
-        const bool fsh = sF[r] & TF_SHEAR;
-        mbar_expect_tx(bar, (fsh ? 5 : 2) * HBOX + PBOX + LW * LH * (int)sizeof(LT));
-        const int ipl = ipl0 + r;
-        const int nb = fsh ? 5 : 2;
-        for (int c = 0; c < nb; c++) tma_load_3d(st + c * HBOX_STRIDE, &tm.sh[c], bar, k0 - HK, j0 - HALO, ipl);
-        tma_load_3d(st + 5 * HBOX_STRIDE, &tm.sxx, bar, k0, j0, ipl);
-        tma_load_3d(st + 5 * HBOX_STRIDE + PBOX, &tm.lab, bar, k0, j0, ipl);
-    };
-    auto issue_p = [&](int r) {
-        unsigned char *st = sm + L::OFF_P + (r % PT_NSP) * L::PSTAGE;
-        uint64_t *bar = barP + (r % PT_NSP);
-        mbar_expect_tx(bar, 3 * PBOX);
-        const int ipl = ipl0 + r;
+    // =============================== producer warp ===============================
+    if (ty == NCW) {
+        if (tx != 0) return;
+        Ring<PT_NSH> rh(1);
+        Ring<PT_NSP> rp(1);
+        for (int r = 0; r < np + 2; r++) {
+            {
+                const int slot = rh.slot;
+                rh.wait(emptyH, slot);
+                unsigned char *st = sm + L::OFF_H + slot * L::HSTAGE;
+                uint64_t *bar = fullH + slot;
+                const int nb = (sF[r] & TF_SHEAR) ? 5 : 2;
+                mbar_expect_tx(bar, nb * HBOX + PBOX + LW * LH * (int)sizeof(LT));
+                const int ipl = ipl0 + r;
+                for (int c = 0; c < nb; c++) tma_load_3d(st + c * HBOX_STRIDE, &tm.sh[c], bar, k0 - HK, j0 - HALO, ipl);
+                tma_load_3d(st + 5 * HBOX_STRIDE, &tm.sxx, bar, k0, j0, ipl);
+                tma_load_3d(st + 5 * HBOX_STRIDE + PBOX, &tm.lab, bar, k0, j0, ipl);
+                rh.advance();
+            }
+            if (r < np) {
+                const int slot = rp.slot;
+                rp.wait(emptyP, slot);
+                unsigned char *st = sm + L::OFF_P + slot * L::PSTAGE;
+                uint64_t *bar = fullP + slot;
+                const int i = ic0 + r, ipl = ipl0 + r;
+                const bool xd = in_pml1(i, p.n1, p.P);
+                mbar_expect_tx(bar, (3 + (xd ? 3 : 0) + (tile_jd ? 3 : 0) + (tile_kd ? 3 : 0)) * PBOX);
 #pragma unroll
-        for (int c = 0; c < 3; c++) tma_load_3d(st + c * PBOX, &tm.v[c], bar, k0, j0, ipl);
-    };
-    if (tid == 0) {
-        for (int r = 0; r < PT_NSH && r < np + 2; r++) issue_h(r);
-        for (int r = 0; r < PT_NSP && r < np; r++) issue_p(r);
+                for (int c = 0; c < 3; c++) tma_load_3d(st + (QB_V + c) * PBOX, &tm.v[c], bar, k0, j0, ipl);
+                if (xd) {
+                    const int ipx = i < p.P ? i - p.i0 : p.nxlo + (i - p.xhi_begin);
+#pragma unroll
+                    for (int c = 0; c < 3; c++) tma_load_3d(st + (QB_X + c) * PBOX, &tm.xp[c], bar, k0, j0, ipx);
+                }
+                if (tile_jd) {
+#pragma unroll
+                    for (int c = 0; c < 3; c++) tma_load_3d(st + (QB_Y + c) * PBOX, &tm.yp[c], bar, k0, yt, i - p.i0);
+                }
+                if (tile_kd) {
+#pragma unroll
+                    for (int c = 0; c < 3; c++) tma_load_3d(st + (QB_Z + c) * PBOX, &tm.zp[c], bar, zt, j0, i - p.i0);
+                }
+                rp.advance();
+            }
+        }
+        return;
     }
+
+    // =============================== consumer warps ===============================
+    const int k = k0 + tx, j = j0 + ty;
+    const bool active = k < p.n3 && j < p.n2;
+    const bool jd = in_pml1(j, p.n2, p.P), kd = in_pml1(k, p.n3, p.P);
+    const bool jkd = jd || kd;
+    const bool jkupd = j < p.n2 - 1 && k < p.n3 - 1;
+    const bool jkedge = j <= 1 || j >= p.n2 - 2 || k <= 1 || k >= p.n3 - 2;
+    const long long s1 = p.plane;
 
     // queues: Sxx holds i-1..i+2 ; Sxy, Sxz hold i-2..i+1 (state before the shift of plane ic0)
     const float *__restrict__ Sxx = p.S[0], *__restrict__ Sxy = p.S[3], *__restrict__ Sxz = p.S[4];
@@ -452,36 +545,42 @@ __global__ void __launch_bounds__(NT, 2) particle_tma(const __grid_constant__ Pa
     const int pc = ty * TX + tx;
     const float dt = p.dt;
     const unsigned MSK = LabelTraits<LT>::MASK;
+    const long long qy_stride = (long long)p.nyrows * p.pitch, qz_stride = (long long)p.n2 * p.zpw;
+    long long qy = ((long long)(ic0 - p.i0) * p.nyrows + yt + ty) * p.pitch + k;
+    long long qz = ((long long)(ic0 - p.i0) * p.n2 + min(j, p.n2 - 1)) * p.zpw + zt + tx;
 
-    auto hbox = [&](int r, int c) { return reinterpret_cast<const float *>(sm + L::OFF_H + (r % PT_NSH) * L::HSTAGE + c * HBOX_STRIDE); };
-    auto xxbox = [&](int r) { return reinterpret_cast<const float *>(sm + L::OFF_H + (r % PT_NSH) * L::HSTAGE + 5 * HBOX_STRIDE); };
-    auto lbox = [&](int r) { return reinterpret_cast<const LT *>(sm + L::OFF_H + (r % PT_NSH) * L::HSTAGE + 5 * HBOX_STRIDE + PBOX); };
-    auto wait_h = [&](int r) { mbar_wait(barH + (r % PT_NSH), (r / PT_NSH) & 1); };
+    auto hbox = [&](int slot, int c) { return reinterpret_cast<const float *>(sm + L::OFF_H + slot * L::HSTAGE + c * HBOX_STRIDE); };
+    auto xxbox = [&](int slot) { return reinterpret_cast<const float *>(sm + L::OFF_H + slot * L::HSTAGE + 5 * HBOX_STRIDE); };
+    auto lbox = [&](int slot) { return reinterpret_cast<const LT *>(sm + L::OFF_H + slot * L::HSTAGE + 5 * HBOX_STRIDE + PBOX); };
+    Ring<PT_NSH> rh(0);
+    Ring<PT_NSP> rp(0);
 
-    wait_h(0);
+    rh.wait(fullH, 0);
     xx_p1 = xxbox(0)[pc];
     if (sF[0] & TF_SHEAR) { xy_p1 = hbox(0, HB_SXY)[sc]; xz_p1 = hbox(0, HB_SXZ)[sc]; }
-    wait_h(1);
+    rh.wait(fullH, 1);
     xx_p2 = xxbox(1)[pc];
 
-    for (int it = 0; it < np; it++, q += s1) {
+    for (int it = 0; it < np; it++, q += s1, qy += qy_stride, qz += qz_stride) {
         const int i = ic0 + it;
         const unsigned f = sF[it];
         const bool fsh = f & TF_SHEAR;
-        wait_h(it + 2);
-        xx_m1 = xx_0; xx_0 = xx_p1; xx_p1 = xx_p2; xx_p2 = xxbox(it + 2)[pc];
+        const int hs = rh.slot, hs1 = Ring<PT_NSH>::next(hs), hs2 = Ring<PT_NSH>::next(hs1);
+        const int ps = rp.slot;
+        rh.wait(fullH, hs2);
+        xx_m1 = xx_0; xx_0 = xx_p1; xx_p1 = xx_p2; xx_p2 = xxbox(hs2)[pc];
         xy_m2 = xy_m1; xy_m1 = xy_0; xy_0 = xy_p1;
         xz_m2 = xz_m1; xz_m1 = xz_0; xz_0 = xz_p1;
-        if (sF[it + 1] & TF_SHEAR) { xy_p1 = hbox(it + 1, HB_SXY)[sc]; xz_p1 = hbox(it + 1, HB_SXZ)[sc]; }
+        if (sF[it + 1] & TF_SHEAR) { xy_p1 = hbox(hs1, HB_SXY)[sc]; xz_p1 = hbox(hs1, HB_SXZ)[sc]; }
         else { xy_p1 = 0.f; xz_p1 = 0.f; }
-        mbar_wait(barP + (it % PT_NSP), (it / PT_NSP) & 1);
+        rp.wait(fullP, ps);
         const bool xd = in_pml1(i, p.n1, p.P);
         const bool cellpml = xd || jkd;
         if (active && (!cellpml || (jkupd && i < p.n1 - 1))) {
-            const float *byy = hbox(it, HB_SYY), *bzz = hbox(it, HB_SZZ);
-            const float *bxy = hbox(it, HB_SXY), *bxz = hbox(it, HB_SXZ), *byz = hbox(it, HB_SYZ);
-            const LT *l0p = lbox(it), *l1p = lbox(it + 1);
-            const float *pb = reinterpret_cast<const float *>(sm + L::OFF_P + (it % PT_NSP) * L::PSTAGE);
+            const float *byy = hbox(hs, HB_SYY), *bzz = hbox(hs, HB_SZZ);
+            const float *bxy = hbox(hs, HB_SXY), *bxz = hbox(hs, HB_SXZ), *byz = hbox(hs, HB_SYZ);
+            const LT *l0p = lbox(hs), *l1p = lbox(hs1);
+            const float *pb = reinterpret_cast<const float *>(sm + L::OFF_P + ps * L::PSTAGE) + pc;
             const unsigned l0 = l0p[lc];
             const unsigned mi = l1p[lc] & MSK, mj = l0p[lc + LW] & MSK, mk = l0p[lc + 1] & MSK;
             float b0, bi, bj, bk;
@@ -515,10 +614,17 @@ __global__ void __launch_bounds__(NT, 2) particle_tma(const __grid_constant__ Pa
                     X[7] = D4C(cj.cab, cj.cbb, byz[sc], byz[sc - SW], byz[sc + SW], byz[sc - 2 * SW]);
                 } else { X[1] = X[2] = X[5] = X[7] = 0.f; }
             }
-            float v[3] = { pb[pc], pb[TX * TY + pc], pb[2 * TX * TY + pc] };
+            float v[3] = { pb[(QB_V + 0) * NT], pb[(QB_V + 1) * NT], pb[(QB_V + 2) * NT] };
             if (cellpml) {
-                const PmlCell pcell = make_pml_cell(p, i, j, k, load_axis(p.axI, i), sJ[ty], sK[tx]);
-                particle_pml(p, pcell, bx, by, bz, X, v);
+                PmlCell pcell;
+                pcell.xd = xd; pcell.jd = jd; pcell.kd = kd;
+                const int ipx = i < p.P ? i - p.i0 : p.nxlo + (i - p.xhi_begin);
+                pcell.qx = (long long)ipx * s1 + col; pcell.qy = qy; pcell.qz = qz;
+                const AxisCoef ci = load_axis(p.axI, i), cj = sJ[ty], ck = sK[tx];
+                pcell.aI = ci.aI; pcell.bI = ci.bI; pcell.aIh = ci.aH; pcell.bIh = ci.bH;
+                pcell.aJ = cj.aI; pcell.bJ = cj.bI; pcell.aJh = cj.aH; pcell.bJh = cj.bH;
+                pcell.aK = ck.aI; pcell.bK = ck.bI; pcell.aKh = ck.aH; pcell.bKh = ck.bH;
+                particle_pml<true>(p, pcell, bx, by, bz, X, v, pb + QB_X * NT, pb + QB_Y * NT, pb + QB_Z * NT);
             } else {
                 v[0] += dt * bx * (X[0] + X[1] + X[2]);
                 v[1] += dt * by * (X[3] + X[4] + X[5]);
@@ -534,11 +640,10 @@ __global__ void __launch_bounds__(NT, 2) particle_tma(const __grid_constant__ Pa
                 accumulate(p, BB_MAP_ALLV, qa, v[0] * v[0] + v[1] * v[1] + v[2] * v[2], true);
             }
         }
-        __syncthreads();
-        if (tid == 0) {
-            if (it + PT_NSH < np + 2) issue_h(it + PT_NSH);
-            if (it + PT_NSP < np) issue_p(it + PT_NSP);
-        }
+        __syncwarp();
+        if (tx == 0) { mbar_arrive(emptyH + hs); mbar_arrive(emptyP + ps); }
+        rh.advance();
+        rp.advance();
     }
 }
 }  // namespace tma

@@ -26,10 +26,41 @@ ROOT = os.path.dirname(os.path.abspath(__file__))
 sys.path.insert(0, ROOT)
 
 WORKLOAD = 'ctx500_skull'
+# dram__bytes_read.sum + dram__bytes_write.sum of one stress_tma launch from the committed ncu --set full capture
+# (profiles/); None until a capture of the current kernel exists
+NCU_TRAFFIC_BYTES = None
 DROP = ('COMPUTING_BACKEND', 'USE_SINGLE', 'DefaultGPUDeviceName')
-# algorithmic bytes per cell of one launch of each kernel (fp32 state, uint8 labels), DESIGN.md section 4
-STRESS_BYTES = {'solid': 12 + 48 + 48 + 1, 'att_fluid': 12 + 24 + 24 + 1, 'lossless': 12 + 24 + 1}
-PARTICLE_BYTES = {'solid': 24 + 24 + 1, 'att_fluid': 24 + 24 + 1, 'lossless': 24 + 24 + 1}
+
+
+def traffic_model(MM, ML, pml, i0, i1, glo, n1g):
+    """Algorithmic (compulsory) bytes of one launch of each half-step kernel over the owned planes, fp32
+    state and uint8 labels.  Interior cells: stress reads 3 V, read-modify-writes
+    the stresses and memory variables that exist for the cell's class (solid 6+6, attenuating fluid 3+3,
+    lossless fluid 3+0); particle reads those stresses and read-modify-writes 3 V.  PML cells carry no
+    memory variables but read-modify-write the damped split parts of each damped axis (3 normal + 2
+    shear stress parts, 3 velocity parts).  The pressure accumulator (8 B/interior cell) is reported
+    separately, as SURVEY.md 8(d) asks."""
+    own = MM[i0 - glo:i1 - glo]
+    n1, n2, n3 = own.shape
+    gi = np.arange(i0, i1)
+    di = ((gi < pml) | (gi >= n1g - pml)).astype(np.int8)[:, None, None]
+    dj = ((np.arange(n2) < pml) | (np.arange(n2) >= n2 - pml)).astype(np.int8)[None, :, None]
+    dk = ((np.arange(n3) < pml) | (np.arange(n3) >= n3 - pml)).astype(np.int8)[None, None, :]
+    nd = di + dj + dk
+    solid = (ML[:, 2] > 0)[own]
+    att = ((ML[:, 3] > 0) | (ML[:, 4] > 0))[own]
+    inner = nd == 0
+    cls = {'solid': int((inner & solid).sum()), 'att_fluid': int((inner & ~solid & att).sum()),
+           'lossless': int((inner & ~solid & ~att).sum()), 'pml': int((~inner).sum())}
+    nds = int(nd[~inner & solid].sum())
+    ndf = int(nd[~inner & ~solid].sum())
+    pml_s, pml_f = int((~inner & solid).sum()), int((~inner & ~solid).sum())
+    stress = (cls['solid'] * (12 + 48 + 48 + 1) + cls['att_fluid'] * (12 + 24 + 24 + 1) + cls['lossless'] * (12 + 24 + 1)
+              + pml_s * (12 + 48 + 1) + nds * 40 + pml_f * (12 + 24 + 1) + ndf * 24)
+    particle = (cls['solid'] * (24 + 24 + 1) + (cls['att_fluid'] + cls['lossless']) * (12 + 24 + 1)
+                + pml_s * (24 + 24 + 1) + pml_f * (12 + 24 + 1) + (nds + ndf) * 24)
+    pressure = 8 * (cls['solid'] + cls['att_fluid'] + cls['lossless'])
+    return cls, {'stress': float(stress), 'particle': float(particle), 'pressure_accumulator': float(pressure)}
 
 
 def measured_peak():
@@ -113,20 +144,6 @@ def build_rank_workload(rank, nranks):
     meta = dict(w['meta'], shape=(n1g, base[1], base[2]), cells=n1g * base[1] * base[2],
                 cell_updates=n1g * base[1] * base[2] * w['meta']['steps'])
     return dict(args=(MMl, ML, f, SMl, SF, h, T, SENl), kwargs=kw, meta=meta), (glo, n1g)
-
-
-def class_counts(MM, ML, pml, i0, i1, glo, n1g):
-    """Interior cell counts by traffic class over the owned planes."""
-    from babelbrain_b200 import workloads
-    own = MM[i0 - glo:i1 - glo]
-    gi = np.arange(i0, i1)
-    keep = (gi >= pml) & (gi < n1g - pml)
-    inner = own[keep][:, pml:-pml, pml:-pml]
-    counts = np.bincount(inner.reshape(-1), minlength=ML.shape[0])
-    solid = int(counts[ML[:, 2] > 0].sum())
-    att = int(counts[(ML[:, 2] == 0) & (ML[:, 3] > 0)].sum())
-    lossless = int(counts[(ML[:, 2] == 0) & (ML[:, 3] == 0)].sum())
-    return {'solid': solid, 'att_fluid': att, 'lossless': lossless, 'pml': int(own.size - inner.size)}
 
 
 def cpu_baseline(sample_steps=None, threads=None):
@@ -216,7 +233,7 @@ def main():
         dist.broadcast_object_list(ids, src=0)
         slab.comm_init(ids[0])
     glo = 0 if origin is None else origin
-    cls = class_counts(w['args'][0], w['args'][1], meta['pml'], slab.i0, slab.i1, glo, meta['shape'][0])
+    cls, alg = traffic_model(w['args'][0], w['args'][1], meta['pml'], slab.i0, slab.i1, glo, meta['shape'][0])
 
     # ---- device-resident metric: reset + run, timed by CUDA events inside the library
     for _ in range(args.warmup):
@@ -275,12 +292,17 @@ def main():
     if rank == 0:
         st = stats[-1]
         peak, peak_kind = measured_peak()
-        stress_bytes = sum(STRESS_BYTES[k] * cls[k] for k in STRESS_BYTES)
+        # the dominant kernel is the stress half-step: one launch per time step over the whole slab
         n_launch = max(st['stress_launches'], 1)
         launches_per_step_call = n_launch / max(st['steps_done'], 1)
+        stress_bytes = alg['stress'] / launches_per_step_call
         avg_ms = st['stress_ms'] / n_launch
-        # one launch per time step covers the interior box of the slab
-        achieved = stress_bytes / launches_per_step_call / (avg_ms * 1e-3) / 1e9 if avg_ms > 0 else None
+        achieved = stress_bytes / (avg_ms * 1e-3) / 1e9 if avg_ms > 0 else None
+        n_pl = max(st['particle_launches'], 1)
+        part_ms = st['particle_ms'] / n_pl
+        part_gbs = alg['particle'] / (n_pl / max(st['steps_done'], 1)) / (part_ms * 1e-3) / 1e9 if part_ms > 0 else None
+        step_bytes = alg['stress'] + alg['particle'] + alg['pressure_accumulator']
+        step_gbs = step_bytes * meta['steps'] / (st['run_ms'] * 1e-3) / 1e9
         nominal = 158.0 * meta['cells'] / world * meta['steps'] / (ms_per_step * 1e-3) / 1e9
         out = {
             'metric': 'FDTD Gcell-updates/s', 'value': value, 'unit': 'Gcell-updates/s', 'n_gpus': world,
@@ -295,10 +317,14 @@ def main():
                     'ms_per_step': float(te.item())},
             'gpu_launches': int(sum(s['stress_launches'] + s['particle_launches'] + s['pml_launches'] + s['other_launches'] for s in stats)),
             'clocks': clocks,
-            'roofline': {'bound': 'hbm', 'kernel': 'stress_tiled (stress half-step, interior box)', 'achieved': achieved, 'peak': peak,
-                         'unit': 'GB/s', 'frac': (achieved / peak) if achieved else None, 'traffic': None, 'peak_kind': peak_kind,
-                         'algorithmic_bytes_per_launch': stress_bytes / launches_per_step_call, 'avg_launch_ms': avg_ms,
+            'roofline': {'bound': 'hbm', 'kernel': 'stress_tma (fused stress half-step: interior + PML shell, RMS folded in)', 'achieved': achieved, 'peak': peak,
+                         'unit': 'GB/s', 'frac': (achieved / peak) if achieved else None, 'traffic': NCU_TRAFFIC_BYTES, 'peak_kind': peak_kind,
+                         'algorithmic_bytes_per_launch': stress_bytes, 'avg_launch_ms': avg_ms,
                          'kernel_share_of_step': st['stress_ms'] / st['run_ms'] if st['run_ms'] else None,
+                         'particle_kernel': {'achieved': part_gbs, 'frac': (part_gbs / peak) if part_gbs else None,
+                                             'algorithmic_bytes_per_launch': alg['particle'], 'avg_launch_ms': part_ms},
+                         'whole_step_algorithmic_GBs': step_gbs, 'whole_step_algorithmic_frac': step_gbs / peak,
+                         'pressure_accumulator_bytes_per_step': alg['pressure_accumulator'],
                          'whole_step_nominal_158B_GBs': nominal, 'whole_step_nominal_frac': nominal / peak,
                          'per_kernel_ms': {'stress': st['stress_ms'], 'particle': st['particle_ms'], 'pml': st['pml_ms'], 'other': st['other_ms'], 'run': st['run_ms']}},
         }
