@@ -95,20 +95,23 @@ struct DevParams {
     int sel_rms_peak;
 };
 
-// TMA descriptors of one half-step kernel (passed as a __grid_constant__ parameter)
+// TMA descriptors (passed as a __grid_constant__ parameter).  The component arrays of a field group
+// (V[3], S[6], R[6], parts[8]) are contiguous, so the group is a 4-D tensor (k, j, plane, component)
+// and one TMA instruction moves the boxes of 2 or 3 components at once.
 struct StressMaps {
-    CUtensorMap v[3];    // Vx Vy Vz, box (TX+8, TY+4, 1)
+    CUtensorMap v3;      // V, box (TX+8, TY+4, 1, 3)
     CUtensorMap lab;     // labels, box (LW, TY+1, 1)
-    CUtensorMap s[6];    // stresses, box (TX, TY, 1)
-    CUtensorMap r[6];    // memory variables
-    CUtensorMap pr;      // pressure accumulator
-    CUtensorMap xp[5], yp[5], zp[5];   // damped stress parts, box (TX, TY, 1)
+    CUtensorMap s3;      // S, box (TX, TY, 1, 3): component 0 = normal, 3 = shear stresses
+    CUtensorMap r3;      // R, same
+    CUtensorMap pr;      // pressure accumulator, box (TX, TY, 1)
+    CUtensorMap xp3, xp2, yp3, yp2, zp3, zp2;   // damped parts: box depth 3 (normal, component 0) / 2 (shear, component 3)
     CUtensorMap acc;     // pressure RMS accumulator (slot 0), box (TX, TY, 1)
 };
 struct ParticleMaps {
-    CUtensorMap sxx;     // box (TX, TY, 1): only the i-stencil
-    CUtensorMap sh[5];   // Syy Szz Sxy Sxz Syz, box (TX+8, TY+4, 1)
+    CUtensorMap sxx;     // S component 0, box (TX, TY, 1, 1): only the i-stencil
+    CUtensorMap sh2;     // S components 1-2 (Syy Szz), box (TX+8, TY+4, 1, 2)
+    CUtensorMap sh3;     // S components 3-5 (Sxy Sxz Syz), box (TX+8, TY+4, 1, 3)
     CUtensorMap lab;
-    CUtensorMap v[3];    // box (TX, TY, 1)
-    CUtensorMap xp[3], yp[3], zp[3];   // damped velocity parts, box (TX, TY, 1)
+    CUtensorMap v3;      // V, box (TX, TY, 1, 3)
+    CUtensorMap xp3, yp3, zp3;   // damped velocity parts: components 5-7 of the part groups
 };

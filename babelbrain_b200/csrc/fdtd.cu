@@ -104,57 +104,57 @@ static EncodeTiledFn encode_tiled_fn() {
     return fn;
 }
 
-// 3-D map over a row-major (d2, d1, d0) volume of `esz`-byte elements with row pitch `rowpitch` elements and
-// plane pitch `planepitch` elements; box (bw, bh, 1); out-of-volume taps read zero
-static int make_map3(CUtensorMap *m, const void *base, CUtensorMapDataType dt, int esz, long long d0, long long d1, long long d2,
-                     long long rowpitch, long long planepitch, int bw, int bh) {
+// 4-D map (k, j, plane, component) over `ncomp` consecutive row-major (d2, d1, d0) volumes of `esz`-byte elements:
+// row pitch `rowpitch`, plane pitch `planepitch`, component pitch `comppitch` (elements); box (bw, bh, 1, depth);
+// out-of-volume taps read zero
+static int make_map4(CUtensorMap *m, const void *base, CUtensorMapDataType dt, int esz, long long d0, long long d1, long long d2, int ncomp,
+                     long long rowpitch, long long planepitch, long long comppitch, int bw, int bh, int depth) {
     EncodeTiledFn enc = encode_tiled_fn();
     if (!enc) { bb_set_error("cuTensorMapEncodeTiled is not available from this driver"); return BB_ERR_CUDA; }
-    const cuuint64_t dims[3] = { (cuuint64_t)std::max<long long>(d0, 1), (cuuint64_t)std::max<long long>(d1, 1), (cuuint64_t)std::max<long long>(d2, 1) };
-    const cuuint64_t strides[2] = { (cuuint64_t)rowpitch * esz, (cuuint64_t)planepitch * esz };
-    const cuuint32_t box[3] = { (cuuint32_t)bw, (cuuint32_t)bh, 1 };
-    const cuuint32_t estr[3] = { 1, 1, 1 };
-    CUresult r = enc(m, dt, 3, const_cast<void *>(base), dims, strides, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_NONE,
+    const cuuint64_t dims[4] = { (cuuint64_t)std::max<long long>(d0, 1), (cuuint64_t)std::max<long long>(d1, 1), (cuuint64_t)std::max<long long>(d2, 1), (cuuint64_t)ncomp };
+    const cuuint64_t strides[3] = { (cuuint64_t)rowpitch * esz, (cuuint64_t)planepitch * esz, (cuuint64_t)comppitch * esz };
+    const cuuint32_t box[4] = { (cuuint32_t)bw, (cuuint32_t)bh, 1, (cuuint32_t)depth };
+    const cuuint32_t estr[4] = { 1, 1, 1, 1 };
+    CUresult r = enc(m, dt, ncomp > 1 ? 4 : 3, const_cast<void *>(base), dims, strides, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_NONE,
                      CU_TENSOR_MAP_L2_PROMOTION_L2_128B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
-    if (r != CUDA_SUCCESS) { bb_set_error("cuTensorMapEncodeTiled failed (%d) for box %dx%d", (int)r, bw, bh); return BB_ERR_CUDA; }
+    if (r != CUDA_SUCCESS) { bb_set_error("cuTensorMapEncodeTiled failed (%d) for box %dx%dx1x%d", (int)r, bw, bh, depth); return BB_ERR_CUDA; }
     return BB_OK;
-}
-// the pitched (planes, n2, n3) field volumes
-static int make_map(CUtensorMap *m, const void *base, CUtensorMapDataType dt, int esz, const DevParams &p, int planes, int bw, int bh) {
-    return make_map3(m, base, dt, esz, p.n3, p.n2, planes, p.pitch, p.plane, bw, bh);
 }
 
 static int make_tensor_maps(bb_fdtd *h) {
     using namespace tma;
     const DevParams &p = h->p;
     const CUtensorMapDataType F = CU_TENSOR_MAP_DATA_TYPE_FLOAT32;
+    const long long vol = (long long)p.nloc * p.plane;
     int rc;
-    for (int c = 0; c < 3; c++) {
-        if ((rc = make_map(&h->smaps.v[c], p.V[c], F, 4, p, p.nloc, SW, SH))) return rc;
-        if ((rc = make_map(&h->pmaps.v[c], p.V[c], F, 4, p, p.nloc, TX, TY))) return rc;
-    }
-    for (int c = 0; c < 6; c++) {
-        if ((rc = make_map(&h->smaps.s[c], p.S[c], F, 4, p, p.nloc, TX, TY))) return rc;
-        if ((rc = make_map(&h->smaps.r[c], p.R[c], F, 4, p, p.nloc, TX, TY))) return rc;
-    }
-    if ((rc = make_map(&h->smaps.pr, p.Pr, F, 4, p, p.nloc, TX, TY))) return rc;
-    if ((rc = make_map(&h->pmaps.sxx, p.S[0], F, 4, p, p.nloc, TX, TY))) return rc;
-    const int order[5] = { 1, 2, 3, 4, 5 };   // Syy Szz Sxy Sxz Syz
-    for (int c = 0; c < 5; c++) if ((rc = make_map(&h->pmaps.sh[c], p.S[order[c]], F, 4, p, p.nloc, SW, SH))) return rc;
+    // field groups over the pitched (nloc, n2, n3) volumes
+    auto field = [&](CUtensorMap *m, const float *base, int ncomp, int bw, int bh, int depth) {
+        return make_map4(m, base, F, 4, p.n3, p.n2, p.nloc, ncomp, p.pitch, p.plane, vol, bw, bh, depth);
+    };
+    if ((rc = field(&h->smaps.v3, p.V[0], 3, SW, SH, 3))) return rc;
+    if ((rc = field(&h->pmaps.v3, p.V[0], 3, TX, TY, 3))) return rc;
+    if ((rc = field(&h->smaps.s3, p.S[0], 6, TX, TY, 3))) return rc;
+    if ((rc = field(&h->smaps.r3, p.R[0], 6, TX, TY, 3))) return rc;
+    if ((rc = field(&h->smaps.pr, p.Pr, 1, TX, TY, 1))) return rc;
+    if ((rc = field(&h->pmaps.sxx, p.S[0], 6, TX, TY, 1))) return rc;
+    if ((rc = field(&h->pmaps.sh2, p.S[0], 6, SW, SH, 2))) return rc;
+    if ((rc = field(&h->pmaps.sh3, p.S[0], 6, SW, SH, 3))) return rc;
     const bool u8 = h->label_bytes == 1;
     const int lw = u8 ? LabBox<uint8_t>::W : LabBox<uint16_t>::W;
-    if ((rc = make_map(&h->smaps.lab, p.lab, u8 ? CU_TENSOR_MAP_DATA_TYPE_UINT8 : CU_TENSOR_MAP_DATA_TYPE_UINT16, h->label_bytes, p, p.nloc + 1, lw, LH))) return rc;
+    if ((rc = make_map4(&h->smaps.lab, p.lab, u8 ? CU_TENSOR_MAP_DATA_TYPE_UINT8 : CU_TENSOR_MAP_DATA_TYPE_UINT16, h->label_bytes,
+                        p.n3, p.n2, p.nloc + 1, 1, p.pitch, p.plane, 0, lw, LH, 1))) return rc;
     h->pmaps.lab = h->smaps.lab;
-    // damped parts: stress kernel uses parts 0..4, particle kernel parts 5..7
-    for (int c = 0; c < BB_NPART; c++) {
-        CUtensorMap *mx = c < 5 ? &h->smaps.xp[c] : &h->pmaps.xp[c - 5];
-        CUtensorMap *my = c < 5 ? &h->smaps.yp[c] : &h->pmaps.yp[c - 5];
-        CUtensorMap *mz = c < 5 ? &h->smaps.zp[c] : &h->pmaps.zp[c - 5];
-        if ((rc = make_map3(mx, p.XP[c], F, 4, p.n3, p.n2, h->nxp, p.pitch, p.plane, TX, TY))) return rc;
-        if ((rc = make_map3(my, p.YP[c], F, 4, p.n3, p.nyrows, h->nown, p.pitch, (long long)p.nyrows * p.pitch, TX, TY))) return rc;
-        if ((rc = make_map3(mz, p.ZP[c], F, 4, p.zpw, p.n2, h->nown, p.zpw, (long long)p.n2 * p.zpw, TX, TY))) return rc;
+    // damped parts: components 0-2 normal stress parts, 3-4 shear stress parts, 5-7 velocity parts
+    const long long ypl = (long long)p.nyrows * p.pitch, zpl = (long long)p.n2 * p.zpw;
+    for (int depth = 2; depth <= 3; depth++) {
+        CUtensorMap *mx = depth == 3 ? &h->smaps.xp3 : &h->smaps.xp2, *my = depth == 3 ? &h->smaps.yp3 : &h->smaps.yp2;
+        CUtensorMap *mz = depth == 3 ? &h->smaps.zp3 : &h->smaps.zp2;
+        if ((rc = make_map4(mx, p.XP[0], F, 4, p.n3, p.n2, h->nxp, BB_NPART, p.pitch, p.plane, (long long)h->xp_floats, TX, TY, depth))) return rc;
+        if ((rc = make_map4(my, p.YP[0], F, 4, p.n3, p.nyrows, h->nown, BB_NPART, p.pitch, ypl, (long long)h->yp_floats, TX, TY, depth))) return rc;
+        if ((rc = make_map4(mz, p.ZP[0], F, 4, p.zpw, p.n2, h->nown, BB_NPART, p.zpw, zpl, (long long)h->zp_floats, TX, TY, depth))) return rc;
     }
-    if (p.acc_rms) { if ((rc = make_map3(&h->smaps.acc, p.acc_rms, F, 4, p.n3, p.n2, h->nown, p.pitch, p.plane, TX, TY))) return rc; }
+    h->pmaps.xp3 = h->smaps.xp3; h->pmaps.yp3 = h->smaps.yp3; h->pmaps.zp3 = h->smaps.zp3;
+    if (p.acc_rms) { if ((rc = make_map4(&h->smaps.acc, p.acc_rms, F, 4, p.n3, p.n2, h->nown, 1, p.pitch, p.plane, 0, TX, TY, 1))) return rc; }
     else h->smaps.acc = h->smaps.pr;
     return BB_OK;
 }
@@ -198,9 +198,12 @@ extern "C" int bb_fdtd_create(const bb_fdtd_desc *d, bb_fdtd **out) {
     if (const char *e = getenv("BB_CHUNK")) h->chunk_override = atoi(e);
     const size_t vol = (size_t)p.nloc * p.plane;
     int rc;
-    for (int c = 0; c < 3; c++) if ((rc = dev_alloc(h, (void **)&p.V[c], vol * 4))) return rc;
-    for (int c = 0; c < 6; c++) if ((rc = dev_alloc(h, (void **)&p.S[c], vol * 4))) return rc;
-    for (int c = 0; c < 6; c++) if ((rc = dev_alloc(h, (void **)&p.R[c], vol * 4))) return rc;
+    // the components of a field group are contiguous (one 4-D TMA descriptor per group)
+    if ((rc = dev_alloc(h, (void **)&p.V[0], 3 * vol * 4))) return rc;
+    if ((rc = dev_alloc(h, (void **)&p.S[0], 6 * vol * 4))) return rc;
+    if ((rc = dev_alloc(h, (void **)&p.R[0], 6 * vol * 4))) return rc;
+    for (int c = 1; c < 3; c++) p.V[c] = p.V[0] + c * vol;
+    for (int c = 1; c < 6; c++) { p.S[c] = p.S[0] + c * vol; p.R[c] = p.R[0] + c * vol; }
     if ((rc = dev_alloc(h, (void **)&p.Pr, vol * 4))) return rc;
     // label planes carry one extra zero plane so that (i+1) lookups of the last halo plane stay in bounds
     if ((rc = dev_alloc(h, (void **)&p.lab, (vol + p.plane) * h->label_bytes))) return rc;
@@ -226,11 +229,11 @@ extern "C" int bb_fdtd_create(const bb_fdtd_desc *d, bb_fdtd **out) {
     h->xp_floats = (size_t)h->nxp * p.plane;
     h->yp_floats = (size_t)h->nown * p.nyrows * p.pitch;
     h->zp_floats = (size_t)h->nown * p.n2 * p.zpw;
-    for (int c = 0; c < BB_NPART; c++) {
-        if ((rc = dev_alloc(h, (void **)&p.XP[c], h->xp_floats * 4))) return rc;
-        if ((rc = dev_alloc(h, (void **)&p.YP[c], h->yp_floats * 4))) return rc;
-        if ((rc = dev_alloc(h, (void **)&p.ZP[c], h->zp_floats * 4))) return rc;
-    }
+    h->xp_floats = std::max<size_t>(h->xp_floats, (size_t)p.plane);   // a slab without i-PML planes still needs a valid descriptor
+    if ((rc = dev_alloc(h, (void **)&p.XP[0], BB_NPART * h->xp_floats * 4))) return rc;
+    if ((rc = dev_alloc(h, (void **)&p.YP[0], BB_NPART * h->yp_floats * 4))) return rc;
+    if ((rc = dev_alloc(h, (void **)&p.ZP[0], BB_NPART * h->zp_floats * 4))) return rc;
+    for (int c = 1; c < BB_NPART; c++) { p.XP[c] = p.XP[0] + c * h->xp_floats; p.YP[c] = p.YP[0] + c * h->yp_floats; p.ZP[c] = p.ZP[0] + c * h->zp_floats; }
     // accumulators
     h->n_acc_maps = popcount32(d->sel_maps_rms);
     h->n_sensor_maps = popcount32(d->sel_maps_sensor);
@@ -524,11 +527,11 @@ static int set_smem(K kernel, int bytes) {
 template <typename LT>
 static int prepare_kernels() {
     int rc;
-    if ((rc = set_smem(tma::stress_tma<LT, 0>, tma::StressSmem::BYTES))) return rc;
-    if ((rc = set_smem(tma::stress_tma<LT, 1>, tma::StressSmem::BYTES))) return rc;
-    if ((rc = set_smem(tma::stress_tma<LT, 2>, tma::StressSmem::BYTES))) return rc;
-    if ((rc = set_smem(tma::particle_tma<LT, 0>, tma::ParticleSmem::BYTES))) return rc;
-    if ((rc = set_smem(tma::particle_tma<LT, 2>, tma::ParticleSmem::BYTES))) return rc;
+    if ((rc = set_smem(tma::stress_tma<LT, 0>, tma::SMEM_BYTES))) return rc;
+    if ((rc = set_smem(tma::stress_tma<LT, 1>, tma::SMEM_BYTES))) return rc;
+    if ((rc = set_smem(tma::stress_tma<LT, 2>, tma::SMEM_BYTES))) return rc;
+    if ((rc = set_smem(tma::particle_tma<LT, 0>, tma::SMEM_BYTES))) return rc;
+    if ((rc = set_smem(tma::particle_tma<LT, 2>, tma::SMEM_BYTES))) return rc;
     return BB_OK;
 }
 
@@ -551,12 +554,12 @@ static int launch_half_step(bb_fdtd *h, bool stress, int acc_mode, int ib, int i
         const int chunk = pick_chunk(h, ie - ib);
         const dim3 blk(tma::TX, tma::NCW + 1, 1), grid(p.ntk, p.ntj, (ie - ib + chunk - 1) / chunk);
         if (stress) {
-            const int sm = tma::StressSmem::BYTES;
+            const int sm = tma::SMEM_BYTES;
             if (acc_mode == 1) tma::stress_tma<LT, 1><<<grid, blk, sm, h->stream>>>(h->smaps, p, ib, ie, chunk);
             else if (acc_mode == 2) tma::stress_tma<LT, 2><<<grid, blk, sm, h->stream>>>(h->smaps, p, ib, ie, chunk);
             else tma::stress_tma<LT, 0><<<grid, blk, sm, h->stream>>>(h->smaps, p, ib, ie, chunk);
         } else {
-            const int sm = tma::ParticleSmem::BYTES;
+            const int sm = tma::SMEM_BYTES;
             if (acc_mode) tma::particle_tma<LT, 2><<<grid, blk, sm, h->stream>>>(h->pmaps, p, ib, ie, chunk);
             else tma::particle_tma<LT, 0><<<grid, blk, sm, h->stream>>>(h->pmaps, p, ib, ie, chunk);
         }
@@ -702,14 +705,13 @@ extern "C" int bb_fdtd_reset(bb_fdtd *h) {
     BB_CUDA(cudaSetDevice(h->d.device));
     const DevParams &p = h->p;
     const size_t vol = (size_t)p.nloc * p.plane * 4;
-    for (int c = 0; c < 3; c++) BB_CUDA(cudaMemsetAsync(p.V[c], 0, vol, h->stream));
-    for (int c = 0; c < 6; c++) { BB_CUDA(cudaMemsetAsync(p.S[c], 0, vol, h->stream)); BB_CUDA(cudaMemsetAsync(p.R[c], 0, vol, h->stream)); }
+    BB_CUDA(cudaMemsetAsync(p.V[0], 0, 3 * vol, h->stream));
+    BB_CUDA(cudaMemsetAsync(p.S[0], 0, 6 * vol, h->stream));
+    BB_CUDA(cudaMemsetAsync(p.R[0], 0, 6 * vol, h->stream));
     BB_CUDA(cudaMemsetAsync(p.Pr, 0, vol, h->stream));
-    for (int c = 0; c < BB_NPART; c++) {
-        BB_CUDA(cudaMemsetAsync(p.XP[c], 0, std::max<size_t>(h->xp_floats * 4, 16), h->stream));
-        BB_CUDA(cudaMemsetAsync(p.YP[c], 0, std::max<size_t>(h->yp_floats * 4, 16), h->stream));
-        BB_CUDA(cudaMemsetAsync(p.ZP[c], 0, std::max<size_t>(h->zp_floats * 4, 16), h->stream));
-    }
+    BB_CUDA(cudaMemsetAsync(p.XP[0], 0, BB_NPART * h->xp_floats * 4, h->stream));
+    BB_CUDA(cudaMemsetAsync(p.YP[0], 0, BB_NPART * h->yp_floats * 4, h->stream));
+    BB_CUDA(cudaMemsetAsync(p.ZP[0], 0, BB_NPART * h->zp_floats * 4, h->stream));
     if (p.acc_rms) BB_CUDA(cudaMemsetAsync(p.acc_rms, 0, (size_t)h->n_acc_maps * p.acc_stride * 4, h->stream));
     if (p.acc_peak) BB_CUDA(cudaMemsetAsync(p.acc_peak, 0, (size_t)h->n_acc_maps * p.acc_stride * 4, h->stream));
     if (h->sensor_out) BB_CUDA(cudaMemsetAsync(h->sensor_out, 0, (size_t)h->n_sensor_maps * h->nsamples * h->nsensors * 4, h->stream));

@@ -68,6 +68,10 @@ __device__ __forceinline__ void tma_load_3d(void *dst, const CUtensorMap *map, u
     asm volatile("cp.async.bulk.tensor.3d.shared::cluster.global.tile.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4, %5}], [%2];"
                  ::"r"(smem_u32(dst)), "l"(reinterpret_cast<uint64_t>(map)), "r"(smem_u32(bar)), "r"(c0), "r"(c1), "r"(c2) : "memory");
 }
+__device__ __forceinline__ void tma_load_4d(void *dst, const CUtensorMap *map, uint64_t *bar, int c0, int c1, int c2, int c3) {
+    asm volatile("cp.async.bulk.tensor.4d.shared::cluster.global.tile.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4, %5, %6}], [%2];"
+                 ::"r"(smem_u32(dst)), "l"(reinterpret_cast<uint64_t>(map)), "r"(smem_u32(bar)), "r"(c0), "r"(c1), "r"(c2), "r"(c3) : "memory");
+}
 __device__ __forceinline__ void mbar_arrive(uint64_t *bar) {
     asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(smem_u32(bar)) : "memory");
 }
@@ -111,49 +115,50 @@ __global__ void __launch_bounds__(NT) flags_kernel(const DevParams p, unsigned c
 }
 
 // ---------------------------------------------------------------- ring bookkeeping
-// slot s of a ring: bit s of `ph` is the parity the next wait on that slot must observe
-template <int NS> struct Ring {
-    int slot = 0;
+// slot s of a ring of `ns` slots: bit s of `ph` is the parity the next wait on that slot must observe
+struct Ring {
+    int slot = 0, ns;
     unsigned ph;
-    __device__ explicit Ring(unsigned initial_parity) : ph(initial_parity ? 0xFFFFFFFFu : 0u) {}
-    __device__ static int next(int s) { return s + 1 == NS ? 0 : s + 1; }
+    __device__ Ring(int nslots, unsigned initial_parity) : ns(nslots), ph(initial_parity ? 0xFFFFFFFFu : 0u) {}
+    __device__ int next(int s) const { return s + 1 == ns ? 0 : s + 1; }
     __device__ void wait(uint64_t *bars, int s) { mbar_wait(bars + s, (ph >> s) & 1u); ph ^= 1u << s; }
     __device__ void advance() { slot = next(slot); }
 };
 
+// ---------------------------------------------------------------- shared-memory layout
+// Every CTA gets the same dynamic allocation (two CTAs per SM); what the point stages of its tile
+// class do not need (no Y parts away from the j-PML, no Z parts away from the k-PML) goes to a
+// deeper halo ring, i.e. more planes of prefetch.
+constexpr int SMEM_BYTES = 112 * 1024;
+constexpr int MAX_NSH = 8, NSP = 3;
+constexpr int OFF_COEF = 0;                                                      // MatCoef[128] (stress) / float B[128] (particle)
+constexpr int OFF_AXJ = OFF_COEF + BB_MAX_SMEM_MAT * (int)sizeof(MatCoef);
+constexpr int OFF_AXK = OFF_AXJ + TY * (int)sizeof(AxisCoef);
+constexpr int OFF_FLAGS = OFF_AXK + TX * (int)sizeof(AxisCoef);
+constexpr int OFF_BAR = OFF_FLAGS + ((MAXCHUNK + 8 + 15) / 16) * 16;
+constexpr int OFF_RINGS = 8192;
+static_assert(OFF_BAR + 2 * (MAX_NSH + NSP) * 8 <= OFF_RINGS, "tables overflow their 8 KB");
+
 // =========================================================================================
 // stress half-step
 // =========================================================================================
-constexpr int ST_NSH = 4, ST_NSP = 3;
-// point-box order inside a stage; on a plane inside the i-PML the X parts use the R boxes (no
-// interior cell exists on such a plane, so memory variables are not needed there)
-enum { PB_SXX = 0, PB_SYY, PB_SZZ, PB_SXY, PB_SXZ, PB_SYZ, PB_RXX, PB_RYY, PB_RZZ, PB_RXY, PB_RXZ, PB_RYZ, PB_PR,
-       PB_Y0, PB_Z0 = PB_Y0 + 5, PB_ACC = PB_Z0 + 5, PB_COUNT };
-struct StressSmem {
-    static constexpr int HSTAGE = 3 * HBOX_STRIDE + LBOX_STRIDE;
-    static constexpr int PSTAGE = PB_COUNT * PBOX;
-    static constexpr int OFF_H = 0;
-    static constexpr int OFF_P = OFF_H + ST_NSH * HSTAGE;
-    static constexpr int OFF_COEF = OFF_P + ST_NSP * PSTAGE;                         // MatCoef[128] (uint8 labels)
-    static constexpr int OFF_AXJ = OFF_COEF + BB_MAX_SMEM_MAT * (int)sizeof(MatCoef);
-    static constexpr int OFF_AXK = OFF_AXJ + TY * (int)sizeof(AxisCoef);
-    static constexpr int OFF_FLAGS = OFF_AXK + TX * (int)sizeof(AxisCoef);
-    static constexpr int OFF_BAR = OFF_FLAGS + ((MAXCHUNK + 8 + 15) / 16) * 16;
-    static constexpr int BYTES = OFF_BAR + 2 * (ST_NSH + ST_NSP) * 8;
-};
+// point-box order inside a stage; on a plane inside the i-PML the X parts use the R boxes (no interior
+// cell exists on such a plane, so memory variables are not needed there); the Y / Z parts follow at
+// box 14 (whichever the tile needs first) and 19
+enum { PB_SXX = 0, PB_SYY, PB_SZZ, PB_SXY, PB_SXZ, PB_SYZ, PB_RXX, PB_RYY, PB_RZZ, PB_RXY, PB_RXZ, PB_RYZ, PB_PR, PB_ACC, PB_PARTS };
+constexpr int ST_HSTAGE = 3 * HBOX_STRIDE + LBOX_STRIDE;
 
 template <typename LT, int ACC>
 __global__ void __launch_bounds__(NTB, 2) stress_tma(const __grid_constant__ StressMaps tm, const DevParams p, int ia, int ie, int chunk) {
     constexpr bool SMC = sizeof(LT) == 1;
     constexpr int LW = LabBox<LT>::W;
-    using L = StressSmem;
     extern __shared__ __align__(1024) unsigned char sm[];   // TMA destinations need 128-byte alignment
-    MatCoef *sC = reinterpret_cast<MatCoef *>(sm + L::OFF_COEF);
-    AxisCoef *sJ = reinterpret_cast<AxisCoef *>(sm + L::OFF_AXJ);
-    AxisCoef *sK = reinterpret_cast<AxisCoef *>(sm + L::OFF_AXK);
-    unsigned char *sF = sm + L::OFF_FLAGS;
-    uint64_t *fullH = reinterpret_cast<uint64_t *>(sm + L::OFF_BAR);
-    uint64_t *emptyH = fullH + ST_NSH, *fullP = emptyH + ST_NSH, *emptyP = fullP + ST_NSP;
+    MatCoef *sC = reinterpret_cast<MatCoef *>(sm + OFF_COEF);
+    AxisCoef *sJ = reinterpret_cast<AxisCoef *>(sm + OFF_AXJ);
+    AxisCoef *sK = reinterpret_cast<AxisCoef *>(sm + OFF_AXK);
+    unsigned char *sF = sm + OFF_FLAGS;
+    uint64_t *fullH = reinterpret_cast<uint64_t *>(sm + OFF_BAR);
+    uint64_t *emptyH = fullH + MAX_NSH, *fullP = emptyH + MAX_NSH, *emptyP = fullP + NSP;
 
     const int tx = threadIdx.x, ty = threadIdx.y, tid = ty * TX + tx;
     const int k0 = blockIdx.x * TX, j0 = blockIdx.y * TY;
@@ -165,6 +170,11 @@ __global__ void __launch_bounds__(NTB, 2) stress_tma(const __grid_constant__ Str
     const bool tile_kd = (int)blockIdx.x < p.nzlo || (int)blockIdx.x >= p.tkhi0;
     const int yt = ((int)blockIdx.y < p.nylo ? (int)blockIdx.y : (int)blockIdx.y - p.tjhi0 + p.nylo) * TY;
     const int zt = ((int)blockIdx.x < p.nzlo ? (int)blockIdx.x : (int)blockIdx.x - p.tkhi0 + p.nzlo) * TX;
+    // ring geometry of this tile class
+    const int yb = PB_PARTS, zb = PB_PARTS + (tile_jd ? 5 : 0);            // first Y / Z part box
+    const int pstage = (PB_PARTS + (tile_jd ? 5 : 0) + (tile_kd ? 5 : 0)) * PBOX;
+    const int offP = OFF_RINGS, offH = OFF_RINGS + NSP * pstage;
+    const int nsh = min(MAX_NSH, (SMEM_BYTES - offH) / ST_HSTAGE);
 
     // ---- per-CTA tables
     if (SMC) for (int t = tid; t < p.nmat * (int)(sizeof(MatCoef) / 4); t += NTB) reinterpret_cast<float *>(sC)[t] = reinterpret_cast<const float *>(p.coef)[t];
@@ -175,8 +185,8 @@ __global__ void __launch_bounds__(NTB, 2) stress_tma(const __grid_constant__ Str
         sF[tid] = ipl < p.nloc ? p.flags[((long long)ipl * p.ntj + blockIdx.y) * p.ntk + blockIdx.x] : 0;
     }
     if (tid == 0) {
-        for (int s = 0; s < ST_NSH; s++) { mbar_init(fullH + s, 1); mbar_init(emptyH + s, NCW); }
-        for (int s = 0; s < ST_NSP; s++) { mbar_init(fullP + s, 1); mbar_init(emptyP + s, NCW); }
+        for (int s = 0; s < nsh; s++) { mbar_init(fullH + s, 1); mbar_init(emptyH + s, NCW); }
+        for (int s = 0; s < NSP; s++) { mbar_init(fullP + s, 1); mbar_init(emptyP + s, NCW); }
         fence_barrier_init();
     }
     __syncthreads();
@@ -184,28 +194,26 @@ __global__ void __launch_bounds__(NTB, 2) stress_tma(const __grid_constant__ Str
     // =============================== producer warp ===============================
     if (ty == NCW) {
         if (tx != 0) return;
-        Ring<ST_NSH> rh(1);
-        Ring<ST_NSP> rp(1);
+        Ring rh(nsh, 1), rp(NSP, 1);
         for (int r = 0; r < np + 2; r++) {
-            {   // halo plane ic0 + r: V boxes + labels
+            {   // halo plane ic0 + r: the three V boxes (one 4-D TMA) + labels
                 const int slot = rh.slot;
                 rh.wait(emptyH, slot);
-                unsigned char *st = sm + L::OFF_H + slot * L::HSTAGE;
+                unsigned char *st = sm + offH + slot * ST_HSTAGE;
                 uint64_t *bar = fullH + slot;
                 mbar_expect_tx(bar, 3 * HBOX + LW * LH * (int)sizeof(LT));
                 const int ipl = ipl0 + r;
-#pragma unroll
-                for (int c = 0; c < 3; c++) tma_load_3d(st + c * HBOX_STRIDE, &tm.v[c], bar, k0 - HK, j0 - HALO, ipl);
+                tma_load_4d(st, &tm.v3, bar, k0 - HK, j0 - HALO, ipl, 0);
                 tma_load_3d(st + 3 * HBOX_STRIDE, &tm.lab, bar, k0, j0, ipl);
                 rh.advance();
             }
             if (r < np) {   // point plane ic0 + r
                 const int slot = rp.slot;
                 rp.wait(emptyP, slot);
-                unsigned char *st = sm + L::OFF_P + slot * L::PSTAGE;
+                unsigned char *st = sm + offP + slot * pstage;
                 uint64_t *bar = fullP + slot;
                 const unsigned f = sF[r];
-                const int i = ic0 + r, ipl = ipl0 + r;
+                const int i = ic0 + r, ipl = ipl0 + r, io = i - p.i0;
                 const bool xd = in_pml1(i, p.n1, p.P);
                 const bool fint = f & TF_INT, fatt = f & TF_ATT, fsol = f & TF_SOLID;
                 const int npart = fsol ? 5 : 3;
@@ -213,29 +221,26 @@ __global__ void __launch_bounds__(NTB, 2) stress_tma(const __grid_constant__ Str
                 const int nbox = 3 + (fsol ? 3 : 0) + (xd ? npart : (fint ? 1 : 0) + (fatt ? 3 : 0) + (fsol && fint ? 3 : 0))
                                + (tile_jd ? npart : 0) + (tile_kd ? npart : 0) + (acc ? 1 : 0);
                 mbar_expect_tx(bar, nbox * PBOX);
-#pragma unroll
-                for (int c = 0; c < 3; c++) tma_load_3d(st + (PB_SXX + c) * PBOX, &tm.s[c], bar, k0, j0, ipl);
-                if (fsol) {
-#pragma unroll
-                    for (int c = 3; c < 6; c++) tma_load_3d(st + (PB_SXX + c) * PBOX, &tm.s[c], bar, k0, j0, ipl);
-                }
+                tma_load_4d(st + PB_SXX * PBOX, &tm.s3, bar, k0, j0, ipl, 0);
+                if (fsol) tma_load_4d(st + PB_SXY * PBOX, &tm.s3, bar, k0, j0, ipl, 3);
                 if (xd) {
-                    const int ipx = i < p.P ? i - p.i0 : p.nxlo + (i - p.xhi_begin);
-                    for (int c = 0; c < npart; c++) tma_load_3d(st + (PB_RXX + c) * PBOX, &tm.xp[c], bar, k0, j0, ipx);
+                    const int ipx = i < p.P ? io : p.nxlo + (i - p.xhi_begin);
+                    tma_load_4d(st + PB_RXX * PBOX, &tm.xp3, bar, k0, j0, ipx, 0);
+                    if (fsol) tma_load_4d(st + PB_RXY * PBOX, &tm.xp2, bar, k0, j0, ipx, 3);
                 } else {
                     if (fint) tma_load_3d(st + PB_PR * PBOX, &tm.pr, bar, k0, j0, ipl);
-                    if (fatt) {
-#pragma unroll
-                        for (int c = 0; c < 3; c++) tma_load_3d(st + (PB_RXX + c) * PBOX, &tm.r[c], bar, k0, j0, ipl);
-                    }
-                    if (fsol && fint) {
-#pragma unroll
-                        for (int c = 3; c < 6; c++) tma_load_3d(st + (PB_RXX + c) * PBOX, &tm.r[c], bar, k0, j0, ipl);
-                    }
+                    if (fatt) tma_load_4d(st + PB_RXX * PBOX, &tm.r3, bar, k0, j0, ipl, 0);
+                    if (fsol && fint) tma_load_4d(st + PB_RXY * PBOX, &tm.r3, bar, k0, j0, ipl, 3);
                 }
-                if (tile_jd) for (int c = 0; c < npart; c++) tma_load_3d(st + (PB_Y0 + c) * PBOX, &tm.yp[c], bar, k0, yt, i - p.i0);
-                if (tile_kd) for (int c = 0; c < npart; c++) tma_load_3d(st + (PB_Z0 + c) * PBOX, &tm.zp[c], bar, zt, j0, i - p.i0);
-                if (acc) tma_load_3d(st + PB_ACC * PBOX, &tm.acc, bar, k0, j0, i - p.i0);
+                if (tile_jd) {
+                    tma_load_4d(st + yb * PBOX, &tm.yp3, bar, k0, yt, io, 0);
+                    if (fsol) tma_load_4d(st + (yb + 3) * PBOX, &tm.yp2, bar, k0, yt, io, 3);
+                }
+                if (tile_kd) {
+                    tma_load_4d(st + zb * PBOX, &tm.zp3, bar, zt, j0, io, 0);
+                    if (fsol) tma_load_4d(st + (zb + 3) * PBOX, &tm.zp2, bar, zt, j0, io, 3);
+                }
+                if (acc) tma_load_3d(st + PB_ACC * PBOX, &tm.acc, bar, k0, j0, io);
                 rp.advance();
             }
         }
@@ -268,10 +273,9 @@ __global__ void __launch_bounds__(NTB, 2) stress_tma(const __grid_constant__ Str
     long long qy = ((long long)(ic0 - p.i0) * p.nyrows + yt + ty) * p.pitch + k;
     long long qz = ((long long)(ic0 - p.i0) * p.n2 + min(j, p.n2 - 1)) * p.zpw + zt + tx;
 
-    auto hbox = [&](int slot, int c) { return reinterpret_cast<const float *>(sm + L::OFF_H + slot * L::HSTAGE + c * HBOX_STRIDE); };
-    auto lbox = [&](int slot) { return reinterpret_cast<const LT *>(sm + L::OFF_H + slot * L::HSTAGE + 3 * HBOX_STRIDE); };
-    Ring<ST_NSH> rh(0);
-    Ring<ST_NSP> rp(0);
+    auto hbox = [&](int slot, int c) { return reinterpret_cast<const float *>(sm + offH + slot * ST_HSTAGE + c * HBOX_STRIDE); };
+    auto lbox = [&](int slot) { return reinterpret_cast<const LT *>(sm + offH + slot * ST_HSTAGE + 3 * HBOX_STRIDE); };
+    Ring rh(nsh, 0), rp(NSP, 0);
 
     // planes ic0 and ic0+1 feed the queue before the loop
     rh.wait(fullH, 0);
@@ -282,7 +286,7 @@ __global__ void __launch_bounds__(NTB, 2) stress_tma(const __grid_constant__ Str
     for (int it = 0; it < np; it++, q += s1, qy += qy_stride, qz += qz_stride) {
         const int i = ic0 + it;
         const unsigned f = sF[it];
-        const int hs = rh.slot, hs1 = Ring<ST_NSH>::next(hs), hs2 = Ring<ST_NSH>::next(hs1);
+        const int hs = rh.slot, hs1 = rh.next(hs), hs2 = rh.next(hs1);
         const int ps = rp.slot;
         rh.wait(fullH, hs2);
         // ---------------- shift the queue: plane i becomes the centre
@@ -295,7 +299,7 @@ __global__ void __launch_bounds__(NTB, 2) stress_tma(const __grid_constant__ Str
         if (active && (!cellpml || (jkupd && i < p.n1 - 1))) {
             const float *bx = hbox(hs, 0), *by = hbox(hs, 1), *bz = hbox(hs, 2);
             const LT *l0p = lbox(hs), *l1p = lbox(hs1);
-            const float *pb = reinterpret_cast<const float *>(sm + L::OFF_P + ps * L::PSTAGE) + pc;
+            const float *pb = reinterpret_cast<const float *>(sm + offP + ps * pstage) + pc;
             const unsigned l0 = l0p[lc];
             const bool refl = (l0 & LabelTraits<LT>::REFL) != 0;
             MatCoef c;
@@ -362,7 +366,7 @@ __global__ void __launch_bounds__(NTB, 2) stress_tma(const __grid_constant__ Str
                 pcell.aI = ci.aI; pcell.bI = ci.bI; pcell.aIh = ci.aH; pcell.bIh = ci.bH;
                 pcell.aJ = cj.aI; pcell.bJ = cj.bI; pcell.aJh = cj.aH; pcell.bJh = cj.bH;
                 pcell.aK = ck.aI; pcell.bK = ck.bI; pcell.aKh = ck.aH; pcell.bKh = ck.bH;
-                stress_pml<true>(p, pcell, c.M, c.L, rigxy, rigxz, rigyz, D, s, pb + PB_RXX * NT, pb + PB_Y0 * NT, pb + PB_Z0 * NT);
+                stress_pml<true>(p, pcell, c.M, c.L, rigxy, rigxz, rigyz, D, s, pb + PB_RXX * NT, pb + yb * NT, pb + zb * NT);
                 if (refl) { s[0] = s[1] = s[2] = s[3] = s[4] = s[5] = 0.f; }
                 p.S[0][q] = s[0]; p.S[1][q] = s[1]; p.S[2][q] = s[2];
                 if (f & TF_SOLID) { p.S[3][q] = s[3]; p.S[4][q] = s[4]; p.S[5][q] = s[5]; }
@@ -421,36 +425,23 @@ __global__ void __launch_bounds__(NTB, 2) stress_tma(const __grid_constant__ Str
 // =========================================================================================
 // particle half-step
 // =========================================================================================
-constexpr int PT_NSH = 4, PT_NSP = 3;
 // halo-stage boxes: Syy Szz Sxy Sxz Syz (halo boxes) then Sxx (point box, i-stencil only) then labels;
-// point-stage boxes: V (3), X parts (3), Y parts (3), Z parts (3)
+// point-stage boxes: V (3), X parts (3), then the Y / Z parts the tile needs (3 each)
 enum { HB_SYY = 0, HB_SZZ, HB_SXY, HB_SXZ, HB_SYZ };
-enum { QB_V = 0, QB_X = 3, QB_Y = 6, QB_Z = 9, QB_COUNT = 12 };
-struct ParticleSmem {
-    static constexpr int HSTAGE = 5 * HBOX_STRIDE + PBOX + LBOX_STRIDE;
-    static constexpr int PSTAGE = QB_COUNT * PBOX;
-    static constexpr int OFF_H = 0;
-    static constexpr int OFF_P = OFF_H + PT_NSH * HSTAGE;
-    static constexpr int OFF_B = OFF_P + PT_NSP * PSTAGE;                           // float B[128]
-    static constexpr int OFF_AXJ = OFF_B + BB_MAX_SMEM_MAT * 4;
-    static constexpr int OFF_AXK = OFF_AXJ + TY * (int)sizeof(AxisCoef);
-    static constexpr int OFF_FLAGS = OFF_AXK + TX * (int)sizeof(AxisCoef);
-    static constexpr int OFF_BAR = OFF_FLAGS + ((MAXCHUNK + 8 + 15) / 16) * 16;
-    static constexpr int BYTES = OFF_BAR + 2 * (PT_NSH + PT_NSP) * 8;
-};
+enum { QB_V = 0, QB_X = 3, QB_PARTS = 6 };
+constexpr int PT_HSTAGE = 5 * HBOX_STRIDE + PBOX + LBOX_STRIDE;
 
 template <typename LT, int ACC>
 __global__ void __launch_bounds__(NTB, 2) particle_tma(const __grid_constant__ ParticleMaps tm, const DevParams p, int ia, int ie, int chunk) {
     constexpr bool SMC = sizeof(LT) == 1;
     constexpr int LW = LabBox<LT>::W;
-    using L = ParticleSmem;
     extern __shared__ __align__(1024) unsigned char sm[];
-    float *sB = reinterpret_cast<float *>(sm + L::OFF_B);
-    AxisCoef *sJ = reinterpret_cast<AxisCoef *>(sm + L::OFF_AXJ);
-    AxisCoef *sK = reinterpret_cast<AxisCoef *>(sm + L::OFF_AXK);
-    unsigned char *sF = sm + L::OFF_FLAGS;
-    uint64_t *fullH = reinterpret_cast<uint64_t *>(sm + L::OFF_BAR);
-    uint64_t *emptyH = fullH + PT_NSH, *fullP = emptyH + PT_NSH, *emptyP = fullP + PT_NSP;
+    float *sB = reinterpret_cast<float *>(sm + OFF_COEF);
+    AxisCoef *sJ = reinterpret_cast<AxisCoef *>(sm + OFF_AXJ);
+    AxisCoef *sK = reinterpret_cast<AxisCoef *>(sm + OFF_AXK);
+    unsigned char *sF = sm + OFF_FLAGS;
+    uint64_t *fullH = reinterpret_cast<uint64_t *>(sm + OFF_BAR);
+    uint64_t *emptyH = fullH + MAX_NSH, *fullP = emptyH + MAX_NSH, *emptyP = fullP + NSP;
 
     const int tx = threadIdx.x, ty = threadIdx.y, tid = ty * TX + tx;
     const int k0 = blockIdx.x * TX, j0 = blockIdx.y * TY;
@@ -461,6 +452,10 @@ __global__ void __launch_bounds__(NTB, 2) particle_tma(const __grid_constant__ P
     const bool tile_kd = (int)blockIdx.x < p.nzlo || (int)blockIdx.x >= p.tkhi0;
     const int yt = ((int)blockIdx.y < p.nylo ? (int)blockIdx.y : (int)blockIdx.y - p.tjhi0 + p.nylo) * TY;
     const int zt = ((int)blockIdx.x < p.nzlo ? (int)blockIdx.x : (int)blockIdx.x - p.tkhi0 + p.nzlo) * TX;
+    const int yb = QB_PARTS, zb = QB_PARTS + (tile_jd ? 3 : 0);
+    const int pstage = (QB_PARTS + (tile_jd ? 3 : 0) + (tile_kd ? 3 : 0)) * PBOX;
+    const int offP = OFF_RINGS, offH = OFF_RINGS + NSP * pstage;
+    const int nsh = min(MAX_NSH, (SMEM_BYTES - offH) / PT_HSTAGE);
 
     if (SMC) for (int t = tid; t < p.nmat; t += NTB) sB[t] = p.coef[t].B;
     if (tid < TY * 8) { const int r = tid >> 3, e = tid & 7; reinterpret_cast<float *>(sJ)[tid] = reinterpret_cast<const float *>(p.axJ + min(j0 + r, p.n2 - 1))[e]; }
@@ -470,8 +465,8 @@ __global__ void __launch_bounds__(NTB, 2) particle_tma(const __grid_constant__ P
         sF[tid] = ipl < p.nloc ? p.flags[((long long)ipl * p.ntj + blockIdx.y) * p.ntk + blockIdx.x] : 0;
     }
     if (tid == 0) {
-        for (int s = 0; s < PT_NSH; s++) { mbar_init(fullH + s, 1); mbar_init(emptyH + s, NCW); }
-        for (int s = 0; s < PT_NSP; s++) { mbar_init(fullP + s, 1); mbar_init(emptyP + s, NCW); }
+        for (int s = 0; s < nsh; s++) { mbar_init(fullH + s, 1); mbar_init(emptyH + s, NCW); }
+        for (int s = 0; s < NSP; s++) { mbar_init(fullP + s, 1); mbar_init(emptyP + s, NCW); }
         fence_barrier_init();
     }
     __syncthreads();
@@ -479,45 +474,34 @@ __global__ void __launch_bounds__(NTB, 2) particle_tma(const __grid_constant__ P
     // =============================== producer warp ===============================
     if (ty == NCW) {
         if (tx != 0) return;
-        Ring<PT_NSH> rh(1);
-        Ring<PT_NSP> rp(1);
+        Ring rh(nsh, 1), rp(NSP, 1);
         for (int r = 0; r < np + 2; r++) {
             {
                 const int slot = rh.slot;
                 rh.wait(emptyH, slot);
-                unsigned char *st = sm + L::OFF_H + slot * L::HSTAGE;
+                unsigned char *st = sm + offH + slot * PT_HSTAGE;
                 uint64_t *bar = fullH + slot;
-                const int nb = (sF[r] & TF_SHEAR) ? 5 : 2;
-                mbar_expect_tx(bar, nb * HBOX + PBOX + LW * LH * (int)sizeof(LT));
+                const bool fsh = sF[r] & TF_SHEAR;
+                mbar_expect_tx(bar, (fsh ? 5 : 2) * HBOX + PBOX + LW * LH * (int)sizeof(LT));
                 const int ipl = ipl0 + r;
-                for (int c = 0; c < nb; c++) tma_load_3d(st + c * HBOX_STRIDE, &tm.sh[c], bar, k0 - HK, j0 - HALO, ipl);
-                tma_load_3d(st + 5 * HBOX_STRIDE, &tm.sxx, bar, k0, j0, ipl);
+                tma_load_4d(st, &tm.sh2, bar, k0 - HK, j0 - HALO, ipl, 1);
+                if (fsh) tma_load_4d(st + 2 * HBOX_STRIDE, &tm.sh3, bar, k0 - HK, j0 - HALO, ipl, 3);
+                tma_load_4d(st + 5 * HBOX_STRIDE, &tm.sxx, bar, k0, j0, ipl, 0);
                 tma_load_3d(st + 5 * HBOX_STRIDE + PBOX, &tm.lab, bar, k0, j0, ipl);
                 rh.advance();
             }
             if (r < np) {
                 const int slot = rp.slot;
                 rp.wait(emptyP, slot);
-                unsigned char *st = sm + L::OFF_P + slot * L::PSTAGE;
+                unsigned char *st = sm + offP + slot * pstage;
                 uint64_t *bar = fullP + slot;
-                const int i = ic0 + r, ipl = ipl0 + r;
+                const int i = ic0 + r, ipl = ipl0 + r, io = i - p.i0;
                 const bool xd = in_pml1(i, p.n1, p.P);
                 mbar_expect_tx(bar, (3 + (xd ? 3 : 0) + (tile_jd ? 3 : 0) + (tile_kd ? 3 : 0)) * PBOX);
-#pragma unroll
-                for (int c = 0; c < 3; c++) tma_load_3d(st + (QB_V + c) * PBOX, &tm.v[c], bar, k0, j0, ipl);
-                if (xd) {
-                    const int ipx = i < p.P ? i - p.i0 : p.nxlo + (i - p.xhi_begin);
-#pragma unroll
-                    for (int c = 0; c < 3; c++) tma_load_3d(st + (QB_X + c) * PBOX, &tm.xp[c], bar, k0, j0, ipx);
-                }
-                if (tile_jd) {
-#pragma unroll
-                    for (int c = 0; c < 3; c++) tma_load_3d(st + (QB_Y + c) * PBOX, &tm.yp[c], bar, k0, yt, i - p.i0);
-                }
-                if (tile_kd) {
-#pragma unroll
-                    for (int c = 0; c < 3; c++) tma_load_3d(st + (QB_Z + c) * PBOX, &tm.zp[c], bar, zt, j0, i - p.i0);
-                }
+                tma_load_4d(st + QB_V * PBOX, &tm.v3, bar, k0, j0, ipl, 0);
+                if (xd) tma_load_4d(st + QB_X * PBOX, &tm.xp3, bar, k0, j0, i < p.P ? io : p.nxlo + (i - p.xhi_begin), 5);
+                if (tile_jd) tma_load_4d(st + yb * PBOX, &tm.yp3, bar, k0, yt, io, 5);
+                if (tile_kd) tma_load_4d(st + zb * PBOX, &tm.zp3, bar, zt, j0, io, 5);
                 rp.advance();
             }
         }
@@ -549,11 +533,10 @@ __global__ void __launch_bounds__(NTB, 2) particle_tma(const __grid_constant__ P
     long long qy = ((long long)(ic0 - p.i0) * p.nyrows + yt + ty) * p.pitch + k;
     long long qz = ((long long)(ic0 - p.i0) * p.n2 + min(j, p.n2 - 1)) * p.zpw + zt + tx;
 
-    auto hbox = [&](int slot, int c) { return reinterpret_cast<const float *>(sm + L::OFF_H + slot * L::HSTAGE + c * HBOX_STRIDE); };
-    auto xxbox = [&](int slot) { return reinterpret_cast<const float *>(sm + L::OFF_H + slot * L::HSTAGE + 5 * HBOX_STRIDE); };
-    auto lbox = [&](int slot) { return reinterpret_cast<const LT *>(sm + L::OFF_H + slot * L::HSTAGE + 5 * HBOX_STRIDE + PBOX); };
-    Ring<PT_NSH> rh(0);
-    Ring<PT_NSP> rp(0);
+    auto hbox = [&](int slot, int c) { return reinterpret_cast<const float *>(sm + offH + slot * PT_HSTAGE + c * HBOX_STRIDE); };
+    auto xxbox = [&](int slot) { return reinterpret_cast<const float *>(sm + offH + slot * PT_HSTAGE + 5 * HBOX_STRIDE); };
+    auto lbox = [&](int slot) { return reinterpret_cast<const LT *>(sm + offH + slot * PT_HSTAGE + 5 * HBOX_STRIDE + PBOX); };
+    Ring rh(nsh, 0), rp(NSP, 0);
 
     rh.wait(fullH, 0);
     xx_p1 = xxbox(0)[pc];
@@ -565,7 +548,7 @@ __global__ void __launch_bounds__(NTB, 2) particle_tma(const __grid_constant__ P
         const int i = ic0 + it;
         const unsigned f = sF[it];
         const bool fsh = f & TF_SHEAR;
-        const int hs = rh.slot, hs1 = Ring<PT_NSH>::next(hs), hs2 = Ring<PT_NSH>::next(hs1);
+        const int hs = rh.slot, hs1 = rh.next(hs), hs2 = rh.next(hs1);
         const int ps = rp.slot;
         rh.wait(fullH, hs2);
         xx_m1 = xx_0; xx_0 = xx_p1; xx_p1 = xx_p2; xx_p2 = xxbox(hs2)[pc];
@@ -580,7 +563,7 @@ __global__ void __launch_bounds__(NTB, 2) particle_tma(const __grid_constant__ P
             const float *byy = hbox(hs, HB_SYY), *bzz = hbox(hs, HB_SZZ);
             const float *bxy = hbox(hs, HB_SXY), *bxz = hbox(hs, HB_SXZ), *byz = hbox(hs, HB_SYZ);
             const LT *l0p = lbox(hs), *l1p = lbox(hs1);
-            const float *pb = reinterpret_cast<const float *>(sm + L::OFF_P + ps * L::PSTAGE) + pc;
+            const float *pb = reinterpret_cast<const float *>(sm + offP + ps * pstage) + pc;
             const unsigned l0 = l0p[lc];
             const unsigned mi = l1p[lc] & MSK, mj = l0p[lc + LW] & MSK, mk = l0p[lc + 1] & MSK;
             float b0, bi, bj, bk;
@@ -624,7 +607,7 @@ __global__ void __launch_bounds__(NTB, 2) particle_tma(const __grid_constant__ P
                 pcell.aI = ci.aI; pcell.bI = ci.bI; pcell.aIh = ci.aH; pcell.bIh = ci.bH;
                 pcell.aJ = cj.aI; pcell.bJ = cj.bI; pcell.aJh = cj.aH; pcell.bJh = cj.bH;
                 pcell.aK = ck.aI; pcell.bK = ck.bI; pcell.aKh = ck.aH; pcell.bKh = ck.bH;
-                particle_pml<true>(p, pcell, bx, by, bz, X, v, pb + QB_X * NT, pb + QB_Y * NT, pb + QB_Z * NT);
+                particle_pml<true>(p, pcell, bx, by, bz, X, v, pb + QB_X * NT, pb + yb * NT, pb + zb * NT);
             } else {
                 v[0] += dt * bx * (X[0] + X[1] + X[2]);
                 v[1] += dt * by * (X[3] + X[4] + X[5]);
