@@ -55,7 +55,7 @@ struct __align__(16) AxisCoef {
 //   Z parts: Sxx Syy Szz Sxz Syz | Vx Vy Vz     (columns with k in the PML)
 constexpr int BB_NPART = 8;
 
-// tile flags, one byte per (local plane, tile row, tile column) of the 8x32 (j,k) tiling
+// tile flags, one byte per (local plane, tile row, tile column) of the 8x64 (j,k) tiling
 enum { TF_ATT = 1,      // a non-PML cell of the tile attenuates -> normal memory variables move
        TF_SOLID = 2,    // a cell of the tile (+1 in j,k, planes i and i+1) has G != 0 -> shear stresses / memory variables move
        TF_SHEAR = 4,    // a cell of the tile (+-2 in j,k) on this plane has G != 0 -> its shear stresses can be non-zero
@@ -81,13 +81,13 @@ struct DevParams {
     // damped parts, stored tile-aligned so that a TMA box of a part maps 1:1 onto a tile:
     //   XP [(ipx*n2 + j)*pitch + k]              over this slab's i-PML planes,
     //   YP [((i-i0)*nyrows + jp)*pitch + k]      jp = ytile(j/8)*8 + j%8 over the tile rows that hold j-PML cells,
-    //   ZP [((i-i0)*n2 + j)*zpw + kp]            kp = ztile(k/32)*32 + k%32 over the tile columns that hold k-PML cells
-    // with ytile(t) = t < nylo ? t : t - tjhi0 + nylo (same for z).
+    //   ZP [((i-i0)*n2 + j)*zpw + kp]            kp = k (low side) or zbw + k - (n3-P) (high side); zbw = P rounded up to 4
+    // with ytile(t) = t < nylo ? t : t - tjhi0 + nylo.
     float *XP[BB_NPART], *YP[BB_NPART], *ZP[BB_NPART];
     int nxlo;            // owned planes inside the low-i PML: global i in [i0, i0+nxlo)
     int xhi_begin;       // first owned plane inside the high-i PML (== i1 when none)
     int nylo, tjhi0, nyrows;   // j tiles [0,nylo) and [tjhi0,ntj) hold PML rows; nyrows = stored rows
-    int nzlo, tkhi0, zpw;      // k tiles [0,nzlo) and [tkhi0,ntk) hold PML columns; zpw = stored columns
+    int zbw, zpw;              // columns stored per side of the k-PML, and per row (2 zbw)
     // RMS / peak accumulators: [slot][(i-i0)*plane + j*pitch + k]
     float *acc_rms, *acc_peak;
     long long acc_stride;

@@ -151,7 +151,7 @@ static int make_tensor_maps(bb_fdtd *h) {
         CUtensorMap *mz = depth == 3 ? &h->smaps.zp3 : &h->smaps.zp2;
         if ((rc = make_map4(mx, p.XP[0], F, 4, p.n3, p.n2, h->nxp, BB_NPART, p.pitch, p.plane, (long long)h->xp_floats, TX, TY, depth))) return rc;
         if ((rc = make_map4(my, p.YP[0], F, 4, p.n3, p.nyrows, h->nown, BB_NPART, p.pitch, ypl, (long long)h->yp_floats, TX, TY, depth))) return rc;
-        if ((rc = make_map4(mz, p.ZP[0], F, 4, p.zpw, p.n2, h->nown, BB_NPART, p.zpw, zpl, (long long)h->zp_floats, TX, TY, depth))) return rc;
+        if ((rc = make_map4(mz, p.ZP[0], F, 4, p.zpw, p.n2, h->nown, BB_NPART, p.zpw, zpl, (long long)h->zp_floats, p.zbw, TY, depth))) return rc;
     }
     h->pmaps.xp3 = h->smaps.xp3; h->pmaps.yp3 = h->smaps.yp3; h->pmaps.zp3 = h->smaps.zp3;
     if (p.acc_rms) { if ((rc = make_map4(&h->smaps.acc, p.acc_rms, F, 4, p.n3, p.n2, h->nown, 1, p.pitch, p.plane, 0, TX, TY, 1))) return rc; }
@@ -164,6 +164,7 @@ extern "C" int bb_fdtd_create(const bb_fdtd_desc *d, bb_fdtd **out) {
     BB_REQUIRE(d->n1 > 0 && d->n2 > 0 && d->n3 > 0, "bad grid %d %d %d", d->n1, d->n2, d->n3);
     BB_REQUIRE(d->pml >= 2 && 2 * d->pml < d->n1 && 2 * d->pml < d->n2 && 2 * d->pml < d->n3,
                "PML thickness %d must be >= 2 and leave an interior", d->pml);
+    BB_REQUIRE(d->pml <= tma::MAX_ZBW, "PML thickness %d above the supported maximum %d", d->pml, (int)tma::MAX_ZBW);
     BB_REQUIRE(d->i0 >= 0 && d->i1 <= d->n1 && d->i1 - d->i0 >= (d->nranks > 1 ? 4 : 1), "bad slab [%d,%d)", d->i0, d->i1);
     BB_REQUIRE(d->nmat >= 1 && d->nmat <= 32767, "nmat %d out of range", d->nmat);
     BB_REQUIRE(d->steps >= 0 && d->sensor_subsampling >= 1 && d->sensor_start >= 0, "bad time parameters");
@@ -188,7 +189,7 @@ extern "C" int bb_fdtd_create(const bb_fdtd_desc *d, bb_fdtd **out) {
     DevParams &p = h->p;
     memset(&p, 0, sizeof(p));
     p.n1 = d->n1; p.n2 = d->n2; p.n3 = d->n3; p.i0 = d->i0; p.i1 = d->i1; p.P = d->pml;
-    p.pitch = (d->n3 + 31) / 32 * 32;
+    p.pitch = (d->n3 + tma::TX - 1) / tma::TX * tma::TX;   // whole tiles: a row is a multiple of 256 bytes
     h->nown = d->i1 - d->i0;
     p.nloc = h->nown + 4;
     p.plane = (long long)p.n2 * p.pitch;
@@ -222,9 +223,8 @@ extern "C" int bb_fdtd_create(const bb_fdtd_desc *d, bb_fdtd **out) {
     p.nylo = (P + tma::TY - 1) / tma::TY; p.tjhi0 = (d->n2 - P) / tma::TY;
     if (p.tjhi0 < p.nylo) { p.nylo = p.ntj; p.tjhi0 = p.ntj; }   // tiny grids: every tile row is stored
     p.nyrows = (p.nylo + (p.ntj - p.tjhi0)) * tma::TY;
-    p.nzlo = (P + tma::TX - 1) / tma::TX; p.tkhi0 = (d->n3 - P) / tma::TX;
-    if (p.tkhi0 < p.nzlo) { p.nzlo = p.ntk; p.tkhi0 = p.ntk; }
-    p.zpw = (p.nzlo + (p.ntk - p.tkhi0)) * tma::TX;
+    p.zbw = (P + 3) / 4 * 4;
+    p.zpw = 2 * p.zbw;
     h->nxp = p.nxlo + (d->i1 - p.xhi_begin);
     h->xp_floats = (size_t)h->nxp * p.plane;
     h->yp_floats = (size_t)h->nown * p.nyrows * p.pitch;
@@ -509,10 +509,10 @@ struct Timer {
 };
 
 static int pick_chunk(const bb_fdtd *h, int nplanes) {
-    // enough CTAs for ~4 full waves of 2 CTAs on each of the 148 SMs, chunks of 8..64 planes
+    // enough CTAs for ~8 waves of one CTA on each of the 148 SMs, chunks of 8..64 planes
     if (h->chunk_override > 0) return std::min(std::min(h->chunk_override, (int)tma::MAXCHUNK), nplanes);
     const int tiles = h->p.ntk * h->p.ntj;
-    int nch = std::max(1, (4 * 296 + tiles - 1) / tiles);
+    int nch = std::max(1, (8 * 148 + tiles - 1) / tiles);
     int chunk = (nplanes + nch - 1) / nch;
     chunk = std::max(chunk, std::min(nplanes, 8));
     return std::min(chunk, (int)tma::MAXCHUNK);
@@ -552,7 +552,7 @@ static int launch_half_step(bb_fdtd *h, bool stress, int acc_mode, int ib, int i
         }
     } else {
         const int chunk = pick_chunk(h, ie - ib);
-        const dim3 blk(tma::TX, tma::NCW + 1, 1), grid(p.ntk, p.ntj, (ie - ib + chunk - 1) / chunk);
+        const dim3 blk(tma::NTB, 1, 1), grid(p.ntk, p.ntj, (ie - ib + chunk - 1) / chunk);
         if (stress) {
             const int sm = tma::SMEM_BYTES;
             if (acc_mode == 1) tma::stress_tma<LT, 1><<<grid, blk, sm, h->stream>>>(h->smaps, p, ib, ie, chunk);

@@ -102,9 +102,9 @@ __device__ __forceinline__ PmlCell make_pml_cell(const DevParams &p, int i, int 
     PmlCell c;
     c.xd = in_pml1(i, p.n1, p.P); c.jd = in_pml1(j, p.n2, p.P); c.kd = in_pml1(k, p.n3, p.P);
     const int ipx = i < p.P ? i - p.i0 : p.nxlo + (i - p.xhi_begin);
-    const int tj = j >> 3, tk = k >> 5;
+    const int tj = j >> 3;
     const int jp = (tj < p.nylo ? tj : tj - p.tjhi0 + p.nylo) * 8 + (j & 7);
-    const int kp = (tk < p.nzlo ? tk : tk - p.tkhi0 + p.nzlo) * 32 + (k & 31);
+    const int kp = k < p.P ? k : p.zbw + (k - (p.n3 - p.P));
     c.qx = ((long long)ipx * p.n2 + j) * p.pitch + k;
     c.qy = ((long long)(i - p.i0) * p.nyrows + jp) * p.pitch + k;
     c.qz = ((long long)(i - p.i0) * p.n2 + j) * p.zpw + kp;
@@ -114,46 +114,44 @@ __device__ __forceinline__ PmlCell make_pml_cell(const DevParams &p, int i, int 
     return c;
 }
 
-constexpr int BB_BOXF = 256;   // floats per staged 8 x 32 part box
-
 // D[9] = Dxx, Dyy, Dzz, Dyx (d+_i Vy), Dxy (d+_j Vx), Dzx (d+_i Vz), Dxz (d+_k Vx), Dzy (d+_j Vz), Dyz (d+_k Vy)
-// ox/oy/oz: this cell's slot in the first staged X/Y/Z part box (boxes BB_BOXF floats apart); unused when !STAGED
+// ox/oy/oz: this cell's slot in the first staged X/Y/Z part box (X and Y boxes B floats apart, Z boxes
+// ZB floats apart); unused when !STAGED
 template <bool STAGED>
 __device__ __forceinline__ void stress_pml(const DevParams &p, const PmlCell &c, float M, float L, float rigxy, float rigxz, float rigyz,
                                            const float *D, float *s, const float *ox = nullptr, const float *oy = nullptr,
-                                           const float *oz = nullptr) {
+                                           const float *oz = nullptr, int B = 0, int ZB = 0) {
     const float dt = p.dt;
-    constexpr int B = BB_BOXF;
     s[0] += pml_delta<STAGED>(c.xd, ox, p.XP[0], c.qx, c.aI, c.bI, dt, M * D[0]) + pml_delta<STAGED>(c.jd, oy, p.YP[0], c.qy, c.aJ, c.bJ, dt, L * D[1])
           + pml_delta<STAGED>(c.kd, oz, p.ZP[0], c.qz, c.aK, c.bK, dt, L * D[2]);
     s[1] += pml_delta<STAGED>(c.xd, ox + B, p.XP[1], c.qx, c.aI, c.bI, dt, L * D[0]) + pml_delta<STAGED>(c.jd, oy + B, p.YP[1], c.qy, c.aJ, c.bJ, dt, M * D[1])
-          + pml_delta<STAGED>(c.kd, oz + B, p.ZP[1], c.qz, c.aK, c.bK, dt, L * D[2]);
+          + pml_delta<STAGED>(c.kd, oz + ZB, p.ZP[1], c.qz, c.aK, c.bK, dt, L * D[2]);
     s[2] += pml_delta<STAGED>(c.xd, ox + 2 * B, p.XP[2], c.qx, c.aI, c.bI, dt, L * D[0]) + pml_delta<STAGED>(c.jd, oy + 2 * B, p.YP[2], c.qy, c.aJ, c.bJ, dt, L * D[1])
-          + pml_delta<STAGED>(c.kd, oz + 2 * B, p.ZP[2], c.qz, c.aK, c.bK, dt, M * D[2]);
+          + pml_delta<STAGED>(c.kd, oz + 2 * ZB, p.ZP[2], c.qz, c.aK, c.bK, dt, M * D[2]);
     if (rigxy != 0.0f)
         s[3] += pml_delta<STAGED>(c.xd, ox + 3 * B, p.XP[3], c.qx, c.aIh, c.bIh, dt, rigxy * D[3])
               + pml_delta<STAGED>(c.jd, oy + 3 * B, p.YP[3], c.qy, c.aJh, c.bJh, dt, rigxy * D[4]);
     if (rigxz != 0.0f)
         s[4] += pml_delta<STAGED>(c.xd, ox + 4 * B, p.XP[4], c.qx, c.aIh, c.bIh, dt, rigxz * D[5])
-              + pml_delta<STAGED>(c.kd, oz + 3 * B, p.ZP[3], c.qz, c.aKh, c.bKh, dt, rigxz * D[6]);
+              + pml_delta<STAGED>(c.kd, oz + 3 * ZB, p.ZP[3], c.qz, c.aKh, c.bKh, dt, rigxz * D[6]);
     if (rigyz != 0.0f)
         s[5] += pml_delta<STAGED>(c.jd, oy + 4 * B, p.YP[4], c.qy, c.aJh, c.bJh, dt, rigyz * D[7])
-              + pml_delta<STAGED>(c.kd, oz + 4 * B, p.ZP[4], c.qz, c.aKh, c.bKh, dt, rigyz * D[8]);
+              + pml_delta<STAGED>(c.kd, oz + 4 * ZB, p.ZP[4], c.qz, c.aKh, c.bKh, dt, rigyz * D[8]);
 }
 
 // X[9] = x1 (d+_i Sxx), x2 (d-_j Sxy), x3 (d-_k Sxz), y1 (d-_i Sxy), y2 (d+_j Syy), y3 (d-_k Syz),
 //        z1 (d-_i Sxz), z2 (d-_j Syz), z3 (d+_k Szz);  b = averaged 1/(rho h) of the three faces
 template <bool STAGED>
 __device__ __forceinline__ void particle_pml(const DevParams &p, const PmlCell &c, float bx, float by, float bz, const float *X, float *v,
-                                             const float *ox = nullptr, const float *oy = nullptr, const float *oz = nullptr) {
+                                             const float *ox = nullptr, const float *oy = nullptr, const float *oz = nullptr, int B = 0,
+                                             int ZB = 0) {
     const float dt = p.dt;
-    constexpr int B = BB_BOXF;
     v[0] += pml_delta<STAGED>(c.xd, ox, p.XP[5], c.qx, c.aIh, c.bIh, dt, bx * X[0]) + pml_delta<STAGED>(c.jd, oy, p.YP[5], c.qy, c.aJ, c.bJ, dt, bx * X[1])
           + pml_delta<STAGED>(c.kd, oz, p.ZP[5], c.qz, c.aK, c.bK, dt, bx * X[2]);
     v[1] += pml_delta<STAGED>(c.xd, ox + B, p.XP[6], c.qx, c.aI, c.bI, dt, by * X[3]) + pml_delta<STAGED>(c.jd, oy + B, p.YP[6], c.qy, c.aJh, c.bJh, dt, by * X[4])
-          + pml_delta<STAGED>(c.kd, oz + B, p.ZP[6], c.qz, c.aK, c.bK, dt, by * X[5]);
+          + pml_delta<STAGED>(c.kd, oz + ZB, p.ZP[6], c.qz, c.aK, c.bK, dt, by * X[5]);
     v[2] += pml_delta<STAGED>(c.xd, ox + 2 * B, p.XP[7], c.qx, c.aI, c.bI, dt, bz * X[6]) + pml_delta<STAGED>(c.jd, oy + 2 * B, p.YP[7], c.qy, c.aJ, c.bJ, dt, bz * X[7])
-          + pml_delta<STAGED>(c.kd, oz + 2 * B, p.ZP[7], c.qz, c.aKh, c.bKh, dt, bz * X[8]);
+          + pml_delta<STAGED>(c.kd, oz + 2 * ZB, p.ZP[7], c.qz, c.aKh, c.bKh, dt, bz * X[8]);
 }
 
 // ------------------------------------------------------------------------------------------

@@ -1,22 +1,23 @@
 // kernel_variant = 0: the production half-step kernels.
 //
-// One CTA owns an 8 x 32 (j,k) tile of the plane (k = the contiguous axis of the caller's C-order
+// One CTA owns an 8 x 64 (j,k) tile of the plane (k = the contiguous axis of the caller's C-order
 // volumes) and marches `chunk` planes along the slab axis i.  Every operand of a plane reaches
 // shared memory through TMA (cp.async.bulk.tensor, 3-D descriptors over the pitched volumes) into
 // two mbarrier-tracked rings that run several planes ahead of the arithmetic:
 //   * the "halo ring" holds the stencil inputs of the half-step (V for the stress kernel, the
-//     stresses for the particle kernel) as (8+4) x (32+8) boxes plus the label box; out-of-volume
+//     stresses for the particle kernel) as (8+4) x (64+8) boxes plus the label box; out-of-volume
 //     taps are zero-filled by the TMA unit, so the kernels carry no boundary branches for loads;
 //   * the "point ring" holds the read-modify-write fields of the cell itself (stresses, memory
 //     variables, pressure and the damped PML parts for the stress kernel; V and its damped parts
-//     for the particle kernel) as 8 x 32 boxes.
-// Warp 8 of the CTA is the producer: one lane waits on the slot's "empty" mbarrier and issues the
-// TMA loads of the next plane against the slot's "full" mbarrier.  Warps 0-7 are consumers (one tile
-// row each): they wait on "full", compute, store, and release the slot with one arrive per warp.
+//     for the particle kernel) as 8 x 64 boxes.
+// Warps 16 and 17 of the CTA are the producers of the halo ring and of the point ring (independent,
+// so neither ring throttles the other's prefetch distance): one lane waits on the slot's "empty"
+// mbarrier and issues the TMA loads of the next plane against the slot's "full" mbarrier.  Warps 0-15 are consumers (half a
+// tile row each): they wait on "full", compute, store, and release the slot with one arrive per warp.
 // There is no CTA-wide barrier inside the plane loop, so warps drift apart by up to the ring depth.
 // The i-direction stencil lives in a register queue fed from the halo ring; the in-plane stencil
-// reads the ring directly (row pitch 40 floats: conflict-free).  Results go straight from registers
-// to global memory (one 128-byte row segment per warp and field).
+// reads the ring directly (row pitch 72 floats: conflict-free).  Results go straight from registers
+// to global memory (one 128-byte row segment per warp and field, two warps side by side).
 //
 // Which fields move at all is decided per (plane, tile) from the flag byte computed once per
 // simulation (flags_kernel): memory variables only where something attenuates, shear stresses only
@@ -27,23 +28,26 @@
 #include "fdtd_cell.cuh"
 
 namespace tma {
-constexpr int TX = 32, TY = 8, HALO = 2;
+// 8 x 64 tile: 256-byte row segments (profiles/tile_bw_probe.cu: 128-byte segments cap the access
+// pattern at ~70% of the HBM copy bandwidth, 256-byte segments at ~90-98%)
+constexpr int TX = 64, TY = 8, HALO = 2;
 // the innermost TMA coordinate must be a multiple of 16 bytes (measured: a box starting at k0-2
 // raises an illegal-instruction fault), so halo boxes start at k0-4 and are TX+8 floats wide
 constexpr int HK = 4;
-constexpr int SW = TX + 2 * HK;          // 40
+constexpr int SW = TX + 2 * HK;          // 72
 constexpr int SH = TY + 2 * HALO;        // 12
-constexpr int NCW = TY;                  // consumer warps (one tile row each)
-constexpr int NT = TX * TY;              // 256 consumer threads
-constexpr int NTB = NT + 32;             // + the producer warp
-constexpr int HBOX = SW * SH * 4;        // 1920 bytes landed per halo box
-constexpr int HBOX_STRIDE = 1920;        // 128-byte aligned slot
-constexpr int PBOX = TX * TY * 4;        // 1024 bytes per point box
+constexpr int NT = TX * TY;              // 512 consumer threads, one cell each
+constexpr int NCW = NT / 32;             // 16 consumer warps
+constexpr int NTB = NT + 64;             // + two producer warps (halo ring, point ring)
+constexpr int HBOX = SW * SH * 4;        // 3456 bytes per halo box (a multiple of 128)
+constexpr int HBOX_STRIDE = HBOX;
+constexpr int PBOX = TX * TY * 4;        // 2048 bytes per point box
 constexpr int LH = TY + 1;               // label rows j0 .. j0+TY
-constexpr int LBOX_STRIDE = 768;         // >= LW*LH*sizeof(LT), 128-byte aligned
-template <typename LT> struct LabBox { static constexpr int W = 16 * 3 / sizeof(LT) < TX + 8 ? TX + 8 : 16 * 3 / sizeof(LT); };
-// uint8: 48 labels = 48 bytes per row; uint16: 40 labels = 80 bytes per row (both multiples of 16 bytes, >= TX+1)
+constexpr int LBOX_STRIDE = 1408;        // >= LW*LH*sizeof(LT), 128-byte aligned
+// label box width: >= TX+1 labels and a multiple of 16 bytes: uint8 80 labels, uint16 72 labels
+template <typename LT> struct LabBox { static constexpr int W = sizeof(LT) == 1 ? TX + 16 : TX + 8; };
 constexpr int MAXCHUNK = 64;
+constexpr int MAX_ZBW = 32;              // PML thickness supported by the compact Z-part boxes
 
 // ---------------------------------------------------------------- PTX wrappers
 __device__ __forceinline__ uint32_t smem_u32(const void *p) { return (uint32_t)__cvta_generic_to_shared(p); }
@@ -129,27 +133,27 @@ struct Ring {
 // Every CTA gets the same dynamic allocation (two CTAs per SM); what the point stages of its tile
 // class do not need (no Y parts away from the j-PML, no Z parts away from the k-PML) goes to a
 // deeper halo ring, i.e. more planes of prefetch.
-constexpr int SMEM_BYTES = 112 * 1024;
-constexpr int MAX_NSH = 8, NSP = 3;
+constexpr int SMEM_BYTES = 222 * 1024;   // one CTA of 17 warps per SM
+constexpr int MAX_NSH = 10, MAX_NSP = 4;
 constexpr int OFF_COEF = 0;                                                      // MatCoef[128] (stress) / float B[128] (particle)
 constexpr int OFF_AXJ = OFF_COEF + BB_MAX_SMEM_MAT * (int)sizeof(MatCoef);
 constexpr int OFF_AXK = OFF_AXJ + TY * (int)sizeof(AxisCoef);
 constexpr int OFF_FLAGS = OFF_AXK + TX * (int)sizeof(AxisCoef);
 constexpr int OFF_BAR = OFF_FLAGS + ((MAXCHUNK + 8 + 15) / 16) * 16;
-constexpr int OFF_RINGS = 8192;
-static_assert(OFF_BAR + 2 * (MAX_NSH + NSP) * 8 <= OFF_RINGS, "tables overflow their 8 KB");
+constexpr int OFF_RINGS = 9216;
+static_assert(OFF_BAR + 2 * (MAX_NSH + MAX_NSP) * 8 <= OFF_RINGS, "tables overflow their 9 KB");
 
 // =========================================================================================
 // stress half-step
 // =========================================================================================
 // point-box order inside a stage; on a plane inside the i-PML the X parts use the R boxes (no interior
 // cell exists on such a plane, so memory variables are not needed there); the Y / Z parts follow at
-// box 14 (whichever the tile needs first) and 19
+// full boxes, the Z parts as compact regions
 enum { PB_SXX = 0, PB_SYY, PB_SZZ, PB_SXY, PB_SXZ, PB_SYZ, PB_RXX, PB_RYY, PB_RZZ, PB_RXY, PB_RXZ, PB_RYZ, PB_PR, PB_ACC, PB_PARTS };
 constexpr int ST_HSTAGE = 3 * HBOX_STRIDE + LBOX_STRIDE;
 
 template <typename LT, int ACC>
-__global__ void __launch_bounds__(NTB, 2) stress_tma(const __grid_constant__ StressMaps tm, const DevParams p, int ia, int ie, int chunk) {
+__global__ void __launch_bounds__(NTB, 1) stress_tma(const __grid_constant__ StressMaps tm, const DevParams p, int ia, int ie, int chunk) {
     constexpr bool SMC = sizeof(LT) == 1;
     constexpr int LW = LabBox<LT>::W;
     extern __shared__ __align__(1024) unsigned char sm[];   // TMA destinations need 128-byte alignment
@@ -158,22 +162,27 @@ __global__ void __launch_bounds__(NTB, 2) stress_tma(const __grid_constant__ Str
     AxisCoef *sK = reinterpret_cast<AxisCoef *>(sm + OFF_AXK);
     unsigned char *sF = sm + OFF_FLAGS;
     uint64_t *fullH = reinterpret_cast<uint64_t *>(sm + OFF_BAR);
-    uint64_t *emptyH = fullH + MAX_NSH, *fullP = emptyH + MAX_NSH, *emptyP = fullP + NSP;
+    uint64_t *emptyH = fullH + MAX_NSH, *fullP = emptyH + MAX_NSH, *emptyP = fullP + MAX_NSP;
 
-    const int tx = threadIdx.x, ty = threadIdx.y, tid = ty * TX + tx;
+    const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+    const int tx = tid & (TX - 1), ty = tid / TX;       // consumer threads: cell (ty, tx) of the tile
     const int k0 = blockIdx.x * TX, j0 = blockIdx.y * TY;
     const int ic0 = ia + blockIdx.z * chunk, ic1 = min(ic0 + chunk, ie);
     const int np = ic1 - ic0;                 // planes of this CTA
     const int ipl0 = ic0 - p.i0 + 2;          // local plane of ic0
     // which damped parts this tile can need (CTA-uniform)
     const bool tile_jd = (int)blockIdx.y < p.nylo || (int)blockIdx.y >= p.tjhi0;
-    const bool tile_kd = (int)blockIdx.x < p.nzlo || (int)blockIdx.x >= p.tkhi0;
+    const bool tile_zlo = k0 < p.P, tile_zhi = k0 + TX > p.n3 - p.P;
     const int yt = ((int)blockIdx.y < p.nylo ? (int)blockIdx.y : (int)blockIdx.y - p.tjhi0 + p.nylo) * TY;
-    const int zt = ((int)blockIdx.x < p.nzlo ? (int)blockIdx.x : (int)blockIdx.x - p.tkhi0 + p.nzlo) * TX;
-    // ring geometry of this tile class
-    const int yb = PB_PARTS, zb = PB_PARTS + (tile_jd ? 5 : 0);            // first Y / Z part box
-    const int pstage = (PB_PARTS + (tile_jd ? 5 : 0) + (tile_kd ? 5 : 0)) * PBOX;
-    const int offP = OFF_RINGS, offH = OFF_RINGS + NSP * pstage;
+    // point-stage layout (bytes): 14 full boxes, then the Y part boxes, then the compact Z part regions
+    // (zbw columns x TY rows per component) of the low and the high side
+    const int zcomp = p.zbw * TY;                                          // floats per Z part component
+    const int zreg = (5 * zcomp * 4 + 127) & ~127;
+    const int yoff = PB_PARTS * PBOX, zlo_off = yoff + (tile_jd ? 5 * PBOX : 0), zhi_off = zlo_off + (tile_zlo ? zreg : 0);
+    const int pstage = zhi_off + (tile_zhi ? zreg : 0);
+    // ring depths: 4 point stages when that still leaves 6 halo stages, else 3
+    const int nsp = (SMEM_BYTES - OFF_RINGS - MAX_NSP * pstage) / ST_HSTAGE >= 6 ? MAX_NSP : MAX_NSP - 1;
+    const int offP = OFF_RINGS, offH = OFF_RINGS + nsp * pstage;
     const int nsh = min(MAX_NSH, (SMEM_BYTES - offH) / ST_HSTAGE);
 
     // ---- per-CTA tables
@@ -186,63 +195,70 @@ __global__ void __launch_bounds__(NTB, 2) stress_tma(const __grid_constant__ Str
     }
     if (tid == 0) {
         for (int s = 0; s < nsh; s++) { mbar_init(fullH + s, 1); mbar_init(emptyH + s, NCW); }
-        for (int s = 0; s < NSP; s++) { mbar_init(fullP + s, 1); mbar_init(emptyP + s, NCW); }
+        for (int s = 0; s < nsp; s++) { mbar_init(fullP + s, 1); mbar_init(emptyP + s, NCW); }
         fence_barrier_init();
     }
     __syncthreads();
 
-    // =============================== producer warp ===============================
-    if (ty == NCW) {
-        if (tx != 0) return;
-        Ring rh(nsh, 1), rp(NSP, 1);
+    // =============================== producer warps ===============================
+    if (warp == NCW) {          // halo ring: the three V boxes (one 4-D TMA) + labels of plane ic0 + r
+        if (lane != 0) return;
+        Ring rh(nsh, 1);
         for (int r = 0; r < np + 2; r++) {
-            {   // halo plane ic0 + r: the three V boxes (one 4-D TMA) + labels
-                const int slot = rh.slot;
-                rh.wait(emptyH, slot);
-                unsigned char *st = sm + offH + slot * ST_HSTAGE;
-                uint64_t *bar = fullH + slot;
-                mbar_expect_tx(bar, 3 * HBOX + LW * LH * (int)sizeof(LT));
-                const int ipl = ipl0 + r;
-                tma_load_4d(st, &tm.v3, bar, k0 - HK, j0 - HALO, ipl, 0);
-                tma_load_3d(st + 3 * HBOX_STRIDE, &tm.lab, bar, k0, j0, ipl);
-                rh.advance();
+            const int slot = rh.slot;
+            rh.wait(emptyH, slot);
+            unsigned char *st = sm + offH + slot * ST_HSTAGE;
+            uint64_t *bar = fullH + slot;
+            mbar_expect_tx(bar, 3 * HBOX + LW * LH * (int)sizeof(LT));
+            const int ipl = ipl0 + r;
+            tma_load_4d(st, &tm.v3, bar, k0 - HK, j0 - HALO, ipl, 0);
+            tma_load_3d(st + 3 * HBOX_STRIDE, &tm.lab, bar, k0, j0, ipl);
+            rh.advance();
+        }
+        return;
+    }
+    if (warp == NCW + 1) {      // point ring: read-modify-write fields and damped parts of plane ic0 + r
+        if (lane != 0) return;
+        Ring rp(nsp, 1);
+        for (int r = 0; r < np; r++) {
+            const int slot = rp.slot;
+            rp.wait(emptyP, slot);
+            unsigned char *st = sm + offP + slot * pstage;
+            uint64_t *bar = fullP + slot;
+            const unsigned f = sF[r];
+            const int i = ic0 + r, ipl = ipl0 + r, io = i - p.i0;
+            const bool xd = in_pml1(i, p.n1, p.P);
+            const bool fint = f & TF_INT, fatt = f & TF_ATT, fsol = f & TF_SOLID;
+            const int npart = fsol ? 5 : 3;
+            const bool acc = ACC == 1 && fint;
+            const int nbox = 3 + (fsol ? 3 : 0) + (xd ? npart : (fint ? 1 : 0) + (fatt ? 3 : 0) + (fsol && fint ? 3 : 0))
+                           + (tile_jd ? npart : 0) + (acc ? 1 : 0);
+            mbar_expect_tx(bar, nbox * PBOX + ((tile_zlo ? npart : 0) + (tile_zhi ? npart : 0)) * zcomp * 4);
+            tma_load_4d(st + PB_SXX * PBOX, &tm.s3, bar, k0, j0, ipl, 0);
+            if (fsol) tma_load_4d(st + PB_SXY * PBOX, &tm.s3, bar, k0, j0, ipl, 3);
+            if (xd) {
+                const int ipx = i < p.P ? io : p.nxlo + (i - p.xhi_begin);
+                tma_load_4d(st + PB_RXX * PBOX, &tm.xp3, bar, k0, j0, ipx, 0);
+                if (fsol) tma_load_4d(st + PB_RXY * PBOX, &tm.xp2, bar, k0, j0, ipx, 3);
+            } else {
+                if (fint) tma_load_3d(st + PB_PR * PBOX, &tm.pr, bar, k0, j0, ipl);
+                if (fatt) tma_load_4d(st + PB_RXX * PBOX, &tm.r3, bar, k0, j0, ipl, 0);
+                if (fsol && fint) tma_load_4d(st + PB_RXY * PBOX, &tm.r3, bar, k0, j0, ipl, 3);
             }
-            if (r < np) {   // point plane ic0 + r
-                const int slot = rp.slot;
-                rp.wait(emptyP, slot);
-                unsigned char *st = sm + offP + slot * pstage;
-                uint64_t *bar = fullP + slot;
-                const unsigned f = sF[r];
-                const int i = ic0 + r, ipl = ipl0 + r, io = i - p.i0;
-                const bool xd = in_pml1(i, p.n1, p.P);
-                const bool fint = f & TF_INT, fatt = f & TF_ATT, fsol = f & TF_SOLID;
-                const int npart = fsol ? 5 : 3;
-                const bool acc = ACC == 1 && fint;
-                const int nbox = 3 + (fsol ? 3 : 0) + (xd ? npart : (fint ? 1 : 0) + (fatt ? 3 : 0) + (fsol && fint ? 3 : 0))
-                               + (tile_jd ? npart : 0) + (tile_kd ? npart : 0) + (acc ? 1 : 0);
-                mbar_expect_tx(bar, nbox * PBOX);
-                tma_load_4d(st + PB_SXX * PBOX, &tm.s3, bar, k0, j0, ipl, 0);
-                if (fsol) tma_load_4d(st + PB_SXY * PBOX, &tm.s3, bar, k0, j0, ipl, 3);
-                if (xd) {
-                    const int ipx = i < p.P ? io : p.nxlo + (i - p.xhi_begin);
-                    tma_load_4d(st + PB_RXX * PBOX, &tm.xp3, bar, k0, j0, ipx, 0);
-                    if (fsol) tma_load_4d(st + PB_RXY * PBOX, &tm.xp2, bar, k0, j0, ipx, 3);
-                } else {
-                    if (fint) tma_load_3d(st + PB_PR * PBOX, &tm.pr, bar, k0, j0, ipl);
-                    if (fatt) tma_load_4d(st + PB_RXX * PBOX, &tm.r3, bar, k0, j0, ipl, 0);
-                    if (fsol && fint) tma_load_4d(st + PB_RXY * PBOX, &tm.r3, bar, k0, j0, ipl, 3);
-                }
-                if (tile_jd) {
-                    tma_load_4d(st + yb * PBOX, &tm.yp3, bar, k0, yt, io, 0);
-                    if (fsol) tma_load_4d(st + (yb + 3) * PBOX, &tm.yp2, bar, k0, yt, io, 3);
-                }
-                if (tile_kd) {
-                    tma_load_4d(st + zb * PBOX, &tm.zp3, bar, zt, j0, io, 0);
-                    if (fsol) tma_load_4d(st + (zb + 3) * PBOX, &tm.zp2, bar, zt, j0, io, 3);
-                }
-                if (acc) tma_load_3d(st + PB_ACC * PBOX, &tm.acc, bar, k0, j0, io);
-                rp.advance();
+            if (tile_jd) {
+                tma_load_4d(st + yoff, &tm.yp3, bar, k0, yt, io, 0);
+                if (fsol) tma_load_4d(st + yoff + 3 * PBOX, &tm.yp2, bar, k0, yt, io, 3);
             }
+            if (tile_zlo) {
+                tma_load_4d(st + zlo_off, &tm.zp3, bar, 0, j0, io, 0);
+                if (fsol) tma_load_4d(st + zlo_off + 3 * zcomp * 4, &tm.zp2, bar, 0, j0, io, 3);
+            }
+            if (tile_zhi) {
+                tma_load_4d(st + zhi_off, &tm.zp3, bar, p.zbw, j0, io, 0);
+                if (fsol) tma_load_4d(st + zhi_off + 3 * zcomp * 4, &tm.zp2, bar, p.zbw, j0, io, 3);
+            }
+            if (acc) tma_load_3d(st + PB_ACC * PBOX, &tm.acc, bar, k0, j0, io);
+            rp.advance();
         }
         return;
     }
@@ -271,11 +287,13 @@ __global__ void __launch_bounds__(NTB, 2) stress_tma(const __grid_constant__ Str
     // part arrays: index of this cell on plane ic0 and the per-plane strides
     const long long qy_stride = (long long)p.nyrows * p.pitch, qz_stride = (long long)p.n2 * p.zpw;
     long long qy = ((long long)(ic0 - p.i0) * p.nyrows + yt + ty) * p.pitch + k;
-    long long qz = ((long long)(ic0 - p.i0) * p.n2 + min(j, p.n2 - 1)) * p.zpw + zt + tx;
+    const int kz = k < p.P ? k : k - (p.n3 - p.P);                       // column inside the Z part box of this cell's side
+    long long qz = ((long long)(ic0 - p.i0) * p.n2 + min(j, p.n2 - 1)) * p.zpw + (k < p.P ? kz : p.zbw + kz);
+    const int zsrc = ((k < p.P ? zlo_off : zhi_off) >> 2) + ty * p.zbw + (kd ? kz : 0);   // float offset inside a point stage
 
     auto hbox = [&](int slot, int c) { return reinterpret_cast<const float *>(sm + offH + slot * ST_HSTAGE + c * HBOX_STRIDE); };
     auto lbox = [&](int slot) { return reinterpret_cast<const LT *>(sm + offH + slot * ST_HSTAGE + 3 * HBOX_STRIDE); };
-    Ring rh(nsh, 0), rp(NSP, 0);
+    Ring rh(nsh, 0), rp(nsp, 0);
 
     // planes ic0 and ic0+1 feed the queue before the loop
     rh.wait(fullH, 0);
@@ -366,7 +384,7 @@ __global__ void __launch_bounds__(NTB, 2) stress_tma(const __grid_constant__ Str
                 pcell.aI = ci.aI; pcell.bI = ci.bI; pcell.aIh = ci.aH; pcell.bIh = ci.bH;
                 pcell.aJ = cj.aI; pcell.bJ = cj.bI; pcell.aJh = cj.aH; pcell.bJh = cj.bH;
                 pcell.aK = ck.aI; pcell.bK = ck.bI; pcell.aKh = ck.aH; pcell.bKh = ck.bH;
-                stress_pml<true>(p, pcell, c.M, c.L, rigxy, rigxz, rigyz, D, s, pb + PB_RXX * NT, pb + yb * NT, pb + zb * NT);
+                stress_pml<true>(p, pcell, c.M, c.L, rigxy, rigxz, rigyz, D, s, pb + PB_RXX * NT, pb + (yoff >> 2), pb - pc + zsrc, NT, zcomp);
                 if (refl) { s[0] = s[1] = s[2] = s[3] = s[4] = s[5] = 0.f; }
                 p.S[0][q] = s[0]; p.S[1][q] = s[1]; p.S[2][q] = s[2];
                 if (f & TF_SOLID) { p.S[3][q] = s[3]; p.S[4][q] = s[4]; p.S[5][q] = s[5]; }
@@ -416,7 +434,7 @@ __global__ void __launch_bounds__(NTB, 2) stress_tma(const __grid_constant__ Str
         }
         // ---------------- this warp is done with the slots of plane i
         __syncwarp();
-        if (tx == 0) { mbar_arrive(emptyH + hs); mbar_arrive(emptyP + ps); }
+        if (lane == 0) { mbar_arrive(emptyH + hs); mbar_arrive(emptyP + ps); }
         rh.advance();
         rp.advance();
     }
@@ -432,7 +450,7 @@ enum { QB_V = 0, QB_X = 3, QB_PARTS = 6 };
 constexpr int PT_HSTAGE = 5 * HBOX_STRIDE + PBOX + LBOX_STRIDE;
 
 template <typename LT, int ACC>
-__global__ void __launch_bounds__(NTB, 2) particle_tma(const __grid_constant__ ParticleMaps tm, const DevParams p, int ia, int ie, int chunk) {
+__global__ void __launch_bounds__(NTB, 1) particle_tma(const __grid_constant__ ParticleMaps tm, const DevParams p, int ia, int ie, int chunk) {
     constexpr bool SMC = sizeof(LT) == 1;
     constexpr int LW = LabBox<LT>::W;
     extern __shared__ __align__(1024) unsigned char sm[];
@@ -441,20 +459,26 @@ __global__ void __launch_bounds__(NTB, 2) particle_tma(const __grid_constant__ P
     AxisCoef *sK = reinterpret_cast<AxisCoef *>(sm + OFF_AXK);
     unsigned char *sF = sm + OFF_FLAGS;
     uint64_t *fullH = reinterpret_cast<uint64_t *>(sm + OFF_BAR);
-    uint64_t *emptyH = fullH + MAX_NSH, *fullP = emptyH + MAX_NSH, *emptyP = fullP + NSP;
+    uint64_t *emptyH = fullH + MAX_NSH, *fullP = emptyH + MAX_NSH, *emptyP = fullP + MAX_NSP;
 
-    const int tx = threadIdx.x, ty = threadIdx.y, tid = ty * TX + tx;
+    const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+    const int tx = tid & (TX - 1), ty = tid / TX;       // consumer threads: cell (ty, tx) of the tile
     const int k0 = blockIdx.x * TX, j0 = blockIdx.y * TY;
     const int ic0 = ia + blockIdx.z * chunk, ic1 = min(ic0 + chunk, ie);
     const int np = ic1 - ic0;
     const int ipl0 = ic0 - p.i0 + 2;
     const bool tile_jd = (int)blockIdx.y < p.nylo || (int)blockIdx.y >= p.tjhi0;
-    const bool tile_kd = (int)blockIdx.x < p.nzlo || (int)blockIdx.x >= p.tkhi0;
+    const bool tile_zlo = k0 < p.P, tile_zhi = k0 + TX > p.n3 - p.P;
     const int yt = ((int)blockIdx.y < p.nylo ? (int)blockIdx.y : (int)blockIdx.y - p.tjhi0 + p.nylo) * TY;
-    const int zt = ((int)blockIdx.x < p.nzlo ? (int)blockIdx.x : (int)blockIdx.x - p.tkhi0 + p.nzlo) * TX;
-    const int yb = QB_PARTS, zb = QB_PARTS + (tile_jd ? 3 : 0);
-    const int pstage = (QB_PARTS + (tile_jd ? 3 : 0) + (tile_kd ? 3 : 0)) * PBOX;
-    const int offP = OFF_RINGS, offH = OFF_RINGS + NSP * pstage;
+    // point-stage layout (bytes): 6 full boxes, then the Y part boxes, then the compact Z part regions
+    // (zbw columns x TY rows per component) of the low and the high side
+    const int zcomp = p.zbw * TY;                                          // floats per Z part component
+    const int zreg = (3 * zcomp * 4 + 127) & ~127;
+    const int yoff = QB_PARTS * PBOX, zlo_off = yoff + (tile_jd ? 3 * PBOX : 0), zhi_off = zlo_off + (tile_zlo ? zreg : 0);
+    const int pstage = zhi_off + (tile_zhi ? zreg : 0);
+    // ring depths: 4 point stages when that still leaves 6 halo stages, else 3
+    const int nsp = (SMEM_BYTES - OFF_RINGS - MAX_NSP * pstage) / PT_HSTAGE >= 6 ? MAX_NSP : MAX_NSP - 1;
+    const int offP = OFF_RINGS, offH = OFF_RINGS + nsp * pstage;
     const int nsh = min(MAX_NSH, (SMEM_BYTES - offH) / PT_HSTAGE);
 
     if (SMC) for (int t = tid; t < p.nmat; t += NTB) sB[t] = p.coef[t].B;
@@ -466,44 +490,48 @@ __global__ void __launch_bounds__(NTB, 2) particle_tma(const __grid_constant__ P
     }
     if (tid == 0) {
         for (int s = 0; s < nsh; s++) { mbar_init(fullH + s, 1); mbar_init(emptyH + s, NCW); }
-        for (int s = 0; s < NSP; s++) { mbar_init(fullP + s, 1); mbar_init(emptyP + s, NCW); }
+        for (int s = 0; s < nsp; s++) { mbar_init(fullP + s, 1); mbar_init(emptyP + s, NCW); }
         fence_barrier_init();
     }
     __syncthreads();
 
-    // =============================== producer warp ===============================
-    if (ty == NCW) {
-        if (tx != 0) return;
-        Ring rh(nsh, 1), rp(NSP, 1);
+    // =============================== producer warps ===============================
+    if (warp == NCW) {          // halo ring: stresses with halo + Sxx + labels of plane ic0 + r
+        if (lane != 0) return;
+        Ring rh(nsh, 1);
         for (int r = 0; r < np + 2; r++) {
-            {
-                const int slot = rh.slot;
-                rh.wait(emptyH, slot);
-                unsigned char *st = sm + offH + slot * PT_HSTAGE;
-                uint64_t *bar = fullH + slot;
-                const bool fsh = sF[r] & TF_SHEAR;
-                mbar_expect_tx(bar, (fsh ? 5 : 2) * HBOX + PBOX + LW * LH * (int)sizeof(LT));
-                const int ipl = ipl0 + r;
-                tma_load_4d(st, &tm.sh2, bar, k0 - HK, j0 - HALO, ipl, 1);
-                if (fsh) tma_load_4d(st + 2 * HBOX_STRIDE, &tm.sh3, bar, k0 - HK, j0 - HALO, ipl, 3);
-                tma_load_4d(st + 5 * HBOX_STRIDE, &tm.sxx, bar, k0, j0, ipl, 0);
-                tma_load_3d(st + 5 * HBOX_STRIDE + PBOX, &tm.lab, bar, k0, j0, ipl);
-                rh.advance();
-            }
-            if (r < np) {
-                const int slot = rp.slot;
-                rp.wait(emptyP, slot);
-                unsigned char *st = sm + offP + slot * pstage;
-                uint64_t *bar = fullP + slot;
-                const int i = ic0 + r, ipl = ipl0 + r, io = i - p.i0;
-                const bool xd = in_pml1(i, p.n1, p.P);
-                mbar_expect_tx(bar, (3 + (xd ? 3 : 0) + (tile_jd ? 3 : 0) + (tile_kd ? 3 : 0)) * PBOX);
-                tma_load_4d(st + QB_V * PBOX, &tm.v3, bar, k0, j0, ipl, 0);
-                if (xd) tma_load_4d(st + QB_X * PBOX, &tm.xp3, bar, k0, j0, i < p.P ? io : p.nxlo + (i - p.xhi_begin), 5);
-                if (tile_jd) tma_load_4d(st + yb * PBOX, &tm.yp3, bar, k0, yt, io, 5);
-                if (tile_kd) tma_load_4d(st + zb * PBOX, &tm.zp3, bar, zt, j0, io, 5);
-                rp.advance();
-            }
+            const int slot = rh.slot;
+            rh.wait(emptyH, slot);
+            unsigned char *st = sm + offH + slot * PT_HSTAGE;
+            uint64_t *bar = fullH + slot;
+            const bool fsh = sF[r] & TF_SHEAR;
+            mbar_expect_tx(bar, (fsh ? 5 : 2) * HBOX + PBOX + LW * LH * (int)sizeof(LT));
+            const int ipl = ipl0 + r;
+            tma_load_4d(st, &tm.sh2, bar, k0 - HK, j0 - HALO, ipl, 1);
+            if (fsh) tma_load_4d(st + 2 * HBOX_STRIDE, &tm.sh3, bar, k0 - HK, j0 - HALO, ipl, 3);
+            tma_load_4d(st + 5 * HBOX_STRIDE, &tm.sxx, bar, k0, j0, ipl, 0);
+            tma_load_3d(st + 5 * HBOX_STRIDE + PBOX, &tm.lab, bar, k0, j0, ipl);
+            rh.advance();
+        }
+        return;
+    }
+    if (warp == NCW + 1) {      // point ring: V and its damped parts of plane ic0 + r
+        if (lane != 0) return;
+        Ring rp(nsp, 1);
+        for (int r = 0; r < np; r++) {
+            const int slot = rp.slot;
+            rp.wait(emptyP, slot);
+            unsigned char *st = sm + offP + slot * pstage;
+            uint64_t *bar = fullP + slot;
+            const int i = ic0 + r, ipl = ipl0 + r, io = i - p.i0;
+            const bool xd = in_pml1(i, p.n1, p.P);
+            mbar_expect_tx(bar, (3 + (xd ? 3 : 0) + (tile_jd ? 3 : 0)) * PBOX + ((tile_zlo ? 3 : 0) + (tile_zhi ? 3 : 0)) * zcomp * 4);
+            tma_load_4d(st + QB_V * PBOX, &tm.v3, bar, k0, j0, ipl, 0);
+            if (xd) tma_load_4d(st + QB_X * PBOX, &tm.xp3, bar, k0, j0, i < p.P ? io : p.nxlo + (i - p.xhi_begin), 5);
+            if (tile_jd) tma_load_4d(st + yoff, &tm.yp3, bar, k0, yt, io, 5);
+            if (tile_zlo) tma_load_4d(st + zlo_off, &tm.zp3, bar, 0, j0, io, 5);
+            if (tile_zhi) tma_load_4d(st + zhi_off, &tm.zp3, bar, p.zbw, j0, io, 5);
+            rp.advance();
         }
         return;
     }
@@ -531,12 +559,14 @@ __global__ void __launch_bounds__(NTB, 2) particle_tma(const __grid_constant__ P
     const unsigned MSK = LabelTraits<LT>::MASK;
     const long long qy_stride = (long long)p.nyrows * p.pitch, qz_stride = (long long)p.n2 * p.zpw;
     long long qy = ((long long)(ic0 - p.i0) * p.nyrows + yt + ty) * p.pitch + k;
-    long long qz = ((long long)(ic0 - p.i0) * p.n2 + min(j, p.n2 - 1)) * p.zpw + zt + tx;
+    const int kz = k < p.P ? k : k - (p.n3 - p.P);                       // column inside the Z part box of this cell's side
+    long long qz = ((long long)(ic0 - p.i0) * p.n2 + min(j, p.n2 - 1)) * p.zpw + (k < p.P ? kz : p.zbw + kz);
+    const int zsrc = ((k < p.P ? zlo_off : zhi_off) >> 2) + ty * p.zbw + (kd ? kz : 0);   // float offset inside a point stage
 
     auto hbox = [&](int slot, int c) { return reinterpret_cast<const float *>(sm + offH + slot * PT_HSTAGE + c * HBOX_STRIDE); };
     auto xxbox = [&](int slot) { return reinterpret_cast<const float *>(sm + offH + slot * PT_HSTAGE + 5 * HBOX_STRIDE); };
     auto lbox = [&](int slot) { return reinterpret_cast<const LT *>(sm + offH + slot * PT_HSTAGE + 5 * HBOX_STRIDE + PBOX); };
-    Ring rh(nsh, 0), rp(NSP, 0);
+    Ring rh(nsh, 0), rp(nsp, 0);
 
     rh.wait(fullH, 0);
     xx_p1 = xxbox(0)[pc];
@@ -607,7 +637,7 @@ __global__ void __launch_bounds__(NTB, 2) particle_tma(const __grid_constant__ P
                 pcell.aI = ci.aI; pcell.bI = ci.bI; pcell.aIh = ci.aH; pcell.bIh = ci.bH;
                 pcell.aJ = cj.aI; pcell.bJ = cj.bI; pcell.aJh = cj.aH; pcell.bJh = cj.bH;
                 pcell.aK = ck.aI; pcell.bK = ck.bI; pcell.aKh = ck.aH; pcell.bKh = ck.bH;
-                particle_pml<true>(p, pcell, bx, by, bz, X, v, pb + QB_X * NT, pb + yb * NT, pb + zb * NT);
+                particle_pml<true>(p, pcell, bx, by, bz, X, v, pb + QB_X * NT, pb + (yoff >> 2), pb - pc + zsrc, NT, zcomp);
             } else {
                 v[0] += dt * bx * (X[0] + X[1] + X[2]);
                 v[1] += dt * by * (X[3] + X[4] + X[5]);
@@ -624,7 +654,7 @@ __global__ void __launch_bounds__(NTB, 2) particle_tma(const __grid_constant__ P
             }
         }
         __syncwarp();
-        if (tx == 0) { mbar_arrive(emptyH + hs); mbar_arrive(emptyP + ps); }
+        if (lane == 0) { mbar_arrive(emptyH + hs); mbar_arrive(emptyP + ps); }
         rh.advance();
         rp.advance();
     }
