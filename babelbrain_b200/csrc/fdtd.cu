@@ -164,6 +164,8 @@ extern "C" int bb_fdtd_create(const bb_fdtd_desc *d, bb_fdtd **out) {
     BB_REQUIRE(d->n1 > 0 && d->n2 > 0 && d->n3 > 0, "bad grid %d %d %d", d->n1, d->n2, d->n3);
     BB_REQUIRE(d->pml >= 2 && 2 * d->pml < d->n1 && 2 * d->pml < d->n2 && 2 * d->pml < d->n3,
                "PML thickness %d must be >= 2 and leave an interior", d->pml);
+    BB_REQUIRE(((long long)(d->i1 - d->i0) + 5) * d->n2 * (((long long)d->n3 + tma::TX - 1) / tma::TX * tma::TX) < (1ll << 32),
+               "slab of %d planes x %d x %d exceeds 2^32 cells per field: split it over more GPUs", d->i1 - d->i0, d->n2, d->n3);
     BB_REQUIRE(d->pml <= tma::MAX_ZBW, "PML thickness %d above the supported maximum %d", d->pml, (int)tma::MAX_ZBW);
     BB_REQUIRE(d->i0 >= 0 && d->i1 <= d->n1 && d->i1 - d->i0 >= (d->nranks > 1 ? 4 : 1), "bad slab [%d,%d)", d->i0, d->i1);
     BB_REQUIRE(d->nmat >= 1 && d->nmat <= 32767, "nmat %d out of range", d->nmat);

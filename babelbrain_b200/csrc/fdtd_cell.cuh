@@ -33,7 +33,11 @@ __device__ __forceinline__ AxisCoef load_axis(const AxisCoef *t, int n) {
 __device__ __forceinline__ bool in_pml1(int n, int N, int P) { return n < P || n >= N - P; }
 __device__ __forceinline__ bool attenuates(const MatCoef &c) { return c.LMCb != 0.0f || c.tauS != 0.0f; }
 // 4/(1/g1+1/g2+1/g3+1/g4); a fluid neighbour has 1/G = +inf -> 0
-__device__ __forceinline__ float rigidity4(float a, float b, float c, float d) { return 4.0f * __frcp_rn(a + b + c + d); }
+__device__ __forceinline__ float rigidity4(float a, float b, float c, float d) {
+    float r;
+    asm("rcp.approx.ftz.f32 %0, %1;" : "=f"(r) : "f"(a + b + c + d));   // rcp(+inf) = +0; 1 ulp is far inside the 1e-4 budget
+    return 4.0f * r;
+}
 
 // ------------------------------------------------------------------------------------------
 // interior (non-PML) rules
@@ -80,14 +84,14 @@ __device__ __forceinline__ void stress_shear_interior(const MatCoef &c, float dt
 // ------------------------------------------------------------------------------------------
 struct PmlCell {
     bool xd, jd, kd;          // which axes are damped at this cell
-    long long qx, qy, qz;     // index of the cell in the X / Y / Z part arrays
+    unsigned qx, qy, qz;      // index of the cell in the X / Y / Z part arrays (32 bits: checked at create)
     float aI, bI, aIh, bIh, aJ, bJ, aJh, bJh, aK, bK, aKh, bKh;
 };
 
 // STAGED: the old part value is already on chip (TMA-staged box, one float per cell at `o`);
 // otherwise it is read from the part array.  Only the damped parts are touched.
 template <bool STAGED>
-__device__ __forceinline__ float pml_delta(bool damped, const float *o, float *__restrict__ part, long long q, float a, float b, float dt, float CD) {
+__device__ __forceinline__ float pml_delta(bool damped, const float *o, float *__restrict__ part, unsigned q, float a, float b, float dt, float CD) {
     if (damped) {
         const float old = STAGED ? *o : part[q];
         const float n = a * old + b * CD;
@@ -105,9 +109,9 @@ __device__ __forceinline__ PmlCell make_pml_cell(const DevParams &p, int i, int 
     const int tj = j >> 3;
     const int jp = (tj < p.nylo ? tj : tj - p.tjhi0 + p.nylo) * 8 + (j & 7);
     const int kp = k < p.P ? k : p.zbw + (k - (p.n3 - p.P));
-    c.qx = ((long long)ipx * p.n2 + j) * p.pitch + k;
-    c.qy = ((long long)(i - p.i0) * p.nyrows + jp) * p.pitch + k;
-    c.qz = ((long long)(i - p.i0) * p.n2 + j) * p.zpw + kp;
+    c.qx = ((unsigned)ipx * p.n2 + j) * p.pitch + k;
+    c.qy = ((unsigned)(i - p.i0) * p.nyrows + jp) * p.pitch + k;
+    c.qz = ((unsigned)(i - p.i0) * p.n2 + j) * p.zpw + kp;
     c.aI = ci.aI; c.bI = ci.bI; c.aIh = ci.aH; c.bIh = ci.bH;
     c.aJ = cj.aI; c.bJ = cj.bI; c.aJh = cj.aH; c.bJh = cj.bH;
     c.aK = ck.aI; c.bK = ck.bI; c.aKh = ck.aH; c.bKh = ck.bH;
@@ -159,7 +163,7 @@ __device__ __forceinline__ void particle_pml(const DevParams &p, const PmlCell &
 // ------------------------------------------------------------------------------------------
 __device__ __forceinline__ int acc_slot(unsigned sel, int map) { return __popc(sel & ((1u << map) - 1u)); }
 
-__device__ __forceinline__ void accumulate(const DevParams &p, int map, long long qa, float v, bool squared_already) {
+__device__ __forceinline__ void accumulate(const DevParams &p, int map, unsigned qa, float v, bool squared_already) {
     if (!(p.sel_maps & (1u << map))) return;
     const long long o = (long long)acc_slot(p.sel_maps, map) * p.acc_stride + qa;
     if (p.sel_rms_peak & 1) p.acc_rms[o] += squared_already ? v : v * v;

@@ -50,34 +50,35 @@ constexpr int MAXCHUNK = 64;
 constexpr int MAX_ZBW = 32;              // PML thickness supported by the compact Z-part boxes
 
 // ---------------------------------------------------------------- PTX wrappers
+// barriers and TMA destinations are addressed by 32-bit shared-window addresses computed once per thread
 __device__ __forceinline__ uint32_t smem_u32(const void *p) { return (uint32_t)__cvta_generic_to_shared(p); }
-__device__ __forceinline__ void mbar_init(uint64_t *bar, int count) {
-    asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(bar)), "r"(count) : "memory");
+__device__ __forceinline__ void mbar_init(uint32_t bar, int count) {
+    asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(bar), "r"(count) : "memory");
 }
-__device__ __forceinline__ void mbar_expect_tx(uint64_t *bar, uint32_t bytes) {
-    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_u32(bar)), "r"(bytes) : "memory");
+__device__ __forceinline__ void mbar_expect_tx(uint32_t bar, uint32_t bytes) {
+    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(bar), "r"(bytes) : "memory");
 }
-__device__ __forceinline__ bool mbar_try_wait(uint64_t *bar, uint32_t parity) {
+__device__ __forceinline__ bool mbar_try_wait(uint32_t bar, uint32_t parity) {
     uint32_t ok;
     asm volatile("{\n\t.reg .pred p;\n\tmbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\tselp.u32 %0, 1, 0, p;\n\t}"
-                 : "=r"(ok) : "r"(smem_u32(bar)), "r"(parity) : "memory");
+                 : "=r"(ok) : "r"(bar), "r"(parity) : "memory");
     return ok != 0;
 }
 // a TMA that never lands (bad descriptor, wrong byte count) must not hang the GPU: trap after ~seconds
-__device__ __forceinline__ void mbar_wait(uint64_t *bar, uint32_t parity) {
+__device__ __forceinline__ void mbar_wait(uint32_t bar, uint32_t parity) {
     unsigned spins = 0;
     while (!mbar_try_wait(bar, parity)) { if (++spins > (1u << 26)) __trap(); }
 }
-__device__ __forceinline__ void tma_load_3d(void *dst, const CUtensorMap *map, uint64_t *bar, int c0, int c1, int c2) {
+__device__ __forceinline__ void tma_load_3d(uint32_t dst, const CUtensorMap *map, uint32_t bar, int c0, int c1, int c2) {
     asm volatile("cp.async.bulk.tensor.3d.shared::cluster.global.tile.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4, %5}], [%2];"
-                 ::"r"(smem_u32(dst)), "l"(reinterpret_cast<uint64_t>(map)), "r"(smem_u32(bar)), "r"(c0), "r"(c1), "r"(c2) : "memory");
+                 ::"r"(dst), "l"(reinterpret_cast<uint64_t>(map)), "r"(bar), "r"(c0), "r"(c1), "r"(c2) : "memory");
 }
-__device__ __forceinline__ void tma_load_4d(void *dst, const CUtensorMap *map, uint64_t *bar, int c0, int c1, int c2, int c3) {
+__device__ __forceinline__ void tma_load_4d(uint32_t dst, const CUtensorMap *map, uint32_t bar, int c0, int c1, int c2, int c3) {
     asm volatile("cp.async.bulk.tensor.4d.shared::cluster.global.tile.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4, %5, %6}], [%2];"
-                 ::"r"(smem_u32(dst)), "l"(reinterpret_cast<uint64_t>(map)), "r"(smem_u32(bar)), "r"(c0), "r"(c1), "r"(c2), "r"(c3) : "memory");
+                 ::"r"(dst), "l"(reinterpret_cast<uint64_t>(map)), "r"(bar), "r"(c0), "r"(c1), "r"(c2), "r"(c3) : "memory");
 }
-__device__ __forceinline__ void mbar_arrive(uint64_t *bar) {
-    asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(smem_u32(bar)) : "memory");
+__device__ __forceinline__ void mbar_arrive(uint32_t bar) {
+    asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(bar) : "memory");
 }
 __device__ __forceinline__ void fence_barrier_init() { asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory"); }
 
@@ -119,14 +120,12 @@ __global__ void __launch_bounds__(NT) flags_kernel(const DevParams p, unsigned c
 }
 
 // ---------------------------------------------------------------- ring bookkeeping
-// slot s of a ring of `ns` slots: bit s of `ph` is the parity the next wait on that slot must observe
-struct Ring {
-    int slot = 0, ns;
-    unsigned ph;
-    __device__ Ring(int nslots, unsigned initial_parity) : ns(nslots), ph(initial_parity ? 0xFFFFFFFFu : 0u) {}
-    __device__ int next(int s) const { return s + 1 == ns ? 0 : s + 1; }
-    __device__ void wait(uint64_t *bars, int s) { mbar_wait(bars + s, (ph >> s) & 1u); ph ^= 1u << s; }
-    __device__ void advance() { slot = next(slot); }
+// position in a ring of `ns` slots: slot index and the parity the next wait on that slot must observe
+struct RingPos {
+    int slot, ns;
+    unsigned par;
+    __device__ RingPos(int nslots, int first_slot, unsigned parity) : slot(first_slot), ns(nslots), par(parity) {}
+    __device__ void advance() { if (++slot == ns) { slot = 0; par ^= 1u; } }
 };
 
 // ---------------------------------------------------------------- shared-memory layout
@@ -161,8 +160,8 @@ __global__ void __launch_bounds__(NTB, 1) stress_tma(const __grid_constant__ Str
     AxisCoef *sJ = reinterpret_cast<AxisCoef *>(sm + OFF_AXJ);
     AxisCoef *sK = reinterpret_cast<AxisCoef *>(sm + OFF_AXK);
     unsigned char *sF = sm + OFF_FLAGS;
-    uint64_t *fullH = reinterpret_cast<uint64_t *>(sm + OFF_BAR);
-    uint64_t *emptyH = fullH + MAX_NSH, *fullP = emptyH + MAX_NSH, *emptyP = fullP + MAX_NSP;
+    const uint32_t sm32 = smem_u32(sm);
+    const uint32_t fullH = sm32 + OFF_BAR, emptyH = fullH + MAX_NSH * 8, fullP = emptyH + MAX_NSH * 8, emptyP = fullP + MAX_NSP * 8;
 
     const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
     const int tx = tid & (TX - 1), ty = tid / TX;       // consumer threads: cell (ty, tx) of the tile
@@ -194,8 +193,8 @@ __global__ void __launch_bounds__(NTB, 1) stress_tma(const __grid_constant__ Str
         sF[tid] = ipl < p.nloc ? p.flags[((long long)ipl * p.ntj + blockIdx.y) * p.ntk + blockIdx.x] : 0;
     }
     if (tid == 0) {
-        for (int s = 0; s < nsh; s++) { mbar_init(fullH + s, 1); mbar_init(emptyH + s, NCW); }
-        for (int s = 0; s < nsp; s++) { mbar_init(fullP + s, 1); mbar_init(emptyP + s, NCW); }
+        for (int s = 0; s < nsh; s++) { mbar_init(fullH + s * 8, 1); mbar_init(emptyH + s * 8, NCW); }
+        for (int s = 0; s < nsp; s++) { mbar_init(fullP + s * 8, 1); mbar_init(emptyP + s * 8, NCW); }
         fence_barrier_init();
     }
     __syncthreads();
@@ -203,12 +202,12 @@ __global__ void __launch_bounds__(NTB, 1) stress_tma(const __grid_constant__ Str
     // =============================== producer warps ===============================
     if (warp == NCW) {          // halo ring: the three V boxes (one 4-D TMA) + labels of plane ic0 + r
         if (lane != 0) return;
-        Ring rh(nsh, 1);
+        RingPos rh(nsh, 0, 1);
         for (int r = 0; r < np + 2; r++) {
             const int slot = rh.slot;
-            rh.wait(emptyH, slot);
-            unsigned char *st = sm + offH + slot * ST_HSTAGE;
-            uint64_t *bar = fullH + slot;
+            mbar_wait(emptyH + slot * 8, rh.par);
+            const uint32_t st = sm32 + offH + slot * ST_HSTAGE;
+            const uint32_t bar = fullH + slot * 8;
             mbar_expect_tx(bar, 3 * HBOX + LW * LH * (int)sizeof(LT));
             const int ipl = ipl0 + r;
             tma_load_4d(st, &tm.v3, bar, k0 - HK, j0 - HALO, ipl, 0);
@@ -219,12 +218,12 @@ __global__ void __launch_bounds__(NTB, 1) stress_tma(const __grid_constant__ Str
     }
     if (warp == NCW + 1) {      // point ring: read-modify-write fields and damped parts of plane ic0 + r
         if (lane != 0) return;
-        Ring rp(nsp, 1);
+        RingPos rp(nsp, 0, 1);
         for (int r = 0; r < np; r++) {
             const int slot = rp.slot;
-            rp.wait(emptyP, slot);
-            unsigned char *st = sm + offP + slot * pstage;
-            uint64_t *bar = fullP + slot;
+            mbar_wait(emptyP + slot * 8, rp.par);
+            const uint32_t st = sm32 + offP + slot * pstage;
+            const uint32_t bar = fullP + slot * 8;
             const unsigned f = sF[r];
             const int i = ic0 + r, ipl = ipl0 + r, io = i - p.i0;
             const bool xd = in_pml1(i, p.n1, p.P);
@@ -270,12 +269,12 @@ __global__ void __launch_bounds__(NTB, 1) stress_tma(const __grid_constant__ Str
     const bool jkd = jd || kd;
     const bool jkupd = j < p.n2 - 1 && k < p.n3 - 1;
     const bool jkedge = j <= 1 || j >= p.n2 - 2 || k <= 1 || k >= p.n3 - 2;
-    const long long s1 = p.plane;
+    const unsigned s1 = (unsigned)p.plane;   // element indices fit 32 bits (checked at create)
 
     // ---- register queue along i (state before the shift of plane ic0)
     const float *__restrict__ Vx = p.V[0], *__restrict__ Vy = p.V[1], *__restrict__ Vz = p.V[2];
-    const long long col = (long long)min(j, p.n2 - 1) * p.pitch + min(k, p.pitch - 1);
-    long long q = (long long)ipl0 * s1 + col;
+    const unsigned col = (unsigned)min(j, p.n2 - 1) * p.pitch + min(k, p.pitch - 1);
+    unsigned q = (unsigned)ipl0 * s1 + col;
     float vx_m2, vx_m1 = Vx[q - 2 * s1], vx_0 = Vx[q - s1], vx_p1 = 0.f;
     float vy_m1, vy_0 = Vy[q - s1], vy_p1 = 0.f, vy_p2 = 0.f;
     float vz_m1, vz_0 = Vz[q - s1], vz_p1 = 0.f, vz_p2 = 0.f;
@@ -285,33 +284,33 @@ __global__ void __launch_bounds__(NTB, 1) stress_tma(const __grid_constant__ Str
     const float dt = p.dt;
     const unsigned MSK = LabelTraits<LT>::MASK;
     // part arrays: index of this cell on plane ic0 and the per-plane strides
-    const long long qy_stride = (long long)p.nyrows * p.pitch, qz_stride = (long long)p.n2 * p.zpw;
-    long long qy = ((long long)(ic0 - p.i0) * p.nyrows + yt + ty) * p.pitch + k;
+    const unsigned qy_stride = (unsigned)p.nyrows * p.pitch, qz_stride = (unsigned)p.n2 * p.zpw;
+    unsigned qy = ((unsigned)(ic0 - p.i0) * p.nyrows + yt + ty) * p.pitch + k;
     const int kz = k < p.P ? k : k - (p.n3 - p.P);                       // column inside the Z part box of this cell's side
-    long long qz = ((long long)(ic0 - p.i0) * p.n2 + min(j, p.n2 - 1)) * p.zpw + (k < p.P ? kz : p.zbw + kz);
+    unsigned qz = ((unsigned)(ic0 - p.i0) * p.n2 + min(j, p.n2 - 1)) * p.zpw + (k < p.P ? kz : p.zbw + kz);
     const int zsrc = ((k < p.P ? zlo_off : zhi_off) >> 2) + ty * p.zbw + (kd ? kz : 0);   // float offset inside a point stage
 
     auto hbox = [&](int slot, int c) { return reinterpret_cast<const float *>(sm + offH + slot * ST_HSTAGE + c * HBOX_STRIDE); };
     auto lbox = [&](int slot) { return reinterpret_cast<const LT *>(sm + offH + slot * ST_HSTAGE + 3 * HBOX_STRIDE); };
-    Ring rh(nsh, 0), rp(nsp, 0);
+    int hs = 0, hs1 = 1;                    // halo slots of planes it, it+1
+    RingPos h2(nsh, 2, 0), pp(nsp, 0, 0);   // halo slot of plane it+2 / point slot of plane it (waited on inside the loop)
 
     // planes ic0 and ic0+1 feed the queue before the loop
-    rh.wait(fullH, 0);
+    mbar_wait(fullH, 0);
     vx_p1 = hbox(0, 0)[sc]; vy_p1 = hbox(0, 1)[sc]; vz_p1 = hbox(0, 2)[sc];
-    rh.wait(fullH, 1);
+    mbar_wait(fullH + 8, 0);
     vy_p2 = hbox(1, 1)[sc]; vz_p2 = hbox(1, 2)[sc];
 
     for (int it = 0; it < np; it++, q += s1, qy += qy_stride, qz += qz_stride) {
         const int i = ic0 + it;
         const unsigned f = sF[it];
-        const int hs = rh.slot, hs1 = rh.next(hs), hs2 = rh.next(hs1);
-        const int ps = rp.slot;
-        rh.wait(fullH, hs2);
+        const int hs2 = h2.slot, ps = pp.slot;
+        mbar_wait(fullH + hs2 * 8, h2.par);
         // ---------------- shift the queue: plane i becomes the centre
         vx_m2 = vx_m1; vx_m1 = vx_0; vx_0 = vx_p1; vx_p1 = hbox(hs1, 0)[sc];
         vy_m1 = vy_0; vy_0 = vy_p1; vy_p1 = vy_p2; vy_p2 = hbox(hs2, 1)[sc];
         vz_m1 = vz_0; vz_0 = vz_p1; vz_p1 = vz_p2; vz_p2 = hbox(hs2, 2)[sc];
-        rp.wait(fullP, ps);
+        mbar_wait(fullP + ps * 8, pp.par);
         const bool xd = in_pml1(i, p.n1, p.P);
         const bool cellpml = xd || jkd;
         if (active && (!cellpml || (jkupd && i < p.n1 - 1))) {
@@ -379,7 +378,7 @@ __global__ void __launch_bounds__(NTB, 1) stress_tma(const __grid_constant__ Str
                 PmlCell pcell;
                 pcell.xd = xd; pcell.jd = jd; pcell.kd = kd;
                 const int ipx = i < p.P ? i - p.i0 : p.nxlo + (i - p.xhi_begin);
-                pcell.qx = (long long)ipx * s1 + col; pcell.qy = qy; pcell.qz = qz;
+                pcell.qx = (unsigned)ipx * s1 + col; pcell.qy = qy; pcell.qz = qz;
                 const AxisCoef ci = load_axis(p.axI, i), cj = sJ[ty], ck = sK[tx];
                 pcell.aI = ci.aI; pcell.bI = ci.bI; pcell.aIh = ci.aH; pcell.bIh = ci.bH;
                 pcell.aJ = cj.aI; pcell.bJ = cj.bI; pcell.aJh = cj.aH; pcell.bJh = cj.bH;
@@ -425,7 +424,7 @@ __global__ void __launch_bounds__(NTB, 1) stress_tma(const __grid_constant__ Str
                     const float v = -c.K * pr;
                     p.acc_rms[q - 2 * s1] = pb[PB_ACC * NT] + v * v;
                 } else if (ACC == 2) {
-                    const long long qa = q - 2 * s1;
+                    const unsigned qa = q - 2 * s1;
 #pragma unroll
                     for (int n = 0; n < 6; n++) accumulate(p, BB_MAP_SXX + n, qa, s[n], false);
                     accumulate(p, BB_MAP_PRESSURE, qa, -c.K * pr, false);
@@ -434,9 +433,10 @@ __global__ void __launch_bounds__(NTB, 1) stress_tma(const __grid_constant__ Str
         }
         // ---------------- this warp is done with the slots of plane i
         __syncwarp();
-        if (lane == 0) { mbar_arrive(emptyH + hs); mbar_arrive(emptyP + ps); }
-        rh.advance();
-        rp.advance();
+        if (lane == 0) { mbar_arrive(emptyH + hs * 8); mbar_arrive(emptyP + ps * 8); }
+        hs = hs1; hs1 = hs2;
+        h2.advance();
+        pp.advance();
     }
 }
 
@@ -458,8 +458,8 @@ __global__ void __launch_bounds__(NTB, 1) particle_tma(const __grid_constant__ P
     AxisCoef *sJ = reinterpret_cast<AxisCoef *>(sm + OFF_AXJ);
     AxisCoef *sK = reinterpret_cast<AxisCoef *>(sm + OFF_AXK);
     unsigned char *sF = sm + OFF_FLAGS;
-    uint64_t *fullH = reinterpret_cast<uint64_t *>(sm + OFF_BAR);
-    uint64_t *emptyH = fullH + MAX_NSH, *fullP = emptyH + MAX_NSH, *emptyP = fullP + MAX_NSP;
+    const uint32_t sm32 = smem_u32(sm);
+    const uint32_t fullH = sm32 + OFF_BAR, emptyH = fullH + MAX_NSH * 8, fullP = emptyH + MAX_NSH * 8, emptyP = fullP + MAX_NSP * 8;
 
     const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
     const int tx = tid & (TX - 1), ty = tid / TX;       // consumer threads: cell (ty, tx) of the tile
@@ -489,8 +489,8 @@ __global__ void __launch_bounds__(NTB, 1) particle_tma(const __grid_constant__ P
         sF[tid] = ipl < p.nloc ? p.flags[((long long)ipl * p.ntj + blockIdx.y) * p.ntk + blockIdx.x] : 0;
     }
     if (tid == 0) {
-        for (int s = 0; s < nsh; s++) { mbar_init(fullH + s, 1); mbar_init(emptyH + s, NCW); }
-        for (int s = 0; s < nsp; s++) { mbar_init(fullP + s, 1); mbar_init(emptyP + s, NCW); }
+        for (int s = 0; s < nsh; s++) { mbar_init(fullH + s * 8, 1); mbar_init(emptyH + s * 8, NCW); }
+        for (int s = 0; s < nsp; s++) { mbar_init(fullP + s * 8, 1); mbar_init(emptyP + s * 8, NCW); }
         fence_barrier_init();
     }
     __syncthreads();
@@ -498,12 +498,12 @@ __global__ void __launch_bounds__(NTB, 1) particle_tma(const __grid_constant__ P
     // =============================== producer warps ===============================
     if (warp == NCW) {          // halo ring: stresses with halo + Sxx + labels of plane ic0 + r
         if (lane != 0) return;
-        Ring rh(nsh, 1);
+        RingPos rh(nsh, 0, 1);
         for (int r = 0; r < np + 2; r++) {
             const int slot = rh.slot;
-            rh.wait(emptyH, slot);
-            unsigned char *st = sm + offH + slot * PT_HSTAGE;
-            uint64_t *bar = fullH + slot;
+            mbar_wait(emptyH + slot * 8, rh.par);
+            const uint32_t st = sm32 + offH + slot * PT_HSTAGE;
+            const uint32_t bar = fullH + slot * 8;
             const bool fsh = sF[r] & TF_SHEAR;
             mbar_expect_tx(bar, (fsh ? 5 : 2) * HBOX + PBOX + LW * LH * (int)sizeof(LT));
             const int ipl = ipl0 + r;
@@ -517,12 +517,12 @@ __global__ void __launch_bounds__(NTB, 1) particle_tma(const __grid_constant__ P
     }
     if (warp == NCW + 1) {      // point ring: V and its damped parts of plane ic0 + r
         if (lane != 0) return;
-        Ring rp(nsp, 1);
+        RingPos rp(nsp, 0, 1);
         for (int r = 0; r < np; r++) {
             const int slot = rp.slot;
-            rp.wait(emptyP, slot);
-            unsigned char *st = sm + offP + slot * pstage;
-            uint64_t *bar = fullP + slot;
+            mbar_wait(emptyP + slot * 8, rp.par);
+            const uint32_t st = sm32 + offP + slot * pstage;
+            const uint32_t bar = fullP + slot * 8;
             const int i = ic0 + r, ipl = ipl0 + r, io = i - p.i0;
             const bool xd = in_pml1(i, p.n1, p.P);
             mbar_expect_tx(bar, (3 + (xd ? 3 : 0) + (tile_jd ? 3 : 0)) * PBOX + ((tile_zlo ? 3 : 0) + (tile_zhi ? 3 : 0)) * zcomp * 4);
@@ -543,12 +543,12 @@ __global__ void __launch_bounds__(NTB, 1) particle_tma(const __grid_constant__ P
     const bool jkd = jd || kd;
     const bool jkupd = j < p.n2 - 1 && k < p.n3 - 1;
     const bool jkedge = j <= 1 || j >= p.n2 - 2 || k <= 1 || k >= p.n3 - 2;
-    const long long s1 = p.plane;
+    const unsigned s1 = (unsigned)p.plane;   // element indices fit 32 bits (checked at create)
 
     // queues: Sxx holds i-1..i+2 ; Sxy, Sxz hold i-2..i+1 (state before the shift of plane ic0)
     const float *__restrict__ Sxx = p.S[0], *__restrict__ Sxy = p.S[3], *__restrict__ Sxz = p.S[4];
-    const long long col = (long long)min(j, p.n2 - 1) * p.pitch + min(k, p.pitch - 1);
-    long long q = (long long)ipl0 * s1 + col;
+    const unsigned col = (unsigned)min(j, p.n2 - 1) * p.pitch + min(k, p.pitch - 1);
+    unsigned q = (unsigned)ipl0 * s1 + col;
     float xx_m1, xx_0 = Sxx[q - s1], xx_p1 = 0.f, xx_p2 = 0.f;
     float xy_m2, xy_m1 = Sxy[q - 2 * s1], xy_0 = Sxy[q - s1], xy_p1 = 0.f;
     float xz_m2, xz_m1 = Sxz[q - 2 * s1], xz_0 = Sxz[q - s1], xz_p1 = 0.f;
@@ -557,36 +557,36 @@ __global__ void __launch_bounds__(NTB, 1) particle_tma(const __grid_constant__ P
     const int pc = ty * TX + tx;
     const float dt = p.dt;
     const unsigned MSK = LabelTraits<LT>::MASK;
-    const long long qy_stride = (long long)p.nyrows * p.pitch, qz_stride = (long long)p.n2 * p.zpw;
-    long long qy = ((long long)(ic0 - p.i0) * p.nyrows + yt + ty) * p.pitch + k;
+    const unsigned qy_stride = (unsigned)p.nyrows * p.pitch, qz_stride = (unsigned)p.n2 * p.zpw;
+    unsigned qy = ((unsigned)(ic0 - p.i0) * p.nyrows + yt + ty) * p.pitch + k;
     const int kz = k < p.P ? k : k - (p.n3 - p.P);                       // column inside the Z part box of this cell's side
-    long long qz = ((long long)(ic0 - p.i0) * p.n2 + min(j, p.n2 - 1)) * p.zpw + (k < p.P ? kz : p.zbw + kz);
+    unsigned qz = ((unsigned)(ic0 - p.i0) * p.n2 + min(j, p.n2 - 1)) * p.zpw + (k < p.P ? kz : p.zbw + kz);
     const int zsrc = ((k < p.P ? zlo_off : zhi_off) >> 2) + ty * p.zbw + (kd ? kz : 0);   // float offset inside a point stage
 
     auto hbox = [&](int slot, int c) { return reinterpret_cast<const float *>(sm + offH + slot * PT_HSTAGE + c * HBOX_STRIDE); };
     auto xxbox = [&](int slot) { return reinterpret_cast<const float *>(sm + offH + slot * PT_HSTAGE + 5 * HBOX_STRIDE); };
     auto lbox = [&](int slot) { return reinterpret_cast<const LT *>(sm + offH + slot * PT_HSTAGE + 5 * HBOX_STRIDE + PBOX); };
-    Ring rh(nsh, 0), rp(nsp, 0);
+    int hs = 0, hs1 = 1;                    // halo slots of planes it, it+1
+    RingPos h2(nsh, 2, 0), pp(nsp, 0, 0);   // halo slot of plane it+2 / point slot of plane it (waited on inside the loop)
 
-    rh.wait(fullH, 0);
+    mbar_wait(fullH, 0);
     xx_p1 = xxbox(0)[pc];
     if (sF[0] & TF_SHEAR) { xy_p1 = hbox(0, HB_SXY)[sc]; xz_p1 = hbox(0, HB_SXZ)[sc]; }
-    rh.wait(fullH, 1);
+    mbar_wait(fullH + 8, 0);
     xx_p2 = xxbox(1)[pc];
 
     for (int it = 0; it < np; it++, q += s1, qy += qy_stride, qz += qz_stride) {
         const int i = ic0 + it;
         const unsigned f = sF[it];
         const bool fsh = f & TF_SHEAR;
-        const int hs = rh.slot, hs1 = rh.next(hs), hs2 = rh.next(hs1);
-        const int ps = rp.slot;
-        rh.wait(fullH, hs2);
+        const int hs2 = h2.slot, ps = pp.slot;
+        mbar_wait(fullH + hs2 * 8, h2.par);
         xx_m1 = xx_0; xx_0 = xx_p1; xx_p1 = xx_p2; xx_p2 = xxbox(hs2)[pc];
         xy_m2 = xy_m1; xy_m1 = xy_0; xy_0 = xy_p1;
         xz_m2 = xz_m1; xz_m1 = xz_0; xz_0 = xz_p1;
         if (sF[it + 1] & TF_SHEAR) { xy_p1 = hbox(hs1, HB_SXY)[sc]; xz_p1 = hbox(hs1, HB_SXZ)[sc]; }
         else { xy_p1 = 0.f; xz_p1 = 0.f; }
-        rp.wait(fullP, ps);
+        mbar_wait(fullP + ps * 8, pp.par);
         const bool xd = in_pml1(i, p.n1, p.P);
         const bool cellpml = xd || jkd;
         if (active && (!cellpml || (jkupd && i < p.n1 - 1))) {
@@ -632,7 +632,7 @@ __global__ void __launch_bounds__(NTB, 1) particle_tma(const __grid_constant__ P
                 PmlCell pcell;
                 pcell.xd = xd; pcell.jd = jd; pcell.kd = kd;
                 const int ipx = i < p.P ? i - p.i0 : p.nxlo + (i - p.xhi_begin);
-                pcell.qx = (long long)ipx * s1 + col; pcell.qy = qy; pcell.qz = qz;
+                pcell.qx = (unsigned)ipx * s1 + col; pcell.qy = qy; pcell.qz = qz;
                 const AxisCoef ci = load_axis(p.axI, i), cj = sJ[ty], ck = sK[tx];
                 pcell.aI = ci.aI; pcell.bI = ci.bI; pcell.aIh = ci.aH; pcell.bIh = ci.bH;
                 pcell.aJ = cj.aI; pcell.bJ = cj.bI; pcell.aJh = cj.aH; pcell.bJh = cj.bH;
@@ -646,7 +646,7 @@ __global__ void __launch_bounds__(NTB, 1) particle_tma(const __grid_constant__ P
             if (l0 & LabelTraits<LT>::REFL) { v[0] = v[1] = v[2] = 0.f; }
             p.V[0][q] = v[0]; p.V[1][q] = v[1]; p.V[2][q] = v[2];
             if (ACC && !cellpml) {
-                const long long qa = q - 2 * s1;
+                const unsigned qa = q - 2 * s1;
                 accumulate(p, BB_MAP_VX, qa, v[0], false);
                 accumulate(p, BB_MAP_VY, qa, v[1], false);
                 accumulate(p, BB_MAP_VZ, qa, v[2], false);
@@ -654,9 +654,10 @@ __global__ void __launch_bounds__(NTB, 1) particle_tma(const __grid_constant__ P
             }
         }
         __syncwarp();
-        if (lane == 0) { mbar_arrive(emptyH + hs); mbar_arrive(emptyP + ps); }
-        rh.advance();
-        rp.advance();
+        if (lane == 0) { mbar_arrive(emptyH + hs * 8); mbar_arrive(emptyP + ps * 8); }
+        hs = hs1; hs1 = hs2;
+        h2.advance();
+        pp.advance();
     }
 }
 }  // namespace tma
