@@ -37,9 +37,10 @@ class FdtdStats(ctypes.Structure):
 
 
 # every symbol include/babelb200.h declares (checked by tests/test_capi.py)
-SYMBOLS = ['bb_last_error', 'bb_version', 'bb_device_count', 'bb_device_name', 'bb_fdtd_create',
+SYMBOLS = ['bb_last_error', 'bb_version', 'bb_device_count', 'bb_device_name', 'bb_host_alloc', 'bb_host_free', 'bb_fdtd_create',
            'bb_fdtd_destroy', 'bb_fdtd_set_stream', 'bb_fdtd_set_materials', 'bb_fdtd_set_maps',
            'bb_fdtd_set_source_cells', 'bb_fdtd_set_source_functions', 'bb_fdtd_set_sensors',
+           'bb_fdtd_set_sensor_map', 'bb_fdtd_get_sensor_index',
            'bb_nccl_unique_id', 'bb_fdtd_comm_init', 'bb_fdtd_run', 'bb_fdtd_reset', 'bb_fdtd_get_map',
            'bb_fdtd_get_sensors', 'bb_fdtd_get_stats', 'bb_rayleigh_forward']
 
@@ -58,6 +59,8 @@ def lib():
         L.bb_version.restype = ctypes.c_char_p
         vp, i64, i32 = ctypes.c_void_p, ctypes.c_int64, ctypes.c_int
         L.bb_device_name.argtypes = [i32, ctypes.c_char_p, i32]
+        L.bb_host_alloc.argtypes = [i64, ctypes.POINTER(vp)]
+        L.bb_host_free.argtypes = [vp]
         L.bb_fdtd_create.argtypes = [ctypes.POINTER(FdtdDesc), ctypes.POINTER(vp)]
         L.bb_fdtd_destroy.argtypes = [vp]
         L.bb_fdtd_destroy.restype = None
@@ -67,6 +70,8 @@ def lib():
         L.bb_fdtd_set_source_cells.argtypes = [vp, i64, vp, vp, vp, vp, vp]
         L.bb_fdtd_set_source_functions.argtypes = [vp, vp, i32, i64]
         L.bb_fdtd_set_sensors.argtypes = [vp, i64, vp]
+        L.bb_fdtd_set_sensor_map.argtypes = [vp, vp, ctypes.POINTER(ctypes.c_int64)]
+        L.bb_fdtd_get_sensor_index.argtypes = [vp, vp, i32]
         L.bb_nccl_unique_id.argtypes = [ctypes.c_char_p]
         L.bb_fdtd_comm_init.argtypes = [vp, ctypes.c_char_p]
         L.bb_fdtd_run.argtypes = [vp, i64, i32]
@@ -111,3 +116,55 @@ def device_names():
 def require_gpu():
     if device_count() == 0:
         raise BabelB200Error('no CUDA device visible: babelbrain_b200 has no CPU fallback')
+
+
+class _PinnedBlock:
+    """One page-locked host allocation; returns itself to the pool when the last numpy view dies."""
+
+    def __init__(self, nbytes):
+        p = ctypes.c_void_p()
+        check(lib().bb_host_alloc(int(nbytes), ctypes.byref(p)))
+        self.ptr, self.nbytes = p.value, int(nbytes)
+
+    def release(self):
+        if self.ptr:
+            lib().bb_host_free(ctypes.c_void_p(self.ptr))
+            self.ptr = None
+
+
+class PinnedPool:
+    """Result buffers (RMS maps, sensor traces, index tables) handed to the caller as ordinary writable
+    numpy arrays backed by page-locked memory.  A block goes back to the pool when the caller drops the
+    array, so a worker that runs several simulations (forward, back-propagation, refocus:
+    BabelIntegrationBASE.py:2338-2428) pays the page-locking once."""
+
+    def __init__(self, max_idle_bytes=8 << 30):
+        self.idle, self.max_idle, self.idle_bytes = [], max_idle_bytes, 0
+
+    def empty(self, shape, dtype):
+        import weakref
+        dtype = np.dtype(dtype)
+        n = int(np.prod(shape, dtype=np.int64)) * dtype.itemsize
+        blk = None
+        for c, b in enumerate(self.idle):     # smallest idle block that fits without wasting more than 2x
+            if n <= b.nbytes <= max(2 * n, 1 << 20) and (blk is None or b.nbytes < blk.nbytes):
+                blk, pos = b, c
+        if blk is not None:
+            self.idle.pop(pos)
+            self.idle_bytes -= blk.nbytes
+        else:
+            blk = _PinnedBlock(max(n, 16))
+        buf = (ctypes.c_char * blk.nbytes).from_address(blk.ptr)
+        arr = np.frombuffer(buf, dtype=dtype, count=int(np.prod(shape, dtype=np.int64))).reshape(shape)
+        weakref.finalize(buf, self._give_back, blk)   # buf lives as long as any view of it
+        return arr
+
+    def _give_back(self, blk):
+        if self.idle_bytes + blk.nbytes <= self.max_idle:
+            self.idle.append(blk)
+            self.idle_bytes += blk.nbytes
+        else:
+            blk.release()
+
+
+pinned = PinnedPool()

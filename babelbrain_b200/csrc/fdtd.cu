@@ -10,6 +10,8 @@
 #include "fdtd_direct.cuh"
 #include "fdtd_tma.cuh"
 #include "nccl_dyn.h"
+#include <cub/device/device_select.cuh>
+#include <cub/iterator/counting_input_iterator.cuh>
 
 static thread_local char g_err[1024] = "";
 void bb_set_error(const char *fmt, ...) {
@@ -34,6 +36,16 @@ extern "C" int bb_device_name(int device, char *out, int out_len) {
     return BB_OK;
 }
 
+extern "C" int bb_host_alloc(int64_t bytes, void **out) {
+    BB_REQUIRE(out && bytes >= 0, "bad argument");
+    BB_CUDA(cudaHostAlloc(out, (size_t)std::max<int64_t>(bytes, 16), cudaHostAllocDefault));
+    return BB_OK;
+}
+extern "C" int bb_host_free(void *ptr) {
+    if (ptr) BB_CUDA(cudaFreeHost(ptr));
+    return BB_OK;
+}
+
 // ------------------------------------------------------------------------------------------
 enum { CAT_STRESS = 0, CAT_PARTICLE, CAT_PML, CAT_OTHER, CAT_COUNT };
 
@@ -55,6 +67,7 @@ struct bb_fdtd {
     // sensors
     int64_t nsensors = 0, nsamples = 0;
     long long *sensor_cell = nullptr;
+    unsigned long long *sensor_findex = nullptr;   // 1-based Fortran-order indices (device-built table only)
     float *sensor_out = nullptr;  // [map][sample][sensor]
     int n_sensor_maps = 0, n_acc_maps = 0;
     int64_t step = 0;
@@ -465,6 +478,105 @@ extern "C" int bb_fdtd_set_sensors(bb_fdtd *h, int64_t nsensors, const int64_t *
     if ((rc = dev_alloc(h, (void **)&h->sensor_out, (size_t)h->n_sensor_maps * h->nsamples * nsensors * 4))) return rc;
     BB_CUDA(cudaStreamSynchronize(h->stream));
     h->nsensors = nsensors;
+    return BB_OK;
+}
+
+// ------------------------------------------------------------------------------------------
+// sensor table built on the device (stream compaction in IndexSensorMap order)
+// ------------------------------------------------------------------------------------------
+struct SensorPred {
+    const uint32_t *sm;   // (nown, n2, n3) C-order planes of the caller's SensorMap
+    int nown, n2, n3;
+    // t enumerates the slab in Fortran order (i fastest): the order of IndexSensorMap
+    __device__ bool operator()(long long t) const {
+        const int il = (int)(t % nown);
+        const long long r = t / nown;
+        const int j = (int)(r % n2), k = (int)(r / n2);
+        return sm[((long long)il * n2 + j) * n3 + k] != 0;
+    }
+};
+
+__global__ void sensor_finish_kernel(const long long *__restrict__ sel, long long n, DevParams p, long long *__restrict__ cell,
+                                     unsigned long long *__restrict__ findex) {
+    const long long s = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    if (s >= n) return;
+    const long long t = sel[s];
+    const int nown = p.i1 - p.i0;
+    const int il = (int)(t % nown);
+    const long long r = t / nown;
+    const int j = (int)(r % p.n2), k = (int)(r / p.n2);
+    cell[s] = ((long long)(il + 2) * p.n2 + j) * p.pitch + k;
+    findex[s] = (unsigned long long)(il + p.i0) + (unsigned long long)j * p.n1 + (unsigned long long)k * p.n1 * p.n2 + 1ull;
+}
+
+__global__ void narrow_index_kernel(const unsigned long long *__restrict__ in, uint32_t *__restrict__ out, long long n) {
+    const long long s = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    if (s < n) out[s] = (uint32_t)in[s];
+}
+
+extern "C" int bb_fdtd_set_sensor_map(bb_fdtd *h, const uint32_t *sensor_map, int64_t *nsensors) {
+    BB_REQUIRE(h && sensor_map && nsensors, "null argument");
+    BB_CUDA(cudaSetDevice(h->d.device));
+    const DevParams &p = h->p;
+    const long long total = (long long)h->nown * p.n2 * p.n3;
+    uint32_t *dmap = nullptr;
+    long long *dsel = nullptr, *dcount = nullptr;
+    BB_CUDA(cudaMalloc(&dmap, (size_t)total * 4));
+    BB_CUDA(cudaMemcpyAsync(dmap, sensor_map, (size_t)total * 4, cudaMemcpyHostToDevice, h->stream));
+    BB_CUDA(cudaMalloc(&dsel, (size_t)total * 8));   // worst case: every voxel is a sensor
+    BB_CUDA(cudaMalloc(&dcount, 8));
+    const SensorPred pred{dmap, h->nown, p.n2, p.n3};
+    long long found = 0;
+    const long long piece = 1ll << 30;               // keep each selection inside 32-bit item counts
+    void *tmp = nullptr;
+    size_t tmp_bytes = 0;
+    for (long long t0 = 0; t0 < total; t0 += piece) {
+        const int n = (int)std::min(piece, total - t0);
+        cub::CountingInputIterator<long long> first(t0);
+        size_t need = 0;
+        BB_CUDA(cub::DeviceSelect::If(nullptr, need, first, dsel + found, dcount, n, pred, h->stream));
+        if (need > tmp_bytes) { if (tmp) cudaFree(tmp); BB_CUDA(cudaMalloc(&tmp, need)); tmp_bytes = need; }
+        BB_CUDA(cub::DeviceSelect::If(tmp, need, first, dsel + found, dcount, n, pred, h->stream));
+        long long c = 0;
+        BB_CUDA(cudaMemcpyAsync(&c, dcount, 8, cudaMemcpyDeviceToHost, h->stream));
+        BB_CUDA(cudaStreamSynchronize(h->stream));
+        found += c;
+    }
+    if (tmp) cudaFree(tmp);
+    cudaFree(dmap); cudaFree(dcount);
+    int rc;
+    if ((rc = dev_alloc(h, (void **)&h->sensor_cell, (size_t)found * 8, false))) return rc;
+    if ((rc = dev_alloc(h, (void **)&h->sensor_findex, (size_t)found * 8, false))) return rc;
+    if (found) {
+        sensor_finish_kernel<<<(unsigned)((found + 255) / 256), 256, 0, h->stream>>>(dsel, found, p, h->sensor_cell, h->sensor_findex);
+        BB_CUDA(cudaGetLastError());
+    }
+    if ((rc = dev_alloc(h, (void **)&h->sensor_out, (size_t)h->n_sensor_maps * h->nsamples * found * 4))) return rc;
+    BB_CUDA(cudaStreamSynchronize(h->stream));
+    cudaFree(dsel);
+    h->nsensors = found;
+    *nsensors = found;
+    return BB_OK;
+}
+
+extern "C" int bb_fdtd_get_sensor_index(bb_fdtd *h, void *out, int elem_bytes) {
+    BB_REQUIRE(h && out && (elem_bytes == 4 || elem_bytes == 8), "bad argument");
+    BB_REQUIRE(h->sensor_findex || h->nsensors == 0, "the sensor table was not built with bb_fdtd_set_sensor_map");
+    BB_CUDA(cudaSetDevice(h->d.device));
+    if (h->nsensors == 0) return BB_OK;
+    if (elem_bytes == 8) {
+        BB_CUDA(cudaMemcpyAsync(out, h->sensor_findex, (size_t)h->nsensors * 8, cudaMemcpyDeviceToHost, h->stream));
+    } else {
+        BB_REQUIRE((long long)h->p.n1 * h->p.n2 * h->p.n3 < (1ll << 32), "grid too large for 32-bit sensor indices");
+        uint32_t *tmp = nullptr;
+        BB_CUDA(cudaMalloc(&tmp, (size_t)h->nsensors * 4));
+        narrow_index_kernel<<<(unsigned)((h->nsensors + 255) / 256), 256, 0, h->stream>>>(h->sensor_findex, tmp, h->nsensors);
+        BB_CUDA(cudaGetLastError());
+        BB_CUDA(cudaMemcpyAsync(out, tmp, (size_t)h->nsensors * 4, cudaMemcpyDeviceToHost, h->stream));
+        BB_CUDA(cudaStreamSynchronize(h->stream));
+        cudaFree(tmp);
+    }
+    BB_CUDA(cudaStreamSynchronize(h->stream));
     return BB_OK;
 }
 

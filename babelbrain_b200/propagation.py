@@ -94,23 +94,27 @@ class FdtdSlab:
             return np.ascontiguousarray(O[i0 - org:i1 - org].reshape(-1)[flat], dtype=np.float32)
         ox, oy, oz = weights(Ox), weights(Oy), weights(Oz)
 
-        # ---- sensors: IndexSensorMap is the 1-based Fortran-order linear index (BASE.py:2503-2511)
-        # (with local volumes only this slab's part of the global table is known)
-        sl, sj, sk = np.nonzero(SensorMap[i0 - org:i1 - org])
-        findex = (sl.astype(np.int64) + i0) + sj.astype(np.int64) * N1 + sk.astype(np.int64) * N1 * N2
-        order = np.argsort(findex, kind='stable')
-        findex = findex[order]
-        scell = (((sl[order].astype(np.int64) + i0) * N2 + sj[order]) * N3 + sk[order]).astype(np.int64)
+        # ---- sensors: IndexSensorMap is the 1-based Fortran-order linear index (BASE.py:2503-2511).
+        # With one slab, or slab-local volumes, the table is built on the device from the SensorMap planes
+        # (bb_fdtd_set_sensor_map); only a multi-rank run fed with whole volumes needs the global table
+        # on the host to place its rows.
         idx_dtype = np.uint32 if N1 * N2 * N3 < 2 ** 32 else np.uint64
-        self.IndexSensorMapLocal = (findex + 1).astype(idx_dtype)
-        if origin is None and self.nranks > 1:
+        self._idx_dtype = idx_dtype
+        self._sensor_planes = None
+        if self.nranks > 1 and origin is None:
+            sl, sj, sk = np.nonzero(SensorMap[i0 - org:i1 - org])
+            findex = (sl.astype(np.int64) + i0) + sj.astype(np.int64) * N1 + sk.astype(np.int64) * N1 * N2
+            order = np.argsort(findex, kind='stable')
+            findex = findex[order]
+            scell = (((sl[order].astype(np.int64) + i0) * N2 + sj[order]) * N3 + sk[order]).astype(np.int64)
+            self.IndexSensorMapLocal = (findex + 1).astype(idx_dtype)
             fl = np.flatnonzero(SensorMap.reshape(-1, order='F'))
             self.IndexSensorMap = (fl + 1).astype(idx_dtype)
             self.sensor_rows = np.searchsorted(fl, findex)
+            self.nsensors_total = self.IndexSensorMap.size
         else:
-            self.IndexSensorMap = self.IndexSensorMapLocal
-            self.sensor_rows = np.arange(findex.size)
-        self.nsensors_total = self.IndexSensorMap.size
+            scell = None
+            self._sensor_planes = np.ascontiguousarray(SensorMap[i0 - org:i1 - org])
 
         _capi.require_gpu()
         L = _capi.lib()
@@ -143,10 +147,23 @@ class FdtdSlab:
         if cells.size:
             _capi.check(L.bb_fdtd_set_source_functions(hp, _capi.ptr(SF), int(SF.dtype == np.float64),
                                                        SF.strides[0] // SF.itemsize))
-        _capi.check(L.bb_fdtd_set_sensors(hp, scell.size, _capi.ptr(scell)))
-        self.h2d_bytes = int(mm.nbytes + (refl.nbytes if refl is not None else 0) + SF.nbytes * (cells.size > 0)
-                             + cells.nbytes + rows32.nbytes + 3 * ox.nbytes + scell.nbytes + t32.nbytes + pml.nbytes)
         self.d2h_bytes = 0
+        if scell is not None:
+            _capi.check(L.bb_fdtd_set_sensors(hp, scell.size, _capi.ptr(scell)))
+            sensor_bytes = scell.nbytes
+        else:
+            ns = ctypes.c_int64()
+            _capi.check(L.bb_fdtd_set_sensor_map(hp, _capi.ptr(self._sensor_planes), ctypes.byref(ns)))
+            sensor_bytes = self._sensor_planes.nbytes
+            self._sensor_planes = None
+            idx = _capi.pinned.empty((ns.value,), self._idx_dtype)
+            _capi.check(L.bb_fdtd_get_sensor_index(hp, _capi.ptr(idx), idx.itemsize))
+            self.d2h_bytes += idx.nbytes
+            self.IndexSensorMap = self.IndexSensorMapLocal = idx
+            self.sensor_rows = np.arange(ns.value)
+            self.nsensors_total = ns.value
+        self.h2d_bytes = int(mm.nbytes + (refl.nbytes if refl is not None else 0) + SF.nbytes * (cells.size > 0)
+                             + cells.nbytes + rows32.nbytes + 3 * ox.nbytes + sensor_bytes + t32.nbytes + pml.nbytes)
 
     # ------------------------------------------------------------------
     def comm_init(self, unique_id):
@@ -177,14 +194,14 @@ class FdtdSlab:
         """which: 0 RMS, 1 peak, 2 last field.  Returns / fills the (i1-i0, N2, N3) float32 slab."""
         N1, N2, N3 = self.shape
         if out is None:
-            out = np.empty((self.i1 - self.i0, N2, N3), np.float32)
+            out = _capi.pinned.empty((self.i1 - self.i0, N2, N3), np.float32)
         assert out.flags.c_contiguous and out.dtype == np.float32
         _capi.check(self._L.bb_fdtd_get_map(self._h, int(which), _capi.MAP_ID[name], _capi.ptr(out)))
         self.d2h_bytes += out.nbytes
         return out
 
     def get_sensors(self, name):
-        out = np.empty((self.sensor_rows.size, self.sample_steps.size), np.float32)
+        out = _capi.pinned.empty((self.sensor_rows.size, self.sample_steps.size), np.float32)
         _capi.check(self._L.bb_fdtd_get_sensors(self._h, _capi.MAP_ID[name], _capi.ptr(out)))
         self.d2h_bytes += out.nbytes
         return out
@@ -274,6 +291,8 @@ class PropagationModel:
         """Same call as the reference.  COMPUTING_BACKEND, DefaultGPUDeviceName, USE_SINGLE and the
         manual work-group sizes are accepted for compatibility; every backend value runs the
         sm_100a CUDA path in float32 (there is no multi-backend dispatch)."""
+        import time
+        t0 = time.perf_counter()
         if IntervalSnapshots > 0:
             raise NotImplementedError('IntervalSnapshots is not supported (BabelBrain never passes it)')
         if SPP_ZONES != 1:
@@ -291,9 +310,14 @@ class PropagationModel:
         if CheckOnlyParams:
             slab.close()
             return None
+        t1 = time.perf_counter()
         slab.run()
+        t2 = time.perf_counter()
         self.last_stats = slab.stats()
         Sensor, RMS, Peak, InputParam = collect_results(slab)
+        # host-side wall clock of the three phases of the call (seconds)
+        self.last_timing = {'setup_upload_s': t1 - t0, 'time_loop_s': t2 - t1, 'download_s': time.perf_counter() - t2,
+                            'h2d_bytes': slab.h2d_bytes, 'd2h_bytes': slab.d2h_bytes}
         last = _LastMap(slab)
         _live_lastmaps.append(last)
         if SelRMSorPeak == 3:

@@ -261,13 +261,15 @@ def main():
     # ---- end to end through the public API (host buffers in, numpy results out)
     e2e_ms = []
     h2d = d2h = 0
+    e2e_phases = None
     for n in range(2):
         barrier()
         t0 = time.perf_counter()
         if world == 1:
             PM = PropagationModel()
             res = PM.StaggeredFDTD_3D_with_relaxation(*w['args'], **w['kwargs'])
-            h2d, d2h = slab.h2d_bytes, sum(v.nbytes for v in res[2].values()) + res[0]['Pressure'].nbytes
+            h2d, d2h = PM.last_timing['h2d_bytes'], PM.last_timing['d2h_bytes']
+            e2e_phases = dict(PM.last_timing)
             del res
         else:
             s2 = FdtdSlab(*w['args'], device=local_rank, rank=rank, nranks=world, kernel_variant=args.variant,
@@ -314,7 +316,7 @@ def main():
                        'l2_policy': 'state (>1.2 GB per GPU) is far larger than the 126 MB L2 and is rewritten by reset() between timed simulations',
                        'kernel_variant': args.variant, 'cell_classes_rank0': cls},
             'e2e': {'value': e2e_val, 'unit': 'Gcell-updates/s', 'h2d_bytes_per_step': int(tb[0].item()), 'd2h_bytes_per_step': int(tb[1].item()),
-                    'ms_per_step': float(te.item())},
+                    'ms_per_step': float(te.item()), 'phases_rank0': e2e_phases},
             'gpu_launches': int(sum(s['stress_launches'] + s['particle_launches'] + s['pml_launches'] + s['other_launches'] for s in stats)),
             'clocks': clocks,
             'roofline': {'bound': 'hbm', 'kernel': 'stress_tma (fused stress half-step: interior + PML shell, RMS folded in)', 'achieved': achieved, 'peak': peak,

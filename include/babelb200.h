@@ -90,6 +90,11 @@ const char *bb_version(void);
 int bb_device_count(void);                                   /* <0 on error */
 int bb_device_name(int device, char *out, int out_len);
 
+/* page-locked host buffers for results (device-to-host copies into them run at link speed and skip
+ * the first-touch page faults of fresh pageable memory); freed with bb_host_free */
+int bb_host_alloc(int64_t bytes, void **out);
+int bb_host_free(void *ptr);
+
 /* ---- FDTD handle ---- */
 int bb_fdtd_create(const bb_fdtd_desc *desc, bb_fdtd **out);
 void bb_fdtd_destroy(bb_fdtd *h);
@@ -108,6 +113,13 @@ int bb_fdtd_set_source_cells(bb_fdtd *h, int64_t ncells, const int64_t *cell, co
 int bb_fdtd_set_source_functions(bb_fdtd *h, const void *data, int is_f64, int64_t row_stride);
 /* sensors owned by this slab: global C-order linear cell index, in IndexSensorMap order */
 int bb_fdtd_set_sensors(bb_fdtd *h, int64_t nsensors, const int64_t *cell);
+/* Alternative to bb_fdtd_set_sensors: build the sensor table on the device from the caller's
+ * SensorMap (BabelIntegrationBASE.py:2283-2290).  sensor_map = planes [i0,i1) of the (N1,N2,N3)
+ * C-order uint32 volume; every non-zero voxel becomes a sensor, ordered like IndexSensorMap
+ * (ascending 1-based Fortran-order linear index i + j*N1 + k*N1*N2 + 1, :2503-2511). */
+int bb_fdtd_set_sensor_map(bb_fdtd *h, const uint32_t *sensor_map, int64_t *nsensors);
+/* the 1-based Fortran-order indices of this slab's sensors, in table order; elem_bytes = 4 or 8 */
+int bb_fdtd_get_sensor_index(bb_fdtd *h, void *out, int elem_bytes);
 /* slab neighbours exchange halos with NCCL send/recv; id = 128-byte ncclUniqueId from rank 0 */
 int bb_nccl_unique_id(char *out128);
 int bb_fdtd_comm_init(bb_fdtd *h, const char *id128);
