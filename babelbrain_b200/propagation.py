@@ -117,6 +117,8 @@ class FdtdSlab:
             self._sensor_planes = np.ascontiguousarray(SensorMap[i0 - org:i1 - org])
 
         _capi.require_gpu()
+        if isinstance(device, tuple):       # (name substring, ordinal): resolved only now, after the argument checks
+            device = _select_device(*device)
         L = _capi.lib()
         self._L = L
         d = _capi.FdtdDesc(n1=N1, n2=N2, n3=N3, i0=i0, i1=i1, pml=int(NDelta), nmat=MP.shape[0],
@@ -306,7 +308,7 @@ class PropagationModel:
                         QCorrection=QCorrection, TypeSource=TypeSource, SelRMSorPeak=SelRMSorPeak,
                         SelMapsRMSPeakList=SelMapsRMSPeakList, SelMapsSensorsList=SelMapsSensorsList,
                         SensorSubSampling=SensorSubSampling, SensorStart=SensorStart, ReflectorMask=ReflectorMask,
-                        device=_select_device(DefaultGPUDeviceName, DefaultGPUDeviceNumber))
+                        device=(DefaultGPUDeviceName, DefaultGPUDeviceNumber))
         if CheckOnlyParams:
             slab.close()
             return None

@@ -40,6 +40,22 @@ class SlabPlan:
         return 3 * HALO * 2 * n2 * pitch * 4
 
 
+def halo_exchange_plan(rank, nranks, nown):
+    """The exchange libbabelb200.so performs after each half-step (fdtd.cu: halo_exchange), as a list of
+    (op, peer, first_local_plane, nplanes) over the local array of nown + 2*HALO planes: the first /
+    last HALO owned planes go to the lower / upper neighbour, whose copies land in this rank's halo
+    planes.  Three fields move per half-step: (Sxx, Sxy, Sxz) after the stress update -- the stresses
+    the particle update differentiates along i -- and (Vx, Vy, Vz) after the particle update."""
+    ops = []
+    if rank > 0:
+        ops.append(('send', rank - 1, HALO, HALO))
+        ops.append(('recv', rank - 1, 0, HALO))
+    if rank < nranks - 1:
+        ops.append(('send', rank + 1, nown, HALO))
+        ops.append(('recv', rank + 1, nown + HALO, HALO))
+    return ops
+
+
 def sensor_rows_of_slab(index_sensor_map, shape, i0, i1):
     """Rows of the global sensor table (IndexSensorMap order: 1-based Fortran linear index,
     BabelIntegrationBASE.py:2503-2511) whose voxel lies in planes [i0,i1)."""

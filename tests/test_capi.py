@@ -1,0 +1,94 @@
+"""The C-ABI library: it loads, exports every symbol include/babelb200.h declares, and fails loudly
+(no CPU fallback) when no CUDA device is present.  No compute call is made here."""
+import ctypes
+import os
+import re
+
+import numpy as np
+import pytest
+
+from babelbrain_b200 import _capi, build, workloads
+from babelbrain_b200.propagation import PropagationModel
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+
+
+@pytest.fixture(scope='module')
+def lib():
+    build.build()
+    return _capi.lib()
+
+
+def header_functions():
+    text = open(os.path.join(ROOT, 'include', 'babelb200.h')).read()
+    text = re.sub(r'/\*.*?\*/', '', text, flags=re.S)
+    return sorted(set(re.findall(r'\b(bb_[a-z0-9_]+)\s*\(', text)))
+
+
+def test_every_declared_symbol_is_exported(lib):
+    names = header_functions()
+    assert len(names) >= 20
+    for n in names:
+        assert hasattr(lib, n), 'include/babelb200.h declares %s but libbabelb200.so does not export it' % n
+    assert sorted(_capi.SYMBOLS) == names, 'babelbrain_b200/_capi.py SYMBOLS is out of sync with the header'
+
+
+def test_struct_layouts_match_the_header(lib):
+    # bb_fdtd_desc: 21 int32/uint32 fields, then a double (8-byte aligned)
+    assert ctypes.sizeof(_capi.FdtdDesc) == 96
+    assert _capi.FdtdDesc.dt.offset == 88
+    assert ctypes.sizeof(_capi.FdtdStats) == 5 * 8 + 8 * 8
+    assert lib.bb_version().decode().startswith('babelb200')
+
+
+def _no_gpu(lib):
+    return lib.bb_device_count() <= 0
+
+
+def test_no_cpu_fallback_without_a_device(lib):
+    if not _no_gpu(lib):
+        pytest.skip('a CUDA device is present')
+    d = _capi.FdtdDesc(n1=32, n2=32, n3=32, i0=0, i1=32, pml=4, nmat=1, nsrc=1, nt_src=1, steps=1, sel_rms_peak=1, sel_maps_rms=1 << 10,
+                       sel_maps_sensor=1 << 10, sensor_subsampling=1, device=0, rank=0, nranks=1, dt=1e-8)
+    h = ctypes.c_void_p()
+    rc = lib.bb_fdtd_create(ctypes.byref(d), ctypes.byref(h))
+    assert rc == 2 and lib.bb_last_error()                       # BB_ERR_CUDA with a message
+    out = np.zeros(2, np.float32)
+    one = np.ones(3, np.float32)
+    rc = lib.bb_rayleigh_forward(1.0, 0.0, 1, _capi.ptr(one), _capi.ptr(one), _capi.ptr(one), 1, _capi.ptr(one), _capi.ptr(out), -1.0, 0, 0, None)
+    assert rc == 2
+    w = workloads.make_workload('single_water', shape=(24, 24, 28), periods=1, pml=4)
+    with pytest.raises(_capi.BabelB200Error):
+        PropagationModel().StaggeredFDTD_3D_with_relaxation(*w['args'], **w['kwargs'])
+
+
+def test_argument_errors_come_before_the_device(lib):
+    """dtype / shape errors are the caller's and are raised as TypeError / ValueError like the reference does."""
+    w = workloads.make_workload('single_water', shape=(24, 24, 28), periods=1, pml=4)
+    PM = PropagationModel()
+    bad = list(w['args'])
+    bad[3] = bad[3].astype(np.int64)
+    with pytest.raises(TypeError):
+        PM.StaggeredFDTD_3D_with_relaxation(*bad, **w['kwargs'])
+    bad = list(w['args'])
+    bad[7] = bad[7][:-1]
+    with pytest.raises(ValueError):
+        PM.StaggeredFDTD_3D_with_relaxation(*bad, **w['kwargs'])
+    bad = list(w['args'])
+    bad[0] = bad[0] + 3
+    with pytest.raises(ValueError):
+        PM.StaggeredFDTD_3D_with_relaxation(*bad, **w['kwargs'])
+    with pytest.raises(ValueError):
+        PM.StaggeredFDTD_3D_with_relaxation(*w['args'], **dict(w['kwargs'], DT=1.0))
+    with pytest.raises(NotImplementedError):
+        PM.StaggeredFDTD_3D_with_relaxation(*w['args'], **dict(w['kwargs'], IntervalSnapshots=10))
+
+
+def test_drop_in_import_surface():
+    """The names BabelBrain imports from BabelViscoFDTD resolve to this package."""
+    from BabelViscoFDTD.PropagationModel import PropagationModel as PM2
+    from BabelViscoFDTD.tools.RayleighAndBHTE import ForwardSimple, InitCuda, InitOpenCL, InitMetal, SpeedofSoundWater  # noqa: F401
+    from BabelViscoFDTD.H5pySimple import ReadFromH5py, SaveToH5py  # noqa: F401
+    import BabelViscoFDTD.StaggeredFDTD_3D_With_Relaxation_CUDA as C
+    assert PM2 is PropagationModel and callable(C.ListDevices)
+    assert 1480 < SpeedofSoundWater(20.0) < 1485

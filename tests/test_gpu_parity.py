@@ -164,3 +164,79 @@ def test_properties_linearity_and_variants_large():
     ww = workloads.make_workload('single_water', shape=(96, 96, 128), periods=8)
     (S4, R4, _, _), l4 = run_cuda(ww, 0, SelMapsRMSPeakList=['Pressure', 'Sigmaxx'])
     assert rl2(R4['Pressure'], R4['Sigmaxx']) <= 1e-5
+
+
+@pytest.mark.parametrize('name', ['water_focus', 'skull_plane', 'skull_allmaps', 'dome_stress'])
+def test_against_committed_golden_vectors(name):
+    """The CUDA path against tests/golden/*.npz (float64 oracle outputs, see make_golden.py)."""
+    import os
+    from tests.golden import make_golden
+    g = np.load(os.path.join(os.path.dirname(os.path.abspath(__file__)), 'golden', name + '.npz'))
+    w = make_golden.build_case(name)
+    assert str(g['digest']) == make_golden.inputs_digest(w)
+    (Sensor, RMS, Peak, IP), last = run_cuda(w, 0)
+    assert np.array_equal(IP['IndexSensorMap'], g['IndexSensorMap'])       # bit-exact index map
+    assert IP['IndexSensorMap'].dtype == g['IndexSensorMap'].dtype
+    for key in g.files:
+        kind, _, mapname = key.partition('_')
+        got = {'RMS': RMS, 'Peak': Peak, 'Sensor': Sensor}.get(kind)
+        if got is None or mapname not in got:
+            continue
+        assert rl2(got[mapname], g[key]) <= TOL, (key, rl2(got[mapname], g[key]))
+    main = RMS if 'Pressure' in RMS else Peak
+    assert same_peak(main['Pressure'], g['RMS_Pressure'] if 'RMS_Pressure' in g.files else g['Peak_Pressure'])
+
+
+def test_device_sensor_table_matches_numpy_order():
+    """bb_fdtd_set_sensor_map: irregular sensor masks give the IndexSensorMap the reference would
+    (ascending 1-based Fortran-order index), bit-exact, and rows in that order."""
+    w = workloads.make_workload('single_water', shape=(40, 36, 44), periods=2, pml=6)
+    rng = np.random.default_rng(11)
+    sen = (rng.random(w['args'][0].shape) < 0.07).astype(np.uint32)
+    sen[:6] = 0; sen[-6:] = 0; sen[:, :6] = 0; sen[:, -6:] = 0; sen[:, :, :7] = 0; sen[:, :, -6:] = 0
+    args = w['args'][:7] + (sen,)
+    w2 = dict(args=args, kwargs=w['kwargs'])
+    (Sensor, RMS, Peak, IP), _ = run_cuda(w2, 0)
+    ref = run_oracle(w2)
+    expect = (np.flatnonzero(sen.reshape(-1, order='F')) + 1).astype(np.uint32)
+    assert np.array_equal(IP['IndexSensorMap'], expect) and np.array_equal(ref['IndexSensorMap'], expect)
+    assert rl2(Sensor['Pressure'], ref['Sensor']['Pressure']) <= TOL
+
+
+def test_two_gpu_slabs_match_single_gpu():
+    """Slab decomposition with NCCL halo exchange (two handles on two devices, one thread each) against
+    the single-GPU run of the same inputs.  Skipped on a one-GPU box."""
+    import threading
+    from babelbrain_b200 import _capi
+    from babelbrain_b200.slab import SlabPlan, assemble_maps
+    if _capi.device_count() < 2:
+        pytest.skip('needs two GPUs')
+    w = workloads.make_workload('ctx500_skull', shape=(64, 56, 72), periods=5, pml=8)
+    kw = {k: v for k, v in w['kwargs'].items() if k not in DROP}
+    (S1, R1, _, IP1), _ = run_cuda(w, 0)
+    uid = FdtdSlab.nccl_unique_id()
+    out, err = [None, None], []
+
+    def rank_main(r):
+        try:
+            s = FdtdSlab(*w['args'], device=r, rank=r, nranks=2, **kw)
+            s.comm_init(uid)
+            s.run()
+            out[r] = (s.get_map(0, 'Pressure'), s.get_sensors('Pressure'), s.sensor_rows, s.IndexSensorMap)
+            s.close()
+        except Exception as e:   # noqa: BLE001
+            err.append(e)
+    th = [threading.Thread(target=rank_main, args=(r,)) for r in range(2)]
+    for t in th:
+        t.start()
+    for t in th:
+        t.join(timeout=300)
+    assert not err, err
+    plan = SlabPlan(64, 2, 8)
+    full = assemble_maps((64, 56, 72), plan, [out[0][0], out[1][0]])
+    assert rl2(full, R1['Pressure']) <= 1e-6                                # same kernels, same order of operations
+    assert np.array_equal(out[0][3], IP1['IndexSensorMap'])
+    sens = np.zeros_like(S1['Pressure'])
+    for r in range(2):
+        sens[out[r][2]] = out[r][1]
+    assert rl2(sens, S1['Pressure']) <= 1e-6

@@ -1,0 +1,106 @@
+"""Slab decomposition (babelbrain_b200/slab.py): host logic of the multi-GPU path.  The exchange
+protocol the CUDA library follows (halo_exchange_plan) is executed here by two gloo ranks on CPU with
+a stand-in update that has the solver's reach along i (two planes one way, one the other, alternating
+like the stress / particle half-steps) and compared with the undecomposed result."""
+import os
+import socket
+
+import numpy as np
+import pytest
+import torch
+import torch.distributed as dist
+import torch.multiprocessing as mp
+
+from babelbrain_b200.slab import HALO, SlabPlan, assemble_maps, assemble_sensors, halo_exchange_plan, sensor_rows_of_slab
+
+
+def test_plan_covers_the_grid():
+    for n1, nr in ((240, 1), (240, 2), (1080, 8), (601, 4), (33, 8)):
+        p = SlabPlan(n1, nr)
+        assert p.owned(0)[0] == 0 and p.owned(nr - 1)[1] == n1
+        sizes = [p.owned(r)[1] - p.owned(r)[0] for r in range(nr)]
+        assert sum(sizes) == n1 and max(sizes) - min(sizes) <= 1
+        for r in range(nr):
+            lo, hi = p.with_halo(r)
+            assert lo == max(p.owned(r)[0] - HALO, 0) and hi == min(p.owned(r)[1] + HALO, n1)
+            assert p.neighbours(r) == (r - 1 if r else None, r + 1 if r < nr - 1 else None)
+            for i in range(*p.owned(r)):
+                assert p.rank_of_plane(i) == r
+    with pytest.raises(ValueError):
+        SlabPlan(12, 8)
+    assert SlabPlan(1080, 8).halo_bytes_per_half_step(1080, 1088) == 3 * 2 * 2 * 1080 * 1088 * 4
+
+
+def test_sensor_rows_and_assembly():
+    rng = np.random.default_rng(0)
+    shape = (20, 6, 7)
+    sm = rng.random(shape) < 0.3
+    index = (np.flatnonzero(sm.reshape(-1, order='F')) + 1).astype(np.uint32)     # IndexSensorMap convention
+    plan = SlabPlan(shape[0], 3)
+    rows = [sensor_rows_of_slab(index, shape, *plan.owned(r)) for r in range(3)]
+    assert sorted(np.concatenate(rows).tolist()) == list(range(index.size))
+    data = rng.random((index.size, 4)).astype(np.float32)
+    out = assemble_sensors(index.size, 4, rows, [data[r] for r in rows])
+    assert np.array_equal(out, data)
+    vol = rng.random(shape).astype(np.float32)
+    assert np.array_equal(assemble_maps(shape, plan, [vol[slice(*plan.owned(r))] for r in range(3)]), vol)
+
+
+def _step(a, forward):
+    """stand-in half-step along axis 0 with the 4-point staggered reach (zero outside)"""
+    p = np.pad(a, ((2, 2), (0, 0)))
+    if forward:   # f(i+1) - f(i) and f(i+2) - f(i-1)
+        return a + 0.1 * (1.125 * (p[3:-1] - p[2:-2]) - (p[4:] - p[1:-3]) / 24)
+    return a + 0.1 * (1.125 * (p[2:-2] - p[1:-3]) - (p[3:-1] - p[:-4]) / 24)
+
+
+def _worker(rank, world, port, n1, width, nsteps, q):
+    os.environ.update(MASTER_ADDR='127.0.0.1', MASTER_PORT=str(port))
+    dist.init_process_group('gloo', rank=rank, world_size=world)
+    plan = SlabPlan(n1, world)
+    i0, i1 = plan.owned(rank)
+    nown = i1 - i0
+    full = np.random.default_rng(7).random((n1, width))
+    loc = np.zeros((nown + 2 * HALO, width))
+    lo, hi = plan.with_halo(rank)
+    loc[HALO - (i0 - lo):HALO + nown + (hi - i1)] = full[lo:hi]              # owned planes + the halos that exist
+    for n in range(nsteps):
+        new = _step(loc, forward=bool(n & 1))
+        loc[HALO:HALO + nown] = new[HALO:HALO + nown]                        # only owned planes are updated
+        reqs, bufs = [], []
+        for op, peer, first, cnt in halo_exchange_plan(rank, world, nown):
+            if op == 'send':
+                reqs.append(dist.isend(torch.from_numpy(loc[first:first + cnt].copy()), peer))
+            else:
+                t = torch.empty((cnt, width), dtype=torch.float64)
+                bufs.append((first, cnt, t))
+                reqs.append(dist.irecv(t, peer))
+        for r in reqs:
+            r.wait()
+        for first, cnt, t in bufs:
+            loc[first:first + cnt] = t.numpy()
+    gathered = [None] * world
+    dist.all_gather_object(gathered, loc[HALO:HALO + nown])
+    if rank == 0:
+        q.put(assemble_maps((n1, width), plan, gathered).astype(np.float64))
+    dist.destroy_process_group()
+
+
+def test_two_rank_halo_protocol_matches_single_domain():
+    n1, width, nsteps, world = 23, 5, 12, 2
+    with socket.socket() as s:
+        s.bind(('127.0.0.1', 0))
+        port = s.getsockname()[1]
+    ctx = mp.get_context('spawn')
+    q = ctx.Queue()
+    procs = [ctx.Process(target=_worker, args=(r, world, port, n1, width, nsteps, q)) for r in range(world)]
+    for p in procs:
+        p.start()
+    got = q.get(timeout=120)
+    for p in procs:
+        p.join(timeout=60)
+        assert p.exitcode == 0
+    ref = np.random.default_rng(7).random((n1, width))
+    for n in range(nsteps):
+        ref = _step(ref, forward=bool(n & 1))
+    assert np.allclose(got, ref, rtol=0, atol=1e-6)   # assemble_maps returns float32 volumes
