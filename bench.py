@@ -167,6 +167,11 @@ def cpu_baseline(sample_steps=None, threads=None):
             'sample': '%s: first %d of %d time steps (%.1f s), C/OpenMP float32 oracle port' % (WORKLOAD, sample_steps, w['meta']['steps'], el)}, w['meta']
 
 
+def workload_name(meta, world):
+    return ('CTX-500 annular array 500 kHz, synthetic skull+brain label map PPW 6, %dx%dx%d, %d time steps per simulation (BASELINE configs[1]%s)'
+            % (tuple(meta['shape']) + (meta['steps'], '' if world == 1 else '; %d slabs of 240 planes, weak scaling' % world)))
+
+
 def run_reference(args):
     rank = int(os.environ.get('RANK', 0))
     if rank != 0:
@@ -183,7 +188,8 @@ def run_reference(args):
     out = {'impl': 'reference', 'metric': 'FDTD Gcell-updates/s', 'value': v, 'unit': 'Gcell-updates/s',
            'n_gpus': args.gpus, 'steps': args.steps, 'warmup': args.warmup, 'ms_per_step': ms, 'higher_is_better': True,
            'scaling': 'weak', 'vs_baseline': None, 'dtype': 'f32', 'data': 'synthetic',
-           'config': {'workload': 'CTX-500 500 kHz PPW6 240x240x320 skull+brain, 12-time-step sample per step'},
+           'config': {'workload': workload_name(meta, 1), 'cells': meta['cells'], 'time_steps': meta['steps'],
+                      'sample': 'each step times the first 12 of the %d time steps of the simulation on the host cores' % meta['steps']},
            'cpu_baseline': cb, 'e2e': {'value': v, 'unit': 'Gcell-updates/s', 'h2d_bytes_per_step': 0, 'd2h_bytes_per_step': 0}}
     print(json.dumps(out))
 
@@ -310,8 +316,7 @@ def main():
             'metric': 'FDTD Gcell-updates/s', 'value': value, 'unit': 'Gcell-updates/s', 'n_gpus': world,
             'steps': args.steps, 'warmup': args.warmup, 'ms_per_step': ms_per_step, 'higher_is_better': True,
             'scaling': 'weak', 'vs_baseline': None, 'dtype': 'f32', 'data': 'synthetic',
-            'config': {'workload': 'CTX-500 annular array 500 kHz, synthetic skull+brain label map PPW 6, %dx%dx%d, %d time steps per simulation (BASELINE configs[1]%s)'
-                                   % (meta['shape'] + (meta['steps'], '' if world == 1 else '; %d slabs of 240 planes, weak scaling' % world)),
+            'config': {'workload': workload_name(meta, world),
                        'cells': meta['cells'], 'time_steps': meta['steps'], 'seconds_per_simulation': ms_per_step * 1e-3,
                        'l2_policy': 'state (>1.2 GB per GPU) is far larger than the 126 MB L2 and is rewritten by reset() between timed simulations',
                        'kernel_variant': args.variant, 'cell_classes_rank0': cls},
