@@ -11,7 +11,7 @@
 #include "fdtd_tma.cuh"
 #include "nccl_dyn.h"
 #include <cub/device/device_select.cuh>
-#include <cub/iterator/counting_input_iterator.cuh>
+#include <thrust/iterator/counting_iterator.h>
 
 static thread_local char g_err[1024] = "";
 void bb_set_error(const char *fmt, ...) {
@@ -532,7 +532,7 @@ extern "C" int bb_fdtd_set_sensor_map(bb_fdtd *h, const uint32_t *sensor_map, in
     size_t tmp_bytes = 0;
     for (long long t0 = 0; t0 < total; t0 += piece) {
         const int n = (int)std::min(piece, total - t0);
-        cub::CountingInputIterator<long long> first(t0);
+        thrust::counting_iterator<long long> first(t0);
         size_t need = 0;
         BB_CUDA(cub::DeviceSelect::If(nullptr, need, first, dsel + found, dcount, n, pred, h->stream));
         if (need > tmp_bytes) { if (tmp) cudaFree(tmp); BB_CUDA(cudaMalloc(&tmp, need)); tmp_bytes = need; }

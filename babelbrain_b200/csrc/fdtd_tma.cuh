@@ -70,11 +70,11 @@ __device__ __forceinline__ void mbar_wait(uint32_t bar, uint32_t parity) {
     while (!mbar_try_wait(bar, parity)) { if (++spins > (1u << 26)) __trap(); }
 }
 __device__ __forceinline__ void tma_load_3d(uint32_t dst, const CUtensorMap *map, uint32_t bar, int c0, int c1, int c2) {
-    asm volatile("cp.async.bulk.tensor.3d.shared::cluster.global.tile.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4, %5}], [%2];"
+    asm volatile("cp.async.bulk.tensor.3d.shared::cta.global.tile.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4, %5}], [%2];"
                  ::"r"(dst), "l"(reinterpret_cast<uint64_t>(map)), "r"(bar), "r"(c0), "r"(c1), "r"(c2) : "memory");
 }
 __device__ __forceinline__ void tma_load_4d(uint32_t dst, const CUtensorMap *map, uint32_t bar, int c0, int c1, int c2, int c3) {
-    asm volatile("cp.async.bulk.tensor.4d.shared::cluster.global.tile.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4, %5, %6}], [%2];"
+    asm volatile("cp.async.bulk.tensor.4d.shared::cta.global.tile.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4, %5, %6}], [%2];"
                  ::"r"(dst), "l"(reinterpret_cast<uint64_t>(map)), "r"(bar), "r"(c0), "r"(c1), "r"(c2), "r"(c3) : "memory");
 }
 __device__ __forceinline__ void mbar_arrive(uint32_t bar) {
@@ -290,34 +290,43 @@ __global__ void __launch_bounds__(NTB, 1) stress_tma(const __grid_constant__ Str
     unsigned qz = ((unsigned)(ic0 - p.i0) * p.n2 + min(j, p.n2 - 1)) * p.zpw + (k < p.P ? kz : p.zbw + kz);
     const int zsrc = ((k < p.P ? zlo_off : zhi_off) >> 2) + ty * p.zbw + (kd ? kz : 0);   // float offset inside a point stage
 
-    auto hbox = [&](int slot, int c) { return reinterpret_cast<const float *>(sm + offH + slot * ST_HSTAGE + c * HBOX_STRIDE); };
-    auto lbox = [&](int slot) { return reinterpret_cast<const LT *>(sm + offH + slot * ST_HSTAGE + 3 * HBOX_STRIDE); };
-    int hs = 0, hs1 = 1;                    // halo slots of planes it, it+1
-    RingPos h2(nsh, 2, 0), pp(nsp, 0, 0);   // halo slot of plane it+2 / point slot of plane it (waited on inside the loop)
+    // per-thread pointers to this thread's own cell in slot 0 of each ring (kept in registers: everything inside
+    // the loop is one of these plus a running byte offset)
+    const char *hsc = reinterpret_cast<const char *>(sm + offH) + sc * 4;                        // halo boxes
+    const char *lsc = reinterpret_cast<const char *>(sm + offH + 3 * HBOX_STRIDE) + lc * sizeof(LT);   // label box
+    const char *psc = reinterpret_cast<const char *>(sm + offP) + pc * 4;                        // point boxes
+    const char *pzs = reinterpret_cast<const char *>(sm + offP) + zsrc * 4;                      // Z part region
+    auto hbox = [&](int off, int c) { return reinterpret_cast<const float *>(hsc + off + c * HBOX_STRIDE); };
+    auto lbox = [&](int off) { return reinterpret_cast<const LT *>(lsc + off); };
+    // ring state as byte offsets / barrier addresses (no multiplies in the loop): halo slots of planes it, it+1,
+    // it+2 (the one waited on inside the loop) and the point slot of plane it
+    int ho = 0, ho1 = ST_HSTAGE, ho2 = 2 * ST_HSTAGE, po = 0;
+    uint32_t hb0 = fullH, hb1 = fullH + 8, hb2 = fullH + 16, pbar = fullP;
+    unsigned hpar = 0, ppar = 0;
+    const int hend = nsh * ST_HSTAGE, pend = nsp * pstage;
 
     // planes ic0 and ic0+1 feed the queue before the loop
     mbar_wait(fullH, 0);
-    vx_p1 = hbox(0, 0)[sc]; vy_p1 = hbox(0, 1)[sc]; vz_p1 = hbox(0, 2)[sc];
+    vx_p1 = hbox(0, 0)[0]; vy_p1 = hbox(0, 1)[0]; vz_p1 = hbox(0, 2)[0];
     mbar_wait(fullH + 8, 0);
-    vy_p2 = hbox(1, 1)[sc]; vz_p2 = hbox(1, 2)[sc];
+    vy_p2 = hbox(ST_HSTAGE, 1)[0]; vz_p2 = hbox(ST_HSTAGE, 2)[0];
 
     for (int it = 0; it < np; it++, q += s1, qy += qy_stride, qz += qz_stride) {
         const int i = ic0 + it;
         const unsigned f = sF[it];
-        const int hs2 = h2.slot, ps = pp.slot;
-        mbar_wait(fullH + hs2 * 8, h2.par);
+        mbar_wait(hb2, hpar);
         // ---------------- shift the queue: plane i becomes the centre
-        vx_m2 = vx_m1; vx_m1 = vx_0; vx_0 = vx_p1; vx_p1 = hbox(hs1, 0)[sc];
-        vy_m1 = vy_0; vy_0 = vy_p1; vy_p1 = vy_p2; vy_p2 = hbox(hs2, 1)[sc];
-        vz_m1 = vz_0; vz_0 = vz_p1; vz_p1 = vz_p2; vz_p2 = hbox(hs2, 2)[sc];
-        mbar_wait(fullP + ps * 8, pp.par);
+        vx_m2 = vx_m1; vx_m1 = vx_0; vx_0 = vx_p1; vx_p1 = hbox(ho1, 0)[0];
+        vy_m1 = vy_0; vy_0 = vy_p1; vy_p1 = vy_p2; vy_p2 = hbox(ho2, 1)[0];
+        vz_m1 = vz_0; vz_0 = vz_p1; vz_p1 = vz_p2; vz_p2 = hbox(ho2, 2)[0];
+        mbar_wait(pbar, ppar);
         const bool xd = in_pml1(i, p.n1, p.P);
         const bool cellpml = xd || jkd;
         if (active && (!cellpml || (jkupd && i < p.n1 - 1))) {
-            const float *bx = hbox(hs, 0), *by = hbox(hs, 1), *bz = hbox(hs, 2);
-            const LT *l0p = lbox(hs), *l1p = lbox(hs1);
-            const float *pb = reinterpret_cast<const float *>(sm + offP + ps * pstage) + pc;
-            const unsigned l0 = l0p[lc];
+            const float *bx = hbox(ho, 0), *by = hbox(ho, 1), *bz = hbox(ho, 2);
+            const LT *l0p = lbox(ho), *l1p = lbox(ho1);
+            const float *pb = reinterpret_cast<const float *>(psc + po);
+            const unsigned l0 = l0p[0];
             const bool refl = (l0 & LabelTraits<LT>::REFL) != 0;
             MatCoef c;
             if (SMC) c = sC[l0 & MSK]; else c = load_coef_global(p.coef, l0 & MSK);
@@ -325,33 +334,33 @@ __global__ void __launch_bounds__(NTB, 1) stress_tma(const __grid_constant__ Str
             float D[9];
             if (!(jkedge || i <= 1 || i >= p.n1 - 2)) {
                 D[0] = D4(vx_0, vx_m1, vx_p1, vx_m2);
-                D[1] = D4(by[sc], by[sc - SW], by[sc + SW], by[sc - 2 * SW]);
-                D[2] = D4(bz[sc], bz[sc - 1], bz[sc + 1], bz[sc - 2]);
+                D[1] = D4(by[0], by[-SW], by[SW], by[-2 * SW]);
+                D[2] = D4(bz[0], bz[-1], bz[1], bz[-2]);
                 if (f & TF_SOLID) {
                     D[3] = D4(vy_p1, vy_0, vy_p2, vy_m1);
-                    D[4] = D4(bx[sc + SW], bx[sc], bx[sc + 2 * SW], bx[sc - SW]);
+                    D[4] = D4(bx[SW], bx[0], bx[2 * SW], bx[-SW]);
                     D[5] = D4(vz_p1, vz_0, vz_p2, vz_m1);
-                    D[6] = D4(bx[sc + 1], bx[sc], bx[sc + 2], bx[sc - 1]);
-                    D[7] = D4(bz[sc + SW], bz[sc], bz[sc + 2 * SW], bz[sc - SW]);
-                    D[8] = D4(by[sc + 1], by[sc], by[sc + 2], by[sc - 1]);
+                    D[6] = D4(bx[1], bx[0], bx[2], bx[-1]);
+                    D[7] = D4(bz[SW], bz[0], bz[2 * SW], bz[-SW]);
+                    D[8] = D4(by[1], by[0], by[2], by[-1]);
                 } else { D[3] = D[4] = D[5] = D[6] = D[7] = D[8] = 0.f; }
             } else {   // cells next to a face of the domain: edge-aware coefficients
                 const AxisCoef ci = load_axis(p.axI, i), cj = sJ[ty], ck = sK[tx];
                 D[0] = D4C(ci.cab, ci.cbb, vx_0, vx_m1, vx_p1, vx_m2);
-                D[1] = D4C(cj.cab, cj.cbb, by[sc], by[sc - SW], by[sc + SW], by[sc - 2 * SW]);
-                D[2] = D4C(ck.cab, ck.cbb, bz[sc], bz[sc - 1], bz[sc + 1], bz[sc - 2]);
+                D[1] = D4C(cj.cab, cj.cbb, by[0], by[-SW], by[SW], by[-2 * SW]);
+                D[2] = D4C(ck.cab, ck.cbb, bz[0], bz[-1], bz[1], bz[-2]);
                 D[3] = D4C(ci.caf, ci.cbf, vy_p1, vy_0, vy_p2, vy_m1);
-                D[4] = D4C(cj.caf, cj.cbf, bx[sc + SW], bx[sc], bx[sc + 2 * SW], bx[sc - SW]);
+                D[4] = D4C(cj.caf, cj.cbf, bx[SW], bx[0], bx[2 * SW], bx[-SW]);
                 D[5] = D4C(ci.caf, ci.cbf, vz_p1, vz_0, vz_p2, vz_m1);
-                D[6] = D4C(ck.caf, ck.cbf, bx[sc + 1], bx[sc], bx[sc + 2], bx[sc - 1]);
-                D[7] = D4C(cj.caf, cj.cbf, bz[sc + SW], bz[sc], bz[sc + 2 * SW], bz[sc - SW]);
-                D[8] = D4C(ck.caf, ck.cbf, by[sc + 1], by[sc], by[sc + 2], by[sc - 1]);
+                D[6] = D4C(ck.caf, ck.cbf, bx[1], bx[0], bx[2], bx[-1]);
+                D[7] = D4C(cj.caf, cj.cbf, bz[SW], bz[0], bz[2 * SW], bz[-SW]);
+                D[8] = D4C(ck.caf, ck.cbf, by[1], by[0], by[2], by[-1]);
             }
             // ---------------- edge rigidities (only where something is solid)
             float rigxy = 0.f, rigxz = 0.f, rigyz = 0.f, texy = 0.f, texz = 0.f, teyz = 0.f;
             if (f & TF_SOLID) {
-                const unsigned mi = l1p[lc] & MSK, mj = l0p[lc + LW] & MSK, mk = l0p[lc + 1] & MSK;
-                const unsigned mij = l1p[lc + LW] & MSK, mik = l1p[lc + 1] & MSK, mjk = l0p[lc + LW + 1] & MSK;
+                const unsigned mi = l1p[0] & MSK, mj = l0p[LW] & MSK, mk = l0p[1] & MSK;
+                const unsigned mij = l1p[LW] & MSK, mik = l1p[1] & MSK, mjk = l0p[LW + 1] & MSK;
                 float igi, igj, igk, igij, igik, igjk, ti, tj, tk, tij, tik, tjk;
                 if (SMC) {
                     igi = sC[mi].invG; igj = sC[mj].invG; igk = sC[mk].invG; igij = sC[mij].invG; igik = sC[mik].invG; igjk = sC[mjk].invG;
@@ -383,7 +392,7 @@ __global__ void __launch_bounds__(NTB, 1) stress_tma(const __grid_constant__ Str
                 pcell.aI = ci.aI; pcell.bI = ci.bI; pcell.aIh = ci.aH; pcell.bIh = ci.bH;
                 pcell.aJ = cj.aI; pcell.bJ = cj.bI; pcell.aJh = cj.aH; pcell.bJh = cj.bH;
                 pcell.aK = ck.aI; pcell.bK = ck.bI; pcell.aKh = ck.aH; pcell.bKh = ck.bH;
-                stress_pml<true>(p, pcell, c.M, c.L, rigxy, rigxz, rigyz, D, s, pb + PB_RXX * NT, pb + (yoff >> 2), pb - pc + zsrc, NT, zcomp);
+                stress_pml<true>(p, pcell, c.M, c.L, rigxy, rigxz, rigyz, D, s, pb + PB_RXX * NT, pb + (yoff >> 2), reinterpret_cast<const float *>(pzs + po), NT, zcomp);
                 if (refl) { s[0] = s[1] = s[2] = s[3] = s[4] = s[5] = 0.f; }
                 p.S[0][q] = s[0]; p.S[1][q] = s[1]; p.S[2][q] = s[2];
                 if (f & TF_SOLID) { p.S[3][q] = s[3]; p.S[4][q] = s[4]; p.S[5][q] = s[5]; }
@@ -433,10 +442,12 @@ __global__ void __launch_bounds__(NTB, 1) stress_tma(const __grid_constant__ Str
         }
         // ---------------- this warp is done with the slots of plane i
         __syncwarp();
-        if (lane == 0) { mbar_arrive(emptyH + hs * 8); mbar_arrive(emptyP + ps * 8); }
-        hs = hs1; hs1 = hs2;
-        h2.advance();
-        pp.advance();
+        if (lane == 0) { mbar_arrive(hb0 + MAX_NSH * 8); mbar_arrive(pbar + MAX_NSP * 8); }
+        ho = ho1; hb0 = hb1; ho1 = ho2; hb1 = hb2;
+        ho2 += ST_HSTAGE; hb2 += 8;
+        if (ho2 == hend) { ho2 = 0; hb2 = fullH; hpar ^= 1u; }
+        po += pstage; pbar += 8;
+        if (po == pend) { po = 0; pbar = fullP; ppar ^= 1u; }
     }
 }
 
@@ -563,39 +574,47 @@ __global__ void __launch_bounds__(NTB, 1) particle_tma(const __grid_constant__ P
     unsigned qz = ((unsigned)(ic0 - p.i0) * p.n2 + min(j, p.n2 - 1)) * p.zpw + (k < p.P ? kz : p.zbw + kz);
     const int zsrc = ((k < p.P ? zlo_off : zhi_off) >> 2) + ty * p.zbw + (kd ? kz : 0);   // float offset inside a point stage
 
-    auto hbox = [&](int slot, int c) { return reinterpret_cast<const float *>(sm + offH + slot * PT_HSTAGE + c * HBOX_STRIDE); };
-    auto xxbox = [&](int slot) { return reinterpret_cast<const float *>(sm + offH + slot * PT_HSTAGE + 5 * HBOX_STRIDE); };
-    auto lbox = [&](int slot) { return reinterpret_cast<const LT *>(sm + offH + slot * PT_HSTAGE + 5 * HBOX_STRIDE + PBOX); };
-    int hs = 0, hs1 = 1;                    // halo slots of planes it, it+1
-    RingPos h2(nsh, 2, 0), pp(nsp, 0, 0);   // halo slot of plane it+2 / point slot of plane it (waited on inside the loop)
+    const char *hsc = reinterpret_cast<const char *>(sm + offH) + sc * 4;                                    // halo boxes
+    const char *xsc = reinterpret_cast<const char *>(sm + offH + 5 * HBOX_STRIDE) + pc * 4;                  // Sxx point box
+    const char *lsc = reinterpret_cast<const char *>(sm + offH + 5 * HBOX_STRIDE + PBOX) + lc * sizeof(LT);  // label box
+    const char *psc = reinterpret_cast<const char *>(sm + offP) + pc * 4;                                    // point boxes
+    const char *pzs = reinterpret_cast<const char *>(sm + offP) + zsrc * 4;                                  // Z part region
+    auto hbox = [&](int off, int c) { return reinterpret_cast<const float *>(hsc + off + c * HBOX_STRIDE); };
+    auto xxbox = [&](int off) { return reinterpret_cast<const float *>(xsc + off); };
+    auto lbox = [&](int off) { return reinterpret_cast<const LT *>(lsc + off); };
+    // ring state as byte offsets / barrier addresses (no multiplies in the loop): halo slots of planes it, it+1,
+    // it+2 (the one waited on inside the loop) and the point slot of plane it
+    int ho = 0, ho1 = PT_HSTAGE, ho2 = 2 * PT_HSTAGE, po = 0;
+    uint32_t hb0 = fullH, hb1 = fullH + 8, hb2 = fullH + 16, pbar = fullP;
+    unsigned hpar = 0, ppar = 0;
+    const int hend = nsh * PT_HSTAGE, pend = nsp * pstage;
 
     mbar_wait(fullH, 0);
-    xx_p1 = xxbox(0)[pc];
-    if (sF[0] & TF_SHEAR) { xy_p1 = hbox(0, HB_SXY)[sc]; xz_p1 = hbox(0, HB_SXZ)[sc]; }
+    xx_p1 = xxbox(0)[0];
+    if (sF[0] & TF_SHEAR) { xy_p1 = hbox(0, HB_SXY)[0]; xz_p1 = hbox(0, HB_SXZ)[0]; }
     mbar_wait(fullH + 8, 0);
-    xx_p2 = xxbox(1)[pc];
+    xx_p2 = xxbox(PT_HSTAGE)[0];
 
     for (int it = 0; it < np; it++, q += s1, qy += qy_stride, qz += qz_stride) {
         const int i = ic0 + it;
         const unsigned f = sF[it];
         const bool fsh = f & TF_SHEAR;
-        const int hs2 = h2.slot, ps = pp.slot;
-        mbar_wait(fullH + hs2 * 8, h2.par);
-        xx_m1 = xx_0; xx_0 = xx_p1; xx_p1 = xx_p2; xx_p2 = xxbox(hs2)[pc];
+        mbar_wait(hb2, hpar);
+        xx_m1 = xx_0; xx_0 = xx_p1; xx_p1 = xx_p2; xx_p2 = xxbox(ho2)[0];
         xy_m2 = xy_m1; xy_m1 = xy_0; xy_0 = xy_p1;
         xz_m2 = xz_m1; xz_m1 = xz_0; xz_0 = xz_p1;
-        if (sF[it + 1] & TF_SHEAR) { xy_p1 = hbox(hs1, HB_SXY)[sc]; xz_p1 = hbox(hs1, HB_SXZ)[sc]; }
+        if (sF[it + 1] & TF_SHEAR) { xy_p1 = hbox(ho1, HB_SXY)[0]; xz_p1 = hbox(ho1, HB_SXZ)[0]; }
         else { xy_p1 = 0.f; xz_p1 = 0.f; }
-        mbar_wait(fullP + ps * 8, pp.par);
+        mbar_wait(pbar, ppar);
         const bool xd = in_pml1(i, p.n1, p.P);
         const bool cellpml = xd || jkd;
         if (active && (!cellpml || (jkupd && i < p.n1 - 1))) {
-            const float *byy = hbox(hs, HB_SYY), *bzz = hbox(hs, HB_SZZ);
-            const float *bxy = hbox(hs, HB_SXY), *bxz = hbox(hs, HB_SXZ), *byz = hbox(hs, HB_SYZ);
-            const LT *l0p = lbox(hs), *l1p = lbox(hs1);
-            const float *pb = reinterpret_cast<const float *>(sm + offP + ps * pstage) + pc;
-            const unsigned l0 = l0p[lc];
-            const unsigned mi = l1p[lc] & MSK, mj = l0p[lc + LW] & MSK, mk = l0p[lc + 1] & MSK;
+            const float *byy = hbox(ho, HB_SYY), *bzz = hbox(ho, HB_SZZ);
+            const float *bxy = hbox(ho, HB_SXY), *bxz = hbox(ho, HB_SXZ), *byz = hbox(ho, HB_SYZ);
+            const LT *l0p = lbox(ho), *l1p = lbox(ho1);
+            const float *pb = reinterpret_cast<const float *>(psc + po);
+            const unsigned l0 = l0p[0];
+            const unsigned mi = l1p[0] & MSK, mj = l0p[LW] & MSK, mk = l0p[1] & MSK;
             float b0, bi, bj, bk;
             if (SMC) { b0 = sB[l0 & MSK]; bi = sB[mi]; bj = sB[mj]; bk = sB[mk]; }
             else { b0 = __ldg(&p.coef[l0 & MSK].B); bi = __ldg(&p.coef[mi].B); bj = __ldg(&p.coef[mj].B); bk = __ldg(&p.coef[mk].B); }
@@ -605,26 +624,26 @@ __global__ void __launch_bounds__(NTB, 1) particle_tma(const __grid_constant__ P
                 X[0] = D4(xx_p1, xx_0, xx_p2, xx_m1);
                 X[3] = D4(xy_0, xy_m1, xy_p1, xy_m2);
                 X[6] = D4(xz_0, xz_m1, xz_p1, xz_m2);
-                X[4] = D4(byy[sc + SW], byy[sc], byy[sc + 2 * SW], byy[sc - SW]);
-                X[8] = D4(bzz[sc + 1], bzz[sc], bzz[sc + 2], bzz[sc - 1]);
+                X[4] = D4(byy[SW], byy[0], byy[2 * SW], byy[-SW]);
+                X[8] = D4(bzz[1], bzz[0], bzz[2], bzz[-1]);
                 if (fsh) {
-                    X[1] = D4(bxy[sc], bxy[sc - SW], bxy[sc + SW], bxy[sc - 2 * SW]);
-                    X[2] = D4(bxz[sc], bxz[sc - 1], bxz[sc + 1], bxz[sc - 2]);
-                    X[5] = D4(byz[sc], byz[sc - 1], byz[sc + 1], byz[sc - 2]);
-                    X[7] = D4(byz[sc], byz[sc - SW], byz[sc + SW], byz[sc - 2 * SW]);
+                    X[1] = D4(bxy[0], bxy[-SW], bxy[SW], bxy[-2 * SW]);
+                    X[2] = D4(bxz[0], bxz[-1], bxz[1], bxz[-2]);
+                    X[5] = D4(byz[0], byz[-1], byz[1], byz[-2]);
+                    X[7] = D4(byz[0], byz[-SW], byz[SW], byz[-2 * SW]);
                 } else { X[1] = X[2] = X[5] = X[7] = 0.f; }
             } else {
                 const AxisCoef ci = load_axis(p.axI, i), cj = sJ[ty], ck = sK[tx];
                 X[0] = D4C(ci.caf, ci.cbf, xx_p1, xx_0, xx_p2, xx_m1);
                 X[3] = D4C(ci.cab, ci.cbb, xy_0, xy_m1, xy_p1, xy_m2);
                 X[6] = D4C(ci.cab, ci.cbb, xz_0, xz_m1, xz_p1, xz_m2);
-                X[4] = D4C(cj.caf, cj.cbf, byy[sc + SW], byy[sc], byy[sc + 2 * SW], byy[sc - SW]);
-                X[8] = D4C(ck.caf, ck.cbf, bzz[sc + 1], bzz[sc], bzz[sc + 2], bzz[sc - 1]);
+                X[4] = D4C(cj.caf, cj.cbf, byy[SW], byy[0], byy[2 * SW], byy[-SW]);
+                X[8] = D4C(ck.caf, ck.cbf, bzz[1], bzz[0], bzz[2], bzz[-1]);
                 if (fsh) {
-                    X[1] = D4C(cj.cab, cj.cbb, bxy[sc], bxy[sc - SW], bxy[sc + SW], bxy[sc - 2 * SW]);
-                    X[2] = D4C(ck.cab, ck.cbb, bxz[sc], bxz[sc - 1], bxz[sc + 1], bxz[sc - 2]);
-                    X[5] = D4C(ck.cab, ck.cbb, byz[sc], byz[sc - 1], byz[sc + 1], byz[sc - 2]);
-                    X[7] = D4C(cj.cab, cj.cbb, byz[sc], byz[sc - SW], byz[sc + SW], byz[sc - 2 * SW]);
+                    X[1] = D4C(cj.cab, cj.cbb, bxy[0], bxy[-SW], bxy[SW], bxy[-2 * SW]);
+                    X[2] = D4C(ck.cab, ck.cbb, bxz[0], bxz[-1], bxz[1], bxz[-2]);
+                    X[5] = D4C(ck.cab, ck.cbb, byz[0], byz[-1], byz[1], byz[-2]);
+                    X[7] = D4C(cj.cab, cj.cbb, byz[0], byz[-SW], byz[SW], byz[-2 * SW]);
                 } else { X[1] = X[2] = X[5] = X[7] = 0.f; }
             }
             float v[3] = { pb[(QB_V + 0) * NT], pb[(QB_V + 1) * NT], pb[(QB_V + 2) * NT] };
@@ -637,7 +656,7 @@ __global__ void __launch_bounds__(NTB, 1) particle_tma(const __grid_constant__ P
                 pcell.aI = ci.aI; pcell.bI = ci.bI; pcell.aIh = ci.aH; pcell.bIh = ci.bH;
                 pcell.aJ = cj.aI; pcell.bJ = cj.bI; pcell.aJh = cj.aH; pcell.bJh = cj.bH;
                 pcell.aK = ck.aI; pcell.bK = ck.bI; pcell.aKh = ck.aH; pcell.bKh = ck.bH;
-                particle_pml<true>(p, pcell, bx, by, bz, X, v, pb + QB_X * NT, pb + (yoff >> 2), pb - pc + zsrc, NT, zcomp);
+                particle_pml<true>(p, pcell, bx, by, bz, X, v, pb + QB_X * NT, pb + (yoff >> 2), reinterpret_cast<const float *>(pzs + po), NT, zcomp);
             } else {
                 v[0] += dt * bx * (X[0] + X[1] + X[2]);
                 v[1] += dt * by * (X[3] + X[4] + X[5]);
@@ -654,10 +673,12 @@ __global__ void __launch_bounds__(NTB, 1) particle_tma(const __grid_constant__ P
             }
         }
         __syncwarp();
-        if (lane == 0) { mbar_arrive(emptyH + hs * 8); mbar_arrive(emptyP + ps * 8); }
-        hs = hs1; hs1 = hs2;
-        h2.advance();
-        pp.advance();
+        if (lane == 0) { mbar_arrive(hb0 + MAX_NSH * 8); mbar_arrive(pbar + MAX_NSP * 8); }
+        ho = ho1; hb0 = hb1; ho1 = ho2; hb1 = hb2;
+        ho2 += PT_HSTAGE; hb2 += 8;
+        if (ho2 == hend) { ho2 = 0; hb2 = fullH; hpar ^= 1u; }
+        po += pstage; pbar += 8;
+        if (po == pend) { po = 0; pbar = fullP; ppar ^= 1u; }
     }
 }
 }  // namespace tma
