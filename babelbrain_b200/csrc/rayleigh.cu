@@ -3,11 +3,16 @@
 //   out[p] = j k/(2 pi) * sum_s ds[s] exp(Im(k) R)/R * u0[s] exp(-j Re(k) R),  R = |rf[p]-center[s]|
 // Compute bound (FP32 + MUFU): sources are staged through shared memory as float4 + float2 records
 // and every thread accumulates PPT field points so each staged source is reused PPT*blockDim times.
+// Per source-point pair: 3 sub, 3 fma (R^2), rsqrt.approx, 1 mul (R), 1 mul (phase), sin.approx +
+// cos.approx on a phase reduced to one revolution with FMAs (error = rounding of R only), 1 mul
+// (amplitude), 6 fma-class accumulations: ~22 FP32 + 3 MUFU issue slots.
+// MUFU runs at a quarter of the FP32 rate, so the SFU bounds the kernel at
+// 148 SMs x 16 MUFU/clk x 1.9 GHz / 3 = 1.5e12 pairs/s.
 #include "common.h"
 
 namespace {
 constexpr int RB = 256;      // threads per CTA
-constexpr int PPT = 2;       // field points per thread
+constexpr int PPT = 4;       // field points per thread
 constexpr int STILE = 512;   // sources per shared-memory tile
 
 template <bool ATT, bool MAXD, bool PERPOINT>
@@ -18,6 +23,8 @@ __global__ void __launch_bounds__(RB) rayleigh_kernel(float k_re, float k_im, lo
     __shared__ float4 s_pos[STILE];  // x, y, z, ds
     __shared__ float2 s_u[STILE];
     float px[PPT], py[PPT], pz[PPT], ar[PPT], ai[PPT];
+    const double krd = (double)k_re * 0.15915494309189535;       // wavenumber in revolutions per metre, hi + lo
+    const float kr_hi = (float)krd, kr_lo = (float)(krd - (double)kr_hi);
     long long pidx[PPT];
 #pragma unroll
     for (int t = 0; t < PPT; t++) {
@@ -43,13 +50,20 @@ __global__ void __launch_bounds__(RB) rayleigh_kernel(float k_re, float k_im, lo
 #pragma unroll
             for (int t = 0; t < PPT; t++) {
                 const float dx = c.x - px[t], dy = c.y - py[t], dz = c.z - pz[t];
-                const float R = sqrtf(dx * dx + dy * dy + dz * dz);
+                const float r2 = fmaf(dx, dx, fmaf(dy, dy, dz * dz));
+                float rinv;
+                asm("rsqrt.approx.ftz.f32 %0, %1;" : "=f"(rinv) : "f"(r2));   // R = 0 -> inf, like the reference's 1/R
+                rinv = rinv * fmaf(-0.5f * r2, rinv * rinv, 1.5f);            // one Newton step: R to ~1 ulp (the phase is R k ~ 1e2..1e3 rad)
+                const float R = r2 * rinv;
                 if (MAXD && R > max_distance) continue;
                 if (PERPOINT) u = u0[(pidx[t] < npts ? pidx[t] : npts - 1) * nsrc + s0 + s];
-                float amp = c.w / R;
-                if (ATT) amp *= expf(R * k_im);
-                float sn, cs;
-                sincosf(R * k_re, &sn, &cs);
+                float amp = c.w * rinv;
+                if (ATT) amp *= __expf(R * k_im);
+                // phase in revolutions, reduced with fused multiply-adds against a two-term k/(2 pi): the only
+                // error left is the rounding of R itself
+                const float n = rintf(R * kr_hi);
+                const float fr = fmaf(R, kr_hi, -n) + R * kr_lo;
+                const float sn = __sinf(fr * 6.283185307f), cs = __cosf(fr * 6.283185307f);
                 ar[t] += amp * (u.x * cs + u.y * sn);
                 ai[t] += amp * (u.y * cs - u.x * sn);
             }
