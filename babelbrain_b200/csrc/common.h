@@ -95,6 +95,11 @@ struct DevParams {
     int sel_rms_peak;
 };
 
+// Plane ranges of the CTAs of one launch along the marching axis: chunk z covers planes [start[z], start[z+1]).
+// Long chunks first, short ones last, so the last wave of CTAs is short (the hardware hands out CTAs in order).
+constexpr int BB_MAX_CHUNKS = 48;
+struct ChunkPlan { int n; int start[BB_MAX_CHUNKS + 1]; };
+
 // TMA descriptors (passed as a __grid_constant__ parameter).  The component arrays of a field group
 // (V[3], S[6], R[6], parts[8]) are contiguous, so the group is a 4-D tensor (k, j, plane, component)
 // and one TMA instruction moves the boxes of 2 or 3 components at once.

@@ -76,7 +76,7 @@ struct bb_fdtd {
     bool materials_set = false, maps_set = false, prepared = false;
     StressMaps smaps;
     ParticleMaps pmaps;
-    int chunk_override = 0;
+    int chunk_override = 0, chunk_tail = 1;
     // NCCL
     ncclComm_t comm = nullptr;
     cudaEvent_t ev_boundary = nullptr, ev_halo = nullptr;
@@ -212,6 +212,7 @@ extern "C" int bb_fdtd_create(const bb_fdtd_desc *d, bb_fdtd **out) {
     p.nmat = d->nmat;
     h->label_bytes = d->nmat <= 127 ? 1 : 2;
     if (const char *e = getenv("BB_CHUNK")) h->chunk_override = atoi(e);
+    if (const char *e = getenv("BB_CHUNK_TAIL")) h->chunk_tail = atoi(e);
     const size_t vol = (size_t)p.nloc * p.plane;
     int rc;
     // the components of a field group are contiguous (one 4-D TMA descriptor per group)
@@ -622,14 +623,32 @@ struct Timer {
     }
 };
 
-static int pick_chunk(const bb_fdtd *h, int nplanes) {
-    // enough CTAs for ~8 waves of one CTA on each of the 148 SMs, chunks of 8..64 planes
-    if (h->chunk_override > 0) return std::min(std::min(h->chunk_override, (int)tma::MAXCHUNK), nplanes);
+// Plane ranges of the CTAs of one launch over the planes [ib, ie).  One CTA per SM is resident; chunks are as long
+// as the flag table allows (64 planes), and the last one is split into pieces of halving length (>= 6 planes) so
+// that the final, partially filled wave costs a few planes instead of a whole chunk.
+static ChunkPlan make_chunk_plan(const bb_fdtd *h, int ib, int ie) {
+    ChunkPlan pl;
+    const int nplanes = ie - ib;
     const int tiles = h->p.ntk * h->p.ntj;
-    int nch = std::max(1, (8 * 148 + tiles - 1) / tiles);
-    int chunk = (nplanes + nch - 1) / nch;
-    chunk = std::max(chunk, std::min(nplanes, 8));
-    return std::min(chunk, (int)tma::MAXCHUNK);
+    int chunk;
+    if (h->chunk_override > 0) chunk = h->chunk_override;
+    else {
+        // long chunks amortise the pipeline fill of a CTA (measured on CTX-500: 64-plane chunks 31.7, 30-plane 30.7,
+        // 16-plane 28.9 Gcell/s); small grids still get at least two CTAs per SM
+        const int nch = std::max(1, (2 * 148 + tiles - 1) / tiles);
+        chunk = std::max((nplanes + nch - 1) / nch, std::min(nplanes, 8));
+    }
+    chunk = std::max(1, std::min(chunk, (int)tma::MAXCHUNK));
+    while ((nplanes + chunk - 1) / chunk + 6 > BB_MAX_CHUNKS) chunk++;    // cannot happen for chunk = 64 below 2688 planes
+    pl.n = 0;
+    int at = ib;
+    pl.start[0] = ib;
+    auto push = [&](int len) { at += len; pl.start[++pl.n] = at; };
+    while (ie - at > chunk) push(chunk);
+    int rest = ie - at;                        // 1 .. chunk planes left: halve it down
+    while (rest >= 12 && h->chunk_tail) { const int len = (rest + 1) / 2; push(len); rest -= len; }
+    if (rest > 0) push(rest);
+    return pl;
 }
 
 template <typename K>
@@ -665,17 +684,17 @@ static int launch_half_step(bb_fdtd *h, bool stress, int acc_mode, int ib, int i
             else direct::particle_direct<LT, false><<<grid, blk, 0, h->stream>>>(p, ib);
         }
     } else {
-        const int chunk = pick_chunk(h, ie - ib);
-        const dim3 blk(tma::NTB, 1, 1), grid(p.ntk, p.ntj, (ie - ib + chunk - 1) / chunk);
+        const ChunkPlan plan = make_chunk_plan(h, ib, ie);
+        const dim3 blk(tma::NTB, 1, 1), grid(p.ntk, p.ntj, plan.n);
         if (stress) {
             const int sm = tma::SMEM_BYTES;
-            if (acc_mode == 1) tma::stress_tma<LT, 1><<<grid, blk, sm, h->stream>>>(h->smaps, p, ib, ie, chunk);
-            else if (acc_mode == 2) tma::stress_tma<LT, 2><<<grid, blk, sm, h->stream>>>(h->smaps, p, ib, ie, chunk);
-            else tma::stress_tma<LT, 0><<<grid, blk, sm, h->stream>>>(h->smaps, p, ib, ie, chunk);
+            if (acc_mode == 1) tma::stress_tma<LT, 1><<<grid, blk, sm, h->stream>>>(h->smaps, p, plan);
+            else if (acc_mode == 2) tma::stress_tma<LT, 2><<<grid, blk, sm, h->stream>>>(h->smaps, p, plan);
+            else tma::stress_tma<LT, 0><<<grid, blk, sm, h->stream>>>(h->smaps, p, plan);
         } else {
             const int sm = tma::SMEM_BYTES;
-            if (acc_mode) tma::particle_tma<LT, 2><<<grid, blk, sm, h->stream>>>(h->pmaps, p, ib, ie, chunk);
-            else tma::particle_tma<LT, 0><<<grid, blk, sm, h->stream>>>(h->pmaps, p, ib, ie, chunk);
+            if (acc_mode) tma::particle_tma<LT, 2><<<grid, blk, sm, h->stream>>>(h->pmaps, p, plan);
+            else tma::particle_tma<LT, 0><<<grid, blk, sm, h->stream>>>(h->pmaps, p, plan);
         }
     }
     tm.end();

@@ -152,7 +152,7 @@ enum { PB_SXX = 0, PB_SYY, PB_SZZ, PB_SXY, PB_SXZ, PB_SYZ, PB_RXX, PB_RYY, PB_RZ
 constexpr int ST_HSTAGE = 3 * HBOX_STRIDE + LBOX_STRIDE;
 
 template <typename LT, int ACC>
-__global__ void __launch_bounds__(NTB, 1) stress_tma(const __grid_constant__ StressMaps tm, const DevParams p, int ia, int ie, int chunk) {
+__global__ void __launch_bounds__(NTB, 1) stress_tma(const __grid_constant__ StressMaps tm, const DevParams p, const ChunkPlan plan) {
     constexpr bool SMC = sizeof(LT) == 1;
     constexpr int LW = LabBox<LT>::W;
     extern __shared__ __align__(1024) unsigned char sm[];   // TMA destinations need 128-byte alignment
@@ -166,7 +166,7 @@ __global__ void __launch_bounds__(NTB, 1) stress_tma(const __grid_constant__ Str
     const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
     const int tx = tid & (TX - 1), ty = tid / TX;       // consumer threads: cell (ty, tx) of the tile
     const int k0 = blockIdx.x * TX, j0 = blockIdx.y * TY;
-    const int ic0 = ia + blockIdx.z * chunk, ic1 = min(ic0 + chunk, ie);
+    const int ic0 = plan.start[blockIdx.z], ic1 = plan.start[blockIdx.z + 1];
     const int np = ic1 - ic0;                 // planes of this CTA
     const int ipl0 = ic0 - p.i0 + 2;          // local plane of ic0
     // which damped parts this tile can need (CTA-uniform)
@@ -461,7 +461,7 @@ enum { QB_V = 0, QB_X = 3, QB_PARTS = 6 };
 constexpr int PT_HSTAGE = 5 * HBOX_STRIDE + PBOX + LBOX_STRIDE;
 
 template <typename LT, int ACC>
-__global__ void __launch_bounds__(NTB, 1) particle_tma(const __grid_constant__ ParticleMaps tm, const DevParams p, int ia, int ie, int chunk) {
+__global__ void __launch_bounds__(NTB, 1) particle_tma(const __grid_constant__ ParticleMaps tm, const DevParams p, const ChunkPlan plan) {
     constexpr bool SMC = sizeof(LT) == 1;
     constexpr int LW = LabBox<LT>::W;
     extern __shared__ __align__(1024) unsigned char sm[];
@@ -475,7 +475,7 @@ __global__ void __launch_bounds__(NTB, 1) particle_tma(const __grid_constant__ P
     const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
     const int tx = tid & (TX - 1), ty = tid / TX;       // consumer threads: cell (ty, tx) of the tile
     const int k0 = blockIdx.x * TX, j0 = blockIdx.y * TY;
-    const int ic0 = ia + blockIdx.z * chunk, ic1 = min(ic0 + chunk, ie);
+    const int ic0 = plan.start[blockIdx.z], ic1 = plan.start[blockIdx.z + 1];
     const int np = ic1 - ic0;
     const int ipl0 = ic0 - p.i0 + 2;
     const bool tile_jd = (int)blockIdx.y < p.nylo || (int)blockIdx.y >= p.tjhi0;
