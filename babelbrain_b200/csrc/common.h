@@ -95,10 +95,10 @@ struct DevParams {
     int sel_rms_peak;
 };
 
-// Plane ranges of the CTAs of one launch along the marching axis: chunk z covers planes [start[z], start[z+1]).
+// Plane ranges of the CTAs of one launch along the marching axis: chunk z covers planes [start[z], end[z]).
 // Long chunks first, short ones last, so the last wave of CTAs is short (the hardware hands out CTAs in order).
 constexpr int BB_MAX_CHUNKS = 48;
-struct ChunkPlan { int n; int start[BB_MAX_CHUNKS + 1]; };
+struct ChunkPlan { int n; int start[BB_MAX_CHUNKS], end[BB_MAX_CHUNKS]; };
 
 // TMA descriptors (passed as a __grid_constant__ parameter).  The component arrays of a field group
 // (V[3], S[6], R[6], parts[8]) are contiguous, so the group is a 4-D tensor (k, j, plane, component)

@@ -194,7 +194,11 @@ extern "C" int bb_fdtd_create(const bb_fdtd_desc *d, bb_fdtd **out) {
     h->d = *d;
     memset(&h->stats, 0, sizeof(h->stats));
     BB_CUDA(cudaStreamCreateWithFlags(&h->stream, cudaStreamNonBlocking));
-    BB_CUDA(cudaStreamCreateWithFlags(&h->comm_stream, cudaStreamNonBlocking));
+    {   // the halo exchange must win SMs against the interior kernel that is already queued: highest priority
+        int lo = 0, hi = 0;
+        BB_CUDA(cudaDeviceGetStreamPriorityRange(&lo, &hi));
+        BB_CUDA(cudaStreamCreateWithPriority(&h->comm_stream, cudaStreamNonBlocking, hi));
+    }
     h->own_stream = true;
     BB_CUDA(cudaEventCreate(&h->ev_run0));
     BB_CUDA(cudaEventCreate(&h->ev_run1));
@@ -639,11 +643,10 @@ static ChunkPlan make_chunk_plan(const bb_fdtd *h, int ib, int ie) {
         chunk = std::max((nplanes + nch - 1) / nch, std::min(nplanes, 8));
     }
     chunk = std::max(1, std::min(chunk, (int)tma::MAXCHUNK));
-    while ((nplanes + chunk - 1) / chunk + 6 > BB_MAX_CHUNKS) chunk++;    // cannot happen for chunk = 64 below 2688 planes
+    while ((nplanes + chunk - 1) / chunk + 6 > BB_MAX_CHUNKS) chunk++;    // only above 2688 planes per GPU
     pl.n = 0;
     int at = ib;
-    pl.start[0] = ib;
-    auto push = [&](int len) { at += len; pl.start[++pl.n] = at; };
+    auto push = [&](int len) { pl.start[pl.n] = at; at += len; pl.end[pl.n++] = at; };
     while (ie - at > chunk) push(chunk);
     int rest = ie - at;                        // 1 .. chunk planes left: halve it down
     while (rest >= 12 && h->chunk_tail) { const int len = (rest + 1) / 2; push(len); rest -= len; }
@@ -670,7 +673,7 @@ static int prepare_kernels() {
 
 // one half-step over the owned planes [ib, ie): a single fused launch (interior + PML shell)
 template <typename LT>
-static int launch_half_step(bb_fdtd *h, bool stress, int acc_mode, int ib, int ie, Timer &tm) {
+static int launch_half_step(bb_fdtd *h, bool stress, int acc_mode, int ib, int ie, Timer &tm, const ChunkPlan *given = nullptr) {
     if (ie <= ib) return BB_OK;
     const DevParams &p = h->p;
     tm.begin(stress ? CAT_STRESS : CAT_PARTICLE);
@@ -684,7 +687,7 @@ static int launch_half_step(bb_fdtd *h, bool stress, int acc_mode, int ib, int i
             else direct::particle_direct<LT, false><<<grid, blk, 0, h->stream>>>(p, ib);
         }
     } else {
-        const ChunkPlan plan = make_chunk_plan(h, ib, ie);
+        const ChunkPlan plan = given ? *given : make_chunk_plan(h, ib, ie);
         const dim3 blk(tma::NTB, 1, 1), grid(p.ntk, p.ntj, plan.n);
         if (stress) {
             const int sm = tma::SMEM_BYTES;
@@ -744,8 +747,16 @@ static int half_step(bb_fdtd *h, bool stress, int n, int acc, Timer &tm) {
     if (h->d.nranks > 1) {
         // inputs of this half-step: halos sent during the previous half-step
         BB_CUDA(cudaStreamWaitEvent(h->stream, h->ev_halo, 0));
-        if ((rc = launch_half_step<LT>(h, stress, acc, p.i0, p.i0 + 2, tm))) return rc;
-        if ((rc = launch_half_step<LT>(h, stress, acc, p.i1 - 2, p.i1, tm))) return rc;
+        // the two boundary plane pairs in one launch (variant 0), so their results can leave while the interior runs
+        if (h->d.kernel_variant == 0) {
+            ChunkPlan edge;
+            edge.n = 2;
+            edge.start[0] = p.i0; edge.end[0] = p.i0 + 2; edge.start[1] = p.i1 - 2; edge.end[1] = p.i1;
+            if ((rc = launch_half_step<LT>(h, stress, acc, p.i0, p.i1, tm, &edge))) return rc;
+        } else {
+            if ((rc = launch_half_step<LT>(h, stress, acc, p.i0, p.i0 + 2, tm))) return rc;
+            if ((rc = launch_half_step<LT>(h, stress, acc, p.i1 - 2, p.i1, tm))) return rc;
+        }
         if (src_here && (rc = launch_sources(h, n, 0, h->nsrc_boundary, tm))) return rc;
         BB_CUDA(cudaEventRecord(h->ev_boundary, h->stream));
         BB_CUDA(cudaStreamWaitEvent(h->comm_stream, h->ev_boundary, 0));

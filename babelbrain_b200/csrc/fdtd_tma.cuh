@@ -166,7 +166,7 @@ __global__ void __launch_bounds__(NTB, 1) stress_tma(const __grid_constant__ Str
     const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
     const int tx = tid & (TX - 1), ty = tid / TX;       // consumer threads: cell (ty, tx) of the tile
     const int k0 = blockIdx.x * TX, j0 = blockIdx.y * TY;
-    const int ic0 = plan.start[blockIdx.z], ic1 = plan.start[blockIdx.z + 1];
+    const int ic0 = plan.start[blockIdx.z], ic1 = plan.end[blockIdx.z];
     const int np = ic1 - ic0;                 // planes of this CTA
     const int ipl0 = ic0 - p.i0 + 2;          // local plane of ic0
     // which damped parts this tile can need (CTA-uniform)
@@ -475,7 +475,7 @@ __global__ void __launch_bounds__(NTB, 1) particle_tma(const __grid_constant__ P
     const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
     const int tx = tid & (TX - 1), ty = tid / TX;       // consumer threads: cell (ty, tx) of the tile
     const int k0 = blockIdx.x * TX, j0 = blockIdx.y * TY;
-    const int ic0 = plan.start[blockIdx.z], ic1 = plan.start[blockIdx.z + 1];
+    const int ic0 = plan.start[blockIdx.z], ic1 = plan.end[blockIdx.z];
     const int np = ic1 - ic0;
     const int ipl0 = ic0 - p.i0 + 2;
     const bool tile_jd = (int)blockIdx.y < p.nylo || (int)blockIdx.y >= p.tjhi0;
