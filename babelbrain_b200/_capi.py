@@ -5,7 +5,7 @@ import os
 import numpy as np
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.path.join(_HERE, 'libbabelb200.so')
+LIB_PATH = os.environ.get('BB_LIB', os.path.join(_HERE, 'libbabelb200.so'))
 
 MAP_NAMES = ['ALLV', 'Vx', 'Vy', 'Vz', 'Sigmaxx', 'Sigmayy', 'Sigmazz', 'Sigmaxy', 'Sigmaxz', 'Sigmayz', 'Pressure']
 MAP_ID = {n: i for i, n in enumerate(MAP_NAMES)}

@@ -6,7 +6,7 @@ import sys
 
 HERE = os.path.dirname(os.path.abspath(__file__))
 CSRC = os.path.join(HERE, 'csrc')
-LIB = os.path.join(HERE, 'libbabelb200.so')
+LIB = os.environ.get('BB_LIB', os.path.join(HERE, 'libbabelb200.so'))   # BB_LIB / BB_NVCC_FLAGS: build experiment variants
 SOURCES = ['fdtd.cu', 'rayleigh.cu']
 HEADERS = ['common.h', 'fdtd_cell.cuh', 'fdtd_kernels.cuh', 'fdtd_direct.cuh', 'fdtd_tma.cuh', 'nccl_dyn.h',
            os.path.join('..', '..', 'include', 'babelb200.h')]
@@ -33,7 +33,7 @@ def build(force=False, verbose=False):
     nvcc = os.environ.get('NVCC', '/usr/local/cuda/bin/nvcc')
     cmd = [nvcc, '-gencode', 'arch=compute_100a,code=sm_100a', '-O3', '-lineinfo', '-std=c++17',
            '-Xcompiler', '-fPIC', '-shared', '-I' + nccl_include(), '-o', LIB] + \
-          [os.path.join(CSRC, s) for s in SOURCES] + ['-ldl']
+          [os.path.join(CSRC, s) for s in SOURCES] + ['-ldl'] + os.environ.get('BB_NVCC_FLAGS', '').split()
     if verbose:
         cmd.insert(1, '-Xptxas')
         cmd.insert(2, '-v')

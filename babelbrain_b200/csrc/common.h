@@ -55,6 +55,12 @@ struct __align__(16) AxisCoef {
 //   Z parts: Sxx Syy Szz Sxz Syz | Vx Vy Vz     (columns with k in the PML)
 constexpr int BB_NPART = 8;
 
+// rows of a (j,k) tile of the half-step kernels: the Y parts are stored for whole tile rows
+#ifndef BB_TILE_ROWS
+#define BB_TILE_ROWS 8
+#endif
+constexpr int BB_TY = BB_TILE_ROWS;
+
 // tile flags, one byte per (local plane, tile row, tile column) of the 8x64 (j,k) tiling
 enum { TF_ATT = 1,      // a non-PML cell of the tile attenuates -> normal memory variables move
        TF_SOLID = 2,    // a cell of the tile (+1 in j,k, planes i and i+1) has G != 0 -> shear stresses / memory variables move

@@ -106,8 +106,8 @@ __device__ __forceinline__ PmlCell make_pml_cell(const DevParams &p, int i, int 
     PmlCell c;
     c.xd = in_pml1(i, p.n1, p.P); c.jd = in_pml1(j, p.n2, p.P); c.kd = in_pml1(k, p.n3, p.P);
     const int ipx = i < p.P ? i - p.i0 : p.nxlo + (i - p.xhi_begin);
-    const int tj = j >> 3;
-    const int jp = (tj < p.nylo ? tj : tj - p.tjhi0 + p.nylo) * 8 + (j & 7);
+    const int tj = j / BB_TY;
+    const int jp = (tj < p.nylo ? tj : tj - p.tjhi0 + p.nylo) * BB_TY + (j - tj * BB_TY);
     const int kp = k < p.P ? k : p.zbw + (k - (p.n3 - p.P));
     c.qx = ((unsigned)ipx * p.n2 + j) * p.pitch + k;
     c.qy = ((unsigned)(i - p.i0) * p.nyrows + jp) * p.pitch + k;
@@ -120,11 +120,11 @@ __device__ __forceinline__ PmlCell make_pml_cell(const DevParams &p, int i, int 
 
 // D[9] = Dxx, Dyy, Dzz, Dyx (d+_i Vy), Dxy (d+_j Vx), Dzx (d+_i Vz), Dxz (d+_k Vx), Dzy (d+_j Vz), Dyz (d+_k Vy)
 // ox/oy/oz: this cell's slot in the first staged X/Y/Z part box (X and Y boxes B floats apart, Z boxes
-// ZB floats apart); unused when !STAGED
+// ZB floats apart, the two shear Z parts starting at ozs); unused when !STAGED
 template <bool STAGED>
 __device__ __forceinline__ void stress_pml(const DevParams &p, const PmlCell &c, float M, float L, float rigxy, float rigxz, float rigyz,
                                            const float *D, float *s, const float *ox = nullptr, const float *oy = nullptr,
-                                           const float *oz = nullptr, int B = 0, int ZB = 0) {
+                                           const float *oz = nullptr, const float *ozs = nullptr, int B = 0, int ZB = 0) {
     const float dt = p.dt;
     s[0] += pml_delta<STAGED>(c.xd, ox, p.XP[0], c.qx, c.aI, c.bI, dt, M * D[0]) + pml_delta<STAGED>(c.jd, oy, p.YP[0], c.qy, c.aJ, c.bJ, dt, L * D[1])
           + pml_delta<STAGED>(c.kd, oz, p.ZP[0], c.qz, c.aK, c.bK, dt, L * D[2]);
@@ -137,18 +137,19 @@ __device__ __forceinline__ void stress_pml(const DevParams &p, const PmlCell &c,
               + pml_delta<STAGED>(c.jd, oy + 3 * B, p.YP[3], c.qy, c.aJh, c.bJh, dt, rigxy * D[4]);
     if (rigxz != 0.0f)
         s[4] += pml_delta<STAGED>(c.xd, ox + 4 * B, p.XP[4], c.qx, c.aIh, c.bIh, dt, rigxz * D[5])
-              + pml_delta<STAGED>(c.kd, oz + 3 * ZB, p.ZP[3], c.qz, c.aKh, c.bKh, dt, rigxz * D[6]);
+              + pml_delta<STAGED>(c.kd, ozs, p.ZP[3], c.qz, c.aKh, c.bKh, dt, rigxz * D[6]);
     if (rigyz != 0.0f)
         s[5] += pml_delta<STAGED>(c.jd, oy + 4 * B, p.YP[4], c.qy, c.aJh, c.bJh, dt, rigyz * D[7])
-              + pml_delta<STAGED>(c.kd, oz + 4 * ZB, p.ZP[4], c.qz, c.aKh, c.bKh, dt, rigyz * D[8]);
+              + pml_delta<STAGED>(c.kd, ozs + ZB, p.ZP[4], c.qz, c.aKh, c.bKh, dt, rigyz * D[8]);
 }
 
 // X[9] = x1 (d+_i Sxx), x2 (d-_j Sxy), x3 (d-_k Sxz), y1 (d-_i Sxy), y2 (d+_j Syy), y3 (d-_k Syz),
 //        z1 (d-_i Sxz), z2 (d-_j Syz), z3 (d+_k Szz);  b = averaged 1/(rho h) of the three faces
 template <bool STAGED>
 __device__ __forceinline__ void particle_pml(const DevParams &p, const PmlCell &c, float bx, float by, float bz, const float *X, float *v,
-                                             const float *ox = nullptr, const float *oy = nullptr, const float *oz = nullptr, int B = 0,
-                                             int ZB = 0) {
+                                             const float *ox = nullptr, const float *oy = nullptr, const float *oz = nullptr,
+                                             const float *ozs = nullptr, int B = 0, int ZB = 0) {
+    (void)ozs;
     const float dt = p.dt;
     v[0] += pml_delta<STAGED>(c.xd, ox, p.XP[5], c.qx, c.aIh, c.bIh, dt, bx * X[0]) + pml_delta<STAGED>(c.jd, oy, p.YP[5], c.qy, c.aJ, c.bJ, dt, bx * X[1])
           + pml_delta<STAGED>(c.kd, oz, p.ZP[5], c.qz, c.aK, c.bK, dt, bx * X[2]);

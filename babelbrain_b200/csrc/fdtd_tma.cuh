@@ -30,20 +30,22 @@
 namespace tma {
 // 8 x 64 tile: 256-byte row segments (profiles/tile_bw_probe.cu: 128-byte segments cap the access
 // pattern at ~70% of the HBM copy bandwidth, 256-byte segments at ~90-98%)
-constexpr int TX = 64, TY = 8, HALO = 2;
+constexpr int TX = 64, TY = BB_TY, HALO = 2;
 // the innermost TMA coordinate must be a multiple of 16 bytes (measured: a box starting at k0-2
 // raises an illegal-instruction fault), so halo boxes start at k0-4 and are TX+8 floats wide
 constexpr int HK = 4;
 constexpr int SW = TX + 2 * HK;          // 72
 constexpr int SH = TY + 2 * HALO;        // 12
 constexpr int NT = TX * TY;              // 512 consumer threads, one cell each
-constexpr int NCW = NT / 32;             // 16 consumer warps
+constexpr int NCW = NT / 32;             // consumer warps
+constexpr int CTAS_PER_SM = TY <= 4 ? 2 : 1;
 constexpr int NTB = NT + 64;             // + two producer warps (halo ring, point ring)
-constexpr int HBOX = SW * SH * 4;        // 3456 bytes per halo box (a multiple of 128)
+constexpr int HBOX = SW * SH * 4;        // bytes per halo box; the boxes of one 4-D TMA land densely
 constexpr int HBOX_STRIDE = HBOX;
+__host__ __device__ constexpr int align128(int x) { return (x + 127) & ~127; }
 constexpr int PBOX = TX * TY * 4;        // 2048 bytes per point box
 constexpr int LH = TY + 1;               // label rows j0 .. j0+TY
-constexpr int LBOX_STRIDE = 1408;        // >= LW*LH*sizeof(LT), 128-byte aligned
+constexpr int LBOX_STRIDE = ((TX + 8) * 2 * LH + 127) & ~127;   // >= LW*LH*sizeof(LT) for both label types, 128-byte aligned
 // label box width: >= TX+1 labels and a multiple of 16 bytes: uint8 80 labels, uint16 72 labels
 template <typename LT> struct LabBox { static constexpr int W = sizeof(LT) == 1 ? TX + 16 : TX + 8; };
 constexpr int MAXCHUNK = 64;
@@ -132,7 +134,7 @@ struct RingPos {
 // Every CTA gets the same dynamic allocation (two CTAs per SM); what the point stages of its tile
 // class do not need (no Y parts away from the j-PML, no Z parts away from the k-PML) goes to a
 // deeper halo ring, i.e. more planes of prefetch.
-constexpr int SMEM_BYTES = 222 * 1024;   // one CTA of 17 warps per SM
+constexpr int SMEM_BYTES = (CTAS_PER_SM == 1 ? 222 : 110) * 1024;
 constexpr int MAX_NSH = 10, MAX_NSP = 4;
 constexpr int OFF_COEF = 0;                                                      // MatCoef[128] (stress) / float B[128] (particle)
 constexpr int OFF_AXJ = OFF_COEF + BB_MAX_SMEM_MAT * (int)sizeof(MatCoef);
@@ -149,10 +151,11 @@ static_assert(OFF_BAR + 2 * (MAX_NSH + MAX_NSP) * 8 <= OFF_RINGS, "tables overfl
 // cell exists on such a plane, so memory variables are not needed there); the Y / Z parts follow at
 // full boxes, the Z parts as compact regions
 enum { PB_SXX = 0, PB_SYY, PB_SZZ, PB_SXY, PB_SXZ, PB_SYZ, PB_RXX, PB_RYY, PB_RZZ, PB_RXY, PB_RXZ, PB_RYZ, PB_PR, PB_ACC, PB_PARTS };
-constexpr int ST_HSTAGE = 3 * HBOX_STRIDE + LBOX_STRIDE;
+constexpr int ST_LOFF = align128(3 * HBOX_STRIDE);         // label box behind the three V boxes
+constexpr int ST_HSTAGE = ST_LOFF + LBOX_STRIDE;
 
 template <typename LT, int ACC>
-__global__ void __launch_bounds__(NTB, 1) stress_tma(const __grid_constant__ StressMaps tm, const DevParams p, const ChunkPlan plan) {
+__global__ void __launch_bounds__(NTB, CTAS_PER_SM) stress_tma(const __grid_constant__ StressMaps tm, const DevParams p, const ChunkPlan plan) {
     constexpr bool SMC = sizeof(LT) == 1;
     constexpr int LW = LabBox<LT>::W;
     extern __shared__ __align__(1024) unsigned char sm[];   // TMA destinations need 128-byte alignment
@@ -176,7 +179,8 @@ __global__ void __launch_bounds__(NTB, 1) stress_tma(const __grid_constant__ Str
     // point-stage layout (bytes): 14 full boxes, then the Y part boxes, then the compact Z part regions
     // (zbw columns x TY rows per component) of the low and the high side
     const int zcomp = p.zbw * TY;                                          // floats per Z part component
-    const int zreg = (5 * zcomp * 4 + 127) & ~127;
+    const int zshear = align128(3 * zcomp * 4);                          // the two shear parts start 128-byte aligned (own TMA)
+    const int zreg = zshear + align128(2 * zcomp * 4);
     const int yoff = PB_PARTS * PBOX, zlo_off = yoff + (tile_jd ? 5 * PBOX : 0), zhi_off = zlo_off + (tile_zlo ? zreg : 0);
     const int pstage = zhi_off + (tile_zhi ? zreg : 0);
     // ring depths: 4 point stages when that still leaves 6 halo stages, else 3
@@ -211,7 +215,7 @@ __global__ void __launch_bounds__(NTB, 1) stress_tma(const __grid_constant__ Str
             mbar_expect_tx(bar, 3 * HBOX + LW * LH * (int)sizeof(LT));
             const int ipl = ipl0 + r;
             tma_load_4d(st, &tm.v3, bar, k0 - HK, j0 - HALO, ipl, 0);
-            tma_load_3d(st + 3 * HBOX_STRIDE, &tm.lab, bar, k0, j0, ipl);
+            tma_load_3d(st + ST_LOFF, &tm.lab, bar, k0, j0, ipl);
             rh.advance();
         }
         return;
@@ -250,11 +254,11 @@ __global__ void __launch_bounds__(NTB, 1) stress_tma(const __grid_constant__ Str
             }
             if (tile_zlo) {
                 tma_load_4d(st + zlo_off, &tm.zp3, bar, 0, j0, io, 0);
-                if (fsol) tma_load_4d(st + zlo_off + 3 * zcomp * 4, &tm.zp2, bar, 0, j0, io, 3);
+                if (fsol) tma_load_4d(st + zlo_off + zshear, &tm.zp2, bar, 0, j0, io, 3);
             }
             if (tile_zhi) {
                 tma_load_4d(st + zhi_off, &tm.zp3, bar, p.zbw, j0, io, 0);
-                if (fsol) tma_load_4d(st + zhi_off + 3 * zcomp * 4, &tm.zp2, bar, p.zbw, j0, io, 3);
+                if (fsol) tma_load_4d(st + zhi_off + zshear, &tm.zp2, bar, p.zbw, j0, io, 3);
             }
             if (acc) tma_load_3d(st + PB_ACC * PBOX, &tm.acc, bar, k0, j0, io);
             rp.advance();
@@ -293,7 +297,7 @@ __global__ void __launch_bounds__(NTB, 1) stress_tma(const __grid_constant__ Str
     // per-thread pointers to this thread's own cell in slot 0 of each ring (kept in registers: everything inside
     // the loop is one of these plus a running byte offset)
     const char *hsc = reinterpret_cast<const char *>(sm + offH) + sc * 4;                        // halo boxes
-    const char *lsc = reinterpret_cast<const char *>(sm + offH + 3 * HBOX_STRIDE) + lc * sizeof(LT);   // label box
+    const char *lsc = reinterpret_cast<const char *>(sm + offH + ST_LOFF) + lc * sizeof(LT);   // label box
     const char *psc = reinterpret_cast<const char *>(sm + offP) + pc * 4;                        // point boxes
     const char *pzs = reinterpret_cast<const char *>(sm + offP) + zsrc * 4;                      // Z part region
     auto hbox = [&](int off, int c) { return reinterpret_cast<const float *>(hsc + off + c * HBOX_STRIDE); };
@@ -392,7 +396,8 @@ __global__ void __launch_bounds__(NTB, 1) stress_tma(const __grid_constant__ Str
                 pcell.aI = ci.aI; pcell.bI = ci.bI; pcell.aIh = ci.aH; pcell.bIh = ci.bH;
                 pcell.aJ = cj.aI; pcell.bJ = cj.bI; pcell.aJh = cj.aH; pcell.bJh = cj.bH;
                 pcell.aK = ck.aI; pcell.bK = ck.bI; pcell.aKh = ck.aH; pcell.bKh = ck.bH;
-                stress_pml<true>(p, pcell, c.M, c.L, rigxy, rigxz, rigyz, D, s, pb + PB_RXX * NT, pb + (yoff >> 2), reinterpret_cast<const float *>(pzs + po), NT, zcomp);
+                stress_pml<true>(p, pcell, c.M, c.L, rigxy, rigxz, rigyz, D, s, pb + PB_RXX * NT, pb + (yoff >> 2), reinterpret_cast<const float *>(pzs + po),
+                                 reinterpret_cast<const float *>(pzs + po + zshear), NT, zcomp);
                 if (refl) { s[0] = s[1] = s[2] = s[3] = s[4] = s[5] = 0.f; }
                 p.S[0][q] = s[0]; p.S[1][q] = s[1]; p.S[2][q] = s[2];
                 if (f & TF_SOLID) { p.S[3][q] = s[3]; p.S[4][q] = s[4]; p.S[5][q] = s[5]; }
@@ -458,10 +463,13 @@ __global__ void __launch_bounds__(NTB, 1) stress_tma(const __grid_constant__ Str
 // point-stage boxes: V (3), X parts (3), then the Y / Z parts the tile needs (3 each)
 enum { HB_SYY = 0, HB_SZZ, HB_SXY, HB_SXZ, HB_SYZ };
 enum { QB_V = 0, QB_X = 3, QB_PARTS = 6 };
-constexpr int PT_HSTAGE = 5 * HBOX_STRIDE + PBOX + LBOX_STRIDE;
+constexpr int PT_S3OFF = align128(2 * HBOX_STRIDE);        // the three shear boxes (own TMA) behind Syy, Szz
+constexpr int PT_XOFF = align128(PT_S3OFF + 3 * HBOX_STRIDE);   // Sxx point box behind the five halo boxes
+constexpr int PT_LOFF = PT_XOFF + PBOX;
+constexpr int PT_HSTAGE = PT_LOFF + LBOX_STRIDE;
 
 template <typename LT, int ACC>
-__global__ void __launch_bounds__(NTB, 1) particle_tma(const __grid_constant__ ParticleMaps tm, const DevParams p, const ChunkPlan plan) {
+__global__ void __launch_bounds__(NTB, CTAS_PER_SM) particle_tma(const __grid_constant__ ParticleMaps tm, const DevParams p, const ChunkPlan plan) {
     constexpr bool SMC = sizeof(LT) == 1;
     constexpr int LW = LabBox<LT>::W;
     extern __shared__ __align__(1024) unsigned char sm[];
@@ -484,7 +492,7 @@ __global__ void __launch_bounds__(NTB, 1) particle_tma(const __grid_constant__ P
     // point-stage layout (bytes): 6 full boxes, then the Y part boxes, then the compact Z part regions
     // (zbw columns x TY rows per component) of the low and the high side
     const int zcomp = p.zbw * TY;                                          // floats per Z part component
-    const int zreg = (3 * zcomp * 4 + 127) & ~127;
+    const int zreg = align128(3 * zcomp * 4);
     const int yoff = QB_PARTS * PBOX, zlo_off = yoff + (tile_jd ? 3 * PBOX : 0), zhi_off = zlo_off + (tile_zlo ? zreg : 0);
     const int pstage = zhi_off + (tile_zhi ? zreg : 0);
     // ring depths: 4 point stages when that still leaves 6 halo stages, else 3
@@ -519,9 +527,9 @@ __global__ void __launch_bounds__(NTB, 1) particle_tma(const __grid_constant__ P
             mbar_expect_tx(bar, (fsh ? 5 : 2) * HBOX + PBOX + LW * LH * (int)sizeof(LT));
             const int ipl = ipl0 + r;
             tma_load_4d(st, &tm.sh2, bar, k0 - HK, j0 - HALO, ipl, 1);
-            if (fsh) tma_load_4d(st + 2 * HBOX_STRIDE, &tm.sh3, bar, k0 - HK, j0 - HALO, ipl, 3);
-            tma_load_4d(st + 5 * HBOX_STRIDE, &tm.sxx, bar, k0, j0, ipl, 0);
-            tma_load_3d(st + 5 * HBOX_STRIDE + PBOX, &tm.lab, bar, k0, j0, ipl);
+            if (fsh) tma_load_4d(st + PT_S3OFF, &tm.sh3, bar, k0 - HK, j0 - HALO, ipl, 3);
+            tma_load_4d(st + PT_XOFF, &tm.sxx, bar, k0, j0, ipl, 0);
+            tma_load_3d(st + PT_LOFF, &tm.lab, bar, k0, j0, ipl);
             rh.advance();
         }
         return;
@@ -575,11 +583,11 @@ __global__ void __launch_bounds__(NTB, 1) particle_tma(const __grid_constant__ P
     const int zsrc = ((k < p.P ? zlo_off : zhi_off) >> 2) + ty * p.zbw + (kd ? kz : 0);   // float offset inside a point stage
 
     const char *hsc = reinterpret_cast<const char *>(sm + offH) + sc * 4;                                    // halo boxes
-    const char *xsc = reinterpret_cast<const char *>(sm + offH + 5 * HBOX_STRIDE) + pc * 4;                  // Sxx point box
-    const char *lsc = reinterpret_cast<const char *>(sm + offH + 5 * HBOX_STRIDE + PBOX) + lc * sizeof(LT);  // label box
+    const char *xsc = reinterpret_cast<const char *>(sm + offH + PT_XOFF) + pc * 4;                  // Sxx point box
+    const char *lsc = reinterpret_cast<const char *>(sm + offH + PT_LOFF) + lc * sizeof(LT);  // label box
     const char *psc = reinterpret_cast<const char *>(sm + offP) + pc * 4;                                    // point boxes
     const char *pzs = reinterpret_cast<const char *>(sm + offP) + zsrc * 4;                                  // Z part region
-    auto hbox = [&](int off, int c) { return reinterpret_cast<const float *>(hsc + off + c * HBOX_STRIDE); };
+    auto hbox = [&](int off, int c) { return reinterpret_cast<const float *>(hsc + off + (c < 2 ? c * HBOX_STRIDE : PT_S3OFF + (c - 2) * HBOX_STRIDE)); };
     auto xxbox = [&](int off) { return reinterpret_cast<const float *>(xsc + off); };
     auto lbox = [&](int off) { return reinterpret_cast<const LT *>(lsc + off); };
     // ring state as byte offsets / barrier addresses (no multiplies in the loop): halo slots of planes it, it+1,
@@ -656,7 +664,7 @@ __global__ void __launch_bounds__(NTB, 1) particle_tma(const __grid_constant__ P
                 pcell.aI = ci.aI; pcell.bI = ci.bI; pcell.aIh = ci.aH; pcell.bIh = ci.bH;
                 pcell.aJ = cj.aI; pcell.bJ = cj.bI; pcell.aJh = cj.aH; pcell.bJh = cj.bH;
                 pcell.aK = ck.aI; pcell.bK = ck.bI; pcell.aKh = ck.aH; pcell.bKh = ck.bH;
-                particle_pml<true>(p, pcell, bx, by, bz, X, v, pb + QB_X * NT, pb + (yoff >> 2), reinterpret_cast<const float *>(pzs + po), NT, zcomp);
+                particle_pml<true>(p, pcell, bx, by, bz, X, v, pb + QB_X * NT, pb + (yoff >> 2), reinterpret_cast<const float *>(pzs + po), nullptr, NT, zcomp);
             } else {
                 v[0] += dt * bx * (X[0] + X[1] + X[2]);
                 v[1] += dt * by * (X[3] + X[4] + X[5]);
