@@ -5,6 +5,9 @@
 #include <string.h>
 #include <vector>
 #include <algorithm>
+#include <map>
+#include <mutex>
+#include <tuple>
 #include "common.h"
 #include "fdtd_kernels.cuh"
 #include "fdtd_direct.cuh"
@@ -276,7 +279,7 @@ extern "C" void bb_fdtd_destroy(bb_fdtd *h) {
     if (!h) return;
     cudaSetDevice(h->d.device);
     cudaDeviceSynchronize();
-    if (h->comm) nccl_api().CommDestroy(h->comm);
+    // h->comm belongs to the process-wide cache (bb_fdtd_comm_init)
     for (void *a : h->allocs) cudaFree(a);
     for (cudaEvent_t e : h->ev_pool) cudaEventDestroy(e);
     if (h->ev_run0) cudaEventDestroy(h->ev_run0);
@@ -595,15 +598,34 @@ extern "C" int bb_nccl_unique_id(char *out128) {
     return BB_OK;
 }
 
+// Communicators outlive handles: a worker that runs several simulations on the same slab layout (forward,
+// back-propagation, refocus) pays ncclCommInitRank once.  Keyed by (device, rank, nranks); id128 == NULL
+// re-attaches the cached communicator of that key.
+struct CommKey { int device, rank, nranks; bool operator<(const CommKey &o) const { return std::tie(device, rank, nranks) < std::tie(o.device, o.rank, o.nranks); } };
+static std::map<CommKey, ncclComm_t> g_comms;
+static std::mutex g_comms_mutex;
+
 extern "C" int bb_fdtd_comm_init(bb_fdtd *h, const char *id128) {
-    BB_REQUIRE(h && id128, "null argument");
+    BB_REQUIRE(h, "null argument");
     BB_REQUIRE(h->d.nranks > 1, "comm_init needs nranks > 1");
     if (!nccl_api().ok) { bb_set_error("NCCL not available: %s", nccl_api().err.c_str()); return BB_ERR_NCCL; }
     BB_CUDA(cudaSetDevice(h->d.device));
+    const CommKey key{h->d.device, h->d.rank, h->d.nranks};
+    std::lock_guard<std::mutex> lock(g_comms_mutex);
+    auto it = g_comms.find(key);
+    if (!id128) {
+        if (it == g_comms.end()) { bb_set_error("no cached communicator for rank %d of %d on device %d", key.rank, key.nranks, key.device); return BB_ERR_STATE; }
+        h->comm = it->second;
+        return BB_OK;
+    }
+    if (it != g_comms.end()) { nccl_api().CommDestroy(it->second); g_comms.erase(it); }
     ncclUniqueId id;
     memcpy(&id, id128, 128);
-    ncclResult_t r = nccl_api().CommInitRank(&h->comm, h->d.nranks, id, h->d.rank);
+    ncclComm_t comm = nullptr;
+    ncclResult_t r = nccl_api().CommInitRank(&comm, h->d.nranks, id, h->d.rank);
     if (r != ncclSuccess) { bb_set_error("ncclCommInitRank: %s", nccl_api().GetErrorString(r)); return BB_ERR_NCCL; }
+    g_comms[key] = comm;
+    h->comm = comm;
     return BB_OK;
 }
 

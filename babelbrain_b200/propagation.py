@@ -168,7 +168,9 @@ class FdtdSlab:
                              + cells.nbytes + rows32.nbytes + 3 * ox.nbytes + sensor_bytes + t32.nbytes + pml.nbytes)
 
     # ------------------------------------------------------------------
-    def comm_init(self, unique_id):
+    def comm_init(self, unique_id=None):
+        """Join the slab communicator; unique_id None re-attaches the one an earlier FdtdSlab of this process
+        created for the same (device, rank, nranks)."""
         _capi.check(self._L.bb_fdtd_comm_init(self._h, unique_id))
 
     @staticmethod

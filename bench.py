@@ -191,7 +191,7 @@ def run_reference(args):
            'config': {'workload': workload_name(meta, 1), 'cells': meta['cells'], 'time_steps': meta['steps'],
                       'sample': 'each step times the first 12 of the %d time steps of the simulation on the host cores' % meta['steps']},
            'cpu_baseline': cb, 'e2e': {'value': v, 'unit': 'Gcell-updates/s', 'h2d_bytes_per_step': 0, 'd2h_bytes_per_step': 0}}
-    print(json.dumps(out))
+    print(json.dumps(out), flush=True)
 
 
 def main():
@@ -280,9 +280,7 @@ def main():
         else:
             s2 = FdtdSlab(*w['args'], device=local_rank, rank=rank, nranks=world, kernel_variant=args.variant,
                           origin=origin, n1_global=n1g, **kw)
-            ids = [FdtdSlab.nccl_unique_id() if rank == 0 else None]
-            dist.broadcast_object_list(ids, src=0)
-            s2.comm_init(ids[0])
+            s2.comm_init()          # the process keeps its slab communicator between simulations
             s2.run()
             collect_results(s2)
             h2d, d2h = s2.h2d_bytes, s2.d2h_bytes
@@ -340,7 +338,7 @@ def main():
                 out['cpu_baseline'], _ = cpu_baseline()
             except Exception as e:  # the baseline is a reported number, never a dependency of the GPU path
                 out['cpu_baseline'] = {'value': None, 'unit': 'Gcell-updates/s', 'cores': None, 'kind': 'port', 'sample': 'failed: %r' % (e,)}
-        print(json.dumps(out))
+        print(json.dumps(out), flush=True)
     slab.close()
     if world > 1:
         dist.destroy_process_group()

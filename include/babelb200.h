@@ -122,7 +122,7 @@ int bb_fdtd_set_sensor_map(bb_fdtd *h, const uint32_t *sensor_map, int64_t *nsen
 int bb_fdtd_get_sensor_index(bb_fdtd *h, void *out, int elem_bytes);
 /* slab neighbours exchange halos with NCCL send/recv; id = 128-byte ncclUniqueId from rank 0 */
 int bb_nccl_unique_id(char *out128);
-int bb_fdtd_comm_init(bb_fdtd *h, const char *id128);
+int bb_fdtd_comm_init(bb_fdtd *h, const char *id128);        /* id128 == NULL: reuse this process's communicator of the same (device, rank, nranks) */
 /* advance nsteps (<0: all remaining).  profile != 0 brackets each kernel with CUDA events. */
 int bb_fdtd_run(bb_fdtd *h, int64_t nsteps, int profile);
 int bb_fdtd_reset(bb_fdtd *h);                               /* zero state, step counter = 0 */
