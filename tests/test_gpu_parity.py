@@ -240,3 +240,65 @@ def test_two_gpu_slabs_match_single_gpu():
     for r in range(2):
         sens[out[r][2]] = out[r][1]
     assert rl2(sens, S1['Pressure']) <= 1e-6
+
+
+def test_full_size_ctx500_properties():
+    """BASELINE configs[1] at full size (240x240x320, 2544 steps), where the oracle is too slow to be the
+    checker: size-independent properties instead.  Linear in the source amplitude, zero RMS inside the PML
+    shell, sensor table = every voxel of the sensor box in IndexSensorMap order, p == -Sigmaxx wherever the
+    wave has only crossed lossless water, finite everywhere."""
+    w = workloads.make_workload('ctx500_skull')
+    over = dict(SelMapsRMSPeakList=['Pressure', 'Sigmaxx'])
+    (S1, R1, _, IP), _ = run_cuda(w, 0, **over)
+    p = R1['Pressure']
+    assert p.shape == (240, 240, 320) and np.isfinite(p).all() and np.isfinite(S1['Pressure']).all()
+    pml = w['meta']['pml']
+    assert not p[:pml].any() and not p[-pml:].any() and not p[:, :pml].any() and not p[:, :, -pml:].any()
+    assert p[pml:-pml, pml:-pml, pml + 1:-pml].min() > 0
+    n1, n2, n3 = p.shape
+    assert IP['IndexSensorMap'].size == (n1 - 2 * pml) * (n2 - 2 * pml) * (n3 - 2 * pml - 1)
+    assert S1['Pressure'].shape == (IP['IndexSensorMap'].size, 2 * w['meta']['ppp'] // w['meta']['sub'])
+    assert np.all(np.diff(IP['IndexSensorMap'].astype(np.int64)) > 0)
+    # in front of the skull the medium is lossless water: pressure and -Sigmaxx coincide there
+    water = (w['args'][0][pml:-pml, pml:-pml, pml + 1:pml + 24] == 0).all()
+    assert water
+    assert rl2(R1['Pressure'][pml:-pml, pml:-pml, pml + 1:pml + 20], R1['Sigmaxx'][pml:-pml, pml:-pml, pml + 1:pml + 20]) <= 1e-4
+    args = list(w['args'])
+    args[4] = args[4] * 0.5
+    (S2, R2, _, _), _ = run_cuda(dict(args=tuple(args), kwargs=w['kwargs']), 0, **over)
+    assert rl2(R2['Pressure'], 0.5 * p.astype(np.float64)) <= 1e-5
+    assert rl2(S2['Pressure'], 0.5 * S1['Pressure'].astype(np.float64)) <= 1e-5
+
+
+def test_rayleigh_variants_against_oracle():
+    """ForwardSimple as the transducer files call it: whole-grid fields, single points (phase programming,
+    BabelIntegrationANNULAR_ARRAY.py:383), attenuating wavenumber, MaxDistance, per-point amplitudes (u0step)."""
+    from BabelViscoFDTD.tools.RayleighAndBHTE import ForwardSimple, InitCuda
+    InitCuda('B200')
+    rng = np.random.default_rng(21)
+    nsrc = 700
+    center = (rng.random((nsrc, 3)).astype(np.float32) - 0.5) * 0.05
+    center[:, 2] = -0.04 - 0.01 * rng.random(nsrc).astype(np.float32)
+    ds = np.full((nsrc, 1), 3e-6, np.float32)
+    u0 = (rng.random(nsrc) + 1j * rng.random(nsrc)).astype(np.complex64)
+    k0 = 2 * np.pi * 7e5 / 1500
+    for npts in (1, 128, 5000):
+        rf = (rng.random((npts, 3)).astype(np.float32) - 0.5) * 0.06
+        rf[:, 2] = rng.random(npts).astype(np.float32) * 0.08
+        for k in (k0 + 0j, k0 - 4.0j):
+            got = ForwardSimple(np.array(k).astype(np.complex64), center, ds, u0, rf)
+            ref = oracle.rayleigh_numpy(np.complex64(k), center, ds, u0, rf)
+            assert got.dtype == np.complex64 and got.shape == (npts,)
+            assert rl2(got, ref) <= TOL, (npts, k, rl2(got, ref))
+        got = ForwardSimple(np.array(k0 + 0j).astype(np.complex64), center, ds, u0, rf, MaxDistance=0.07)
+        ref = oracle.rayleigh_numpy(np.complex64(k0), center, ds, u0, rf, MaxDistance=0.07)
+        assert rl2(got, ref) <= TOL
+    # per-point source amplitudes
+    npts = 64
+    rf = (rng.random((npts, 3)).astype(np.float32) - 0.5) * 0.06
+    u0pp = (rng.random((npts, nsrc)) + 1j * rng.random((npts, nsrc))).astype(np.complex64)
+    got = ForwardSimple(np.array(k0 + 0j).astype(np.complex64), center, ds, u0pp.reshape(-1), rf, u0step=nsrc)
+    ref = np.array([oracle.rayleigh_numpy(np.complex64(k0), center, ds, u0pp[n], rf[n:n + 1])[0] for n in range(npts)])
+    assert rl2(got, ref) <= TOL
+    with pytest.raises(ValueError):
+        ForwardSimple(np.array(k0 + 0j).astype(np.complex64), center, ds[:-1], u0, rf)
