@@ -3,7 +3,7 @@
 //   out[p] = j k/(2 pi) * sum_s ds[s] exp(Im(k) R)/R * u0[s] exp(-j Re(k) R),  R = |rf[p]-center[s]|
 // Compute bound (FP32 + MUFU): sources are staged through shared memory as float4 + float2 records
 // and every thread accumulates PPT field points so each staged source is reused PPT*blockDim times.
-// Per source-point pair: 3 sub, 3 fma (R^2), rsqrt.approx, 1 mul (R), 1 mul (phase), sin.approx +
+// Per source-point pair: 3 sub, 3 fma (R^2), rsqrt.approx + residual correction of R, sin.approx +
 // cos.approx on a phase reduced to one revolution with FMAs (error = rounding of R only), 1 mul
 // (amplitude), 6 fma-class accumulations: ~22 FP32 + 3 MUFU issue slots.
 // MUFU runs at a quarter of the FP32 rate, so the SFU bounds the kernel at
@@ -53,8 +53,10 @@ __global__ void __launch_bounds__(RB) rayleigh_kernel(float k_re, float k_im, lo
                 const float r2 = fmaf(dx, dx, fmaf(dy, dy, dz * dz));
                 float rinv;
                 asm("rsqrt.approx.ftz.f32 %0, %1;" : "=f"(rinv) : "f"(r2));   // R = 0 -> inf, like the reference's 1/R
-                rinv = rinv * fmaf(-0.5f * r2, rinv * rinv, 1.5f);            // one Newton step: R to ~1 ulp (the phase is R k ~ 1e2..1e3 rad)
-                const float R = r2 * rinv;
+                // R = sqrt(r2) to ~0.5 ulp: the phase R k is 1e2..1e3 rad, so an ulp of R is what sets the error of the sum.
+                // (the amplitude keeps the 2-ulp rinv: 1e-7 relative)
+                const float R0 = r2 * rinv;
+                const float R = fmaf(fmaf(-R0, R0, r2), 0.5f * rinv, R0);
                 if (MAXD && R > max_distance) continue;
                 if (PERPOINT) u = u0[(pidx[t] < npts ? pidx[t] : npts - 1) * nsrc + s0 + s];
                 float amp = c.w * rinv;
