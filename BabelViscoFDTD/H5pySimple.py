@@ -73,3 +73,9 @@ def _read(o):
     if t == 'scalar' and np.ndim(v) == 0:
         return v.item() if hasattr(v, 'item') else v
     return v
+
+
+# prefer the genuine implementation when a BabelViscoFDTD install is shadowed by this shim (same on-disk format)
+from BabelViscoFDTD import upstream_attr as _up  # noqa: E402
+ReadFromH5py = _up('H5pySimple', 'ReadFromH5py') or ReadFromH5py
+SaveToH5py = _up('H5pySimple', 'SaveToH5py') or SaveToH5py

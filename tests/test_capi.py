@@ -92,3 +92,35 @@ def test_drop_in_import_surface():
     import BabelViscoFDTD.StaggeredFDTD_3D_With_Relaxation_CUDA as C
     assert PM2 is PropagationModel and callable(C.ListDevices)
     assert 1480 < SpeedofSoundWater(20.0) < 1485
+
+
+def test_shim_delegates_non_hot_path_names_to_a_genuine_install(tmp_path):
+    """With a genuine BabelViscoFDTD further down sys.path, the shim keeps the hot path (ForwardSimple,
+    PropagationModel) and hands out the genuine bio-heat functions / H5pySimple (thermal step unmodified)."""
+    import subprocess
+    import sys
+    up = tmp_path / 'site' / 'BabelViscoFDTD'
+    (up / 'tools').mkdir(parents=True)
+    (up / '__init__.py').write_text('__version__ = "1.2.4"\n')
+    (up / 'tools' / '__init__.py').write_text('')
+    (up / 'tools' / 'RayleighAndBHTE.py').write_text('def BHTE(*a, **k):\n    return "genuine BHTE"\n'
+                                                    'def BHTEMultiplePressureFields(*a, **k):\n    return "genuine multi"\n'
+                                                    'def ForwardSimple(*a, **k):\n    return "genuine FS"\n')
+    (up / 'H5pySimple.py').write_text('def ReadFromH5py(f):\n    return "genuine read"\ndef SaveToH5py(d, f):\n    return "genuine save"\n')
+    code = ('import sys; sys.path.insert(0, %r); sys.path.append(%r)\n'
+            'from BabelViscoFDTD.tools.RayleighAndBHTE import BHTE, BHTEMultiplePressureFields, ForwardSimple\n'
+            'from BabelViscoFDTD.H5pySimple import ReadFromH5py\n'
+            'from BabelViscoFDTD.PropagationModel import PropagationModel\n'
+            'print(BHTE(), BHTEMultiplePressureFields(), ForwardSimple.__module__, ReadFromH5py(None), PropagationModel.__module__)\n'
+            % (ROOT, str(tmp_path / 'site')))
+    out = subprocess.run([sys.executable, '-c', code], capture_output=True, text=True, check=True).stdout.split('\n')[0]
+    assert out == 'genuine BHTE genuine multi babelbrain_b200.rayleigh genuine read babelbrain_b200.propagation'
+
+
+def test_bhte_without_a_genuine_install_says_so():
+    from BabelViscoFDTD.tools.RayleighAndBHTE import BHTE
+    import BabelViscoFDTD
+    if BabelViscoFDTD.upstream() is not None:
+        pytest.skip('a genuine BabelViscoFDTD is installed')
+    with pytest.raises(NotImplementedError):
+        BHTE()
