@@ -304,3 +304,37 @@ def test_rayleigh_variants_against_oracle():
     assert rl2(got, ref) <= TOL
     with pytest.raises(ValueError):
         ForwardSimple(np.array(k0 + 0j).astype(np.complex64), center, ds[:-1], u0, rf)
+
+
+def test_edge_cases_empty_sources_sensors_peak_only_short_pulse():
+    """Empty and ragged inputs: no source voxel, no sensor voxel, peak-only maps, a pulse table shorter than
+    the run (the source stops, BabelIntegrationSingle.py:315-316), DT=None (stable step), odd sizes that are
+    not multiples of the 8 x 64 tile, CheckOnlyParams."""
+    w = workloads.make_workload('ctx500_skull', shape=(37, 43, 67), periods=4, pml=5)
+    MM, ML, f, SM, SF, h, T, SEN = w['args']
+    kw = {k: v for k, v in w['kwargs'].items() if k not in DROP}
+    # no sources: everything stays exactly zero
+    s = FdtdSlab(MM, ML, f, np.zeros_like(SM), SF, h, T, SEN, **kw)
+    s.run()
+    Sensor, RMS, Peak, IP = collect_results(s)
+    s.close()
+    assert not RMS['Pressure'].any() and not Sensor['Pressure'].any()
+    # no sensors: empty table with the right number of columns
+    (S0, R0, _, IP0), _ = run_cuda(dict(args=(MM, ML, f, SM, SF, h, T, np.zeros_like(SEN)), kwargs=w['kwargs']), 0)
+    assert S0['Pressure'].shape == (0, S0['time'].size) and IP0['IndexSensorMap'].size == 0
+    ref = run_oracle(w)
+    assert rl2(R0['Pressure'], ref['RMS']['Pressure']) <= TOL
+    # peak only
+    (S2, _, P2, _), _ = run_cuda(w, 0, SelRMSorPeak=2)
+    refp = run_oracle(w, SelRMSorPeak=2)
+    assert rl2(P2['Pressure'], refp['Peak']['Pressure']) <= TOL
+    r4 = PropagationModel().StaggeredFDTD_3D_with_relaxation(*w['args'], **dict(w['kwargs'], SelRMSorPeak=2))
+    assert len(r4) == 4 and rl2(r4[2]['Pressure'], refp['Peak']['Pressure']) <= TOL
+    # pulse shorter than the run, and the solver's own stable step
+    short = SF[:, :SF.shape[1] // 2]
+    w3 = dict(args=(MM, ML, f, SM, short, h, T, SEN), kwargs=dict(w['kwargs'], DT=None, AlphaCFL=0.9))
+    (S3, R3, _, _), _ = run_cuda(w3, 0)
+    ref3 = run_oracle(w3)
+    assert S3['time'].size == ref3['Sensor']['time'].size
+    assert rl2(R3['Pressure'], ref3['RMS']['Pressure']) <= TOL and rl2(S3['Pressure'], ref3['Sensor']['Pressure']) <= TOL
+    assert PropagationModel().StaggeredFDTD_3D_with_relaxation(*w['args'], **dict(w['kwargs'], CheckOnlyParams=True)) is None
