@@ -27,6 +27,12 @@ class FdtdDesc(ctypes.Structure):
                 ('kernel_variant', ctypes.c_int32), ('reserved', ctypes.c_int32), ('dt', ctypes.c_double)]
 
 
+class PeerInfo(ctypes.Structure):
+    _fields_ = [('pid', ctypes.c_int64), ('device', ctypes.c_int32), ('nown', ctypes.c_int32), ('n2', ctypes.c_int32),
+                ('pitch', ctypes.c_int32), ('v_ptr', ctypes.c_uint64), ('s_ptr', ctypes.c_uint64), ('flag_ptr', ctypes.c_uint64),
+                ('v_ipc', ctypes.c_ubyte * 64), ('s_ipc', ctypes.c_ubyte * 64), ('flag_ipc', ctypes.c_ubyte * 64)]
+
+
 class FdtdStats(ctypes.Structure):
     _fields_ = [('run_ms', ctypes.c_double), ('stress_ms', ctypes.c_double), ('particle_ms', ctypes.c_double),
                 ('pml_ms', ctypes.c_double), ('other_ms', ctypes.c_double),
@@ -41,7 +47,7 @@ SYMBOLS = ['bb_last_error', 'bb_version', 'bb_device_count', 'bb_device_name', '
            'bb_fdtd_destroy', 'bb_fdtd_set_stream', 'bb_fdtd_set_materials', 'bb_fdtd_set_maps',
            'bb_fdtd_set_source_cells', 'bb_fdtd_set_source_functions', 'bb_fdtd_set_sensors',
            'bb_fdtd_set_sensor_map', 'bb_fdtd_get_sensor_index',
-           'bb_nccl_unique_id', 'bb_fdtd_comm_init', 'bb_fdtd_run', 'bb_fdtd_reset', 'bb_fdtd_get_map',
+           'bb_nccl_unique_id', 'bb_fdtd_comm_init', 'bb_fdtd_peer_export', 'bb_fdtd_peer_attach', 'bb_fdtd_run', 'bb_fdtd_reset', 'bb_fdtd_get_map',
            'bb_fdtd_get_sensors', 'bb_fdtd_get_stats', 'bb_rayleigh_forward']
 
 _lib = None
@@ -74,6 +80,8 @@ def lib():
         L.bb_fdtd_get_sensor_index.argtypes = [vp, vp, i32]
         L.bb_nccl_unique_id.argtypes = [ctypes.c_char_p]
         L.bb_fdtd_comm_init.argtypes = [vp, ctypes.c_char_p]
+        L.bb_fdtd_peer_export.argtypes = [vp, ctypes.POINTER(PeerInfo)]
+        L.bb_fdtd_peer_attach.argtypes = [vp, ctypes.POINTER(PeerInfo), ctypes.POINTER(PeerInfo)]
         L.bb_fdtd_run.argtypes = [vp, i64, i32]
         L.bb_fdtd_reset.argtypes = [vp]
         L.bb_fdtd_get_map.argtypes = [vp, i32, i32, vp]

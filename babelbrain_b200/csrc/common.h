@@ -94,6 +94,17 @@ struct DevParams {
     int xhi_begin;       // first owned plane inside the high-i PML (== i1 when none)
     int nylo, tjhi0, nyrows;   // j tiles [0,nylo) and [tjhi0,ntj) hold PML rows; nyrows = stored rows
     int zbw, zpw;              // columns stored per side of the k-PML, and per row (2 zbw)
+    // slab neighbours reached through NVLink peer memory (index 0: lower neighbour, 1: upper).  The boundary CTAs of
+    // a half-step store the two planes the neighbour needs straight into its halo planes and, when the last of
+    // them is done, publish the half-step's sequence number in the neighbour's flag word.
+    float *peerV[2], *peerS[2];          // base of the neighbour's V / S component groups (nullptr: no such neighbour)
+    unsigned peer_plane[2];              // neighbour-local plane that receives this slab's first pushed plane of that side
+    long long peer_vol[2];               // component pitch of the neighbour's groups (its nloc * plane)
+    unsigned long long *flag_local;      // [2] written by the lower / upper neighbour
+    unsigned long long *flag_peer[2];    // where this slab publishes: lower neighbour's [1], upper neighbour's [0]
+    unsigned *push_count;                // [2] plane-pushes completed so far in this launch (last CTA publishes)
+    unsigned long long seq;              // (epoch << 32) | (half-step index + 1) of this launch
+    int publish;                         // 1: the half-step kernel publishes seq itself; 0: a source kernel follows, publish_kernel does
     // RMS / peak accumulators: [slot][(i-i0)*plane + j*pitch + k]
     float *acc_rms, *acc_peak;
     long long acc_stride;

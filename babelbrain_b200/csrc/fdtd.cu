@@ -8,6 +8,7 @@
 #include <map>
 #include <mutex>
 #include <tuple>
+#include <unistd.h>
 #include "common.h"
 #include "fdtd_kernels.cuh"
 #include "fdtd_direct.cuh"
@@ -80,6 +81,11 @@ struct bb_fdtd {
     StressMaps smaps;
     ParticleMaps pmaps;
     int chunk_override = 0, chunk_tail = 1;
+    // NVLink halo push
+    bool peer_mode = false;
+    unsigned long long *flags = nullptr;      // [2] flag words + [2] push counters (device)
+    unsigned epoch = 1;
+    void *ipc_opened[6] = {nullptr, nullptr, nullptr, nullptr, nullptr, nullptr};
     // NCCL
     ncclComm_t comm = nullptr;
     cudaEvent_t ev_boundary = nullptr, ev_halo = nullptr;
@@ -269,6 +275,9 @@ extern "C" int bb_fdtd_create(const bb_fdtd_desc *d, bb_fdtd **out) {
         if ((rc = dev_alloc(h, (void **)&p.acc_peak, (size_t)h->n_acc_maps * p.acc_stride * 4))) return rc;
     for (int n = 0; n < d->steps; n++)
         if (n % d->sensor_subsampling == 0 && n / d->sensor_subsampling >= d->sensor_start) h->nsamples++;
+    if ((rc = dev_alloc(h, (void **)&h->flags, 64))) return rc;
+    p.flag_local = h->flags;
+    p.push_count = reinterpret_cast<unsigned *>(h->flags + 2);
     if (d->kernel_variant == 0 && (rc = make_tensor_maps(h))) return rc;
     BB_CUDA(cudaStreamSynchronize(h->stream));
     *out = h;
@@ -280,6 +289,7 @@ extern "C" void bb_fdtd_destroy(bb_fdtd *h) {
     cudaSetDevice(h->d.device);
     cudaDeviceSynchronize();
     // h->comm belongs to the process-wide cache (bb_fdtd_comm_init)
+    for (void *m : h->ipc_opened) if (m) cudaIpcCloseMemHandle(m);
     for (void *a : h->allocs) cudaFree(a);
     for (cudaEvent_t e : h->ev_pool) cudaEventDestroy(e);
     if (h->ev_run0) cudaEventDestroy(h->ev_run0);
@@ -611,21 +621,89 @@ extern "C" int bb_fdtd_comm_init(bb_fdtd *h, const char *id128) {
     if (!nccl_api().ok) { bb_set_error("NCCL not available: %s", nccl_api().err.c_str()); return BB_ERR_NCCL; }
     BB_CUDA(cudaSetDevice(h->d.device));
     const CommKey key{h->d.device, h->d.rank, h->d.nranks};
-    std::lock_guard<std::mutex> lock(g_comms_mutex);
-    auto it = g_comms.find(key);
-    if (!id128) {
-        if (it == g_comms.end()) { bb_set_error("no cached communicator for rank %d of %d on device %d", key.rank, key.nranks, key.device); return BB_ERR_STATE; }
-        h->comm = it->second;
-        return BB_OK;
+    ncclComm_t old = nullptr;
+    {
+        std::lock_guard<std::mutex> lock(g_comms_mutex);
+        auto it = g_comms.find(key);
+        if (!id128) {
+            if (it == g_comms.end()) { bb_set_error("no cached communicator for rank %d of %d on device %d", key.rank, key.nranks, key.device); return BB_ERR_STATE; }
+            h->comm = it->second;
+            return BB_OK;
+        }
+        if (it != g_comms.end()) { old = it->second; g_comms.erase(it); }
     }
-    if (it != g_comms.end()) { nccl_api().CommDestroy(it->second); g_comms.erase(it); }
+    // ncclCommInitRank blocks until every rank has joined: the cache lock must not be held here (ranks may be threads)
+    if (old) nccl_api().CommDestroy(old);
     ncclUniqueId id;
     memcpy(&id, id128, 128);
     ncclComm_t comm = nullptr;
     ncclResult_t r = nccl_api().CommInitRank(&comm, h->d.nranks, id, h->d.rank);
     if (r != ncclSuccess) { bb_set_error("ncclCommInitRank: %s", nccl_api().GetErrorString(r)); return BB_ERR_NCCL; }
-    g_comms[key] = comm;
+    {
+        std::lock_guard<std::mutex> lock(g_comms_mutex);
+        g_comms[key] = comm;
+    }
     h->comm = comm;
+    return BB_OK;
+}
+
+// ------------------------------------------------------------------------------------------
+// NVLink halo push: descriptors of the slab for its neighbours
+// ------------------------------------------------------------------------------------------
+extern "C" int bb_fdtd_peer_export(bb_fdtd *h, bb_peer_info *out) {
+    BB_REQUIRE(h && out, "null argument");
+    BB_CUDA(cudaSetDevice(h->d.device));
+    memset(out, 0, sizeof(*out));
+    out->pid = (int64_t)getpid();
+    out->device = h->d.device; out->nown = h->nown; out->n2 = h->p.n2; out->pitch = h->p.pitch;
+    out->v_ptr = (uint64_t)h->p.V[0]; out->s_ptr = (uint64_t)h->p.S[0]; out->flag_ptr = (uint64_t)h->flags;
+    static_assert(sizeof(cudaIpcMemHandle_t) == 64, "IPC handle size");
+    BB_CUDA(cudaIpcGetMemHandle((cudaIpcMemHandle_t *)out->v_ipc, h->p.V[0]));
+    BB_CUDA(cudaIpcGetMemHandle((cudaIpcMemHandle_t *)out->s_ipc, h->p.S[0]));
+    BB_CUDA(cudaIpcGetMemHandle((cudaIpcMemHandle_t *)out->flag_ipc, h->flags));
+    return BB_OK;
+}
+
+static int map_peer(bb_fdtd *h, const bb_peer_info *nb, int side) {
+    DevParams &p = h->p;
+    BB_REQUIRE(nb->n2 == p.n2 && nb->pitch == p.pitch, "neighbour slab has a different transverse geometry");
+    void *v = nullptr, *s = nullptr, *f = nullptr;
+    if (nb->pid == (int64_t)getpid()) {          // same process (one thread per GPU): plain peer pointers
+        if (nb->device != h->d.device) {
+            int can = 0;
+            BB_CUDA(cudaDeviceCanAccessPeer(&can, h->d.device, nb->device));
+            if (!can) { bb_set_error("device %d cannot access device %d as a peer", h->d.device, nb->device); return BB_ERR_CUDA; }
+            cudaError_t e = cudaDeviceEnablePeerAccess(nb->device, 0);
+            if (e != cudaSuccess && e != cudaErrorPeerAccessAlreadyEnabled) { bb_set_error("cudaDeviceEnablePeerAccess: %s", cudaGetErrorString(e)); return BB_ERR_CUDA; }
+            cudaGetLastError();
+        }
+        v = (void *)nb->v_ptr; s = (void *)nb->s_ptr; f = (void *)nb->flag_ptr;
+    } else {                                     // another process: CUDA IPC mappings
+        BB_CUDA(cudaIpcOpenMemHandle(&v, *(const cudaIpcMemHandle_t *)nb->v_ipc, cudaIpcMemLazyEnablePeerAccess));
+        BB_CUDA(cudaIpcOpenMemHandle(&s, *(const cudaIpcMemHandle_t *)nb->s_ipc, cudaIpcMemLazyEnablePeerAccess));
+        BB_CUDA(cudaIpcOpenMemHandle(&f, *(const cudaIpcMemHandle_t *)nb->flag_ipc, cudaIpcMemLazyEnablePeerAccess));
+        h->ipc_opened[3 * side] = v; h->ipc_opened[3 * side + 1] = s; h->ipc_opened[3 * side + 2] = f;
+    }
+    p.peerV[side] = (float *)v; p.peerS[side] = (float *)s;
+    p.peer_vol[side] = (long long)(nb->nown + 4) * p.plane;
+    // my planes i0, i0+1 are the lower neighbour's upper halo (its local planes nown+2, nown+3);
+    // my planes i1-2, i1-1 are the upper neighbour's lower halo (its local planes 0, 1)
+    p.peer_plane[side] = side == 0 ? (unsigned)(nb->nown + 2) : 0u;
+    // I am the lower neighbour's upper side (its flag word 1) and the upper neighbour's lower side (word 0)
+    p.flag_peer[side] = (unsigned long long *)f + (side == 0 ? 1 : 0);
+    return BB_OK;
+}
+
+extern "C" int bb_fdtd_peer_attach(bb_fdtd *h, const bb_peer_info *lower, const bb_peer_info *upper) {
+    BB_REQUIRE(h, "null handle");
+    BB_REQUIRE(h->d.kernel_variant == 0, "the NVLink halo push needs the default kernels");
+    BB_REQUIRE((lower != nullptr) == (h->d.rank > 0) && (upper != nullptr) == (h->d.rank < h->d.nranks - 1),
+               "rank %d of %d needs exactly its existing neighbours", h->d.rank, h->d.nranks);
+    BB_CUDA(cudaSetDevice(h->d.device));
+    int rc;
+    if (lower && (rc = map_peer(h, lower, 0))) return rc;
+    if (upper && (rc = map_peer(h, upper, 1))) return rc;
+    h->peer_mode = true;
     return BB_OK;
 }
 
@@ -673,7 +751,21 @@ static ChunkPlan make_chunk_plan(const bb_fdtd *h, int ib, int ie) {
     int rest = ie - at;                        // 1 .. chunk planes left: halve it down
     while (rest >= 12 && h->chunk_tail) { const int len = (rest + 1) / 2; push(len); rest -= len; }
     if (rest > 0) push(rest);
+    // NVLink halo push: the piece(s) holding the last two planes go first, so that the upper neighbour has their
+    // results early in the next half-step (the first chunk, which serves the lower neighbour, is early anyway)
+    if (h->peer_mode && h->p.peerS[1] && ie == h->p.i1 && pl.n > 2) {
+        const int move = (pl.end[pl.n - 1] - pl.start[pl.n - 1] >= 2) ? 1 : 2;
+        for (int m = 0; m < move; m++) {
+            const int s0 = pl.start[pl.n - 1], e0 = pl.end[pl.n - 1];
+            for (int z = pl.n - 1; z > 0; z--) { pl.start[z] = pl.start[z - 1]; pl.end[z] = pl.end[z - 1]; }
+            pl.start[0] = s0; pl.end[0] = e0;
+        }
+    }
     return pl;
+}
+
+static unsigned long long half_step_seq(const bb_fdtd *h, bool stress) {
+    return ((unsigned long long)h->epoch << 32) | (unsigned long long)(2 * h->step + (stress ? 0 : 1) + 1);
 }
 
 template <typename K>
@@ -695,7 +787,8 @@ static int prepare_kernels() {
 
 // one half-step over the owned planes [ib, ie): a single fused launch (interior + PML shell)
 template <typename LT>
-static int launch_half_step(bb_fdtd *h, bool stress, int acc_mode, int ib, int ie, Timer &tm, const ChunkPlan *given = nullptr) {
+static int launch_half_step(bb_fdtd *h, bool stress, int acc_mode, int ib, int ie, Timer &tm, const ChunkPlan *given = nullptr,
+                            bool publish_in_kernel = true) {
     if (ie <= ib) return BB_OK;
     const DevParams &p = h->p;
     tm.begin(stress ? CAT_STRESS : CAT_PARTICLE);
@@ -710,6 +803,9 @@ static int launch_half_step(bb_fdtd *h, bool stress, int acc_mode, int ib, int i
         }
     } else {
         const ChunkPlan plan = given ? *given : make_chunk_plan(h, ib, ie);
+        DevParams p = h->p;       // per-launch copy: the sequence number of this half-step for the NVLink halo push
+        p.seq = half_step_seq(h, stress);
+        p.publish = publish_in_kernel ? 1 : 0;
         const dim3 blk(tma::NTB, 1, 1), grid(p.ntk, p.ntj, plan.n);
         if (stress) {
             const int sm = tma::SMEM_BYTES;
@@ -766,6 +862,20 @@ static int half_step(bb_fdtd *h, bool stress, int n, int acc, Timer &tm) {
     const DevParams &p = h->p;
     const bool src_here = stress ? (h->d.type_source >= 2) : (h->d.type_source < 2);
     int rc;
+    if (h->peer_mode) {
+        // NVLink halo push: one launch; the boundary CTAs store into the neighbours' halo planes.  When sources are
+        // injected behind the kernel they push their cells too and a one-thread kernel publishes the half-step.
+        const bool src_now = src_here && h->nsrc_cells > 0 && n < h->d.nt_src && h->srcfun;
+        if ((rc = launch_half_step<LT>(h, stress, acc, p.i0, p.i1, tm, nullptr, !src_now))) return rc;
+        if (src_now) {
+            if ((rc = launch_sources(h, n, 0, h->nsrc_cells, tm))) return rc;
+            DevParams pp = h->p;
+            pp.seq = half_step_seq(h, stress);
+            publish_kernel<<<1, 1, 0, h->stream>>>(pp);
+            BB_CUDA(cudaGetLastError());
+        }
+        return BB_OK;
+    }
     if (h->d.nranks > 1) {
         // inputs of this half-step: halos sent during the previous half-step
         BB_CUDA(cudaStreamWaitEvent(h->stream, h->ev_halo, 0));
@@ -823,7 +933,7 @@ static int run_steps(bb_fdtd *h, int64_t nsteps, Timer &tm) {
 extern "C" int bb_fdtd_run(bb_fdtd *h, int64_t nsteps, int profile) {
     BB_REQUIRE(h, "null handle");
     if (!h->materials_set || !h->maps_set) { bb_set_error("set_materials / set_maps must be called before run"); return BB_ERR_STATE; }
-    if (h->d.nranks > 1 && !h->comm) { bb_set_error("multi-rank handle without comm_init"); return BB_ERR_STATE; }
+    if (h->d.nranks > 1 && !h->comm && !h->peer_mode) { bb_set_error("multi-rank handle without comm_init / peer_attach"); return BB_ERR_STATE; }
     BB_CUDA(cudaSetDevice(h->d.device));
     if (nsteps < 0 || h->step + nsteps > h->d.steps) nsteps = h->d.steps - h->step;
     if (!h->prepared) {
@@ -838,11 +948,11 @@ extern "C" int bb_fdtd_run(bb_fdtd *h, int64_t nsteps, int profile) {
     Timer tm{h, profile != 0};
     h->ev_used = 0;
     h->ev_cat.clear();
-    if (h->d.nranks > 1) BB_CUDA(cudaEventRecord(h->ev_halo, h->comm_stream));
+    if (h->d.nranks > 1 && !h->peer_mode) BB_CUDA(cudaEventRecord(h->ev_halo, h->comm_stream));
     BB_CUDA(cudaEventRecord(h->ev_run0, h->stream));
     int rc = h->label_bytes == 1 ? run_steps<uint8_t>(h, nsteps, tm) : run_steps<uint16_t>(h, nsteps, tm);
     if (rc) return rc;
-    if (h->d.nranks > 1) BB_CUDA(cudaStreamWaitEvent(h->stream, h->ev_halo, 0));
+    if (h->d.nranks > 1 && !h->peer_mode) BB_CUDA(cudaStreamWaitEvent(h->stream, h->ev_halo, 0));
     BB_CUDA(cudaEventRecord(h->ev_run1, h->stream));
     BB_CUDA(cudaStreamSynchronize(h->stream));
     BB_CUDA(cudaGetLastError());
@@ -883,6 +993,7 @@ extern "C" int bb_fdtd_reset(bb_fdtd *h) {
     if (h->sensor_out) BB_CUDA(cudaMemsetAsync(h->sensor_out, 0, (size_t)h->n_sensor_maps * h->nsamples * h->nsensors * 4, h->stream));
     BB_CUDA(cudaStreamSynchronize(h->stream));
     h->step = 0;
+    h->epoch++;                   // sequence numbers of the NVLink halo push never repeat: flags of an earlier epoch are just smaller
     return BB_OK;
 }
 

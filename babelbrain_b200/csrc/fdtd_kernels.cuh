@@ -5,7 +5,22 @@
 // ------------------------------------------------------------------------------------------
 // sources, sensors, bookkeeping
 // ------------------------------------------------------------------------------------------
-// one thread per source cell; sf is [nt_src][nsrc] (row n contiguous)
+// one thread per source cell; sf is [nt_src][nsrc] (row n contiguous).  A source in one of the slab's boundary
+// planes also updates the copy the slab neighbour holds in its halo (NVLink halo push, DevParams::peerV).
+__device__ __forceinline__ void push_source_cell(const DevParams &p, float *const *peer, int ncomp, const int *comp, const float *val, long long q) {
+    const long long ipl = q / p.plane;
+    const int i = (int)ipl - 2 + p.i0;
+    const long long col = q - ipl * p.plane;
+#pragma unroll
+    for (int side = 0; side < 2; side++) {
+        if (!peer[side]) continue;
+        const bool mine = side == 0 ? (i < p.i0 + 2) : (i >= p.i1 - 2);
+        if (!mine) continue;
+        const long long qn = (long long)(p.peer_plane[side] + (side == 0 ? i - p.i0 : i - (p.i1 - 2))) * p.plane + col;
+        for (int c = 0; c < ncomp; c++) peer[side][comp[c] * p.peer_vol[side] + qn] = val[c];
+    }
+}
+
 __global__ void source_kernel(const DevParams p, int type_source, long long ncells, const long long *__restrict__ cell,
                               const int *__restrict__ row, const float *__restrict__ ox,
                               const float *__restrict__ oy, const float *__restrict__ oz,
@@ -18,10 +33,29 @@ __global__ void source_kernel(const DevParams p, int type_source, long long ncel
         const float w = v * ox[s];
         if (type_source == 2) { p.S[0][q] += w; p.S[1][q] += w; p.S[2][q] += w; }
         else { p.S[0][q] = w; p.S[1][q] = w; p.S[2][q] = w; }
+        if (p.peerS[0] || p.peerS[1]) {
+            const int comp[1] = { 0 };
+            const float val[1] = { p.S[0][q] };
+            push_source_cell(p, p.peerS, 1, comp, val, q);
+            __threadfence_system();
+        }
     } else {
         if (type_source == 0) { p.V[0][q] += v * ox[s]; p.V[1][q] += v * oy[s]; p.V[2][q] += v * oz[s]; }
         else { p.V[0][q] = v * ox[s]; p.V[1][q] = v * oy[s]; p.V[2][q] = v * oz[s]; }
+        if (p.peerV[0] || p.peerV[1]) {
+            const int comp[3] = { 0, 1, 2 };
+            const float val[3] = { p.V[0][q], p.V[1][q], p.V[2][q] };
+            push_source_cell(p, p.peerV, 3, comp, val, q);
+            __threadfence_system();
+        }
     }
+}
+
+// publishes the sequence number of a half-step whose pushes were completed by earlier kernels of the stream
+__global__ void publish_kernel(const DevParams p) {
+    __threadfence_system();
+    if (p.flag_peer[0]) *reinterpret_cast<volatile unsigned long long *>(p.flag_peer[0]) = p.seq;
+    if (p.flag_peer[1]) *reinterpret_cast<volatile unsigned long long *>(p.flag_peer[1]) = p.seq;
 }
 
 template <typename LT>

@@ -82,6 +82,25 @@ __device__ __forceinline__ void tma_load_4d(uint32_t dst, const CUtensorMap *map
 __device__ __forceinline__ void mbar_arrive(uint32_t bar) {
     asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(bar) : "memory");
 }
+// ---- NVLink halo push (see DevParams::peerV): wait for the neighbours' previous half-step, publish this one
+__device__ __forceinline__ void peer_wait(const DevParams &p, int side) {
+    const unsigned long long want = p.seq - 1;                   // the neighbour's previous half-step of this epoch
+    const volatile unsigned long long *f = p.flag_local + side;
+    unsigned spins = 0;
+    while (*f < want) { if (++spins > (1u << 24)) __trap(); __nanosleep(64); }
+    __threadfence();
+    asm volatile("fence.proxy.async;" ::: "memory");             // the TMA unit reads what the neighbour wrote
+}
+// called by one thread of a CTA whose consumers have all finished (and fenced) their peer stores
+__device__ __forceinline__ void peer_publish(const DevParams &p, int side, unsigned planes_pushed, unsigned expected) {
+    const unsigned before = atomicAdd(p.push_count + side, planes_pushed);
+    if (before + planes_pushed == expected) {
+        p.push_count[side] = 0;                                   // ready for the next launch
+        __threadfence_system();
+        *reinterpret_cast<volatile unsigned long long *>(p.flag_peer[side]) = p.seq;
+    }
+}
+__device__ __forceinline__ void consumer_bar() { asm volatile("bar.sync 1, %0;" ::"n"(NT) : "memory"); }
 __device__ __forceinline__ void fence_barrier_init() { asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory"); }
 
 // ---------------------------------------------------------------- tile flags
@@ -196,7 +215,13 @@ __global__ void __launch_bounds__(NTB, CTAS_PER_SM) stress_tma(const __grid_cons
         const int ipl = ipl0 + tid;
         sF[tid] = ipl < p.nloc ? p.flags[((long long)ipl * p.ntj + blockIdx.y) * p.ntk + blockIdx.x] : 0;
     }
+    // halo planes received through NVLink: the neighbour's previous half-step must have landed before this CTA
+    // (its TMA loads and its queue prologue) reads them
+    const bool first_hs = (unsigned)(p.seq & 0xffffffffu) <= 1u;
+    const bool near_lo = ic0 < p.i0 + 2 && p.peerV[0] != nullptr, near_hi = ic1 > p.i1 - 2 && p.peerV[1] != nullptr;
     if (tid == 0) {
+        if (!first_hs && near_lo) peer_wait(p, 0);
+        if (!first_hs && near_hi) peer_wait(p, 1);
         for (int s = 0; s < nsh; s++) { mbar_init(fullH + s * 8, 1); mbar_init(emptyH + s * 8, NCW); }
         for (int s = 0; s < nsp; s++) { mbar_init(fullP + s * 8, 1); mbar_init(emptyP + s * 8, NCW); }
         fence_barrier_init();
@@ -444,6 +469,19 @@ __global__ void __launch_bounds__(NTB, CTAS_PER_SM) stress_tma(const __grid_cons
                     accumulate(p, BB_MAP_PRESSURE, qa, -c.K * pr, false);
                 }
             }
+            // ---------------- boundary planes also go to the slab neighbour (the stresses its particle update differentiates along i)
+            if (i < p.i0 + 2 && p.peerS[0]) {
+                float *b = p.peerS[0];
+                const unsigned qn = (p.peer_plane[0] + (unsigned)(i - p.i0)) * s1 + col;
+                b[qn] = s[0];
+                if (f & TF_SOLID) { b[3 * p.peer_vol[0] + qn] = s[3]; b[4 * p.peer_vol[0] + qn] = s[4]; }
+            }
+            if (i >= p.i1 - 2 && p.peerS[1]) {
+                float *b = p.peerS[1];
+                const unsigned qn = (p.peer_plane[1] + (unsigned)(i - (p.i1 - 2))) * s1 + col;
+                b[qn] = s[0];
+                if (f & TF_SOLID) { b[3 * p.peer_vol[1] + qn] = s[3]; b[4 * p.peer_vol[1] + qn] = s[4]; }
+            }
         }
         // ---------------- this warp is done with the slots of plane i
         __syncwarp();
@@ -453,6 +491,20 @@ __global__ void __launch_bounds__(NTB, CTAS_PER_SM) stress_tma(const __grid_cons
         if (ho2 == hend) { ho2 = 0; hb2 = fullH; hpar ^= 1u; }
         po += pstage; pbar += 8;
         if (po == pend) { po = 0; pbar = fullP; ppar ^= 1u; }
+    }
+    // ---- boundary planes pushed by this CTA: fence them system-wide, then one thread counts them in; the CTA that
+    // completes the count publishes the sequence number in the neighbour's flag word
+    // (when sources are injected after this kernel, the host launches publish_kernel behind them instead)
+    const int push_lo = p.peerS[0] ? max(0, min(ic1, p.i0 + 2) - ic0) : 0;
+    const int push_hi = p.peerS[1] ? max(0, ic1 - max(ic0, p.i1 - 2)) : 0;
+    if ((push_lo || push_hi) && p.publish) {
+        __threadfence_system();
+        consumer_bar();
+        if (tid == 0) {
+            const unsigned expected = 2u * gridDim.x * gridDim.y;
+            if (push_lo) peer_publish(p, 0, push_lo, expected);
+            if (push_hi) peer_publish(p, 1, push_hi, expected);
+        }
     }
 }
 
@@ -507,7 +559,13 @@ __global__ void __launch_bounds__(NTB, CTAS_PER_SM) particle_tma(const __grid_co
         const int ipl = ipl0 + tid;
         sF[tid] = ipl < p.nloc ? p.flags[((long long)ipl * p.ntj + blockIdx.y) * p.ntk + blockIdx.x] : 0;
     }
+    // halo planes received through NVLink: the neighbour's previous half-step must have landed before this CTA
+    // (its TMA loads and its queue prologue) reads them
+    const bool first_hs = (unsigned)(p.seq & 0xffffffffu) <= 1u;
+    const bool near_lo = ic0 < p.i0 + 2 && p.peerS[0] != nullptr, near_hi = ic1 > p.i1 - 2 && p.peerS[1] != nullptr;
     if (tid == 0) {
+        if (!first_hs && near_lo) peer_wait(p, 0);
+        if (!first_hs && near_hi) peer_wait(p, 1);
         for (int s = 0; s < nsh; s++) { mbar_init(fullH + s * 8, 1); mbar_init(emptyH + s * 8, NCW); }
         for (int s = 0; s < nsp; s++) { mbar_init(fullP + s * 8, 1); mbar_init(emptyP + s * 8, NCW); }
         fence_barrier_init();
@@ -672,6 +730,16 @@ __global__ void __launch_bounds__(NTB, CTAS_PER_SM) particle_tma(const __grid_co
             }
             if (l0 & LabelTraits<LT>::REFL) { v[0] = v[1] = v[2] = 0.f; }
             p.V[0][q] = v[0]; p.V[1][q] = v[1]; p.V[2][q] = v[2];
+            if (i < p.i0 + 2 && p.peerV[0]) {
+                float *b = p.peerV[0];
+                const unsigned qn = (p.peer_plane[0] + (unsigned)(i - p.i0)) * s1 + col;
+                b[qn] = v[0]; b[p.peer_vol[0] + qn] = v[1]; b[2 * p.peer_vol[0] + qn] = v[2];
+            }
+            if (i >= p.i1 - 2 && p.peerV[1]) {
+                float *b = p.peerV[1];
+                const unsigned qn = (p.peer_plane[1] + (unsigned)(i - (p.i1 - 2))) * s1 + col;
+                b[qn] = v[0]; b[p.peer_vol[1] + qn] = v[1]; b[2 * p.peer_vol[1] + qn] = v[2];
+            }
             if (ACC && !cellpml) {
                 const unsigned qa = q - 2 * s1;
                 accumulate(p, BB_MAP_VX, qa, v[0], false);
@@ -687,6 +755,19 @@ __global__ void __launch_bounds__(NTB, CTAS_PER_SM) particle_tma(const __grid_co
         if (ho2 == hend) { ho2 = 0; hb2 = fullH; hpar ^= 1u; }
         po += pstage; pbar += 8;
         if (po == pend) { po = 0; pbar = fullP; ppar ^= 1u; }
+    }
+    // ---- boundary planes pushed by this CTA: fence them system-wide, then one thread counts them in; the CTA that
+    // completes the count publishes the sequence number in the neighbour's flag word
+    const int push_lo = p.peerV[0] ? max(0, min(ic1, p.i0 + 2) - ic0) : 0;
+    const int push_hi = p.peerV[1] ? max(0, ic1 - max(ic0, p.i1 - 2)) : 0;
+    if ((push_lo || push_hi) && p.publish) {
+        __threadfence_system();
+        consumer_bar();
+        if (tid == 0) {
+            const unsigned expected = 2u * gridDim.x * gridDim.y;
+            if (push_lo) peer_publish(p, 0, push_lo, expected);
+            if (push_hi) peer_publish(p, 1, push_hi, expected);
+        }
     }
 }
 }  // namespace tma

@@ -173,6 +173,20 @@ class FdtdSlab:
         created for the same (device, rank, nranks)."""
         _capi.check(self._L.bb_fdtd_comm_init(self._h, unique_id))
 
+    def peer_export(self):
+        """Descriptor of this slab for its neighbours (bytes; may cross process boundaries)."""
+        info = _capi.PeerInfo()
+        _capi.check(self._L.bb_fdtd_peer_export(self._h, ctypes.byref(info)))
+        return bytes(info)
+
+    def peer_attach(self, lower, upper):
+        """NVLink halo push: lower / upper = peer_export() of the ranks below / above (None at the ends).
+        Replaces comm_init: no NCCL call remains in the time loop."""
+        lo = _capi.PeerInfo.from_buffer_copy(lower) if lower is not None else None
+        up = _capi.PeerInfo.from_buffer_copy(upper) if upper is not None else None
+        _capi.check(self._L.bb_fdtd_peer_attach(self._h, ctypes.byref(lo) if lo is not None else None,
+                                                ctypes.byref(up) if up is not None else None))
+
     @staticmethod
     def nccl_unique_id():
         buf = ctypes.create_string_buffer(128)

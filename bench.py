@@ -234,10 +234,24 @@ def main():
     origin, n1g = (None, None) if local is None else local
     slab = FdtdSlab(*w['args'], device=local_rank, rank=rank, nranks=world, kernel_variant=args.variant,
                     origin=origin, n1_global=n1g, **kw)
-    if world > 1:
-        ids = [FdtdSlab.nccl_unique_id() if rank == 0 else None]
-        dist.broadcast_object_list(ids, src=0)
-        slab.comm_init(ids[0])
+    halo = os.environ.get('BB_HALO', 'peer')     # 'peer': NVLink halo push from the boundary CTAs; 'nccl': send/recv exchange
+
+    def connect(s, first):
+        if world == 1:
+            return
+        if halo == 'nccl':
+            if first:
+                ids = [FdtdSlab.nccl_unique_id() if rank == 0 else None]
+                dist.broadcast_object_list(ids, src=0)
+                s.comm_init(ids[0])
+            else:
+                s.comm_init()          # the process keeps its slab communicator between simulations
+        else:
+            exports = [None] * world
+            dist.all_gather_object(exports, s.peer_export())
+            s.peer_attach(exports[rank - 1] if rank > 0 else None, exports[rank + 1] if rank < world - 1 else None)
+            dist.barrier()
+    connect(slab, True)
     glo = 0 if origin is None else origin
     cls, alg = traffic_model(w['args'][0], w['args'][1], meta['pml'], slab.i0, slab.i1, glo, meta['shape'][0])
 
@@ -280,10 +294,11 @@ def main():
         else:
             s2 = FdtdSlab(*w['args'], device=local_rank, rank=rank, nranks=world, kernel_variant=args.variant,
                           origin=origin, n1_global=n1g, **kw)
-            s2.comm_init()          # the process keeps its slab communicator between simulations
+            connect(s2, False)
             s2.run()
             collect_results(s2)
             h2d, d2h = s2.h2d_bytes, s2.d2h_bytes
+            barrier()                   # nobody frees memory a neighbour may still be writing to
             s2.close()
         barrier()
         if n > 0:
@@ -317,7 +332,8 @@ def main():
             'config': {'workload': workload_name(meta, world),
                        'cells': meta['cells'], 'time_steps': meta['steps'], 'seconds_per_simulation': ms_per_step * 1e-3,
                        'l2_policy': 'state (>1.2 GB per GPU) is far larger than the 126 MB L2 and is rewritten by reset() between timed simulations',
-                       'kernel_variant': args.variant, 'cell_classes_rank0': cls},
+                       'kernel_variant': args.variant, 'cell_classes_rank0': cls,
+                       'halo_exchange': None if world == 1 else ('NVLink peer stores from the boundary CTAs' if halo == 'peer' else 'NCCL send/recv')},
             'e2e': {'value': e2e_val, 'unit': 'Gcell-updates/s', 'h2d_bytes_per_step': int(tb[0].item()), 'd2h_bytes_per_step': int(tb[1].item()),
                     'ms_per_step': float(te.item()), 'phases_rank0': e2e_phases},
             'gpu_launches': int(sum(s['stress_launches'] + s['particle_launches'] + s['pml_launches'] + s['other_launches'] for s in stats)),

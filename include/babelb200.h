@@ -123,6 +123,21 @@ int bb_fdtd_get_sensor_index(bb_fdtd *h, void *out, int elem_bytes);
 /* slab neighbours exchange halos with NCCL send/recv; id = 128-byte ncclUniqueId from rank 0 */
 int bb_nccl_unique_id(char *out128);
 int bb_fdtd_comm_init(bb_fdtd *h, const char *id128);        /* id128 == NULL: reuse this process's communicator of the same (device, rank, nranks) */
+/* NVLink halo push (preferred over the NCCL exchange when every neighbour is reachable as CUDA peer memory):
+ * each rank exports a descriptor of its slab, the host side hands every rank its neighbours' descriptors
+ * (same process: raw peer pointers; another process: CUDA IPC handles), and from then on the boundary CTAs of each
+ * half-step kernel store the two planes a neighbour needs straight into its halo planes and publish a sequence
+ * number there; no separate exchange step, no NCCL call in the time loop. */
+typedef struct bb_peer_info {
+    int64_t pid;                 /* exporting process */
+    int32_t device, nown;        /* CUDA ordinal, planes owned */
+    int32_t n2, pitch;           /* transverse geometry (must match) */
+    uint64_t v_ptr, s_ptr, flag_ptr;          /* device addresses in the exporting process */
+    unsigned char v_ipc[64], s_ipc[64], flag_ipc[64];   /* cudaIpcMemHandle_t of the three allocations */
+} bb_peer_info;
+int bb_fdtd_peer_export(bb_fdtd *h, bb_peer_info *out);
+/* lower / upper = descriptor of the rank owning the planes below / above this slab; NULL where there is none */
+int bb_fdtd_peer_attach(bb_fdtd *h, const bb_peer_info *lower, const bb_peer_info *upper);
 /* advance nsteps (<0: all remaining).  profile != 0 brackets each kernel with CUDA events. */
 int bb_fdtd_run(bb_fdtd *h, int64_t nsteps, int profile);
 int bb_fdtd_reset(bb_fdtd *h);                               /* zero state, step counter = 0 */
