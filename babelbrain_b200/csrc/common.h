@@ -105,6 +105,8 @@ struct DevParams {
     unsigned *push_count;                // [2] plane-pushes completed so far in this launch (last CTA publishes)
     unsigned long long seq;              // (epoch << 32) | (half-step index + 1) of this launch
     int publish;                         // 1: the half-step kernel publishes seq itself; 0: a source kernel follows, publish_kernel does
+    // profiling aid (BB_CTA_TIMING=1): per CTA of the last launch {globaltimer at start, at end, blockIdx packed, planes}
+    unsigned long long *dbg;
     // RMS / peak accumulators: [slot][(i-i0)*plane + j*pitch + k]
     float *acc_rms, *acc_peak;
     long long acc_stride;

@@ -275,6 +275,7 @@ extern "C" int bb_fdtd_create(const bb_fdtd_desc *d, bb_fdtd **out) {
         if ((rc = dev_alloc(h, (void **)&p.acc_peak, (size_t)h->n_acc_maps * p.acc_stride * 4))) return rc;
     for (int n = 0; n < d->steps; n++)
         if (n % d->sensor_subsampling == 0 && n / d->sensor_subsampling >= d->sensor_start) h->nsamples++;
+    if (getenv("BB_CTA_TIMING")) { if ((rc = dev_alloc(h, (void **)&p.dbg, (size_t)4 * 8 * 65536))) return rc; }
     if ((rc = dev_alloc(h, (void **)&h->flags, 64))) return rc;
     p.flag_local = h->flags;
     p.push_count = reinterpret_cast<unsigned *>(h->flags + 2);
@@ -1046,6 +1047,15 @@ extern "C" int bb_fdtd_get_sensors(bb_fdtd *h, int map_id, float *out) {
     BB_CUDA(cudaMemcpyAsync(out, tmp, n * 4, cudaMemcpyDeviceToHost, h->stream));
     BB_CUDA(cudaStreamSynchronize(h->stream));
     cudaFree(tmp);
+    return BB_OK;
+}
+
+// profiling aid: the per-CTA records of the most recent half-step launch (needs BB_CTA_TIMING=1 at create); out = 4 x n uint64
+extern "C" int bb_fdtd_debug_cta_times(bb_fdtd *h, unsigned long long *out, int64_t n) {
+    BB_REQUIRE(h && out && n > 0 && n <= 65536, "bad argument");
+    BB_REQUIRE(h->p.dbg, "create the handle with BB_CTA_TIMING=1 in the environment");
+    BB_CUDA(cudaSetDevice(h->d.device));
+    BB_CUDA(cudaMemcpy(out, h->p.dbg, (size_t)n * 32, cudaMemcpyDeviceToHost));
     return BB_OK;
 }
 

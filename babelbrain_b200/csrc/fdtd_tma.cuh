@@ -101,6 +101,7 @@ __device__ __forceinline__ void peer_publish(const DevParams &p, int side, unsig
     }
 }
 __device__ __forceinline__ void consumer_bar() { asm volatile("bar.sync 1, %0;" ::"n"(NT) : "memory"); }
+__device__ __forceinline__ unsigned long long globaltimer_ns() { unsigned long long t; asm volatile("mov.u64 %0, %globaltimer;" : "=l"(t)); return t; }
 __device__ __forceinline__ void fence_barrier_init() { asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory"); }
 
 // ---------------------------------------------------------------- tile flags
@@ -190,6 +191,7 @@ __global__ void __launch_bounds__(NTB, CTAS_PER_SM) stress_tma(const __grid_cons
     const int k0 = blockIdx.x * TX, j0 = blockIdx.y * TY;
     const int ic0 = plan.start[blockIdx.z], ic1 = plan.end[blockIdx.z];
     const int np = ic1 - ic0;                 // planes of this CTA
+    const unsigned long long dbg_t0 = (p.dbg && tid == 0) ? globaltimer_ns() : 0ull;
     const int ipl0 = ic0 - p.i0 + 2;          // local plane of ic0
     // which damped parts this tile can need (CTA-uniform)
     const bool tile_jd = (int)blockIdx.y < p.nylo || (int)blockIdx.y >= p.tjhi0;
@@ -506,6 +508,10 @@ __global__ void __launch_bounds__(NTB, CTAS_PER_SM) stress_tma(const __grid_cons
             if (push_hi) peer_publish(p, 1, push_hi, expected);
         }
     }
+    if (p.dbg && tid == 0) {    // tid 0 is a consumer thread: it leaves the loop when the CTA's last plane is done
+        unsigned long long *d = p.dbg + 4ull * ((blockIdx.z * gridDim.y + blockIdx.y) * gridDim.x + blockIdx.x);
+        d[0] = dbg_t0; d[1] = globaltimer_ns(); d[2] = ((unsigned long long)blockIdx.z << 40) | ((unsigned long long)blockIdx.y << 20) | blockIdx.x; d[3] = (unsigned long long)np;
+    }
 }
 
 // =========================================================================================
@@ -537,6 +543,7 @@ __global__ void __launch_bounds__(NTB, CTAS_PER_SM) particle_tma(const __grid_co
     const int k0 = blockIdx.x * TX, j0 = blockIdx.y * TY;
     const int ic0 = plan.start[blockIdx.z], ic1 = plan.end[blockIdx.z];
     const int np = ic1 - ic0;
+    const unsigned long long dbg_t0 = (p.dbg && tid == 0) ? globaltimer_ns() : 0ull;
     const int ipl0 = ic0 - p.i0 + 2;
     const bool tile_jd = (int)blockIdx.y < p.nylo || (int)blockIdx.y >= p.tjhi0;
     const bool tile_zlo = k0 < p.P, tile_zhi = k0 + TX > p.n3 - p.P;
@@ -768,6 +775,10 @@ __global__ void __launch_bounds__(NTB, CTAS_PER_SM) particle_tma(const __grid_co
             if (push_lo) peer_publish(p, 0, push_lo, expected);
             if (push_hi) peer_publish(p, 1, push_hi, expected);
         }
+    }
+    if (p.dbg && tid == 0) {    // tid 0 is a consumer thread: it leaves the loop when the CTA's last plane is done
+        unsigned long long *d = p.dbg + 4ull * ((blockIdx.z * gridDim.y + blockIdx.y) * gridDim.x + blockIdx.x);
+        d[0] = dbg_t0; d[1] = globaltimer_ns(); d[2] = ((unsigned long long)blockIdx.z << 40) | ((unsigned long long)blockIdx.y << 20) | blockIdx.x; d[3] = (unsigned long long)np;
     }
 }
 }  // namespace tma

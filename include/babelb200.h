@@ -146,6 +146,9 @@ int bb_fdtd_get_map(bb_fdtd *h, int which, int map_id, float *out);
 /* out = (nsensors, nsamples) float32 for one selected sensor map */
 int bb_fdtd_get_sensors(bb_fdtd *h, int map_id, float *out);
 int bb_fdtd_get_stats(bb_fdtd *h, bb_fdtd_stats *out);
+/* profiling aid (handle created with BB_CTA_TIMING=1 in the environment): per CTA of the most recent half-step launch
+ * {start ns, end ns, blockIdx packed z<<40|y<<20|x, planes}; out holds 4*n uint64 */
+int bb_fdtd_debug_cta_times(bb_fdtd *h, unsigned long long *out, int64_t n);
 
 /* ---- Rayleigh integral ---- */
 /* out[p] = j k /(2 pi) * sum_s ds[s] exp(Im(k) R)/R u0[s] exp(-j Re(k) R); host pointers;
