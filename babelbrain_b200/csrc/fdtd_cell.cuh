@@ -83,26 +83,22 @@ __device__ __forceinline__ void stress_shear_interior(const MatCoef &c, float dt
 // total field advances by the sum of the parts' increments (identical up to rounding).
 // ------------------------------------------------------------------------------------------
 struct PmlCell {
-    bool xd, jd, kd;          // which axes are damped at this cell
-    unsigned qx, qy, qz;      // index of the cell in the X / Y / Z part arrays (32 bits: checked at create)
-    float aI, bI, aIh, bIh, aJ, bJ, aJh, bJh, aK, bK, aKh, bKh;
+    bool xd, jd, kd;                  // which axes are damped at this cell
+    unsigned qx, qy, qz;              // index of the cell in the X / Y / Z part arrays (32 bits: checked at create)
+    const AxisCoef *cI, *cJ, *cK;     // coefficient rows of the cell's i, j, k (global or shared); read only for damped axes
 };
 
-// STAGED: the old part value is already on chip (TMA-staged box, one float per cell at `o`);
-// otherwise it is read from the part array.  Only the damped parts are touched.
+// one damped part: f_a' = a f_a + b C D_a; returns the increment f_a' - f_a.  STAGED: the old value is already on
+// chip (TMA-staged box, one float per cell at `o`), otherwise it is read from the part array.
 template <bool STAGED>
-__device__ __forceinline__ float pml_delta(bool damped, const float *o, float *__restrict__ part, unsigned q, float a, float b, float dt, float CD) {
-    if (damped) {
-        const float old = STAGED ? *o : part[q];
-        const float n = a * old + b * CD;
-        part[q] = n;
-        return n - old;
-    }
-    return dt * CD;
+__device__ __forceinline__ float pml_part(const float *o, float *__restrict__ part, unsigned q, float a, float b, float CD) {
+    const float old = STAGED ? *o : part[q];
+    const float n = a * old + b * CD;
+    part[q] = n;
+    return n - old;
 }
 
-__device__ __forceinline__ PmlCell make_pml_cell(const DevParams &p, int i, int j, int k, const AxisCoef &ci, const AxisCoef &cj,
-                                                 const AxisCoef &ck) {
+__device__ __forceinline__ PmlCell make_pml_cell(const DevParams &p, int i, int j, int k) {
     PmlCell c;
     c.xd = in_pml1(i, p.n1, p.P); c.jd = in_pml1(j, p.n2, p.P); c.kd = in_pml1(k, p.n3, p.P);
     const int ipx = i < p.P ? i - p.i0 : p.nxlo + (i - p.xhi_begin);
@@ -112,35 +108,50 @@ __device__ __forceinline__ PmlCell make_pml_cell(const DevParams &p, int i, int 
     c.qx = ((unsigned)ipx * p.n2 + j) * p.pitch + k;
     c.qy = ((unsigned)(i - p.i0) * p.nyrows + jp) * p.pitch + k;
     c.qz = ((unsigned)(i - p.i0) * p.n2 + j) * p.zpw + kp;
-    c.aI = ci.aI; c.bI = ci.bI; c.aIh = ci.aH; c.bIh = ci.bH;
-    c.aJ = cj.aI; c.bJ = cj.bI; c.aJh = cj.aH; c.bJh = cj.bH;
-    c.aK = ck.aI; c.bK = ck.bI; c.aKh = ck.aH; c.bKh = ck.bH;
+    c.cI = p.axI + i; c.cJ = p.axJ + j; c.cK = p.axK + k;
     return c;
 }
 
 // D[9] = Dxx, Dyy, Dzz, Dyx (d+_i Vy), Dxy (d+_j Vx), Dzx (d+_i Vz), Dxz (d+_k Vx), Dzy (d+_j Vz), Dyz (d+_k Vy)
-// ox/oy/oz: this cell's slot in the first staged X/Y/Z part box (X and Y boxes B floats apart, Z boxes
-// ZB floats apart, the two shear Z parts starting at ozs); unused when !STAGED
+// ox/oy/oz: this cell's slot in the first staged X/Y/Z part box (X and Y boxes B floats apart, Z boxes ZB floats
+// apart, the two shear Z parts starting at ozs); unused when !STAGED.  Undamped axes first (one explicit increment),
+// then one block per damped axis.
 template <bool STAGED>
 __device__ __forceinline__ void stress_pml(const DevParams &p, const PmlCell &c, float M, float L, float rigxy, float rigxz, float rigyz,
                                            const float *D, float *s, const float *ox = nullptr, const float *oy = nullptr,
                                            const float *oz = nullptr, const float *ozs = nullptr, int B = 0, int ZB = 0) {
     const float dt = p.dt;
-    s[0] += pml_delta<STAGED>(c.xd, ox, p.XP[0], c.qx, c.aI, c.bI, dt, M * D[0]) + pml_delta<STAGED>(c.jd, oy, p.YP[0], c.qy, c.aJ, c.bJ, dt, L * D[1])
-          + pml_delta<STAGED>(c.kd, oz, p.ZP[0], c.qz, c.aK, c.bK, dt, L * D[2]);
-    s[1] += pml_delta<STAGED>(c.xd, ox + B, p.XP[1], c.qx, c.aI, c.bI, dt, L * D[0]) + pml_delta<STAGED>(c.jd, oy + B, p.YP[1], c.qy, c.aJ, c.bJ, dt, M * D[1])
-          + pml_delta<STAGED>(c.kd, oz + ZB, p.ZP[1], c.qz, c.aK, c.bK, dt, L * D[2]);
-    s[2] += pml_delta<STAGED>(c.xd, ox + 2 * B, p.XP[2], c.qx, c.aI, c.bI, dt, L * D[0]) + pml_delta<STAGED>(c.jd, oy + 2 * B, p.YP[2], c.qy, c.aJ, c.bJ, dt, L * D[1])
-          + pml_delta<STAGED>(c.kd, oz + 2 * ZB, p.ZP[2], c.qz, c.aK, c.bK, dt, M * D[2]);
-    if (rigxy != 0.0f)
-        s[3] += pml_delta<STAGED>(c.xd, ox + 3 * B, p.XP[3], c.qx, c.aIh, c.bIh, dt, rigxy * D[3])
-              + pml_delta<STAGED>(c.jd, oy + 3 * B, p.YP[3], c.qy, c.aJh, c.bJh, dt, rigxy * D[4]);
-    if (rigxz != 0.0f)
-        s[4] += pml_delta<STAGED>(c.xd, ox + 4 * B, p.XP[4], c.qx, c.aIh, c.bIh, dt, rigxz * D[5])
-              + pml_delta<STAGED>(c.kd, ozs, p.ZP[3], c.qz, c.aKh, c.bKh, dt, rigxz * D[6]);
-    if (rigyz != 0.0f)
-        s[5] += pml_delta<STAGED>(c.jd, oy + 4 * B, p.YP[4], c.qy, c.aJh, c.bJh, dt, rigyz * D[7])
-              + pml_delta<STAGED>(c.kd, ozs + ZB, p.ZP[4], c.qz, c.aKh, c.bKh, dt, rigyz * D[8]);
+    const float d0 = c.xd ? 0.f : D[0], d1 = c.jd ? 0.f : D[1], d2 = c.kd ? 0.f : D[2];
+    s[0] += dt * (M * d0 + L * (d1 + d2));
+    s[1] += dt * (M * d1 + L * (d0 + d2));
+    s[2] += dt * (M * d2 + L * (d0 + d1));
+    s[3] += dt * rigxy * ((c.xd ? 0.f : D[3]) + (c.jd ? 0.f : D[4]));
+    s[4] += dt * rigxz * ((c.xd ? 0.f : D[5]) + (c.kd ? 0.f : D[6]));
+    s[5] += dt * rigyz * ((c.jd ? 0.f : D[7]) + (c.kd ? 0.f : D[8]));
+    if (c.xd) {
+        const AxisCoef a = *c.cI;
+        s[0] += pml_part<STAGED>(ox, p.XP[0], c.qx, a.aI, a.bI, M * D[0]);
+        s[1] += pml_part<STAGED>(ox + B, p.XP[1], c.qx, a.aI, a.bI, L * D[0]);
+        s[2] += pml_part<STAGED>(ox + 2 * B, p.XP[2], c.qx, a.aI, a.bI, L * D[0]);
+        if (rigxy != 0.0f) s[3] += pml_part<STAGED>(ox + 3 * B, p.XP[3], c.qx, a.aH, a.bH, rigxy * D[3]);
+        if (rigxz != 0.0f) s[4] += pml_part<STAGED>(ox + 4 * B, p.XP[4], c.qx, a.aH, a.bH, rigxz * D[5]);
+    }
+    if (c.jd) {
+        const AxisCoef a = *c.cJ;
+        s[0] += pml_part<STAGED>(oy, p.YP[0], c.qy, a.aI, a.bI, L * D[1]);
+        s[1] += pml_part<STAGED>(oy + B, p.YP[1], c.qy, a.aI, a.bI, M * D[1]);
+        s[2] += pml_part<STAGED>(oy + 2 * B, p.YP[2], c.qy, a.aI, a.bI, L * D[1]);
+        if (rigxy != 0.0f) s[3] += pml_part<STAGED>(oy + 3 * B, p.YP[3], c.qy, a.aH, a.bH, rigxy * D[4]);
+        if (rigyz != 0.0f) s[5] += pml_part<STAGED>(oy + 4 * B, p.YP[4], c.qy, a.aH, a.bH, rigyz * D[7]);
+    }
+    if (c.kd) {
+        const AxisCoef a = *c.cK;
+        s[0] += pml_part<STAGED>(oz, p.ZP[0], c.qz, a.aI, a.bI, L * D[2]);
+        s[1] += pml_part<STAGED>(oz + ZB, p.ZP[1], c.qz, a.aI, a.bI, L * D[2]);
+        s[2] += pml_part<STAGED>(oz + 2 * ZB, p.ZP[2], c.qz, a.aI, a.bI, M * D[2]);
+        if (rigxz != 0.0f) s[4] += pml_part<STAGED>(ozs, p.ZP[3], c.qz, a.aH, a.bH, rigxz * D[6]);
+        if (rigyz != 0.0f) s[5] += pml_part<STAGED>(ozs + ZB, p.ZP[4], c.qz, a.aH, a.bH, rigyz * D[8]);
+    }
 }
 
 // X[9] = x1 (d+_i Sxx), x2 (d-_j Sxy), x3 (d-_k Sxz), y1 (d-_i Sxy), y2 (d+_j Syy), y3 (d-_k Syz),
@@ -148,15 +159,29 @@ __device__ __forceinline__ void stress_pml(const DevParams &p, const PmlCell &c,
 template <bool STAGED>
 __device__ __forceinline__ void particle_pml(const DevParams &p, const PmlCell &c, float bx, float by, float bz, const float *X, float *v,
                                              const float *ox = nullptr, const float *oy = nullptr, const float *oz = nullptr,
-                                             const float *ozs = nullptr, int B = 0, int ZB = 0) {
-    (void)ozs;
+                                             int B = 0, int ZB = 0) {
     const float dt = p.dt;
-    v[0] += pml_delta<STAGED>(c.xd, ox, p.XP[5], c.qx, c.aIh, c.bIh, dt, bx * X[0]) + pml_delta<STAGED>(c.jd, oy, p.YP[5], c.qy, c.aJ, c.bJ, dt, bx * X[1])
-          + pml_delta<STAGED>(c.kd, oz, p.ZP[5], c.qz, c.aK, c.bK, dt, bx * X[2]);
-    v[1] += pml_delta<STAGED>(c.xd, ox + B, p.XP[6], c.qx, c.aI, c.bI, dt, by * X[3]) + pml_delta<STAGED>(c.jd, oy + B, p.YP[6], c.qy, c.aJh, c.bJh, dt, by * X[4])
-          + pml_delta<STAGED>(c.kd, oz + ZB, p.ZP[6], c.qz, c.aK, c.bK, dt, by * X[5]);
-    v[2] += pml_delta<STAGED>(c.xd, ox + 2 * B, p.XP[7], c.qx, c.aI, c.bI, dt, bz * X[6]) + pml_delta<STAGED>(c.jd, oy + 2 * B, p.YP[7], c.qy, c.aJ, c.bJ, dt, bz * X[7])
-          + pml_delta<STAGED>(c.kd, oz + 2 * ZB, p.ZP[7], c.qz, c.aKh, c.bKh, dt, bz * X[8]);
+    v[0] += dt * bx * ((c.xd ? 0.f : X[0]) + (c.jd ? 0.f : X[1]) + (c.kd ? 0.f : X[2]));
+    v[1] += dt * by * ((c.xd ? 0.f : X[3]) + (c.jd ? 0.f : X[4]) + (c.kd ? 0.f : X[5]));
+    v[2] += dt * bz * ((c.xd ? 0.f : X[6]) + (c.jd ? 0.f : X[7]) + (c.kd ? 0.f : X[8]));
+    if (c.xd) {      // Vx sits on a half node of i, Vy and Vz on integer nodes
+        const AxisCoef a = *c.cI;
+        v[0] += pml_part<STAGED>(ox, p.XP[5], c.qx, a.aH, a.bH, bx * X[0]);
+        v[1] += pml_part<STAGED>(ox + B, p.XP[6], c.qx, a.aI, a.bI, by * X[3]);
+        v[2] += pml_part<STAGED>(ox + 2 * B, p.XP[7], c.qx, a.aI, a.bI, bz * X[6]);
+    }
+    if (c.jd) {
+        const AxisCoef a = *c.cJ;
+        v[0] += pml_part<STAGED>(oy, p.YP[5], c.qy, a.aI, a.bI, bx * X[1]);
+        v[1] += pml_part<STAGED>(oy + B, p.YP[6], c.qy, a.aH, a.bH, by * X[4]);
+        v[2] += pml_part<STAGED>(oy + 2 * B, p.YP[7], c.qy, a.aI, a.bI, bz * X[7]);
+    }
+    if (c.kd) {
+        const AxisCoef a = *c.cK;
+        v[0] += pml_part<STAGED>(oz, p.ZP[5], c.qz, a.aI, a.bI, bx * X[2]);
+        v[1] += pml_part<STAGED>(oz + ZB, p.ZP[6], c.qz, a.aI, a.bI, by * X[5]);
+        v[2] += pml_part<STAGED>(oz + 2 * ZB, p.ZP[7], c.qz, a.aH, a.bH, bz * X[8]);
+    }
 }
 
 // ------------------------------------------------------------------------------------------

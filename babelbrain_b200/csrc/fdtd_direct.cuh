@@ -61,7 +61,7 @@ __global__ void __launch_bounds__(256) stress_direct(const DevParams p, int ib) 
 #pragma unroll
     for (int n = 0; n < 6; n++) s[n] = p.S[n][q];
     if (pml) {
-        const PmlCell pc = make_pml_cell(p, i, j, k, ci, cj, ck);
+        const PmlCell pc = make_pml_cell(p, i, j, k);
         stress_pml<false>(p, pc, c.M, c.L, rigxy, rigxz, rigyz, D, s);
         if (refl) { s[0] = s[1] = s[2] = s[3] = s[4] = s[5] = 0.0f; }
 #pragma unroll
@@ -140,7 +140,7 @@ __global__ void __launch_bounds__(256) particle_direct(const DevParams p, int ib
     X[8] = D4C(ck.caf, ck.cbf, Szz[q + k1p], Szz[q], Szz[q + k2p], Szz[q - k1m]);
     float v[3] = { p.V[0][q], p.V[1][q], p.V[2][q] };
     if (pml) {
-        const PmlCell pc = make_pml_cell(p, i, j, k, ci, cj, ck);
+        const PmlCell pc = make_pml_cell(p, i, j, k);
         particle_pml<false>(p, pc, bx, by, bz, X, v);
     } else {
         v[0] += p.dt * bx * (X[0] + X[1] + X[2]);

@@ -299,7 +299,9 @@ __global__ void __launch_bounds__(NTB, CTAS_PER_SM) stress_tma(const __grid_cons
     const bool jd = in_pml1(j, p.n2, p.P), kd = in_pml1(k, p.n3, p.P);
     const bool jkd = jd || kd;
     const bool jkupd = j < p.n2 - 1 && k < p.n3 - 1;
-    const bool jkedge = j <= 1 || j >= p.n2 - 2 || k <= 1 || k >= p.n3 - 2;
+    // difference coefficients of this thread's row and column (9/8, 1/24 away from the faces of the domain)
+    const float cjb_a = sJ[ty].cab, cjb_b = sJ[ty].cbb, cjf_a = sJ[ty].caf, cjf_b = sJ[ty].cbf;
+    const float ckb_a = sK[tx].cab, ckb_b = sK[tx].cbb, ckf_a = sK[tx].caf, ckf_b = sK[tx].cbf;
     const unsigned s1 = (unsigned)p.plane;   // element indices fit 32 bits (checked at create)
 
     // ---- register queue along i (state before the shift of plane ic0)
@@ -362,31 +364,22 @@ __global__ void __launch_bounds__(NTB, CTAS_PER_SM) stress_tma(const __grid_cons
             MatCoef c;
             if (SMC) c = sC[l0 & MSK]; else c = load_coef_global(p.coef, l0 & MSK);
             // ---------------- the nine staggered differences
+            // staggered differences with the domain-edge rules folded into coefficients: j/k per thread (hoisted out of
+            // the loop), i per plane (uniform) -- one code path for every cell
+            float cib_a = BB_CA, cib_b = BB_CB, cif_a = BB_CA, cif_b = BB_CB;
+            if (i <= 1 || i >= p.n1 - 2) { const AxisCoef ci = load_axis(p.axI, i); cib_a = ci.cab; cib_b = ci.cbb; cif_a = ci.caf; cif_b = ci.cbf; }
             float D[9];
-            if (!(jkedge || i <= 1 || i >= p.n1 - 2)) {
-                D[0] = D4(vx_0, vx_m1, vx_p1, vx_m2);
-                D[1] = D4(by[0], by[-SW], by[SW], by[-2 * SW]);
-                D[2] = D4(bz[0], bz[-1], bz[1], bz[-2]);
-                if (f & TF_SOLID) {
-                    D[3] = D4(vy_p1, vy_0, vy_p2, vy_m1);
-                    D[4] = D4(bx[SW], bx[0], bx[2 * SW], bx[-SW]);
-                    D[5] = D4(vz_p1, vz_0, vz_p2, vz_m1);
-                    D[6] = D4(bx[1], bx[0], bx[2], bx[-1]);
-                    D[7] = D4(bz[SW], bz[0], bz[2 * SW], bz[-SW]);
-                    D[8] = D4(by[1], by[0], by[2], by[-1]);
-                } else { D[3] = D[4] = D[5] = D[6] = D[7] = D[8] = 0.f; }
-            } else {   // cells next to a face of the domain: edge-aware coefficients
-                const AxisCoef ci = load_axis(p.axI, i), cj = sJ[ty], ck = sK[tx];
-                D[0] = D4C(ci.cab, ci.cbb, vx_0, vx_m1, vx_p1, vx_m2);
-                D[1] = D4C(cj.cab, cj.cbb, by[0], by[-SW], by[SW], by[-2 * SW]);
-                D[2] = D4C(ck.cab, ck.cbb, bz[0], bz[-1], bz[1], bz[-2]);
-                D[3] = D4C(ci.caf, ci.cbf, vy_p1, vy_0, vy_p2, vy_m1);
-                D[4] = D4C(cj.caf, cj.cbf, bx[SW], bx[0], bx[2 * SW], bx[-SW]);
-                D[5] = D4C(ci.caf, ci.cbf, vz_p1, vz_0, vz_p2, vz_m1);
-                D[6] = D4C(ck.caf, ck.cbf, bx[1], bx[0], bx[2], bx[-1]);
-                D[7] = D4C(cj.caf, cj.cbf, bz[SW], bz[0], bz[2 * SW], bz[-SW]);
-                D[8] = D4C(ck.caf, ck.cbf, by[1], by[0], by[2], by[-1]);
-            }
+            D[0] = D4C(cib_a, cib_b, vx_0, vx_m1, vx_p1, vx_m2);
+            D[1] = D4C(cjb_a, cjb_b, by[0], by[-SW], by[SW], by[-2 * SW]);
+            D[2] = D4C(ckb_a, ckb_b, bz[0], bz[-1], bz[1], bz[-2]);
+            if (f & TF_SOLID) {
+                D[3] = D4C(cif_a, cif_b, vy_p1, vy_0, vy_p2, vy_m1);
+                D[4] = D4C(cjf_a, cjf_b, bx[SW], bx[0], bx[2 * SW], bx[-SW]);
+                D[5] = D4C(cif_a, cif_b, vz_p1, vz_0, vz_p2, vz_m1);
+                D[6] = D4C(ckf_a, ckf_b, bx[1], bx[0], bx[2], bx[-1]);
+                D[7] = D4C(cjf_a, cjf_b, bz[SW], bz[0], bz[2 * SW], bz[-SW]);
+                D[8] = D4C(ckf_a, ckf_b, by[1], by[0], by[2], by[-1]);
+            } else { D[3] = D[4] = D[5] = D[6] = D[7] = D[8] = 0.f; }
             // ---------------- edge rigidities (only where something is solid)
             float rigxy = 0.f, rigxz = 0.f, rigyz = 0.f, texy = 0.f, texz = 0.f, teyz = 0.f;
             if (f & TF_SOLID) {
@@ -419,10 +412,7 @@ __global__ void __launch_bounds__(NTB, CTAS_PER_SM) stress_tma(const __grid_cons
                 pcell.xd = xd; pcell.jd = jd; pcell.kd = kd;
                 const int ipx = i < p.P ? i - p.i0 : p.nxlo + (i - p.xhi_begin);
                 pcell.qx = (unsigned)ipx * s1 + col; pcell.qy = qy; pcell.qz = qz;
-                const AxisCoef ci = load_axis(p.axI, i), cj = sJ[ty], ck = sK[tx];
-                pcell.aI = ci.aI; pcell.bI = ci.bI; pcell.aIh = ci.aH; pcell.bIh = ci.bH;
-                pcell.aJ = cj.aI; pcell.bJ = cj.bI; pcell.aJh = cj.aH; pcell.bJh = cj.bH;
-                pcell.aK = ck.aI; pcell.bK = ck.bI; pcell.aKh = ck.aH; pcell.bKh = ck.bH;
+                pcell.cI = p.axI + i; pcell.cJ = sJ + ty; pcell.cK = sK + tx;
                 stress_pml<true>(p, pcell, c.M, c.L, rigxy, rigxz, rigyz, D, s, pb + PB_RXX * NT, pb + (yoff >> 2), reinterpret_cast<const float *>(pzs + po),
                                  reinterpret_cast<const float *>(pzs + po + zshear), NT, zcomp);
                 if (refl) { s[0] = s[1] = s[2] = s[3] = s[4] = s[5] = 0.f; }
@@ -626,7 +616,9 @@ __global__ void __launch_bounds__(NTB, CTAS_PER_SM) particle_tma(const __grid_co
     const bool jd = in_pml1(j, p.n2, p.P), kd = in_pml1(k, p.n3, p.P);
     const bool jkd = jd || kd;
     const bool jkupd = j < p.n2 - 1 && k < p.n3 - 1;
-    const bool jkedge = j <= 1 || j >= p.n2 - 2 || k <= 1 || k >= p.n3 - 2;
+    // difference coefficients of this thread's row and column (9/8, 1/24 away from the faces of the domain)
+    const float cjb_a = sJ[ty].cab, cjb_b = sJ[ty].cbb, cjf_a = sJ[ty].caf, cjf_b = sJ[ty].cbf;
+    const float ckb_a = sK[tx].cab, ckb_b = sK[tx].cbb, ckf_a = sK[tx].caf, ckf_b = sK[tx].cbf;
     const unsigned s1 = (unsigned)p.plane;   // element indices fit 32 bits (checked at create)
 
     // queues: Sxx holds i-1..i+2 ; Sxy, Sxz hold i-2..i+1 (state before the shift of plane ic0)
@@ -692,44 +684,28 @@ __global__ void __launch_bounds__(NTB, CTAS_PER_SM) particle_tma(const __grid_co
             if (SMC) { b0 = sB[l0 & MSK]; bi = sB[mi]; bj = sB[mj]; bk = sB[mk]; }
             else { b0 = __ldg(&p.coef[l0 & MSK].B); bi = __ldg(&p.coef[mi].B); bj = __ldg(&p.coef[mj].B); bk = __ldg(&p.coef[mk].B); }
             const float bx = 0.5f * (b0 + bi), by = 0.5f * (b0 + bj), bz = 0.5f * (b0 + bk);
+            float cib_a = BB_CA, cib_b = BB_CB, cif_a = BB_CA, cif_b = BB_CB;
+            if (i <= 1 || i >= p.n1 - 2) { const AxisCoef ci = load_axis(p.axI, i); cib_a = ci.cab; cib_b = ci.cbb; cif_a = ci.caf; cif_b = ci.cbf; }
             float X[9];
-            if (!(jkedge || i <= 1 || i >= p.n1 - 2)) {
-                X[0] = D4(xx_p1, xx_0, xx_p2, xx_m1);
-                X[3] = D4(xy_0, xy_m1, xy_p1, xy_m2);
-                X[6] = D4(xz_0, xz_m1, xz_p1, xz_m2);
-                X[4] = D4(byy[SW], byy[0], byy[2 * SW], byy[-SW]);
-                X[8] = D4(bzz[1], bzz[0], bzz[2], bzz[-1]);
-                if (fsh) {
-                    X[1] = D4(bxy[0], bxy[-SW], bxy[SW], bxy[-2 * SW]);
-                    X[2] = D4(bxz[0], bxz[-1], bxz[1], bxz[-2]);
-                    X[5] = D4(byz[0], byz[-1], byz[1], byz[-2]);
-                    X[7] = D4(byz[0], byz[-SW], byz[SW], byz[-2 * SW]);
-                } else { X[1] = X[2] = X[5] = X[7] = 0.f; }
-            } else {
-                const AxisCoef ci = load_axis(p.axI, i), cj = sJ[ty], ck = sK[tx];
-                X[0] = D4C(ci.caf, ci.cbf, xx_p1, xx_0, xx_p2, xx_m1);
-                X[3] = D4C(ci.cab, ci.cbb, xy_0, xy_m1, xy_p1, xy_m2);
-                X[6] = D4C(ci.cab, ci.cbb, xz_0, xz_m1, xz_p1, xz_m2);
-                X[4] = D4C(cj.caf, cj.cbf, byy[SW], byy[0], byy[2 * SW], byy[-SW]);
-                X[8] = D4C(ck.caf, ck.cbf, bzz[1], bzz[0], bzz[2], bzz[-1]);
-                if (fsh) {
-                    X[1] = D4C(cj.cab, cj.cbb, bxy[0], bxy[-SW], bxy[SW], bxy[-2 * SW]);
-                    X[2] = D4C(ck.cab, ck.cbb, bxz[0], bxz[-1], bxz[1], bxz[-2]);
-                    X[5] = D4C(ck.cab, ck.cbb, byz[0], byz[-1], byz[1], byz[-2]);
-                    X[7] = D4C(cj.cab, cj.cbb, byz[0], byz[-SW], byz[SW], byz[-2 * SW]);
-                } else { X[1] = X[2] = X[5] = X[7] = 0.f; }
-            }
+            X[0] = D4C(cif_a, cif_b, xx_p1, xx_0, xx_p2, xx_m1);
+            X[3] = D4C(cib_a, cib_b, xy_0, xy_m1, xy_p1, xy_m2);
+            X[6] = D4C(cib_a, cib_b, xz_0, xz_m1, xz_p1, xz_m2);
+            X[4] = D4C(cjf_a, cjf_b, byy[SW], byy[0], byy[2 * SW], byy[-SW]);
+            X[8] = D4C(ckf_a, ckf_b, bzz[1], bzz[0], bzz[2], bzz[-1]);
+            if (fsh) {
+                X[1] = D4C(cjb_a, cjb_b, bxy[0], bxy[-SW], bxy[SW], bxy[-2 * SW]);
+                X[2] = D4C(ckb_a, ckb_b, bxz[0], bxz[-1], bxz[1], bxz[-2]);
+                X[5] = D4C(ckb_a, ckb_b, byz[0], byz[-1], byz[1], byz[-2]);
+                X[7] = D4C(cjb_a, cjb_b, byz[0], byz[-SW], byz[SW], byz[-2 * SW]);
+            } else { X[1] = X[2] = X[5] = X[7] = 0.f; }
             float v[3] = { pb[(QB_V + 0) * NT], pb[(QB_V + 1) * NT], pb[(QB_V + 2) * NT] };
             if (cellpml) {
                 PmlCell pcell;
                 pcell.xd = xd; pcell.jd = jd; pcell.kd = kd;
                 const int ipx = i < p.P ? i - p.i0 : p.nxlo + (i - p.xhi_begin);
                 pcell.qx = (unsigned)ipx * s1 + col; pcell.qy = qy; pcell.qz = qz;
-                const AxisCoef ci = load_axis(p.axI, i), cj = sJ[ty], ck = sK[tx];
-                pcell.aI = ci.aI; pcell.bI = ci.bI; pcell.aIh = ci.aH; pcell.bIh = ci.bH;
-                pcell.aJ = cj.aI; pcell.bJ = cj.bI; pcell.aJh = cj.aH; pcell.bJh = cj.bH;
-                pcell.aK = ck.aI; pcell.bK = ck.bI; pcell.aKh = ck.aH; pcell.bKh = ck.bH;
-                particle_pml<true>(p, pcell, bx, by, bz, X, v, pb + QB_X * NT, pb + (yoff >> 2), reinterpret_cast<const float *>(pzs + po), nullptr, NT, zcomp);
+                pcell.cI = p.axI + i; pcell.cJ = sJ + ty; pcell.cK = sK + tx;
+                particle_pml<true>(p, pcell, bx, by, bz, X, v, pb + QB_X * NT, pb + (yoff >> 2), reinterpret_cast<const float *>(pzs + po), NT, zcomp);
             } else {
                 v[0] += dt * bx * (X[0] + X[1] + X[2]);
                 v[1] += dt * by * (X[3] + X[4] + X[5]);
