@@ -187,7 +187,6 @@ __global__ void __launch_bounds__(NTB, CTAS_PER_SM) stress_tma(const __grid_cons
     const uint32_t fullH = sm32 + OFF_BAR, emptyH = fullH + MAX_NSH * 8, fullP = emptyH + MAX_NSH * 8, emptyP = fullP + MAX_NSP * 8;
 
     const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
-    const int tx = tid & (TX - 1), ty = tid / TX;       // consumer threads: cell (ty, tx) of the tile
     const int k0 = blockIdx.x * TX, j0 = blockIdx.y * TY;
     const int ic0 = plan.start[blockIdx.z], ic1 = plan.end[blockIdx.z];
     const int np = ic1 - ic0;                 // planes of this CTA
@@ -294,8 +293,23 @@ __global__ void __launch_bounds__(NTB, CTAS_PER_SM) stress_tma(const __grid_cons
     }
 
     // =============================== consumer warps ===============================
+    // thread -> cell (ty, tx) of the tile.  Plain tiles: a warp is half a row.  Tiles holding k-PML columns: the PML
+    // cells of all rows are enumerated first, then the interior cells, so that a warp runs either the split-field
+    // path or the interior path instead of both (8 rows x 12 PML columns are exactly three warps).
+    int tx, ty;
+    bool mapped = true;
+    if (!(tile_zlo || tile_zhi)) { tx = tid & (TX - 1); ty = tid / TX; }
+    else {
+        const int wcols = min(TX, p.n3 - k0);                                   // columns of the tile inside the grid
+        const int nlo = tile_zlo ? min(p.P - k0, wcols) : 0;                    // PML columns [0, nlo)
+        const int hi0 = tile_zhi ? max(p.n3 - p.P - k0, nlo) : wcols;           // PML columns [hi0, wcols)
+        const int npc = nlo + (wcols - hi0), nic = hi0 - nlo;
+        if (tid < TY * npc) { ty = tid / npc; const int c = tid - ty * npc; tx = c < nlo ? c : hi0 + (c - nlo); }
+        else if (tid - TY * npc < TY * nic) { const int t2 = tid - TY * npc; ty = t2 / nic; tx = nlo + (t2 - ty * nic); }
+        else { tx = 0; ty = 0; mapped = false; }                                // columns beyond the grid: nothing to do
+    }
     const int k = k0 + tx, j = j0 + ty;
-    const bool active = k < p.n3 && j < p.n2;
+    const bool active = mapped && k < p.n3 && j < p.n2;
     const bool jd = in_pml1(j, p.n2, p.P), kd = in_pml1(k, p.n3, p.P);
     const bool jkd = jd || kd;
     const bool jkupd = j < p.n2 - 1 && k < p.n3 - 1;
@@ -529,7 +543,6 @@ __global__ void __launch_bounds__(NTB, CTAS_PER_SM) particle_tma(const __grid_co
     const uint32_t fullH = sm32 + OFF_BAR, emptyH = fullH + MAX_NSH * 8, fullP = emptyH + MAX_NSH * 8, emptyP = fullP + MAX_NSP * 8;
 
     const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
-    const int tx = tid & (TX - 1), ty = tid / TX;       // consumer threads: cell (ty, tx) of the tile
     const int k0 = blockIdx.x * TX, j0 = blockIdx.y * TY;
     const int ic0 = plan.start[blockIdx.z], ic1 = plan.end[blockIdx.z];
     const int np = ic1 - ic0;
@@ -611,8 +624,23 @@ __global__ void __launch_bounds__(NTB, CTAS_PER_SM) particle_tma(const __grid_co
     }
 
     // =============================== consumer warps ===============================
+    // thread -> cell (ty, tx) of the tile.  Plain tiles: a warp is half a row.  Tiles holding k-PML columns: the PML
+    // cells of all rows are enumerated first, then the interior cells, so that a warp runs either the split-field
+    // path or the interior path instead of both (8 rows x 12 PML columns are exactly three warps).
+    int tx, ty;
+    bool mapped = true;
+    if (!(tile_zlo || tile_zhi)) { tx = tid & (TX - 1); ty = tid / TX; }
+    else {
+        const int wcols = min(TX, p.n3 - k0);                                   // columns of the tile inside the grid
+        const int nlo = tile_zlo ? min(p.P - k0, wcols) : 0;                    // PML columns [0, nlo)
+        const int hi0 = tile_zhi ? max(p.n3 - p.P - k0, nlo) : wcols;           // PML columns [hi0, wcols)
+        const int npc = nlo + (wcols - hi0), nic = hi0 - nlo;
+        if (tid < TY * npc) { ty = tid / npc; const int c = tid - ty * npc; tx = c < nlo ? c : hi0 + (c - nlo); }
+        else if (tid - TY * npc < TY * nic) { const int t2 = tid - TY * npc; ty = t2 / nic; tx = nlo + (t2 - ty * nic); }
+        else { tx = 0; ty = 0; mapped = false; }                                // columns beyond the grid: nothing to do
+    }
     const int k = k0 + tx, j = j0 + ty;
-    const bool active = k < p.n3 && j < p.n2;
+    const bool active = mapped && k < p.n3 && j < p.n2;
     const bool jd = in_pml1(j, p.n2, p.P), kd = in_pml1(k, p.n3, p.P);
     const bool jkd = jd || kd;
     const bool jkupd = j < p.n2 - 1 && k < p.n3 - 1;
