@@ -80,7 +80,7 @@ struct bb_fdtd {
     bool materials_set = false, maps_set = false, prepared = false;
     StressMaps smaps;
     ParticleMaps pmaps;
-    int chunk_override = 0, chunk_tail = 1;
+    int chunk_override = 0, chunk_tail = 1, dbg_kernel = -1;
     // NVLink halo push
     bool peer_mode = false;
     unsigned long long *flags = nullptr;      // [2] flag words + [2] push counters (device)
@@ -275,6 +275,7 @@ extern "C" int bb_fdtd_create(const bb_fdtd_desc *d, bb_fdtd **out) {
         if ((rc = dev_alloc(h, (void **)&p.acc_peak, (size_t)h->n_acc_maps * p.acc_stride * 4))) return rc;
     for (int n = 0; n < d->steps; n++)
         if (n % d->sensor_subsampling == 0 && n / d->sensor_subsampling >= d->sensor_start) h->nsamples++;
+    if (const char *e = getenv("BB_CTA_TIMING")) h->dbg_kernel = !strcmp(e, "stress") ? 0 : (!strcmp(e, "particle") ? 1 : -1);
     if (getenv("BB_CTA_TIMING")) { if ((rc = dev_alloc(h, (void **)&p.dbg, (size_t)4 * 8 * 65536))) return rc; }
     if ((rc = dev_alloc(h, (void **)&h->flags, 64))) return rc;
     p.flag_local = h->flags;
@@ -807,6 +808,7 @@ static int launch_half_step(bb_fdtd *h, bool stress, int acc_mode, int ib, int i
         DevParams p = h->p;       // per-launch copy: the sequence number of this half-step for the NVLink halo push
         p.seq = half_step_seq(h, stress);
         p.publish = publish_in_kernel ? 1 : 0;
+        if (h->dbg_kernel >= 0 && h->dbg_kernel != (stress ? 0 : 1)) p.dbg = nullptr;   // BB_CTA_TIMING=stress|particle
         const dim3 blk(tma::NTB, 1, 1), grid(p.ntk, p.ntj, plan.n);
         if (stress) {
             const int sm = tma::SMEM_BYTES;

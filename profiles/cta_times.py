@@ -1,7 +1,7 @@
 """Where does a half-step launch spend its time?  Per-CTA start/end times (globaltimer) of the last particle launch,
 aggregated by tile class.   BB_CTA_TIMING=1 python profiles/cta_times.py [workload] [steps]"""
 import os, sys
-os.environ['BB_CTA_TIMING'] = '1'
+os.environ.setdefault('BB_CTA_TIMING', 'particle')   # or 'stress'
 sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
 import numpy as np
 from babelbrain_b200 import workloads, _capi
@@ -26,7 +26,7 @@ per_plane = (end - start) / planes
 P = w['meta']['pml']
 kedge = (bx * 64 < P) | (bx * 64 + 64 > n3 - P)
 jedge = (by * 8 < P) | (by * 8 + 8 > n2 - P)
-print('%s: %d CTAs of the last launch (particle half-step), makespan %.1f us' % (name, len(rec), end.max()))
+print('%s: %d CTAs of the last %s launch, makespan %.1f us' % (name, len(rec), os.environ['BB_CTA_TIMING'], end.max()))
 for label, m in (('interior tiles', ~kedge & ~jedge), ('k-PML tiles', kedge & ~jedge), ('j-PML tiles', jedge & ~kedge), ('corner tiles', kedge & jedge)):
     if m.any():
         print('  %-15s n=%5d  us/plane: mean %.3f  p10 %.3f  p90 %.3f   (chunks >= 32 planes: %.3f)' % (
