@@ -220,6 +220,7 @@ __global__ void __launch_bounds__(NTB, CTAS_PER_SM) stress_tma(const __grid_cons
     // (its TMA loads and its queue prologue) reads them
     const bool first_hs = (unsigned)(p.seq & 0xffffffffu) <= 1u;
     const bool near_lo = ic0 < p.i0 + 2 && p.peerV[0] != nullptr, near_hi = ic1 > p.i1 - 2 && p.peerV[1] != nullptr;
+    const bool has_peer = (ic0 < p.i0 + 2 || ic1 > p.i1 - 2) && (p.peerV[0] != nullptr || p.peerV[1] != nullptr);   // this CTA may push planes
     if (tid == 0) {
         if (!first_hs && near_lo) peer_wait(p, 0);
         if (!first_hs && near_hi) peer_wait(p, 1);
@@ -476,13 +477,13 @@ __global__ void __launch_bounds__(NTB, CTAS_PER_SM) stress_tma(const __grid_cons
                 }
             }
             // ---------------- boundary planes also go to the slab neighbour (the stresses its particle update differentiates along i)
-            if (i < p.i0 + 2 && p.peerS[0]) {
+            if (has_peer && i < p.i0 + 2 && p.peerS[0]) {
                 float *b = p.peerS[0];
                 const unsigned qn = (p.peer_plane[0] + (unsigned)(i - p.i0)) * s1 + col;
                 b[qn] = s[0];
                 if (f & TF_SOLID) { b[3 * p.peer_vol[0] + qn] = s[3]; b[4 * p.peer_vol[0] + qn] = s[4]; }
             }
-            if (i >= p.i1 - 2 && p.peerS[1]) {
+            if (has_peer && i >= p.i1 - 2 && p.peerS[1]) {
                 float *b = p.peerS[1];
                 const unsigned qn = (p.peer_plane[1] + (unsigned)(i - (p.i1 - 2))) * s1 + col;
                 b[qn] = s[0];
@@ -573,6 +574,7 @@ __global__ void __launch_bounds__(NTB, CTAS_PER_SM) particle_tma(const __grid_co
     // (its TMA loads and its queue prologue) reads them
     const bool first_hs = (unsigned)(p.seq & 0xffffffffu) <= 1u;
     const bool near_lo = ic0 < p.i0 + 2 && p.peerS[0] != nullptr, near_hi = ic1 > p.i1 - 2 && p.peerS[1] != nullptr;
+    const bool has_peer = (ic0 < p.i0 + 2 || ic1 > p.i1 - 2) && (p.peerV[0] != nullptr || p.peerV[1] != nullptr);   // this CTA may push planes
     if (tid == 0) {
         if (!first_hs && near_lo) peer_wait(p, 0);
         if (!first_hs && near_hi) peer_wait(p, 1);
@@ -741,12 +743,12 @@ __global__ void __launch_bounds__(NTB, CTAS_PER_SM) particle_tma(const __grid_co
             }
             if (l0 & LabelTraits<LT>::REFL) { v[0] = v[1] = v[2] = 0.f; }
             p.V[0][q] = v[0]; p.V[1][q] = v[1]; p.V[2][q] = v[2];
-            if (i < p.i0 + 2 && p.peerV[0]) {
+            if (has_peer && i < p.i0 + 2 && p.peerV[0]) {
                 float *b = p.peerV[0];
                 const unsigned qn = (p.peer_plane[0] + (unsigned)(i - p.i0)) * s1 + col;
                 b[qn] = v[0]; b[p.peer_vol[0] + qn] = v[1]; b[2 * p.peer_vol[0] + qn] = v[2];
             }
-            if (i >= p.i1 - 2 && p.peerV[1]) {
+            if (has_peer && i >= p.i1 - 2 && p.peerV[1]) {
                 float *b = p.peerV[1];
                 const unsigned qn = (p.peer_plane[1] + (unsigned)(i - (p.i1 - 2))) * s1 + col;
                 b[qn] = v[0]; b[p.peer_vol[1] + qn] = v[1]; b[2 * p.peer_vol[1] + qn] = v[2];
