@@ -149,6 +149,7 @@ class PinnedPool:
 
     def __init__(self, max_idle_bytes=8 << 30):
         self.idle, self.max_idle, self.idle_bytes = [], max_idle_bytes, 0
+        self.hits = self.misses = 0
 
     def empty(self, shape, dtype):
         import weakref
@@ -161,8 +162,10 @@ class PinnedPool:
         if blk is not None:
             self.idle.pop(pos)
             self.idle_bytes -= blk.nbytes
+            self.hits += 1
         else:
             blk = _PinnedBlock(max(n, 16))
+            self.misses += 1
         buf = (ctypes.c_char * blk.nbytes).from_address(blk.ptr)
         arr = np.frombuffer(buf, dtype=dtype, count=int(np.prod(shape, dtype=np.int64))).reshape(shape)
         weakref.finalize(buf, self._give_back, blk)   # buf lives as long as any view of it

@@ -8,6 +8,7 @@ include/babelb200.h.  No CPU fallback: without the library or a GPU the call rai
 """
 import collections.abc
 import ctypes
+import os
 import weakref
 import numpy as np
 
@@ -128,8 +129,16 @@ class FdtdSlab:
                            sensor_subsampling=self.sub, sensor_start=self.sensor_start, device=int(device),
                            rank=self.rank, nranks=self.nranks, kernel_variant=int(kernel_variant), reserved=0,
                            dt=dt)
+        import time
+        _t = [time.perf_counter()]
+        _marks = []
+
+        def _mark(name):
+            _t.append(time.perf_counter())
+            _marks.append('%s %.3f' % (name, _t[-1] - _t[-2]))
         hp = ctypes.c_void_p()
         _capi.check(L.bb_fdtd_create(ctypes.byref(d), ctypes.byref(hp)))
+        _mark('create')
         self._h = hp
         self._finalizer = weakref.finalize(self, L.bb_fdtd_destroy, hp)
         t32 = np.ascontiguousarray(table, dtype=np.float32)
@@ -143,12 +152,14 @@ class FdtdSlab:
                 raise ValueError('ReflectorMask must have the shape of MaterialMap')
             refl = np.ascontiguousarray(RM[glo - org:ghi - org], dtype=np.uint32)
         _capi.check(L.bb_fdtd_set_maps(hp, _capi.ptr(mm), _capi.ptr(refl)))
+        _mark('maps')
         rows32 = np.ascontiguousarray(rows, dtype=np.int32)
         _capi.check(L.bb_fdtd_set_source_cells(hp, cells.size, _capi.ptr(cells), _capi.ptr(rows32),
                                                _capi.ptr(ox), _capi.ptr(oy), _capi.ptr(oz)))
         if cells.size:
             _capi.check(L.bb_fdtd_set_source_functions(hp, _capi.ptr(SF), int(SF.dtype == np.float64),
                                                        SF.strides[0] // SF.itemsize))
+        _mark('sources')
         self.d2h_bytes = 0
         if scell is not None:
             _capi.check(L.bb_fdtd_set_sensors(hp, scell.size, _capi.ptr(scell)))
@@ -164,6 +175,9 @@ class FdtdSlab:
             self.IndexSensorMap = self.IndexSensorMapLocal = idx
             self.sensor_rows = np.arange(ns.value)
             self.nsensors_total = ns.value
+        _mark('sensors')
+        if os.environ.get('BB_TIMING'):
+            print('FdtdSlab setup: ' + ', '.join(_marks), flush=True)
         self.h2d_bytes = int(mm.nbytes + (refl.nbytes if refl is not None else 0) + SF.nbytes * (cells.size > 0)
                              + cells.nbytes + rows32.nbytes + 3 * ox.nbytes + sensor_bytes + t32.nbytes + pml.nbytes)
 
@@ -219,8 +233,13 @@ class FdtdSlab:
         return out
 
     def get_sensors(self, name):
+        import time
+        t0 = time.perf_counter()
         out = _capi.pinned.empty((self.sensor_rows.size, self.sample_steps.size), np.float32)
+        t1 = time.perf_counter()
         _capi.check(self._L.bb_fdtd_get_sensors(self._h, _capi.MAP_ID[name], _capi.ptr(out)))
+        if os.environ.get('BB_TIMING'):
+            print('get_sensors: alloc %.3f s copy %.3f s (pool hits %d misses %d)' % (t1 - t0, time.perf_counter() - t1, _capi.pinned.hits, _capi.pinned.misses), flush=True)
         self.d2h_bytes += out.nbytes
         return out
 
