@@ -27,7 +27,7 @@ class FdtdSlab:
                  QCorrection=1.0, TypeSource=0, SelRMSorPeak=1, SelMapsRMSPeakList=('ALLV',),
                  SelMapsSensorsList=('Vx', 'Vy', 'Vz'), SensorSubSampling=2, SensorStart=0,
                  ReflectorMask=None, device=0, rank=0, nranks=1, kernel_variant=0, steps=None,
-                 origin=None, n1_global=None):
+                 origin=None, n1_global=None, global_sensor_table=True):
         self._h = None
         if not isinstance(MaterialMap, np.ndarray) or MaterialMap.ndim != 3:
             raise ValueError('MaterialMap must be a 3-D numpy array')
@@ -86,13 +86,15 @@ class FdtdSlab:
             raise ValueError('SourceMap refers to source %d but SourceFunctions has %d rows' % (rows.max() + 1, SF.shape[0]))
         cells = flat.astype(np.int64) + np.int64(i0) * N2 * N3
 
+        where = np.unravel_index(flat, sm_slab.shape)
+
         def weights(O):
             O = np.asarray(O)
             if O.size == 1:
                 return np.full(cells.shape, float(O.reshape(-1)[0]), np.float32)
             if O.shape != MaterialMap.shape:
                 raise ValueError('Ox/Oy/Oz must be single values or volumes of the MaterialMap shape')
-            return np.ascontiguousarray(O[i0 - org:i1 - org].reshape(-1)[flat], dtype=np.float32)
+            return np.ascontiguousarray(O[i0 - org:i1 - org][where], dtype=np.float32)   # no copy of a strided volume
         ox, oy, oz = weights(Ox), weights(Oy), weights(Oz)
 
         # ---- sensors: IndexSensorMap is the 1-based Fortran-order linear index (BASE.py:2503-2511).
@@ -102,7 +104,7 @@ class FdtdSlab:
         idx_dtype = np.uint32 if N1 * N2 * N3 < 2 ** 32 else np.uint64
         self._idx_dtype = idx_dtype
         self._sensor_planes = None
-        if self.nranks > 1 and origin is None:
+        if self.nranks > 1 and origin is None and global_sensor_table:
             sl, sj, sk = np.nonzero(SensorMap[i0 - org:i1 - org])
             findex = (sl.astype(np.int64) + i0) + sj.astype(np.int64) * N1 + sk.astype(np.int64) * N1 * N2
             order = np.argsort(findex, kind='stable')
@@ -280,6 +282,104 @@ class _LastMap(collections.abc.Mapping):
             self._slab = None
 
 
+class _LastMapSlabs(_LastMap):
+    """LastMap of a slab-decomposed run: a key is assembled from every slab on first access."""
+
+    def __init__(self, slabs):
+        self._slabs, self._cache = list(slabs), {}
+
+    def __getitem__(self, k):
+        if k not in self._keys:
+            raise KeyError(k)
+        if k not in self._cache:
+            if not self._slabs:
+                raise RuntimeError('LastMap of an earlier simulation was released when a newer one started')
+            out = _capi.pinned.empty(self._slabs[0].shape, np.float32)
+            for s in self._slabs:
+                s.get_map(2, k, out=out[s.i0:s.i1])
+            self._cache[k] = out
+        return self._cache[k]
+
+    def _release(self):
+        for s in self._slabs:
+            s.close()
+        self._slabs = []
+
+
+def run_slabs_in_process(devices, args, kwargs, timeout=None):
+    """One simulation cut into len(devices) slabs along axis 0, one thread and one bb_fdtd handle per GPU of
+    this process, halos pushed over NVLink from the boundary CTAs (bb_fdtd_peer_attach).  The volumes in
+    `args` / `kwargs` are the caller's whole-grid arrays; every thread uploads only its planes.  Returns
+    (Sensor, RMS, Peak, InputParam, slabs, timing) with the maps and sensor rows of all slabs gathered into
+    whole-grid arrays in the reference's order."""
+    import threading
+    import time
+    from .slab import merge_sensor_tables
+    n = len(devices)
+    gate = threading.Barrier(n, timeout=timeout)
+    slabs, exports, errors = [None] * n, [None] * n, []
+    shared = {}
+    marks = [dict() for _ in range(n)]
+
+    def stage(r, body):
+        try:
+            body(r)
+        except threading.BrokenBarrierError:
+            pass
+        except BaseException as e:  # noqa: BLE001 -- re-raised in the calling thread
+            errors.append(e)
+            gate.abort()
+
+    def rank_main(r):
+        t0 = time.perf_counter()
+        s = slabs[r] = FdtdSlab(*args, device=devices[r], rank=r, nranks=n, global_sensor_table=False, **kwargs)
+        exports[r] = s.peer_export()
+        gate.wait()
+        s.peer_attach(exports[r - 1] if r > 0 else None, exports[r + 1] if r < n - 1 else None)
+        gate.wait()
+        t1 = time.perf_counter()
+        s.run()
+        gate.wait()                     # every slab has finished writing into its neighbours
+        t2 = time.perf_counter()
+        if r == 0:                      # whole-grid result arrays, page-locked, filled by every thread
+            N1, N2, N3 = s.shape
+            index, rows = merge_sensor_tables([x.IndexSensorMapLocal for x in slabs], N1, N2 * N3)
+            shared['index'], shared['rows'] = index, rows
+            shared['sensor'] = {k: _capi.pinned.empty((index.size, s.sample_steps.size), np.float32) for k in s.sensor_names}
+            shared['rms'] = {k: _capi.pinned.empty(s.shape, np.float32) for k in s.rms_names if s.sel_rms_peak & 1}
+            shared['peak'] = {k: _capi.pinned.empty(s.shape, np.float32) for k in s.rms_names if s.sel_rms_peak & 2}
+        gate.wait()
+        for k, full in shared['rms'].items():
+            s.get_map(0, k, out=full[s.i0:s.i1])
+        for k, full in shared['peak'].items():
+            s.get_map(1, k, out=full[s.i0:s.i1])
+        for k, full in shared['sensor'].items():
+            full[shared['rows'][r]] = s.get_sensors(k)
+        gate.wait()
+        marks[r].update(setup_upload_s=t1 - t0, time_loop_s=t2 - t1, download_s=time.perf_counter() - t2)
+
+    threads = [threading.Thread(target=stage, args=(r, rank_main), name='bb_slab_%d' % r) for r in range(n)]
+    for t in threads:
+        t.start()
+    for t in threads:
+        t.join()
+    if errors:
+        for s in slabs:
+            if s is not None:
+                s.close()
+        raise errors[0]
+    s0 = slabs[0]
+    N1, N2, N3 = s0.shape
+    Sensor = {'time': s0.sample_steps.astype(np.float64) * s0.dt}
+    Sensor.update(shared['sensor'])
+    InputParam = {'IndexSensorMap': shared['index'], 'DT': s0.dt, 'N1': N1, 'N2': N2, 'N3': N3, 'TimeSteps': s0.steps,
+                  'SensorSubSampling': s0.sub, 'SensorStart': s0.sensor_start}
+    timing = {k: max(m[k] for m in marks) for k in marks[0]}
+    timing['h2d_bytes'] = sum(s.h2d_bytes for s in slabs)
+    timing['d2h_bytes'] = sum(s.d2h_bytes for s in slabs)
+    return Sensor, shared['rms'], shared['peak'], InputParam, slabs, timing
+
+
 def collect_results(slab):
     """Assemble the reference's return values from a finished single-slab run."""
     N1, N2, N3 = slab.shape
@@ -324,10 +424,14 @@ class PropagationModel:
                                          SelMapsSensorsList=['Vx', 'Vy', 'Vz'], SensorSubSampling=2,
                                          SensorStart=0, DefaultGPUDeviceName='B200', DefaultGPUDeviceNumber=0,
                                          ReflectorMask=None, SILENT=0, ManualGroupSize=None, ManualLocalSize=None,
-                                         **_ignored):
+                                         NumberGPUs=None, **_ignored):
         """Same call as the reference.  COMPUTING_BACKEND, DefaultGPUDeviceName, USE_SINGLE and the
         manual work-group sizes are accepted for compatibility; every backend value runs the
-        sm_100a CUDA path in float32 (there is no multi-backend dispatch)."""
+        sm_100a CUDA path in float32 (there is no multi-backend dispatch).
+
+        NumberGPUs (extension; default: environment variable BABELB200_NGPUS, else 1) cuts the domain into that
+        many slabs along axis 0, one per GPU of this box, with NVLink halo exchange; the return values are the
+        same whole-grid arrays.  An unmodified BabelBrain enables it through the environment variable."""
         import time
         t0 = time.perf_counter()
         if IntervalSnapshots > 0:
@@ -337,6 +441,18 @@ class PropagationModel:
         for v in _live_lastmaps:
             v._release()
         del _live_lastmaps[:]
+        ngpu = int(NumberGPUs if NumberGPUs is not None else os.environ.get('BABELB200_NGPUS', 1))
+        if ngpu < 1:
+            raise ValueError('NumberGPUs must be >= 1')
+        if ngpu > 1 and not CheckOnlyParams:
+            return self._run_multi_gpu(ngpu, t0, (MaterialMap, MaterialProperties, Frequency, SourceMap, SourceFunctions,
+                                                  SpatialStep, DurationSimulation, SensorMap),
+                                       dict(Ox=Ox, Oy=Oy, Oz=Oz, AlphaCFL=AlphaCFL, NDelta=NDelta, ReflectionLimit=ReflectionLimit,
+                                            DT=DT, QfactorCorrection=QfactorCorrection, QCorrection=QCorrection,
+                                            TypeSource=TypeSource, SelRMSorPeak=SelRMSorPeak,
+                                            SelMapsRMSPeakList=SelMapsRMSPeakList, SelMapsSensorsList=SelMapsSensorsList,
+                                            SensorSubSampling=SensorSubSampling, SensorStart=SensorStart,
+                                            ReflectorMask=ReflectorMask), DefaultGPUDeviceName, DefaultGPUDeviceNumber)
         slab = FdtdSlab(MaterialMap, MaterialProperties, Frequency, SourceMap, SourceFunctions, SpatialStep,
                         DurationSimulation, SensorMap, Ox=Ox, Oy=Oy, Oz=Oz, AlphaCFL=AlphaCFL, NDelta=NDelta,
                         ReflectionLimit=ReflectionLimit, DT=DT, QfactorCorrection=QfactorCorrection,
@@ -360,6 +476,30 @@ class PropagationModel:
         if SelRMSorPeak == 3:
             return Sensor, last, RMS, Peak, InputParam
         return Sensor, last, (RMS if SelRMSorPeak == 1 else Peak), InputParam
+
+    def _run_multi_gpu(self, ngpu, t0, args, kwargs, name, number):
+        import time
+        _capi.require_gpu()
+        devices = _select_devices(name, number, ngpu)
+        Sensor, RMS, Peak, InputParam, slabs, timing = run_slabs_in_process(devices, args, kwargs)
+        self.last_stats = [s.stats() for s in slabs]
+        self.last_timing = dict(timing, total_s=time.perf_counter() - t0, devices=devices)
+        last = _LastMapSlabs(slabs)
+        _live_lastmaps.append(last)
+        if kwargs['SelRMSorPeak'] == 3:
+            return Sensor, last, RMS, Peak, InputParam
+        return Sensor, last, (RMS if kwargs['SelRMSorPeak'] == 1 else Peak), InputParam
+
+
+def _select_devices(name, number, count):
+    """`count` device ordinals for a slab-decomposed run: the devices whose name holds `name`
+    (all devices if none does), starting at the `number`-th of them."""
+    names = _capi.device_names()
+    hits = [n for n, s in enumerate(names) if isinstance(name, str) and name and name in s] or list(range(len(names)))
+    hits = hits[min(int(number), max(len(hits) - 1, 0)):] + hits[:min(int(number), max(len(hits) - 1, 0))]
+    if len(hits) < count:
+        raise ValueError('NumberGPUs=%d but only %d CUDA device(s) are visible' % (count, len(hits)))
+    return hits[:count]
 
 
 def _select_device(name, number=0):

@@ -78,3 +78,29 @@ def assemble_sensors(nsensors, nsamples, rows_per_rank, data_per_rank):
     for rows, data in zip(rows_per_rank, data_per_rank):
         out[rows] = data
     return out
+
+
+def merge_sensor_tables(local_tables, n1, n23):
+    """Global sensor table of a slab-decomposed run.  local_tables: per slab, the ascending 1-based
+    Fortran-order indices (i + j*N1 + k*N1*N2 + 1, BabelIntegrationBASE.py:2503-2511) of the sensors in
+    that slab's planes, as the device builds them.  Slabs cut axis 0, the fastest axis of that index, so
+    within one (j,k) line the slabs' entries follow each other in rank order.  Returns (IndexSensorMap of
+    the whole grid, list over slabs of the rows their sensors occupy in it) in O(sensors) without sorting."""
+    lines, counts = [], []
+    for t in local_tables:
+        ln = (np.asarray(t).astype(np.int64) - 1) // int(n1)
+        lines.append(ln)
+        counts.append(np.bincount(ln, minlength=int(n23)).astype(np.int64))
+    total = np.sum(counts, axis=0) if counts else np.zeros(int(n23), np.int64)
+    before = np.cumsum(total) - total
+    nall = int(total.sum())
+    dtype = np.asarray(local_tables[0]).dtype if local_tables else np.uint32
+    index = np.empty(nall, dtype)
+    rows = []
+    for t, ln, c in zip(local_tables, lines, counts):
+        first = np.cumsum(c) - c
+        r = before[ln] + (np.arange(ln.size, dtype=np.int64) - first[ln])
+        index[r] = t
+        rows.append(r)
+        before = before + c
+    return index, rows

@@ -77,7 +77,7 @@ def _smooth_field(rng, n1, n2, amp):
     return amp * f / max(np.abs(f).max(), 1e-9)
 
 
-def skull_labels(shape, h, pml, seed=1234, skin_depth_frac=0.14):
+def skull_labels(shape, h, pml, seed=1234, skin_depth_frac=0.14, planes=None):
     """Labels 0 water, 1 skin, 2 cortical, 3 trabecular, 4 brain: spherical shell (outer radius
     85 mm; 1.5 mm skin; 2/2/2 mm cortical/trabecular/cortical) centred below the domain, radius
     perturbed by a smooth +-1 mm field so interfaces are not grid aligned."""
@@ -89,12 +89,14 @@ def skull_labels(shape, h, pml, seed=1234, skin_depth_frac=0.14):
     r_out = 0.085
     zc = (pml + skin_depth_frac * n3) * h + r_out
     dr = _smooth_field(rng, n1, n2, 1e-3)
-    lab = np.zeros(shape, np.uint32)
+    if planes is not None:          # only planes [lo,hi) of axis 0 (one slab of a decomposed run)
+        x, dr = x[planes[0]:planes[1]], dr[planes[0]:planes[1]]
+    lab = np.zeros((x.size, n2, n3), np.uint32)
     rxy2 = (x[:, None] ** 2 + y[None, :] ** 2)
     for k0 in range(0, n3, 64):
         zz = z[k0:k0 + 64]
         r = np.sqrt(rxy2[:, :, None] + (zz[None, None, :] - zc) ** 2) + dr[:, :, None]
-        l = np.zeros(r.shape, np.uint32)
+        l = np.zeros(r.shape, np.uint8)
         l[r < r_out] = 1
         l[r < r_out - 1.5e-3] = 2
         l[r < r_out - 3.5e-3] = 3
@@ -133,9 +135,12 @@ CONFIGS = {
 }
 
 
-def make_workload(name='ctx500_skull', shape=None, periods=None, seed=1234, pml=12, amplitude=1e5):
+def make_workload(name='ctx500_skull', shape=None, periods=None, seed=1234, pml=12, amplitude=1e5, planes=None, lean=False):
     """Returns dict(args=tuple of the 8 positional arguments, kwargs=dict of the keyword arguments
-    of StaggeredFDTD_3D_with_relaxation as BabelIntegrationBASE.py:2338-2365 passes them, meta=...)."""
+    of StaggeredFDTD_3D_with_relaxation as BabelIntegrationBASE.py:2338-2365 passes them, meta=...).
+    planes=(lo,hi): materialise only planes [lo,hi) of axis 0 of every volume (a slab with its halo, for
+    FdtdSlab(origin=lo, n1_global=shape[0])); the source table then holds this slab's rows only.  lean=True
+    makes Ox/Oy/Oz read-only broadcast views instead of dense float64 volumes (plane sources only)."""
     cfg = dict(CONFIGS[name])
     if shape is not None:
         cfg['shape'] = tuple(int(s) for s in shape)
@@ -154,8 +159,12 @@ def make_workload(name='ctx500_skull', shape=None, periods=None, seed=1234, pml=
     if cfg['medium'] == 'water':  # dt still limited by the fastest material BabelBrain would load
         S = sizing(f, cfg['ppw'], ML, cfg['shape'], pml=pml, periods=periods)
     h, dt, steps = S['h'], S['dt'], S['steps']
-    MaterialMap = np.zeros(cfg['shape'], np.uint32) if cfg['medium'] == 'water' else skull_labels(cfg['shape'], h, pml, seed)
-    SourceMap = np.zeros(cfg['shape'], np.uint32)
+    lo, hi = (0, n1) if planes is None else (int(planes[0]), int(planes[1]))
+    if planes is not None and cfg['source'] != 'plane':
+        raise ValueError('planes= is implemented for plane sources')
+    lshape = (hi - lo, n2, n3)
+    MaterialMap = np.zeros(lshape, np.uint32) if cfg['medium'] == 'water' else skull_labels(cfg['shape'], h, pml, seed, planes=planes)
+    SourceMap = np.zeros(lshape, np.uint32)
     kw = dict(NDelta=pml, DT=dt, ReflectionLimit=1e-5, COMPUTING_BACKEND=1, USE_SINGLE=True,
               SelMapsRMSPeakList=list(cfg.get('rms_maps', ['Pressure'])), SelMapsSensorsList=['Pressure'],
               SelRMSorPeak=cfg.get('sel_rms_peak', 1), DefaultGPUDeviceName='B200', AlphaCFL=1.0,
@@ -165,9 +174,10 @@ def make_workload(name='ctx500_skull', shape=None, periods=None, seed=1234, pml=
     x = (np.arange(n1) - n1 / 2 + 0.5) * h
     y = (np.arange(n2) - n2 / 2 + 0.5) * h
     if cfg['source'] == 'plane':
-        ii, jj = np.meshgrid(np.arange(pml, n1 - pml), np.arange(pml, n2 - pml), indexing='ij')
+        ilo, ihi = max(pml, lo), max(min(n1 - pml, hi), max(pml, lo))
+        ii, jj = np.meshgrid(np.arange(ilo, ihi), np.arange(pml, n2 - pml), indexing='ij')
         ids = np.arange(1, ii.size + 1, dtype=np.uint32).reshape(ii.shape)
-        SourceMap[pml:n1 - pml, pml:n2 - pml, pml] = ids
+        SourceMap[ilo - lo:ihi - lo, pml:n2 - pml, pml] = ids
         focal = min(cfg['focal'], 0.75 * (n3 - 2 * pml) * h)
         r2 = x[ii] ** 2 + y[jj] ** 2
         dist = np.sqrt(r2 + focal ** 2)
@@ -175,9 +185,13 @@ def make_workload(name='ctx500_skull', shape=None, periods=None, seed=1234, pml=
         amp = amplitude * (0.98 * np.exp(-(np.sqrt(r2) / (ap / 2)) ** 8) + 0.02) * focal / dist
         phase = -kwater * (dist - focal)
         SF = cw_sources(amp.reshape(-1), phase.reshape(-1), f, dt, steps)
-        Ox = np.zeros(cfg['shape'])
-        Oy = np.zeros(cfg['shape'])
-        Oz = np.ones(cfg['shape']) / (1000.0 * 1500.0)
+        if lean:
+            Ox = Oy = np.broadcast_to(np.float64(0.0), lshape)
+            Oz = np.broadcast_to(np.float64(1.0 / (1000.0 * 1500.0)), lshape)
+        else:
+            Ox = np.zeros(lshape)
+            Oy = np.zeros(lshape)
+            Oz = np.ones(lshape) / (1000.0 * 1500.0)
         kw.update(Ox=Ox, Oy=Oy, Oz=Oz, TypeSource=0)
         zsrc = pml
     else:  # hemispherical dome of small volumetric stress sources inside the domain
@@ -201,12 +215,13 @@ def make_workload(name='ctx500_skull', shape=None, periods=None, seed=1234, pml=
         kw.update(Ox=np.array([1]), Oy=np.array([1]), Oz=np.array([1]), TypeSource=2)
         kw['SelMapsRMSPeakList'] = ['Pressure']
         zsrc = pml
-    SensorMap = np.zeros(cfg['shape'], np.uint32)
-    SensorMap[pml:-pml, pml:-pml, zsrc + 1:-pml] = 1
+    SensorMap = np.zeros(lshape, np.uint32)
+    slo, shi = max(pml, lo), max(min(n1 - pml, hi), max(pml, lo))
+    SensorMap[slo - lo:shi - lo, pml:-pml, zsrc + 1:-pml] = 1
     args = (MaterialMap, ML, f, SourceMap, SF, h, dt * steps, SensorMap)
     meta = dict(name=name, shape=cfg['shape'], cells=n1 * n2 * n3, steps=steps, ppp=S['ppp'], dt=dt, h=h,
                 sub=S['sub'], sensor_start=S['sensor_start'], nsrc=SF.shape[0], cell_updates=n1 * n2 * n3 * steps,
-                frequency=f, ppw=cfg['ppw'], pml=pml)
+                frequency=f, ppw=cfg['ppw'], pml=pml, planes=(lo, hi))
     return dict(args=args, kwargs=kw, meta=meta)
 
 

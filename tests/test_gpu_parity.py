@@ -252,3 +252,27 @@ def test_two_gpu_slabs_match_single_gpu(halo):
     for r in range(2):
         sens[out[r][2]] = out[r][1]
     assert rl2(sens, S1['Pressure']) <= 1e-6
+
+
+def test_public_call_on_two_gpus_returns_the_single_gpu_arrays(monkeypatch):
+    """NumberGPUs=2 (or BABELB200_NGPUS=2 for an unmodified caller) through the reference-shaped call: same
+    tuple, whole-grid arrays, IndexSensorMap bit-exact, maps and sensor traces equal to the one-GPU run."""
+    from babelbrain_b200 import _capi
+    if _capi.device_count() < 2:
+        pytest.skip('needs two GPUs')
+    w = workloads.make_workload('h317_skull', shape=(66, 52, 60), periods=4, pml=8)
+    PM = PropagationModel()
+    S1, L1, R1, P1, IP1 = PM.StaggeredFDTD_3D_with_relaxation(*w['args'], **w['kwargs'])
+    vz1 = np.array(L1['Vz'])
+    S2, L2, R2, P2, IP2 = PM.StaggeredFDTD_3D_with_relaxation(*w['args'], NumberGPUs=2, **w['kwargs'])
+    assert np.array_equal(IP2['IndexSensorMap'], IP1['IndexSensorMap'])
+    assert S2['Pressure'].shape == S1['Pressure'].shape and rl2(S2['Pressure'], S1['Pressure']) <= 1e-6
+    for k in R1:
+        assert R2[k].shape == w['args'][0].shape and R2[k].flags.writeable
+        assert rl2(R2[k], R1[k]) <= 1e-6 and rl2(P2[k], P1[k]) <= 1e-6
+    assert rl2(L2['Vz'], vz1) <= 1e-6
+    monkeypatch.setenv('BABELB200_NGPUS', '2')
+    S3, _, R3, P3, IP3 = PM.StaggeredFDTD_3D_with_relaxation(*w['args'], **w['kwargs'])
+    assert len(PM.last_timing['devices']) == 2 and np.array_equal(R3['Pressure'], R2['Pressure'])
+    with pytest.raises(ValueError):
+        PM.StaggeredFDTD_3D_with_relaxation(*w['args'], NumberGPUs=64, **w['kwargs'])

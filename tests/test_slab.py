@@ -11,7 +11,8 @@ import torch
 import torch.distributed as dist
 import torch.multiprocessing as mp
 
-from babelbrain_b200.slab import HALO, SlabPlan, assemble_maps, assemble_sensors, halo_exchange_plan, sensor_rows_of_slab
+from babelbrain_b200.slab import (HALO, SlabPlan, assemble_maps, assemble_sensors, halo_exchange_plan, merge_sensor_tables,
+                                  sensor_rows_of_slab)
 
 
 def test_plan_covers_the_grid():
@@ -44,6 +45,27 @@ def test_sensor_rows_and_assembly():
     assert np.array_equal(out, data)
     vol = rng.random(shape).astype(np.float32)
     assert np.array_equal(assemble_maps(shape, plan, [vol[slice(*plan.owned(r))] for r in range(3)]), vol)
+
+
+@pytest.mark.parametrize('shape,nranks,density', [((23, 9, 11), 3, 0.4), ((64, 5, 7), 8, 0.05), ((16, 4, 4), 2, 1.0), ((16, 4, 4), 4, 0.0)])
+def test_merge_of_slab_sensor_tables_is_the_global_table(shape, nranks, density):
+    """Each slab's device-built table (ascending Fortran-order indices of its planes) merged without sorting
+    equals the table of the whole SensorMap, ragged slabs and empty lines included."""
+    rng = np.random.default_rng(3)
+    sen = rng.random(shape) < density
+    expect = (np.flatnonzero(sen.reshape(-1, order='F')) + 1).astype(np.uint32)
+    plan = SlabPlan(shape[0], nranks, 2)
+    local = []
+    for r in range(nranks):
+        i0, i1 = plan.owned(r)
+        m = np.zeros(shape, bool)
+        m[i0:i1] = sen[i0:i1]
+        local.append((np.flatnonzero(m.reshape(-1, order='F')) + 1).astype(np.uint32))
+    index, rows = merge_sensor_tables(local, shape[0], shape[1] * shape[2])
+    assert index.dtype == np.uint32 and np.array_equal(index, expect)
+    for r in range(nranks):
+        assert np.array_equal(index[rows[r]], local[r])
+        assert np.array_equal(rows[r], sensor_rows_of_slab(expect, shape, *plan.owned(r)))
 
 
 def _step(a, forward):
