@@ -65,7 +65,11 @@ constexpr int BB_TY = BB_TILE_ROWS;
 enum { TF_ATT = 1,      // a non-PML cell of the tile attenuates -> normal memory variables move
        TF_SOLID = 2,    // a cell of the tile (+1 in j,k, planes i and i+1) has G != 0 -> shear stresses / memory variables move
        TF_SHEAR = 4,    // a cell of the tile (+-2 in j,k) on this plane has G != 0 -> its shear stresses can be non-zero
-       TF_INT = 8 };    // the tile holds non-PML cells on this plane
+       TF_INT = 8,      // the tile holds non-PML cells on this plane
+       // properties of the plane itself (the same for every tile), so that the plane loop tests bits instead of comparing indices:
+       TF_XD = 16,      // the plane lies inside the i-PML
+       TF_IEDGE = 32,   // i <= 1 or i >= n1-2: the i-differences use the domain-edge coefficients
+       TF_ILAST = 64 }; // i == n1-1 (split-field cells of the last plane are not updated)
 
 // Device-side view of one slab.  Local plane ip <-> global i = i0 - 2 + ip (two halo planes on
 // each side are always allocated); element (ip, j, k) lives at (ip*n2 + j)*pitch + k.

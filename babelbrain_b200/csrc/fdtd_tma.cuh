@@ -100,6 +100,12 @@ __device__ __forceinline__ void peer_publish(const DevParams &p, int side, unsig
         *reinterpret_cast<volatile unsigned long long *>(p.flag_peer[side]) = p.seq;
     }
 }
+// keep a loop-invariant value in a register: the compiler otherwise re-derives it from the constant bank / special
+// registers in every iteration of the plane loop (S2R + LDC + IMAD chains seen in the SASS)
+// (ptxas does the re-deriving, so the value has to pass through an instruction it cannot see through: a shuffle from
+// the thread's own lane, executed once per CTA)
+__device__ __forceinline__ void keep(int &x) { x = __shfl_sync(0xffffffffu, x, threadIdx.x & 31); }
+__device__ __forceinline__ void keep(unsigned &x) { x = __shfl_sync(0xffffffffu, x, threadIdx.x & 31); }
 __device__ __forceinline__ void consumer_bar() { asm volatile("bar.sync 1, %0;" ::"n"(NT) : "memory"); }
 __device__ __forceinline__ unsigned long long globaltimer_ns() { unsigned long long t; asm volatile("mov.u64 %0, %globaltimer;" : "=l"(t)); return t; }
 __device__ __forceinline__ void fence_barrier_init() { asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory"); }
@@ -138,7 +144,10 @@ __global__ void __launch_bounds__(NT) flags_kernel(const DevParams p, unsigned c
     }
     if (f) atomicOr(&sflag, f);
     __syncthreads();
-    if (tid == 0) flags[((long long)ip * p.ntj + blockIdx.y) * p.ntk + blockIdx.x] = (unsigned char)sflag;
+    if (tid == 0) {
+        const unsigned plane_bits = (xd ? TF_XD : 0) | (i <= 1 || i >= p.n1 - 2 ? TF_IEDGE : 0) | (i >= p.n1 - 1 ? TF_ILAST : 0);
+        flags[((long long)ip * p.ntj + blockIdx.y) * p.ntk + blockIdx.x] = (unsigned char)(sflag | plane_bits);
+    }
 }
 
 // ---------------------------------------------------------------- ring bookkeeping
@@ -155,7 +164,7 @@ struct RingPos {
 // class do not need (no Y parts away from the j-PML, no Z parts away from the k-PML) goes to a
 // deeper halo ring, i.e. more planes of prefetch.
 constexpr int SMEM_BYTES = (CTAS_PER_SM == 1 ? 222 : 110) * 1024;
-constexpr int MAX_NSH = 10, MAX_NSP = 4;
+constexpr int MAX_NSH = 12, MAX_NSP = 8, MIN_NSH = 6;
 constexpr int OFF_COEF = 0;                                                      // MatCoef[128] (stress) / float B[128] (particle)
 constexpr int OFF_AXJ = OFF_COEF + BB_MAX_SMEM_MAT * (int)sizeof(MatCoef);
 constexpr int OFF_AXK = OFF_AXJ + TY * (int)sizeof(AxisCoef);
@@ -163,14 +172,24 @@ constexpr int OFF_FLAGS = OFF_AXK + TX * (int)sizeof(AxisCoef);
 constexpr int OFF_BAR = OFF_FLAGS + ((MAXCHUNK + 8 + 15) / 16) * 16;
 constexpr int OFF_RINGS = 9216;
 static_assert(OFF_BAR + 2 * (MAX_NSH + MAX_NSP) * 8 <= OFF_RINGS, "tables overflow their 9 KB");
+// ring depths of a CTA: as many point stages as fit beside MIN_NSH halo stages (the consumers hold three halo
+// slots at a time, so that is three planes of halo prefetch), the rest of the shared memory as halo stages.
+// (ncu, 4 point stages for every CTA: the consumers spent 8 % of their time waiting for the point ring.)
+__device__ __forceinline__ void ring_depths(int pstage, int hstage, int &nsp, int &nsh) {
+    constexpr int avail = SMEM_BYTES - OFF_RINGS;
+    nsp = max(3, min(MAX_NSP, (avail - MIN_NSH * hstage) / pstage));
+    nsh = min(MAX_NSH, (avail - nsp * pstage) / hstage);
+}
 
 // =========================================================================================
 // stress half-step
 // =========================================================================================
-// point-box order inside a stage; on a plane inside the i-PML the X parts use the R boxes (no interior
-// cell exists on such a plane, so memory variables are not needed there); the Y / Z parts follow at
-// full boxes, the Z parts as compact regions
-enum { PB_SXX = 0, PB_SYY, PB_SZZ, PB_SXY, PB_SXZ, PB_SYZ, PB_RXX, PB_RYY, PB_RZZ, PB_RXY, PB_RXZ, PB_RYZ, PB_PR, PB_ACC, PB_PARTS };
+// point-box order inside a stage: the eight boxes every tile needs first, the shear stresses and their memory
+// variables behind them -- a CTA whose planes hold nothing solid (TF_SOLID clear on all of them) leaves those six
+// boxes out of its stages and gets deeper rings instead.  On a plane inside the i-PML the X parts use the five
+// boxes from PB_RXX on (no interior cell exists on such a plane, so neither memory variables nor the pressure
+// boxes are needed there); the Y / Z parts follow at full boxes, the Z parts as compact regions
+enum { PB_SXX = 0, PB_SYY, PB_SZZ, PB_RXX, PB_RYY, PB_RZZ, PB_PR, PB_ACC, PB_FLUID, PB_SXY = PB_FLUID, PB_SXZ, PB_SYZ, PB_RXY, PB_RXZ, PB_RYZ, PB_PARTS };
 constexpr int ST_LOFF = align128(3 * HBOX_STRIDE);         // label box behind the three V boxes
 constexpr int ST_HSTAGE = ST_LOFF + LBOX_STRIDE;
 
@@ -198,24 +217,28 @@ __global__ void __launch_bounds__(NTB, CTAS_PER_SM) stress_tma(const __grid_cons
     const int yt = ((int)blockIdx.y < p.nylo ? (int)blockIdx.y : (int)blockIdx.y - p.tjhi0 + p.nylo) * TY;
     // point-stage layout (bytes): 14 full boxes, then the Y part boxes, then the compact Z part regions
     // (zbw columns x TY rows per component) of the low and the high side
+    // per-plane traffic flags of this CTA's planes; any_solid = some plane of the chunk moves shear fields
+    int fl = 0;
+    if (tid < np + 2) {
+        const int ipl = ipl0 + tid;
+        fl = ipl < p.nloc ? p.flags[((long long)ipl * p.ntj + blockIdx.y) * p.ntk + blockIdx.x] : 0;
+        sF[tid] = (unsigned char)fl;
+    }
+    const bool any_solid = __syncthreads_or(tid < np && (fl & TF_SOLID)) != 0;
     const int zcomp = p.zbw * TY;                                          // floats per Z part component
     const int zshear = align128(3 * zcomp * 4);                          // the two shear parts start 128-byte aligned (own TMA)
-    const int zreg = zshear + align128(2 * zcomp * 4);
-    const int yoff = PB_PARTS * PBOX, zlo_off = yoff + (tile_jd ? 5 * PBOX : 0), zhi_off = zlo_off + (tile_zlo ? zreg : 0);
+    const int zreg = zshear + (any_solid ? align128(2 * zcomp * 4) : 0);
+    const int yoff = (any_solid ? PB_PARTS : PB_FLUID) * PBOX, zlo_off = yoff + (tile_jd ? (any_solid ? 5 : 3) * PBOX : 0);
+    const int zhi_off = zlo_off + (tile_zlo ? zreg : 0);
     const int pstage = zhi_off + (tile_zhi ? zreg : 0);
-    // ring depths: 4 point stages when that still leaves 6 halo stages, else 3
-    const int nsp = (SMEM_BYTES - OFF_RINGS - MAX_NSP * pstage) / ST_HSTAGE >= 6 ? MAX_NSP : MAX_NSP - 1;
+    int nsp, nsh;
+    ring_depths(pstage, ST_HSTAGE, nsp, nsh);
     const int offP = OFF_RINGS, offH = OFF_RINGS + nsp * pstage;
-    const int nsh = min(MAX_NSH, (SMEM_BYTES - offH) / ST_HSTAGE);
 
     // ---- per-CTA tables
     if (SMC) for (int t = tid; t < p.nmat * (int)(sizeof(MatCoef) / 4); t += NTB) reinterpret_cast<float *>(sC)[t] = reinterpret_cast<const float *>(p.coef)[t];
     if (tid < TY * 8) { const int r = tid >> 3, e = tid & 7; reinterpret_cast<float *>(sJ)[tid] = reinterpret_cast<const float *>(p.axJ + min(j0 + r, p.n2 - 1))[e]; }
     if (tid < TX * 8) { const int r = tid >> 3, e = tid & 7; reinterpret_cast<float *>(sK)[tid] = reinterpret_cast<const float *>(p.axK + min(k0 + r, p.n3 - 1))[e]; }
-    if (tid < np + 2) {
-        const int ipl = ipl0 + tid;
-        sF[tid] = ipl < p.nloc ? p.flags[((long long)ipl * p.ntj + blockIdx.y) * p.ntk + blockIdx.x] : 0;
-    }
     // halo planes received through NVLink: the neighbour's previous half-step must have landed before this CTA
     // (its TMA loads and its queue prologue) reads them
     const bool first_hs = (unsigned)(p.seq & 0xffffffffu) <= 1u;
@@ -269,7 +292,7 @@ __global__ void __launch_bounds__(NTB, CTAS_PER_SM) stress_tma(const __grid_cons
             if (xd) {
                 const int ipx = i < p.P ? io : p.nxlo + (i - p.xhi_begin);
                 tma_load_4d(st + PB_RXX * PBOX, &tm.xp3, bar, k0, j0, ipx, 0);
-                if (fsol) tma_load_4d(st + PB_RXY * PBOX, &tm.xp2, bar, k0, j0, ipx, 3);
+                if (fsol) tma_load_4d(st + (PB_RXX + 3) * PBOX, &tm.xp2, bar, k0, j0, ipx, 3);
             } else {
                 if (fint) tma_load_3d(st + PB_PR * PBOX, &tm.pr, bar, k0, j0, ipl);
                 if (fatt) tma_load_4d(st + PB_RXX * PBOX, &tm.r3, bar, k0, j0, ipl, 0);
@@ -313,11 +336,14 @@ __global__ void __launch_bounds__(NTB, CTAS_PER_SM) stress_tma(const __grid_cons
     const bool active = mapped && k < p.n3 && j < p.n2;
     const bool jd = in_pml1(j, p.n2, p.P), kd = in_pml1(k, p.n3, p.P);
     const bool jkd = jd || kd;
-    const bool jkupd = j < p.n2 - 1 && k < p.n3 - 1;
+    // which cells this thread updates: every in-grid cell outside the PML, split-field cells except those on the last
+    // row / column / plane of the grid
+    const bool upd_pml = active && j < p.n2 - 1 && k < p.n3 - 1;
     // difference coefficients of this thread's row and column (9/8, 1/24 away from the faces of the domain)
     const float cjb_a = sJ[ty].cab, cjb_b = sJ[ty].cbb, cjf_a = sJ[ty].caf, cjf_b = sJ[ty].cbf;
     const float ckb_a = sK[tx].cab, ckb_b = sK[tx].cbb, ckf_a = sK[tx].caf, ckf_b = sK[tx].cbf;
-    const unsigned s1 = (unsigned)p.plane;   // element indices fit 32 bits (checked at create)
+    unsigned s1 = (unsigned)p.plane;   // element indices fit 32 bits (checked at create)
+    keep(s1);
 
     // ---- register queue along i (state before the shift of plane ic0)
     const float *__restrict__ Vx = p.V[0], *__restrict__ Vy = p.V[1], *__restrict__ Vz = p.V[2];
@@ -332,7 +358,13 @@ __global__ void __launch_bounds__(NTB, CTAS_PER_SM) stress_tma(const __grid_cons
     const float dt = p.dt;
     const unsigned MSK = LabelTraits<LT>::MASK;
     // part arrays: index of this cell on plane ic0 and the per-plane strides
-    const unsigned qy_stride = (unsigned)p.nyrows * p.pitch, qz_stride = (unsigned)p.n2 * p.zpw;
+    unsigned qy_stride = (unsigned)p.nyrows * p.pitch, qz_stride = (unsigned)p.n2 * p.zpw;
+    keep(qy_stride); keep(qz_stride);
+    // boundary planes this CTA pushes to the slab neighbours: bit 0 lower, bit 1 upper (0 for almost every CTA)
+    int pushsel = has_peer ? ((ic0 < p.i0 + 2 && p.peerS[0] ? 1 : 0) | (ic1 > p.i1 - 2 && p.peerS[1] ? 2 : 0)) : 0;
+    keep(pushsel);
+    int nplanes = np, lane0 = lane == 0;
+    keep(nplanes); keep(lane0);
     unsigned qy = ((unsigned)(ic0 - p.i0) * p.nyrows + yt + ty) * p.pitch + k;
     const int kz = k < p.P ? k : k - (p.n3 - p.P);                       // column inside the Z part box of this cell's side
     unsigned qz = ((unsigned)(ic0 - p.i0) * p.n2 + min(j, p.n2 - 1)) * p.zpw + (k < p.P ? kz : p.zbw + kz);
@@ -359,7 +391,7 @@ __global__ void __launch_bounds__(NTB, CTAS_PER_SM) stress_tma(const __grid_cons
     mbar_wait(fullH + 8, 0);
     vy_p2 = hbox(ST_HSTAGE, 1)[0]; vz_p2 = hbox(ST_HSTAGE, 2)[0];
 
-    for (int it = 0; it < np; it++, q += s1, qy += qy_stride, qz += qz_stride) {
+    for (int it = 0; it < nplanes; it++, q += s1, qy += qy_stride, qz += qz_stride) {
         const int i = ic0 + it;
         const unsigned f = sF[it];
         mbar_wait(hb2, hpar);
@@ -368,9 +400,9 @@ __global__ void __launch_bounds__(NTB, CTAS_PER_SM) stress_tma(const __grid_cons
         vy_m1 = vy_0; vy_0 = vy_p1; vy_p1 = vy_p2; vy_p2 = hbox(ho2, 1)[0];
         vz_m1 = vz_0; vz_0 = vz_p1; vz_p1 = vz_p2; vz_p2 = hbox(ho2, 2)[0];
         mbar_wait(pbar, ppar);
-        const bool xd = in_pml1(i, p.n1, p.P);
+        const bool xd = (f & TF_XD) != 0;
         const bool cellpml = xd || jkd;
-        if (active && (!cellpml || (jkupd && i < p.n1 - 1))) {
+        if (cellpml ? (upd_pml && !(f & TF_ILAST)) : active) {
             const float *bx = hbox(ho, 0), *by = hbox(ho, 1), *bz = hbox(ho, 2);
             const LT *l0p = lbox(ho), *l1p = lbox(ho1);
             const float *pb = reinterpret_cast<const float *>(psc + po);
@@ -382,7 +414,7 @@ __global__ void __launch_bounds__(NTB, CTAS_PER_SM) stress_tma(const __grid_cons
             // staggered differences with the domain-edge rules folded into coefficients: j/k per thread (hoisted out of
             // the loop), i per plane (uniform) -- one code path for every cell
             float cib_a = BB_CA, cib_b = BB_CB, cif_a = BB_CA, cif_b = BB_CB;
-            if (i <= 1 || i >= p.n1 - 2) { const AxisCoef ci = load_axis(p.axI, i); cib_a = ci.cab; cib_b = ci.cbb; cif_a = ci.caf; cif_b = ci.cbf; }
+            if (f & TF_IEDGE) { const AxisCoef ci = load_axis(p.axI, i); cib_a = ci.cab; cib_b = ci.cbb; cif_a = ci.caf; cif_b = ci.cbf; }
             float D[9];
             D[0] = D4C(cib_a, cib_b, vx_0, vx_m1, vx_p1, vx_m2);
             D[1] = D4C(cjb_a, cjb_b, by[0], by[-SW], by[SW], by[-2 * SW]);
@@ -477,22 +509,24 @@ __global__ void __launch_bounds__(NTB, CTAS_PER_SM) stress_tma(const __grid_cons
                 }
             }
             // ---------------- boundary planes also go to the slab neighbour (the stresses its particle update differentiates along i)
-            if (has_peer && i < p.i0 + 2 && p.peerS[0]) {
+            if (pushsel) {
+            if ((pushsel & 1) && i < p.i0 + 2) {
                 float *b = p.peerS[0];
                 const unsigned qn = (p.peer_plane[0] + (unsigned)(i - p.i0)) * s1 + col;
                 b[qn] = s[0];
                 if (f & TF_SOLID) { b[3 * p.peer_vol[0] + qn] = s[3]; b[4 * p.peer_vol[0] + qn] = s[4]; }
             }
-            if (has_peer && i >= p.i1 - 2 && p.peerS[1]) {
+            if ((pushsel & 2) && i >= p.i1 - 2) {
                 float *b = p.peerS[1];
                 const unsigned qn = (p.peer_plane[1] + (unsigned)(i - (p.i1 - 2))) * s1 + col;
                 b[qn] = s[0];
                 if (f & TF_SOLID) { b[3 * p.peer_vol[1] + qn] = s[3]; b[4 * p.peer_vol[1] + qn] = s[4]; }
             }
+            }
         }
         // ---------------- this warp is done with the slots of plane i
         __syncwarp();
-        if (lane == 0) { mbar_arrive(hb0 + MAX_NSH * 8); mbar_arrive(pbar + MAX_NSP * 8); }
+        if (lane0) { mbar_arrive(hb0 + MAX_NSH * 8); mbar_arrive(pbar + MAX_NSP * 8); }
         ho = ho1; hb0 = hb1; ho1 = ho2; hb1 = hb2;
         ho2 += ST_HSTAGE; hb2 += 8;
         if (ho2 == hend) { ho2 = 0; hb2 = fullH; hpar ^= 1u; }
@@ -522,14 +556,16 @@ __global__ void __launch_bounds__(NTB, CTAS_PER_SM) stress_tma(const __grid_cons
 // =========================================================================================
 // particle half-step
 // =========================================================================================
-// halo-stage boxes: Syy Szz Sxy Sxz Syz (halo boxes) then Sxx (point box, i-stencil only) then labels;
-// point-stage boxes: V (3), X parts (3), then the Y / Z parts the tile needs (3 each)
+// halo-stage boxes: Syy Szz (halo boxes), Sxx (point box, i-stencil only), labels, then the shear stresses Sxy Sxz Syz
+// (halo boxes) -- a CTA whose planes carry no shear stress (TF_SHEAR clear on all of them) ends its stages before them;
+// point-stage boxes: V (3), X parts (3, only when the chunk reaches into the i-PML), then the Y / Z parts the tile
+// needs (3 each)
 enum { HB_SYY = 0, HB_SZZ, HB_SXY, HB_SXZ, HB_SYZ };
 enum { QB_V = 0, QB_X = 3, QB_PARTS = 6 };
-constexpr int PT_S3OFF = align128(2 * HBOX_STRIDE);        // the three shear boxes (own TMA) behind Syy, Szz
-constexpr int PT_XOFF = align128(PT_S3OFF + 3 * HBOX_STRIDE);   // Sxx point box behind the five halo boxes
+constexpr int PT_XOFF = align128(2 * HBOX_STRIDE);         // Sxx point box behind Syy, Szz
 constexpr int PT_LOFF = PT_XOFF + PBOX;
-constexpr int PT_HSTAGE = PT_LOFF + LBOX_STRIDE;
+constexpr int PT_S3OFF = align128(PT_LOFF + LBOX_STRIDE);  // the three shear boxes (own TMA)
+constexpr int PT_HSTAGE = PT_S3OFF + align128(3 * HBOX_STRIDE);
 
 template <typename LT, int ACC>
 __global__ void __launch_bounds__(NTB, CTAS_PER_SM) particle_tma(const __grid_constant__ ParticleMaps tm, const DevParams p, const ChunkPlan plan) {
@@ -554,22 +590,27 @@ __global__ void __launch_bounds__(NTB, CTAS_PER_SM) particle_tma(const __grid_co
     const int yt = ((int)blockIdx.y < p.nylo ? (int)blockIdx.y : (int)blockIdx.y - p.tjhi0 + p.nylo) * TY;
     // point-stage layout (bytes): 6 full boxes, then the Y part boxes, then the compact Z part regions
     // (zbw columns x TY rows per component) of the low and the high side
+    // per-plane traffic flags of this CTA's planes; any_shear = some plane the chunk reads carries shear stresses
+    int fl = 0;
+    if (tid < np + 2) {
+        const int ipl = ipl0 + tid;
+        fl = ipl < p.nloc ? p.flags[((long long)ipl * p.ntj + blockIdx.y) * p.ntk + blockIdx.x] : 0;
+        sF[tid] = (unsigned char)fl;
+    }
+    const bool any_shear = __syncthreads_or(fl & TF_SHEAR) != 0;
+    const bool any_xd = ic0 < p.P || ic1 > p.n1 - p.P;                    // the chunk holds planes of the i-PML
+    const int hstage = any_shear ? PT_HSTAGE : PT_S3OFF;
     const int zcomp = p.zbw * TY;                                          // floats per Z part component
     const int zreg = align128(3 * zcomp * 4);
-    const int yoff = QB_PARTS * PBOX, zlo_off = yoff + (tile_jd ? 3 * PBOX : 0), zhi_off = zlo_off + (tile_zlo ? zreg : 0);
+    const int yoff = (any_xd ? QB_PARTS : QB_X) * PBOX, zlo_off = yoff + (tile_jd ? 3 * PBOX : 0), zhi_off = zlo_off + (tile_zlo ? zreg : 0);
     const int pstage = zhi_off + (tile_zhi ? zreg : 0);
-    // ring depths: 4 point stages when that still leaves 6 halo stages, else 3
-    const int nsp = (SMEM_BYTES - OFF_RINGS - MAX_NSP * pstage) / PT_HSTAGE >= 6 ? MAX_NSP : MAX_NSP - 1;
+    int nsp, nsh;
+    ring_depths(pstage, hstage, nsp, nsh);
     const int offP = OFF_RINGS, offH = OFF_RINGS + nsp * pstage;
-    const int nsh = min(MAX_NSH, (SMEM_BYTES - offH) / PT_HSTAGE);
 
     if (SMC) for (int t = tid; t < p.nmat; t += NTB) sB[t] = p.coef[t].B;
     if (tid < TY * 8) { const int r = tid >> 3, e = tid & 7; reinterpret_cast<float *>(sJ)[tid] = reinterpret_cast<const float *>(p.axJ + min(j0 + r, p.n2 - 1))[e]; }
     if (tid < TX * 8) { const int r = tid >> 3, e = tid & 7; reinterpret_cast<float *>(sK)[tid] = reinterpret_cast<const float *>(p.axK + min(k0 + r, p.n3 - 1))[e]; }
-    if (tid < np + 2) {
-        const int ipl = ipl0 + tid;
-        sF[tid] = ipl < p.nloc ? p.flags[((long long)ipl * p.ntj + blockIdx.y) * p.ntk + blockIdx.x] : 0;
-    }
     // halo planes received through NVLink: the neighbour's previous half-step must have landed before this CTA
     // (its TMA loads and its queue prologue) reads them
     const bool first_hs = (unsigned)(p.seq & 0xffffffffu) <= 1u;
@@ -591,7 +632,7 @@ __global__ void __launch_bounds__(NTB, CTAS_PER_SM) particle_tma(const __grid_co
         for (int r = 0; r < np + 2; r++) {
             const int slot = rh.slot;
             mbar_wait(emptyH + slot * 8, rh.par);
-            const uint32_t st = sm32 + offH + slot * PT_HSTAGE;
+            const uint32_t st = sm32 + offH + slot * hstage;
             const uint32_t bar = fullH + slot * 8;
             const bool fsh = sF[r] & TF_SHEAR;
             mbar_expect_tx(bar, (fsh ? 5 : 2) * HBOX + PBOX + LW * LH * (int)sizeof(LT));
@@ -645,11 +686,14 @@ __global__ void __launch_bounds__(NTB, CTAS_PER_SM) particle_tma(const __grid_co
     const bool active = mapped && k < p.n3 && j < p.n2;
     const bool jd = in_pml1(j, p.n2, p.P), kd = in_pml1(k, p.n3, p.P);
     const bool jkd = jd || kd;
-    const bool jkupd = j < p.n2 - 1 && k < p.n3 - 1;
+    // which cells this thread updates: every in-grid cell outside the PML, split-field cells except those on the last
+    // row / column / plane of the grid
+    const bool upd_pml = active && j < p.n2 - 1 && k < p.n3 - 1;
     // difference coefficients of this thread's row and column (9/8, 1/24 away from the faces of the domain)
     const float cjb_a = sJ[ty].cab, cjb_b = sJ[ty].cbb, cjf_a = sJ[ty].caf, cjf_b = sJ[ty].cbf;
     const float ckb_a = sK[tx].cab, ckb_b = sK[tx].cbb, ckf_a = sK[tx].caf, ckf_b = sK[tx].cbf;
-    const unsigned s1 = (unsigned)p.plane;   // element indices fit 32 bits (checked at create)
+    unsigned s1 = (unsigned)p.plane;   // element indices fit 32 bits (checked at create)
+    keep(s1);
 
     // queues: Sxx holds i-1..i+2 ; Sxy, Sxz hold i-2..i+1 (state before the shift of plane ic0)
     const float *__restrict__ Sxx = p.S[0], *__restrict__ Sxy = p.S[3], *__restrict__ Sxz = p.S[4];
@@ -663,7 +707,13 @@ __global__ void __launch_bounds__(NTB, CTAS_PER_SM) particle_tma(const __grid_co
     const int pc = ty * TX + tx;
     const float dt = p.dt;
     const unsigned MSK = LabelTraits<LT>::MASK;
-    const unsigned qy_stride = (unsigned)p.nyrows * p.pitch, qz_stride = (unsigned)p.n2 * p.zpw;
+    unsigned qy_stride = (unsigned)p.nyrows * p.pitch, qz_stride = (unsigned)p.n2 * p.zpw;
+    keep(qy_stride); keep(qz_stride);
+    // boundary planes this CTA pushes to the slab neighbours: bit 0 lower, bit 1 upper (0 for almost every CTA)
+    int pushsel = has_peer ? ((ic0 < p.i0 + 2 && p.peerV[0] ? 1 : 0) | (ic1 > p.i1 - 2 && p.peerV[1] ? 2 : 0)) : 0;
+    keep(pushsel);
+    int nplanes = np, lane0 = lane == 0;
+    keep(nplanes); keep(lane0);
     unsigned qy = ((unsigned)(ic0 - p.i0) * p.nyrows + yt + ty) * p.pitch + k;
     const int kz = k < p.P ? k : k - (p.n3 - p.P);                       // column inside the Z part box of this cell's side
     unsigned qz = ((unsigned)(ic0 - p.i0) * p.n2 + min(j, p.n2 - 1)) * p.zpw + (k < p.P ? kz : p.zbw + kz);
@@ -679,18 +729,18 @@ __global__ void __launch_bounds__(NTB, CTAS_PER_SM) particle_tma(const __grid_co
     auto lbox = [&](int off) { return reinterpret_cast<const LT *>(lsc + off); };
     // ring state as byte offsets / barrier addresses (no multiplies in the loop): halo slots of planes it, it+1,
     // it+2 (the one waited on inside the loop) and the point slot of plane it
-    int ho = 0, ho1 = PT_HSTAGE, ho2 = 2 * PT_HSTAGE, po = 0;
+    int ho = 0, ho1 = hstage, ho2 = 2 * hstage, po = 0;
     uint32_t hb0 = fullH, hb1 = fullH + 8, hb2 = fullH + 16, pbar = fullP;
     unsigned hpar = 0, ppar = 0;
-    const int hend = nsh * PT_HSTAGE, pend = nsp * pstage;
+    const int hend = nsh * hstage, pend = nsp * pstage;
 
     mbar_wait(fullH, 0);
     xx_p1 = xxbox(0)[0];
     if (sF[0] & TF_SHEAR) { xy_p1 = hbox(0, HB_SXY)[0]; xz_p1 = hbox(0, HB_SXZ)[0]; }
     mbar_wait(fullH + 8, 0);
-    xx_p2 = xxbox(PT_HSTAGE)[0];
+    xx_p2 = xxbox(hstage)[0];
 
-    for (int it = 0; it < np; it++, q += s1, qy += qy_stride, qz += qz_stride) {
+    for (int it = 0; it < nplanes; it++, q += s1, qy += qy_stride, qz += qz_stride) {
         const int i = ic0 + it;
         const unsigned f = sF[it];
         const bool fsh = f & TF_SHEAR;
@@ -701,9 +751,9 @@ __global__ void __launch_bounds__(NTB, CTAS_PER_SM) particle_tma(const __grid_co
         if (sF[it + 1] & TF_SHEAR) { xy_p1 = hbox(ho1, HB_SXY)[0]; xz_p1 = hbox(ho1, HB_SXZ)[0]; }
         else { xy_p1 = 0.f; xz_p1 = 0.f; }
         mbar_wait(pbar, ppar);
-        const bool xd = in_pml1(i, p.n1, p.P);
+        const bool xd = (f & TF_XD) != 0;
         const bool cellpml = xd || jkd;
-        if (active && (!cellpml || (jkupd && i < p.n1 - 1))) {
+        if (cellpml ? (upd_pml && !(f & TF_ILAST)) : active) {
             const float *byy = hbox(ho, HB_SYY), *bzz = hbox(ho, HB_SZZ);
             const float *bxy = hbox(ho, HB_SXY), *bxz = hbox(ho, HB_SXZ), *byz = hbox(ho, HB_SYZ);
             const LT *l0p = lbox(ho), *l1p = lbox(ho1);
@@ -715,7 +765,7 @@ __global__ void __launch_bounds__(NTB, CTAS_PER_SM) particle_tma(const __grid_co
             else { b0 = __ldg(&p.coef[l0 & MSK].B); bi = __ldg(&p.coef[mi].B); bj = __ldg(&p.coef[mj].B); bk = __ldg(&p.coef[mk].B); }
             const float bx = 0.5f * (b0 + bi), by = 0.5f * (b0 + bj), bz = 0.5f * (b0 + bk);
             float cib_a = BB_CA, cib_b = BB_CB, cif_a = BB_CA, cif_b = BB_CB;
-            if (i <= 1 || i >= p.n1 - 2) { const AxisCoef ci = load_axis(p.axI, i); cib_a = ci.cab; cib_b = ci.cbb; cif_a = ci.caf; cif_b = ci.cbf; }
+            if (f & TF_IEDGE) { const AxisCoef ci = load_axis(p.axI, i); cib_a = ci.cab; cib_b = ci.cbb; cif_a = ci.caf; cif_b = ci.cbf; }
             float X[9];
             X[0] = D4C(cif_a, cif_b, xx_p1, xx_0, xx_p2, xx_m1);
             X[3] = D4C(cib_a, cib_b, xy_0, xy_m1, xy_p1, xy_m2);
@@ -743,15 +793,17 @@ __global__ void __launch_bounds__(NTB, CTAS_PER_SM) particle_tma(const __grid_co
             }
             if (l0 & LabelTraits<LT>::REFL) { v[0] = v[1] = v[2] = 0.f; }
             p.V[0][q] = v[0]; p.V[1][q] = v[1]; p.V[2][q] = v[2];
-            if (has_peer && i < p.i0 + 2 && p.peerV[0]) {
+            if (pushsel) {
+            if ((pushsel & 1) && i < p.i0 + 2) {
                 float *b = p.peerV[0];
                 const unsigned qn = (p.peer_plane[0] + (unsigned)(i - p.i0)) * s1 + col;
                 b[qn] = v[0]; b[p.peer_vol[0] + qn] = v[1]; b[2 * p.peer_vol[0] + qn] = v[2];
             }
-            if (has_peer && i >= p.i1 - 2 && p.peerV[1]) {
+            if ((pushsel & 2) && i >= p.i1 - 2) {
                 float *b = p.peerV[1];
                 const unsigned qn = (p.peer_plane[1] + (unsigned)(i - (p.i1 - 2))) * s1 + col;
                 b[qn] = v[0]; b[p.peer_vol[1] + qn] = v[1]; b[2 * p.peer_vol[1] + qn] = v[2];
+            }
             }
             if (ACC && !cellpml) {
                 const unsigned qa = q - 2 * s1;
@@ -762,9 +814,9 @@ __global__ void __launch_bounds__(NTB, CTAS_PER_SM) particle_tma(const __grid_co
             }
         }
         __syncwarp();
-        if (lane == 0) { mbar_arrive(hb0 + MAX_NSH * 8); mbar_arrive(pbar + MAX_NSP * 8); }
+        if (lane0) { mbar_arrive(hb0 + MAX_NSH * 8); mbar_arrive(pbar + MAX_NSP * 8); }
         ho = ho1; hb0 = hb1; ho1 = ho2; hb1 = hb2;
-        ho2 += PT_HSTAGE; hb2 += 8;
+        ho2 += hstage; hb2 += 8;
         if (ho2 == hend) { ho2 = 0; hb2 = fullH; hpar ^= 1u; }
         po += pstage; pbar += 8;
         if (po == pend) { po = 0; pbar = fullP; ppar ^= 1u; }
