@@ -25,6 +25,7 @@
 // in the same launch: a cell whose axis is damped updates the stored damped part of that axis and
 // adds the increment to the total field (fdtd_cell.cuh).
 #pragma once
+#include <type_traits>
 #include "fdtd_cell.cuh"
 
 namespace tma {
@@ -402,7 +403,10 @@ __global__ void __launch_bounds__(NTB, CTAS_PER_SM) stress_tma(const __grid_cons
         mbar_wait(pbar, ppar);
         const bool xd = (f & TF_XD) != 0;
         const bool cellpml = xd || jkd;
-        if (cellpml ? (upd_pml && !(f & TF_ILAST)) : active) {
+        // the cell update, compiled twice: for planes of the tile where shear fields move (TF_SOLID) and for the others,
+        // where every shear term (differences, rigidities, zero-filled registers, stores) is absent from the instruction stream
+        auto cell_update = [&](auto solid_tag) {
+            constexpr bool SOL = decltype(solid_tag)::value;
             const float *bx = hbox(ho, 0), *by = hbox(ho, 1), *bz = hbox(ho, 2);
             const LT *l0p = lbox(ho), *l1p = lbox(ho1);
             const float *pb = reinterpret_cast<const float *>(psc + po);
@@ -419,7 +423,7 @@ __global__ void __launch_bounds__(NTB, CTAS_PER_SM) stress_tma(const __grid_cons
             D[0] = D4C(cib_a, cib_b, vx_0, vx_m1, vx_p1, vx_m2);
             D[1] = D4C(cjb_a, cjb_b, by[0], by[-SW], by[SW], by[-2 * SW]);
             D[2] = D4C(ckb_a, ckb_b, bz[0], bz[-1], bz[1], bz[-2]);
-            if (f & TF_SOLID) {
+            if constexpr (SOL) {
                 D[3] = D4C(cif_a, cif_b, vy_p1, vy_0, vy_p2, vy_m1);
                 D[4] = D4C(cjf_a, cjf_b, bx[SW], bx[0], bx[2 * SW], bx[-SW]);
                 D[5] = D4C(cif_a, cif_b, vz_p1, vz_0, vz_p2, vz_m1);
@@ -429,7 +433,7 @@ __global__ void __launch_bounds__(NTB, CTAS_PER_SM) stress_tma(const __grid_cons
             } else { D[3] = D[4] = D[5] = D[6] = D[7] = D[8] = 0.f; }
             // ---------------- edge rigidities (only where something is solid)
             float rigxy = 0.f, rigxz = 0.f, rigyz = 0.f, texy = 0.f, texz = 0.f, teyz = 0.f;
-            if (f & TF_SOLID) {
+            if constexpr (SOL) {
                 const unsigned mi = l1p[0] & MSK, mj = l0p[LW] & MSK, mk = l0p[1] & MSK;
                 const unsigned mij = l1p[LW] & MSK, mik = l1p[1] & MSK, mjk = l0p[LW + 1] & MSK;
                 float igi, igj, igk, igij, igik, igjk, ti, tj, tk, tij, tik, tjk;
@@ -451,7 +455,7 @@ __global__ void __launch_bounds__(NTB, CTAS_PER_SM) stress_tma(const __grid_cons
             }
             float s[6];
             s[0] = pb[PB_SXX * NT]; s[1] = pb[PB_SYY * NT]; s[2] = pb[PB_SZZ * NT];
-            if (f & TF_SOLID) { s[3] = pb[PB_SXY * NT]; s[4] = pb[PB_SXZ * NT]; s[5] = pb[PB_SYZ * NT]; }
+            if constexpr (SOL) { s[3] = pb[PB_SXY * NT]; s[4] = pb[PB_SXZ * NT]; s[5] = pb[PB_SYZ * NT]; }
             else { s[3] = s[4] = s[5] = 0.f; }
             if (cellpml) {
                 // ---------------- PML shell: damped split parts (old values staged by TMA)
@@ -464,7 +468,7 @@ __global__ void __launch_bounds__(NTB, CTAS_PER_SM) stress_tma(const __grid_cons
                                  reinterpret_cast<const float *>(pzs + po + zshear), NT, zcomp);
                 if (refl) { s[0] = s[1] = s[2] = s[3] = s[4] = s[5] = 0.f; }
                 p.S[0][q] = s[0]; p.S[1][q] = s[1]; p.S[2][q] = s[2];
-                if (f & TF_SOLID) { p.S[3][q] = s[3]; p.S[4][q] = s[4]; p.S[5][q] = s[5]; }
+                if constexpr (SOL) { p.S[3][q] = s[3]; p.S[4][q] = s[4]; p.S[5][q] = s[5]; }
             } else {
                 // ---------------- interior: viscoelastic update
                 const bool att = attenuates(c);
@@ -475,7 +479,7 @@ __global__ void __launch_bounds__(NTB, CTAS_PER_SM) stress_tma(const __grid_cons
                 if (refl) { s[0] = s[1] = s[2] = 0.f; pr = 0.f; }
                 p.S[0][q] = s[0]; p.S[1][q] = s[1]; p.S[2][q] = s[2]; p.Pr[q] = pr;
                 if (att) { p.R[0][q] = r0; p.R[1][q] = r1; p.R[2][q] = r2; }
-                if (f & TF_SOLID) {
+                if constexpr (SOL) {
                     if (rigxy != 0.f) {
                         float r = pb[PB_RXY * NT];
                         stress_shear_interior(c, dt, rigxy, texy, D[3] + D[4], s[3], r);
@@ -514,15 +518,18 @@ __global__ void __launch_bounds__(NTB, CTAS_PER_SM) stress_tma(const __grid_cons
                 float *b = p.peerS[0];
                 const unsigned qn = (p.peer_plane[0] + (unsigned)(i - p.i0)) * s1 + col;
                 b[qn] = s[0];
-                if (f & TF_SOLID) { b[3 * p.peer_vol[0] + qn] = s[3]; b[4 * p.peer_vol[0] + qn] = s[4]; }
+                if constexpr (SOL) { b[3 * p.peer_vol[0] + qn] = s[3]; b[4 * p.peer_vol[0] + qn] = s[4]; }
             }
             if ((pushsel & 2) && i >= p.i1 - 2) {
                 float *b = p.peerS[1];
                 const unsigned qn = (p.peer_plane[1] + (unsigned)(i - (p.i1 - 2))) * s1 + col;
                 b[qn] = s[0];
-                if (f & TF_SOLID) { b[3 * p.peer_vol[1] + qn] = s[3]; b[4 * p.peer_vol[1] + qn] = s[4]; }
+                if constexpr (SOL) { b[3 * p.peer_vol[1] + qn] = s[3]; b[4 * p.peer_vol[1] + qn] = s[4]; }
             }
             }
+        };
+        if (cellpml ? (upd_pml && !(f & TF_ILAST)) : active) {
+            if (f & TF_SOLID) cell_update(std::true_type{}); else cell_update(std::false_type{});
         }
         // ---------------- this warp is done with the slots of plane i
         __syncwarp();
@@ -753,7 +760,9 @@ __global__ void __launch_bounds__(NTB, CTAS_PER_SM) particle_tma(const __grid_co
         mbar_wait(pbar, ppar);
         const bool xd = (f & TF_XD) != 0;
         const bool cellpml = xd || jkd;
-        if (cellpml ? (upd_pml && !(f & TF_ILAST)) : active) {
+        // the cell update, compiled twice: with and without the shear-stress differences (TF_SHEAR of this plane)
+        auto cell_update = [&](auto shear_tag) {
+            constexpr bool SHEAR = decltype(shear_tag)::value;
             const float *byy = hbox(ho, HB_SYY), *bzz = hbox(ho, HB_SZZ);
             const float *bxy = hbox(ho, HB_SXY), *bxz = hbox(ho, HB_SXZ), *byz = hbox(ho, HB_SYZ);
             const LT *l0p = lbox(ho), *l1p = lbox(ho1);
@@ -772,7 +781,7 @@ __global__ void __launch_bounds__(NTB, CTAS_PER_SM) particle_tma(const __grid_co
             X[6] = D4C(cib_a, cib_b, xz_0, xz_m1, xz_p1, xz_m2);
             X[4] = D4C(cjf_a, cjf_b, byy[SW], byy[0], byy[2 * SW], byy[-SW]);
             X[8] = D4C(ckf_a, ckf_b, bzz[1], bzz[0], bzz[2], bzz[-1]);
-            if (fsh) {
+            if constexpr (SHEAR) {
                 X[1] = D4C(cjb_a, cjb_b, bxy[0], bxy[-SW], bxy[SW], bxy[-2 * SW]);
                 X[2] = D4C(ckb_a, ckb_b, bxz[0], bxz[-1], bxz[1], bxz[-2]);
                 X[5] = D4C(ckb_a, ckb_b, byz[0], byz[-1], byz[1], byz[-2]);
@@ -786,10 +795,14 @@ __global__ void __launch_bounds__(NTB, CTAS_PER_SM) particle_tma(const __grid_co
                 pcell.qx = (unsigned)ipx * s1 + col; pcell.qy = qy; pcell.qz = qz;
                 pcell.cI = p.axI + i; pcell.cJ = sJ + ty; pcell.cK = sK + tx;
                 particle_pml<true>(p, pcell, bx, by, bz, X, v, pb + QB_X * NT, pb + (yoff >> 2), reinterpret_cast<const float *>(pzs + po), NT, zcomp);
-            } else {
+            } else if constexpr (SHEAR) {
                 v[0] += dt * bx * (X[0] + X[1] + X[2]);
                 v[1] += dt * by * (X[3] + X[4] + X[5]);
                 v[2] += dt * bz * (X[6] + X[7] + X[8]);
+            } else {
+                v[0] += dt * bx * X[0];
+                v[1] += dt * by * (X[3] + X[4]);
+                v[2] += dt * bz * (X[6] + X[8]);
             }
             if (l0 & LabelTraits<LT>::REFL) { v[0] = v[1] = v[2] = 0.f; }
             p.V[0][q] = v[0]; p.V[1][q] = v[1]; p.V[2][q] = v[2];
@@ -812,6 +825,9 @@ __global__ void __launch_bounds__(NTB, CTAS_PER_SM) particle_tma(const __grid_co
                 accumulate(p, BB_MAP_VZ, qa, v[2], false);
                 accumulate(p, BB_MAP_ALLV, qa, v[0] * v[0] + v[1] * v[1] + v[2] * v[2], true);
             }
+        };
+        if (cellpml ? (upd_pml && !(f & TF_ILAST)) : active) {
+            if (fsh) cell_update(std::true_type{}); else cell_update(std::false_type{});
         }
         __syncwarp();
         if (lane0) { mbar_arrive(hb0 + MAX_NSH * 8); mbar_arrive(pbar + MAX_NSP * 8); }
