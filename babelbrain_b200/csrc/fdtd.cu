@@ -1052,6 +1052,45 @@ extern "C" int bb_fdtd_get_sensors(bb_fdtd *h, int map_id, float *out) {
     return BB_OK;
 }
 
+extern "C" int bb_fdtd_get_phase_data(bb_fdtd *h, int map_id, int bin, int nsamples_used, float scale,
+                                      float *fourier_reim, float *phase, float *peak) {
+    BB_REQUIRE(h && fourier_reim, "null argument");
+    BB_REQUIRE(map_id >= 0 && map_id < BB_MAP_COUNT && (h->d.sel_maps_sensor & (1u << map_id)), "sensor map %d not selected", map_id);
+    BB_REQUIRE(nsamples_used >= 1 && nsamples_used <= h->nsamples, "nsamples_used %d outside [1, %lld]", nsamples_used, (long long)h->nsamples);
+    BB_REQUIRE(bin >= 0 && bin < nsamples_used, "DFT bin %d outside [0, %d)", bin, nsamples_used);
+    BB_CUDA(cudaSetDevice(h->d.device));
+    const size_t cells = (size_t)h->nown * h->p.n2 * h->p.n3;
+    const int slot = popcount32(h->d.sel_maps_sensor & ((1u << map_id) - 1u));
+    std::vector<float2> tw(nsamples_used);
+    for (int n = 0; n < nsamples_used; n++) {
+        const double a = -2.0 * M_PI * (double)(((long long)bin * n) % nsamples_used) / (double)nsamples_used;
+        tw[n] = make_float2((float)cos(a), (float)sin(a));
+    }
+    float2 *dtw = nullptr, *dfou = nullptr;
+    float *dph = nullptr, *dpk = nullptr;
+    auto cleanup = [&]() { if (dtw) cudaFree(dtw); if (dfou) cudaFree(dfou); if (dph) cudaFree(dph); if (dpk) cudaFree(dpk); };
+    cudaError_t e = cudaMalloc(&dtw, tw.size() * sizeof(float2));
+    if (e == cudaSuccess) e = cudaMalloc(&dfou, cells * sizeof(float2));
+    if (e == cudaSuccess && phase) e = cudaMalloc(&dph, cells * 4);
+    if (e == cudaSuccess && peak) e = cudaMalloc(&dpk, cells * 4);
+    if (e == cudaSuccess) e = cudaMemcpyAsync(dtw, tw.data(), tw.size() * sizeof(float2), cudaMemcpyHostToDevice, h->stream);
+    if (e == cudaSuccess) e = cudaMemsetAsync(dfou, 0, cells * sizeof(float2), h->stream);
+    if (e == cudaSuccess && dph) e = cudaMemsetAsync(dph, 0, cells * 4, h->stream);
+    if (e == cudaSuccess && dpk) e = cudaMemsetAsync(dpk, 0, cells * 4, h->stream);
+    if (e == cudaSuccess && h->nsensors > 0) {
+        phase_data_kernel<<<(unsigned)((h->nsensors + 255) / 256), 256, 0, h->stream>>>(
+            h->p, h->sensor_out + (size_t)slot * h->nsensors * h->nsamples, h->sensor_cell, h->nsensors, nsamples_used, dtw, scale, dfou, dph, dpk);
+        e = cudaGetLastError();
+    }
+    if (e == cudaSuccess) e = cudaMemcpyAsync(fourier_reim, dfou, cells * sizeof(float2), cudaMemcpyDeviceToHost, h->stream);
+    if (e == cudaSuccess && dph) e = cudaMemcpyAsync(phase, dph, cells * 4, cudaMemcpyDeviceToHost, h->stream);
+    if (e == cudaSuccess && dpk) e = cudaMemcpyAsync(peak, dpk, cells * 4, cudaMemcpyDeviceToHost, h->stream);
+    if (e == cudaSuccess) e = cudaStreamSynchronize(h->stream);
+    cleanup();
+    if (e != cudaSuccess) { bb_set_error("bb_fdtd_get_phase_data: %s", cudaGetErrorString(e)); return BB_ERR_CUDA; }
+    return BB_OK;
+}
+
 // profiling aid: the per-CTA records of the most recent half-step launch (needs BB_CTA_TIMING=1 at create); out = 4 x n uint64
 extern "C" int bb_fdtd_debug_cta_times(bb_fdtd *h, unsigned long long *out, int64_t n) {
     BB_REQUIRE(h && out && n > 0 && n <= 65536, "bad argument");

@@ -96,6 +96,30 @@ __global__ void sensor_transpose_kernel(const float *__restrict__ in, float *__r
     for (int t = 0; t < nsamples; t++) out[s * nsamples + t] = in[(long long)t * nsensors + s];
 }
 
+// Single-bin DFT of each sensor's trace (in: [sample][sensor]), its angle and the largest sample, scattered to the dense
+// (nown, n2, n3) volumes of the slab.  tw = nsamples (cos, -sin) pairs of the bin, rounded from double on the host.
+__global__ void phase_data_kernel(const DevParams p, const float *__restrict__ in, const long long *__restrict__ cell, long long nsensors,
+                                  int nsamples, const float2 *__restrict__ tw, float scale, float2 *__restrict__ fourier,
+                                  float *__restrict__ phase, float *__restrict__ peak) {
+    const long long s = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    if (s >= nsensors) return;
+    float re = 0.f, im = 0.f, mx = -INFINITY;
+    for (int n = 0; n < nsamples; n++) {
+        const float x = in[(long long)n * nsensors + s];
+        const float2 w = __ldg(tw + n);
+        re = fmaf(x, w.x, re);
+        im = fmaf(x, w.y, im);
+        mx = fmaxf(mx, x);
+    }
+    const long long q = cell[s];                       // pitched local index (ipl * n2 + j) * pitch + k, ipl = i - i0 + 2
+    const long long ipl = q / p.plane, rem = q - ipl * p.plane;
+    const long long j = rem / p.pitch, k = rem - j * p.pitch;
+    const long long o = ((ipl - 2) * p.n2 + j) * p.n3 + k;
+    fourier[o] = make_float2(re * scale, im * scale);
+    if (phase) phase[o] = atan2f(im, re);
+    if (peak) peak[o] = mx;
+}
+
 // uint32 host labels (dense rows of n3) -> LT labels (pitched rows), reflector -> top bit
 template <typename LT>
 __global__ void label_convert_kernel(const uint32_t *__restrict__ in, const uint32_t *__restrict__ refl, LT *__restrict__ out,

@@ -245,6 +245,26 @@ class FdtdSlab:
         self.d2h_bytes += out.nbytes
         return out
 
+    def get_phase_data(self, name, bin_index, nsamples_used=None, scale=None, fourier=None, phase=None, peak=None):
+        """Single-bin DFT, angle and largest sample of every sensor trace of this slab, computed on the device and
+        scattered to (i1-i0, N2, N3) volumes (bb_fdtd_get_phase_data).  Arrays passed in are filled in place."""
+        N1, N2, N3 = self.shape
+        sh = (self.i1 - self.i0, N2, N3)
+        n = int(self.sample_steps.size if nsamples_used is None else nsamples_used)
+        if fourier is None:
+            fourier = _capi.pinned.empty(sh, np.complex64)
+        if phase is None:
+            phase = _capi.pinned.empty(sh, np.float32)
+        if peak is None:
+            peak = _capi.pinned.empty(sh, np.float32)
+        for a, dt in ((fourier, np.complex64), (phase, np.float32), (peak, np.float32)):
+            assert a.shape == sh and a.dtype == dt and a.flags.c_contiguous
+        _capi.check(self._L.bb_fdtd_get_phase_data(self._h, _capi.MAP_ID[name], int(bin_index), n,
+                                                   ctypes.c_float(2.0 / n if scale is None else scale),
+                                                   _capi.ptr(fourier), _capi.ptr(phase), _capi.ptr(peak)))
+        self.d2h_bytes += fourier.nbytes + phase.nbytes + peak.nbytes
+        return fourier, phase, peak
+
     def close(self):
         if self._h is not None:
             self._finalizer()
@@ -398,7 +418,55 @@ def collect_results(slab):
 
 
 class PropagationModel:
-    """Drop-in for BabelViscoFDTD.PropagationModel.PropagationModel (the two methods BabelBrain uses)."""
+    """Drop-in for BabelViscoFDTD.PropagationModel.PropagationModel (the two methods BabelBrain uses), plus
+    CalculatePhaseDataOnDevice."""
+
+    _last_slabs = ()
+
+    def CalculatePhaseDataOnDevice(self, Frequency, MapName='Pressure'):
+        """What the caller's CalculatePhaseData (BabelIntegrationBASE.py:2460-2518, forward branch) derives on the
+        host from Sensor[MapName] and InputParam['IndexSensorMap'] -- computed on the GPU(s) from the traces of the
+        most recent simulation of this object, which are still resident: the DFT bin closest to Frequency of every
+        sensor (times 2/Nsamples), its angle, and the largest sample, as whole-grid volumes with zeros where there
+        is no sensor.  Returns {'PhaseMap': float32, 'PressMapFourier': complex64, 'PressMapPeak': float32,
+        'IndSpectrum': int}.  Nothing but those three volumes crosses PCIe, and no host FFT runs."""
+        slabs = [s for s in self._last_slabs if s._h is not None]
+        if not slabs:
+            raise RuntimeError('no finished simulation of this PropagationModel holds device state '
+                               '(a newer simulation releases the previous one)')
+        s0 = slabs[0]
+        if MapName not in s0.sensor_names:
+            raise ValueError('%s was not in SelMapsSensorsList' % MapName)
+        t = s0.sample_steps.astype(np.float64) * s0.dt
+        if t.size < 2:
+            raise ValueError('phase data need at least two sensor samples')
+        freqs = np.fft.fftfreq(t.size, np.diff(t).mean())           # BabelIntegrationBASE.py:2489, :2498-2499
+        ind = int(np.argmin(np.abs(freqs - Frequency)))
+        fourier = _capi.pinned.empty(s0.shape, np.complex64)
+        phase = _capi.pinned.empty(s0.shape, np.float32)
+        peak = _capi.pinned.empty(s0.shape, np.float32)
+
+        def one(s):
+            s.get_phase_data(MapName, ind, fourier=fourier[s.i0:s.i1], phase=phase[s.i0:s.i1], peak=peak[s.i0:s.i1])
+        if len(slabs) == 1:
+            one(s0)
+        else:
+            import threading
+            errors = []
+
+            def guarded(s):
+                try:
+                    one(s)
+                except BaseException as e:  # noqa: BLE001
+                    errors.append(e)
+            th = [threading.Thread(target=guarded, args=(s,)) for s in slabs]
+            for x in th:
+                x.start()
+            for x in th:
+                x.join()
+            if errors:
+                raise errors[0]
+        return {'PhaseMap': phase, 'PressMapFourier': fourier, 'PressMapPeak': peak, 'IndSpectrum': ind}
 
     def CalculateMatricesForPropagation(self, MaterialMap, MaterialProperties, Frequency, QfactorCorrection, h,
                                         AlphaCFL, QCorrection=1.0):
@@ -473,6 +541,7 @@ class PropagationModel:
                             'h2d_bytes': slab.h2d_bytes, 'd2h_bytes': slab.d2h_bytes}
         last = _LastMap(slab)
         _live_lastmaps.append(last)
+        self._last_slabs = (slab,)
         if SelRMSorPeak == 3:
             return Sensor, last, RMS, Peak, InputParam
         return Sensor, last, (RMS if SelRMSorPeak == 1 else Peak), InputParam
@@ -486,6 +555,7 @@ class PropagationModel:
         self.last_timing = dict(timing, total_s=time.perf_counter() - t0, devices=devices)
         last = _LastMapSlabs(slabs)
         _live_lastmaps.append(last)
+        self._last_slabs = tuple(slabs)
         if kwargs['SelRMSorPeak'] == 3:
             return Sensor, last, RMS, Peak, InputParam
         return Sensor, last, (RMS if kwargs['SelRMSorPeak'] == 1 else Peak), InputParam

@@ -145,6 +145,15 @@ int bb_fdtd_reset(bb_fdtd *h);                               /* zero state, step
 int bb_fdtd_get_map(bb_fdtd *h, int which, int map_id, float *out);
 /* out = (nsensors, nsamples) float32 for one selected sensor map */
 int bb_fdtd_get_sensors(bb_fdtd *h, int map_id, float *out);
+/* Phase / amplitude extraction of the sampled traces on the device -- what the caller's CalculatePhaseData does on the
+ * host with an FFT over Sensor['Pressure'] (BabelIntegrationBASE.py:2498-2518): for every sensor of this slab, bin `bin`
+ * of the DFT of its first nsamples_used samples (sum_n x[n] exp(-2 pi j bin n / nsamples_used)) times `scale`
+ * (the caller's 2/nsamples, :2518), the angle of that bin and the largest sample, scattered to the sensor's voxel of
+ * dense (i1-i0, N2, N3) volumes; voxels without a sensor are 0 (:2474-2476).  fourier_reim holds (re, im) pairs
+ * (a numpy complex64 volume); phase and peak may be NULL.  Replaces the download of (nsensors, nsamples) traces plus
+ * IndexSensorMap and the host FFT by two or three volume downloads. */
+int bb_fdtd_get_phase_data(bb_fdtd *h, int map_id, int bin, int nsamples_used, float scale,
+                           float *fourier_reim, float *phase, float *peak);
 int bb_fdtd_get_stats(bb_fdtd *h, bb_fdtd_stats *out);
 /* profiling aid (handle created with BB_CTA_TIMING=1 in the environment): per CTA of the most recent half-step launch
  * {start ns, end ns, blockIdx packed z<<40|y<<20|x, planes}; out holds 4*n uint64 */
