@@ -68,6 +68,9 @@ struct bb_fdtd {
     int *src_row = nullptr;
     float *src_o[3] = {nullptr, nullptr, nullptr};
     float *srcfun = nullptr;  // [nt_src][nsrc]
+    // continuous-wave sources synthesised in the source kernel instead of read from srcfun (bb_fdtd_set_source_tones)
+    float *tone_ac = nullptr, *tone_as = nullptr;     // [nsrc] A cos(phi), A sin(phi)
+    std::vector<float> tone_es, tone_ec;              // [nt_src] ramp(n) sin(w t_n), ramp(n) cos(w t_n)
     // sensors
     int64_t nsensors = 0, nsamples = 0;
     long long *sensor_cell = nullptr;
@@ -484,6 +487,24 @@ extern "C" int bb_fdtd_set_source_functions(bb_fdtd *h, const void *data, int is
     return BB_OK;
 }
 
+extern "C" int bb_fdtd_set_source_tones(bb_fdtd *h, const float *a_cos, const float *a_sin, const float *env_sin, const float *env_cos) {
+    BB_REQUIRE(h && a_cos && a_sin && env_sin && env_cos, "null argument");
+    BB_REQUIRE(!h->srcfun, "SourceFunctions were already set as a table");
+    BB_CUDA(cudaSetDevice(h->d.device));
+    const int nsrc = h->d.nsrc, nt = h->d.nt_src;
+    BB_REQUIRE(nsrc > 0 && nt > 0, "bad SourceFunctions shape");
+    int rc;
+    if (!h->tone_ac) {
+        if ((rc = dev_alloc(h, (void **)&h->tone_ac, (size_t)nsrc * 4, false))) return rc;
+        if ((rc = dev_alloc(h, (void **)&h->tone_as, (size_t)nsrc * 4, false))) return rc;
+    }
+    BB_CUDA(cudaMemcpy(h->tone_ac, a_cos, (size_t)nsrc * 4, cudaMemcpyHostToDevice));
+    BB_CUDA(cudaMemcpy(h->tone_as, a_sin, (size_t)nsrc * 4, cudaMemcpyHostToDevice));
+    h->tone_es.assign(env_sin, env_sin + nt);
+    h->tone_ec.assign(env_cos, env_cos + nt);
+    return BB_OK;
+}
+
 extern "C" int bb_fdtd_set_sensors(bb_fdtd *h, int64_t nsensors, const int64_t *cell) {
     BB_REQUIRE(h && nsensors >= 0 && (nsensors == 0 || cell), "bad argument");
     BB_CUDA(cudaSetDevice(h->d.device));
@@ -827,11 +848,13 @@ static int launch_half_step(bb_fdtd *h, bool stress, int acc_mode, int ib, int i
 }
 
 static int launch_sources(bb_fdtd *h, int n, int64_t first, int64_t count, Timer &tm) {
-    if (count <= 0 || n >= h->d.nt_src || !h->srcfun) return BB_OK;
+    if (count <= 0 || n >= h->d.nt_src || !(h->srcfun || h->tone_ac)) return BB_OK;
     tm.begin(CAT_OTHER);
     source_kernel<<<(unsigned)((count + 127) / 128), 128, 0, h->stream>>>(h->p, h->d.type_source, count, h->src_cell + first, h->src_row + first,
                                                                          h->src_o[0] + first, h->src_o[1] + first, h->src_o[2] + first,
-                                                                         h->srcfun + (size_t)n * h->d.nsrc);
+                                                                         h->tone_ac ? nullptr : h->srcfun + (size_t)n * h->d.nsrc,
+                                                                         h->tone_ac, h->tone_as, h->tone_ac ? h->tone_es[n] : 0.f,
+                                                                         h->tone_ac ? h->tone_ec[n] : 0.f);
     tm.end();
     BB_CUDA(cudaGetLastError());
     return BB_OK;
@@ -868,7 +891,7 @@ static int half_step(bb_fdtd *h, bool stress, int n, int acc, Timer &tm) {
     if (h->peer_mode) {
         // NVLink halo push: one launch; the boundary CTAs store into the neighbours' halo planes.  When sources are
         // injected behind the kernel they push their cells too and a one-thread kernel publishes the half-step.
-        const bool src_now = src_here && h->nsrc_cells > 0 && n < h->d.nt_src && h->srcfun;
+        const bool src_now = src_here && h->nsrc_cells > 0 && n < h->d.nt_src && (h->srcfun || h->tone_ac);
         if ((rc = launch_half_step<LT>(h, stress, acc, p.i0, p.i1, tm, nullptr, !src_now))) return rc;
         if (src_now) {
             if ((rc = launch_sources(h, n, 0, h->nsrc_cells, tm))) return rc;

@@ -24,10 +24,13 @@ __device__ __forceinline__ void push_source_cell(const DevParams &p, float *cons
 __global__ void source_kernel(const DevParams p, int type_source, long long ncells, const long long *__restrict__ cell,
                               const int *__restrict__ row, const float *__restrict__ ox,
                               const float *__restrict__ oy, const float *__restrict__ oz,
-                              const float *__restrict__ sf_row) {
+                              const float *__restrict__ sf_row, const float *__restrict__ tone_ac,
+                              const float *__restrict__ tone_as, float env_sin, float env_cos) {
     const long long s = (long long)blockIdx.x * blockDim.x + threadIdx.x;
     if (s >= ncells) return;
-    const float v = sf_row[row[s]];
+    // table row of this time step, or the continuous-wave source evaluated in place:
+    // ramp(n) A sin(w t_n + phi) = [ramp sin(w t_n)] A cos(phi) + [ramp cos(w t_n)] A sin(phi)
+    const float v = tone_ac ? fmaf(env_sin, tone_ac[row[s]], env_cos * tone_as[row[s]]) : sf_row[row[s]];
     const long long q = cell[s];
     if (type_source >= 2) {
         const float w = v * ox[s];

@@ -14,6 +14,7 @@ import numpy as np
 
 from . import _capi, hostprep
 from .slab import SlabPlan
+from .sources import CWSourceFunctions
 
 _live_lastmaps = []
 
@@ -65,10 +66,11 @@ class FdtdSlab:
         self.sel_rms_peak = int(SelRMSorPeak)
         if self.sel_rms_peak not in (1, 2, 3):
             raise ValueError('SelRMSorPeak must be 1 (RMS), 2 (peak) or 3 (both)')
-        SF = np.asarray(SourceFunctions)
+        cw = SourceFunctions if isinstance(SourceFunctions, CWSourceFunctions) else None
+        SF = SourceFunctions if cw is not None else np.asarray(SourceFunctions)
         if SF.ndim != 2:
             raise ValueError('SourceFunctions must be (Nsources, Ntime)')
-        if SF.dtype not in (np.float64, np.float32) or SF.strides[1] != SF.itemsize:
+        if cw is None and (SF.dtype not in (np.float64, np.float32) or SF.strides[1] != SF.itemsize):
             SF = np.ascontiguousarray(SF, dtype=np.float64)
         self.plan = SlabPlan(N1, nranks, NDelta)
         self.rank, self.nranks = int(rank), int(nranks)
@@ -158,9 +160,15 @@ class FdtdSlab:
         rows32 = np.ascontiguousarray(rows, dtype=np.int32)
         _capi.check(L.bb_fdtd_set_source_cells(hp, cells.size, _capi.ptr(cells), _capi.ptr(rows32),
                                                _capi.ptr(ox), _capi.ptr(oy), _capi.ptr(oz)))
-        if cells.size:
+        sf_bytes = 0
+        if cells.size and cw is not None:        # continuous-wave rows evaluated in the source kernel: no table anywhere
+            tones = cw.tone_tables()
+            _capi.check(L.bb_fdtd_set_source_tones(hp, *[_capi.ptr(a) for a in tones]))
+            sf_bytes = sum(a.nbytes for a in tones)
+        elif cells.size:
             _capi.check(L.bb_fdtd_set_source_functions(hp, _capi.ptr(SF), int(SF.dtype == np.float64),
                                                        SF.strides[0] // SF.itemsize))
+            sf_bytes = SF.nbytes
         _mark('sources')
         self.d2h_bytes = 0
         if scell is not None:
@@ -180,7 +188,7 @@ class FdtdSlab:
         _mark('sensors')
         if os.environ.get('BB_TIMING'):
             print('FdtdSlab setup: ' + ', '.join(_marks), flush=True)
-        self.h2d_bytes = int(mm.nbytes + (refl.nbytes if refl is not None else 0) + SF.nbytes * (cells.size > 0)
+        self.h2d_bytes = int(mm.nbytes + (refl.nbytes if refl is not None else 0) + sf_bytes
                              + cells.nbytes + rows32.nbytes + 3 * ox.nbytes + sensor_bytes + t32.nbytes + pml.nbytes)
 
     # ------------------------------------------------------------------

@@ -107,17 +107,15 @@ def skull_labels(shape, h, pml, seed=1234, skin_depth_frac=0.14, planes=None):
     return lab
 
 
+def cw_source_object(amp, phase, frequency, dt, steps, ramp_cycles=4):
+    from .sources import CWSourceFunctions
+    return CWSourceFunctions(amp, phase, frequency, dt, dt * steps, ramp_cycles)
+
+
 def cw_sources(amp, phase, frequency, dt, steps, ramp_cycles=4):
-    """(Nsrc, Nt) float64 pulse table, as CreateSources builds it (BabelIntegrationSingle.py:313-346)."""
-    tsim = dt * steps
-    length = np.floor(tsim / (1.0 / frequency)) * 1 / frequency
-    t = np.arange(0, length + dt, dt)
-    npts = int(np.round(ramp_cycles / frequency / dt))
-    ramp = (-np.cos(np.arange(0, np.pi, np.pi / npts)) + 1) * 0.5
-    P = amp[:, None] * np.sin(2 * np.pi * frequency * t[None, :] + phase[:, None])
-    nr = min(len(ramp), P.shape[1])
-    P[:, :nr] *= ramp[None, :nr]
-    return P
+    """(Nsrc, Nt) float64 pulse table, as CreateSources builds it (BabelIntegrationSingle.py:313-346; the formula lives
+    in sources.CWSourceFunctions, pinned against the reference's method by tests/test_sources.py)."""
+    return cw_source_object(amp, phase, frequency, dt, steps, ramp_cycles).dense()
 
 
 CONFIGS = {
@@ -184,7 +182,8 @@ def make_workload(name='ctx500_skull', shape=None, periods=None, seed=1234, pml=
         ap = min(cfg['aperture'], 0.8 * (min(n1, n2) - 2 * pml) * h)
         amp = amplitude * (0.98 * np.exp(-(np.sqrt(r2) / (ap / 2)) ** 8) + 0.02) * focal / dist
         phase = -kwater * (dist - focal)
-        SF = cw_sources(amp.reshape(-1), phase.reshape(-1), f, dt, steps)
+        cw = cw_source_object(amp.reshape(-1), phase.reshape(-1), f, dt, steps)
+        SF = cw.dense()
         if lean:
             Ox = Oy = np.broadcast_to(np.float64(0.0), lshape)
             Oz = np.broadcast_to(np.float64(1.0 / (1000.0 * 1500.0)), lshape)
@@ -210,7 +209,8 @@ def make_workload(name='ctx500_skull', shape=None, periods=None, seed=1234, pml=
             ci, cj, ck = (int(np.clip(c, pml + 1, n - pml - 3)) for c, n in ((ci, n1), (cj, n2), (ck, n3)))
             SourceMap[ci:ci + 2, cj:cj + 2, ck:ck + 2] = e + 1
         dist = np.sqrt(ce[:, 0] ** 2 + ce[:, 1] ** 2 + (ce[:, 2] - zc) ** 2)
-        SF = cw_sources(np.full(nel, amplitude), -kwater * (dist - rad), f, dt, steps)
+        cw = cw_source_object(np.full(nel, amplitude), -kwater * (dist - rad), f, dt, steps)
+        SF = cw.dense()
         MaterialMap[SourceMap > 0] = 0
         kw.update(Ox=np.array([1]), Oy=np.array([1]), Oz=np.array([1]), TypeSource=2)
         kw['SelMapsRMSPeakList'] = ['Pressure']
@@ -221,7 +221,7 @@ def make_workload(name='ctx500_skull', shape=None, periods=None, seed=1234, pml=
     args = (MaterialMap, ML, f, SourceMap, SF, h, dt * steps, SensorMap)
     meta = dict(name=name, shape=cfg['shape'], cells=n1 * n2 * n3, steps=steps, ppp=S['ppp'], dt=dt, h=h,
                 sub=S['sub'], sensor_start=S['sensor_start'], nsrc=SF.shape[0], cell_updates=n1 * n2 * n3 * steps,
-                frequency=f, ppw=cfg['ppw'], pml=pml, planes=(lo, hi))
+                frequency=f, ppw=cfg['ppw'], pml=pml, planes=(lo, hi), cw_sources=cw)
     return dict(args=args, kwargs=kw, meta=meta)
 
 

@@ -111,6 +111,13 @@ int bb_fdtd_set_source_cells(bb_fdtd *h, int64_t ncells, const int64_t *cell, co
 /* SourceFunctions as the caller holds it: (nsrc, nt_src), float64 or float32, row stride in
  * elements (BabelIntegrationSingle.py:335).  Converted and transposed on the device. */
 int bb_fdtd_set_source_functions(bb_fdtd *h, const void *data, int is_f64, int64_t row_stride);
+/* Alternative to bb_fdtd_set_source_functions for the continuous-wave sources every transducer model builds
+ * (CreateSources, BabelIntegrationSingle.py:313-346: row s = |u0_s| sin(2 pi f t + angle(u0_s)), the first ramp samples
+ * scaled by a raised cosine): the rows are evaluated in the source kernel from a_cos[s] = |u0_s| cos(angle), a_sin[s] =
+ * |u0_s| sin(angle) (nsrc floats each) and the two time envelopes env_sin[n] = ramp(n) sin(2 pi f t_n), env_cos[n] =
+ * ramp(n) cos(2 pi f t_n) (nt_src floats each, rounded from double by the caller).  No (nsrc, nt_src) table exists on
+ * either side of the PCIe link (at 1 MHz / 1080^3 that table is 100 GB of float64 on the host). */
+int bb_fdtd_set_source_tones(bb_fdtd *h, const float *a_cos, const float *a_sin, const float *env_sin, const float *env_cos);
 /* sensors owned by this slab: global C-order linear cell index, in IndexSensorMap order */
 int bb_fdtd_set_sensors(bb_fdtd *h, int64_t nsensors, const int64_t *cell);
 /* Alternative to bb_fdtd_set_sensors: build the sensor table on the device from the caller's
