@@ -24,7 +24,7 @@ class FdtdDesc(ctypes.Structure):
                 ('sel_maps_rms', ctypes.c_uint32), ('sel_maps_sensor', ctypes.c_uint32),
                 ('sensor_subsampling', ctypes.c_int32), ('sensor_start', ctypes.c_int32),
                 ('device', ctypes.c_int32), ('rank', ctypes.c_int32), ('nranks', ctypes.c_int32),
-                ('kernel_variant', ctypes.c_int32), ('reserved', ctypes.c_int32), ('dt', ctypes.c_double)]
+                ('kernel_variant', ctypes.c_int32), ('mpml_ratio', ctypes.c_float), ('dt', ctypes.c_double)]
 
 
 class PeerInfo(ctypes.Structure):

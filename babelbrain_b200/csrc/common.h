@@ -40,12 +40,15 @@ struct __align__(16) MatCoef {
 constexpr int BB_MAX_SMEM_MAT = 128;   // uint8 labels hold at most 127 materials -> table in smem
 
 // Per-index coefficients of one grid axis (built on the host from the PML table):
-//   damping of a split part  f_a' = aI f_a + bI C D   at integer nodes, (aH, bH) at half nodes;
-//   outside the PML of that axis aI = aH = 1, bI = bH = dt (plain explicit update);
+//   eI, eH = half the damping d/2 of the axis at the integer node n and at the half node n + 1/2 (0 outside the PML
+//   of that axis).  A split part advances as f' = a f + b C D with b = 1/(1/dt + e), a = (1/dt - e) b, where
+//   e = e_own(staggering of the part) + mpml * (eI of the two other axes): the multi-axial layer of Meza-Fajardo &
+//   Papageorgiou (2008).  The classical layer (mpml = 0) is unstable where a fluid-solid interface enters the shell
+//   (DESIGN.md section 4.3), so the coefficients are formed per cell from the three axes' values;
 //   staggered differences  D- = cab (f0 - f-1) - cbb (f+1 - f-2),  D+ = caf (f+1 - f0) - cbf (f+2 - f-1)
 //   with the domain-edge rules folded into the coefficients (9/8,1/24 | 1,0 | 0,0).
 struct __align__(16) AxisCoef {
-    float aI, bI, aH, bH;
+    float eI, eH, pad0, pad1;
     float cab, cbb, caf, cbf;
 };
 
@@ -80,7 +83,8 @@ struct DevParams {
     int pitch;           // floats per k-row (multiple of 32)
     int nloc;            // i1 - i0 + 4
     long long plane;     // n2 * pitch
-    float dt;
+    float dt, idt;       // time step and 1/dt
+    float mpml;          // multi-axial damping ratio of the PML (bb_fdtd_desc::mpml_ratio)
     float *V[3], *S[6], *R[6], *Pr;
     const void *lab;     // uint8_t or uint16_t labels, same layout; top bit = reflector
     const MatCoef *coef; // derived rows indexed by label

@@ -225,6 +225,8 @@ extern "C" int bb_fdtd_create(const bb_fdtd_desc *d, bb_fdtd **out) {
     p.nloc = h->nown + 4;
     p.plane = (long long)p.n2 * p.pitch;
     p.dt = (float)d->dt;
+    p.idt = (float)(1.0 / d->dt);
+    p.mpml = d->mpml_ratio;
     p.nmat = d->nmat;
     h->label_bytes = d->nmat <= 127 ? 1 : 2;
     if (const char *e = getenv("BB_CHUNK")) h->chunk_override = atoi(e);
@@ -316,17 +318,17 @@ extern "C" int bb_fdtd_set_stream(bb_fdtd *h, void *s) {
     return BB_OK;
 }
 
-static void fill_axis(std::vector<AxisCoef> &t, int N, int P, const float *pml, double dt) {
-    const float *Inv = pml, *DX = pml + (P + 1), *InvH = pml + 2 * (P + 1), *DXH = pml + 3 * (P + 1);
+static void fill_axis(std::vector<AxisCoef> &t, int N, int P, const float *pml) {
+    const float *D = pml, *DH = pml + (P + 1);     // damping at integer depth / half depth
     t.resize(N);
     for (int n = 0; n < N; n++) {
         AxisCoef &c = t[n];
-        c.aI = c.aH = 1.0f; c.bI = c.bH = (float)dt;
+        c.eI = c.eH = c.pad0 = c.pad1 = 0.0f;
         int d = 0, dh = -1;
         if (n < P) { d = P - n; dh = P - 1 - n; }
         else if (n >= N - P) { d = n - (N - P - 1); dh = d; }
-        if (d > 0) { c.aI = (float)((double)Inv[d] * (double)DX[d]); c.bI = Inv[d]; }
-        if (dh >= 0) { c.aH = (float)((double)InvH[dh] * (double)DXH[dh]); c.bH = InvH[dh]; }
+        if (d > 0) c.eI = 0.5f * D[d];
+        if (dh >= 0) c.eH = 0.5f * DH[dh];
         // backward difference landing on n, forward difference landing on n + 1/2
         if (n > 1 && n < N - 1) { c.cab = 1.125f; c.cbb = 1.0f / 24.0f; } else if (n > 0) { c.cab = 1.0f; c.cbb = 0.0f; } else { c.cab = c.cbb = 0.0f; }
         if (n > 0 && n < N - 2) { c.caf = 1.125f; c.cbf = 1.0f / 24.0f; } else if (n < N - 1) { c.caf = 1.0f; c.cbf = 0.0f; } else { c.caf = c.cbf = 0.0f; }
@@ -355,7 +357,7 @@ extern "C" int bb_fdtd_set_materials(bb_fdtd *h, const float *table, const float
     const int N[3] = { h->d.n1, h->d.n2, h->d.n3 };
     const AxisCoef *dst[3] = { h->p.axI, h->p.axJ, h->p.axK };
     for (int a = 0; a < 3; a++) {
-        fill_axis(ax[a], N[a], h->d.pml, pml_table, dt);
+        fill_axis(ax[a], N[a], h->d.pml, pml_table);
         BB_CUDA(cudaMemcpyAsync((void *)dst[a], ax[a].data(), sizeof(AxisCoef) * N[a], cudaMemcpyHostToDevice, h->stream));
     }
     BB_CUDA(cudaStreamSynchronize(h->stream));

@@ -26,7 +26,7 @@ __device__ __forceinline__ AxisCoef load_axis(const AxisCoef *t, int n) {
     const float4 *q = reinterpret_cast<const float4 *>(t + n);
     const float4 a = __ldg(q), b = __ldg(q + 1);
     AxisCoef r;
-    r.aI = a.x; r.bI = a.y; r.aH = a.z; r.bH = a.w; r.cab = b.x; r.cbb = b.y; r.caf = b.z; r.cbf = b.w;
+    r.eI = a.x; r.eH = a.y; r.pad0 = a.z; r.pad1 = a.w; r.cab = b.x; r.cbb = b.y; r.caf = b.z; r.cbf = b.w;
     return r;
 }
 
@@ -78,9 +78,11 @@ __device__ __forceinline__ void stress_shear_interior(const MatCoef &c, float dt
 }
 
 // ------------------------------------------------------------------------------------------
-// PML rules.  The reference keeps three split parts per field and sums them; a part whose axis
-// is not damped at this cell obeys f_a += dt C D_a, so only the damped parts are stored and the
-// total field advances by the sum of the parts' increments (identical up to rounding).
+// PML rules.  The reference formulation keeps three split parts per field and sums them.  Here a part is stored only
+// where its own axis is damped; the parts of the other axes all carry the same multi-axial damping
+// (mpml x the damping of the damped axes), so their sum -- the "rest" of the field, rest = f - sum(stored parts) --
+// advances as one quantity:  rest' = a_r rest + b_r C sum(D of the undamped axes).  Identical to the 24-array
+// formulation of the oracle up to rounding.
 // ------------------------------------------------------------------------------------------
 struct PmlCell {
     bool xd, jd, kd;                  // which axes are damped at this cell
@@ -88,14 +90,21 @@ struct PmlCell {
     const AxisCoef *cI, *cJ, *cK;     // coefficient rows of the cell's i, j, k (global or shared); read only for damped axes
 };
 
-// one damped part: f_a' = a f_a + b C D_a; returns the increment f_a' - f_a.  STAGED: the old value is already on
-// chip (TMA-staged box, one float per cell at `o`), otherwise it is read from the part array.
+// f' = a f + b C D for half-damping e:  b = 1/(1/dt + e), a = (1/dt - e) b
+__device__ __forceinline__ void pml_ab(float idt, float e, float &a, float &b) {
+    asm("rcp.approx.ftz.f32 %0, %1;" : "=f"(b) : "f"(idt + e));
+    a = (idt - e) * b;
+}
+
+// one stored part: new value written back; old and new are accumulated for the caller.  STAGED: the old value is
+// already on chip (TMA-staged box, one float per cell at `o`), otherwise it is read from the part array.
 template <bool STAGED>
-__device__ __forceinline__ float pml_part(const float *o, float *__restrict__ part, unsigned q, float a, float b, float CD) {
+__device__ __forceinline__ void pml_part(const float *o, float *__restrict__ part, unsigned q, float a, float b, float CD,
+                                         float &sum_old, float &sum_new) {
     const float old = STAGED ? *o : part[q];
     const float n = a * old + b * CD;
     part[q] = n;
-    return n - old;
+    sum_old += old; sum_new += n;
 }
 
 __device__ __forceinline__ PmlCell make_pml_cell(const DevParams &p, int i, int j, int k) {
@@ -114,44 +123,67 @@ __device__ __forceinline__ PmlCell make_pml_cell(const DevParams &p, int i, int 
 
 // D[9] = Dxx, Dyy, Dzz, Dyx (d+_i Vy), Dxy (d+_j Vx), Dzx (d+_i Vz), Dxz (d+_k Vx), Dzy (d+_j Vz), Dyz (d+_k Vy)
 // ox/oy/oz: this cell's slot in the first staged X/Y/Z part box (X and Y boxes B floats apart, Z boxes ZB floats
-// apart, the two shear Z parts starting at ozs); unused when !STAGED.  Undamped axes first (one explicit increment),
-// then one block per damped axis.
+// apart, the two shear Z parts starting at ozs); unused when !STAGED.
 template <bool STAGED>
 __device__ __forceinline__ void stress_pml(const DevParams &p, const PmlCell &c, float M, float L, float rigxy, float rigxz, float rigyz,
                                            const float *D, float *s, const float *ox = nullptr, const float *oy = nullptr,
                                            const float *oz = nullptr, const float *ozs = nullptr, int B = 0, int ZB = 0) {
-    const float dt = p.dt;
-    const float d0 = c.xd ? 0.f : D[0], d1 = c.jd ? 0.f : D[1], d2 = c.kd ? 0.f : D[2];
-    s[0] += dt * (M * d0 + L * (d1 + d2));
-    s[1] += dt * (M * d1 + L * (d0 + d2));
-    s[2] += dt * (M * d2 + L * (d0 + d1));
-    s[3] += dt * rigxy * ((c.xd ? 0.f : D[3]) + (c.jd ? 0.f : D[4]));
-    s[4] += dt * rigxz * ((c.xd ? 0.f : D[5]) + (c.kd ? 0.f : D[6]));
-    s[5] += dt * rigyz * ((c.jd ? 0.f : D[7]) + (c.kd ? 0.f : D[8]));
+    const float idt = p.idt, r = p.mpml;
+    float eIx = 0.f, eHx = 0.f, eIy = 0.f, eHy = 0.f, eIz = 0.f, eHz = 0.f;
+    if (c.xd) { eIx = c.cI->eI; eHx = c.cI->eH; }
+    if (c.jd) { eIy = c.cJ->eI; eHy = c.cJ->eH; }
+    if (c.kd) { eIz = c.cK->eI; eHz = c.cK->eH; }
+    const float esum = eIx + eIy + eIz;
+    float so[6] = { 0.f, 0.f, 0.f, 0.f, 0.f, 0.f }, sn[6] = { 0.f, 0.f, 0.f, 0.f, 0.f, 0.f };   // stored parts: old / new sums
+    float dr[6] = { 0.f, 0.f, 0.f, 0.f, 0.f, 0.f };                                               // C D of the undamped axes
+    float a, b;
     if (c.xd) {
-        const AxisCoef a = *c.cI;
-        s[0] += pml_part<STAGED>(ox, p.XP[0], c.qx, a.aI, a.bI, M * D[0]);
-        s[1] += pml_part<STAGED>(ox + B, p.XP[1], c.qx, a.aI, a.bI, L * D[0]);
-        s[2] += pml_part<STAGED>(ox + 2 * B, p.XP[2], c.qx, a.aI, a.bI, L * D[0]);
-        if (rigxy != 0.0f) s[3] += pml_part<STAGED>(ox + 3 * B, p.XP[3], c.qx, a.aH, a.bH, rigxy * D[3]);
-        if (rigxz != 0.0f) s[4] += pml_part<STAGED>(ox + 4 * B, p.XP[4], c.qx, a.aH, a.bH, rigxz * D[5]);
+        pml_ab(idt, eIx + r * (esum - eIx), a, b);
+        pml_part<STAGED>(ox, p.XP[0], c.qx, a, b, M * D[0], so[0], sn[0]);
+        pml_part<STAGED>(ox + B, p.XP[1], c.qx, a, b, L * D[0], so[1], sn[1]);
+        pml_part<STAGED>(ox + 2 * B, p.XP[2], c.qx, a, b, L * D[0], so[2], sn[2]);
+        if (rigxy != 0.0f || rigxz != 0.0f) {
+            pml_ab(idt, eHx + r * (esum - eIx), a, b);
+            if (rigxy != 0.0f) pml_part<STAGED>(ox + 3 * B, p.XP[3], c.qx, a, b, rigxy * D[3], so[3], sn[3]);
+            if (rigxz != 0.0f) pml_part<STAGED>(ox + 4 * B, p.XP[4], c.qx, a, b, rigxz * D[5], so[4], sn[4]);
+        }
+    } else {
+        dr[0] += M * D[0]; dr[1] += L * D[0]; dr[2] += L * D[0]; dr[3] += D[3]; dr[4] += D[5];
     }
     if (c.jd) {
-        const AxisCoef a = *c.cJ;
-        s[0] += pml_part<STAGED>(oy, p.YP[0], c.qy, a.aI, a.bI, L * D[1]);
-        s[1] += pml_part<STAGED>(oy + B, p.YP[1], c.qy, a.aI, a.bI, M * D[1]);
-        s[2] += pml_part<STAGED>(oy + 2 * B, p.YP[2], c.qy, a.aI, a.bI, L * D[1]);
-        if (rigxy != 0.0f) s[3] += pml_part<STAGED>(oy + 3 * B, p.YP[3], c.qy, a.aH, a.bH, rigxy * D[4]);
-        if (rigyz != 0.0f) s[5] += pml_part<STAGED>(oy + 4 * B, p.YP[4], c.qy, a.aH, a.bH, rigyz * D[7]);
+        pml_ab(idt, eIy + r * (esum - eIy), a, b);
+        pml_part<STAGED>(oy, p.YP[0], c.qy, a, b, L * D[1], so[0], sn[0]);
+        pml_part<STAGED>(oy + B, p.YP[1], c.qy, a, b, M * D[1], so[1], sn[1]);
+        pml_part<STAGED>(oy + 2 * B, p.YP[2], c.qy, a, b, L * D[1], so[2], sn[2]);
+        if (rigxy != 0.0f || rigyz != 0.0f) {
+            pml_ab(idt, eHy + r * (esum - eIy), a, b);
+            if (rigxy != 0.0f) pml_part<STAGED>(oy + 3 * B, p.YP[3], c.qy, a, b, rigxy * D[4], so[3], sn[3]);
+            if (rigyz != 0.0f) pml_part<STAGED>(oy + 4 * B, p.YP[4], c.qy, a, b, rigyz * D[7], so[5], sn[5]);
+        }
+    } else {
+        dr[0] += L * D[1]; dr[1] += M * D[1]; dr[2] += L * D[1]; dr[3] += D[4]; dr[5] += D[7];
     }
     if (c.kd) {
-        const AxisCoef a = *c.cK;
-        s[0] += pml_part<STAGED>(oz, p.ZP[0], c.qz, a.aI, a.bI, L * D[2]);
-        s[1] += pml_part<STAGED>(oz + ZB, p.ZP[1], c.qz, a.aI, a.bI, L * D[2]);
-        s[2] += pml_part<STAGED>(oz + 2 * ZB, p.ZP[2], c.qz, a.aI, a.bI, M * D[2]);
-        if (rigxz != 0.0f) s[4] += pml_part<STAGED>(ozs, p.ZP[3], c.qz, a.aH, a.bH, rigxz * D[6]);
-        if (rigyz != 0.0f) s[5] += pml_part<STAGED>(ozs + ZB, p.ZP[4], c.qz, a.aH, a.bH, rigyz * D[8]);
+        pml_ab(idt, eIz + r * (esum - eIz), a, b);
+        pml_part<STAGED>(oz, p.ZP[0], c.qz, a, b, L * D[2], so[0], sn[0]);
+        pml_part<STAGED>(oz + ZB, p.ZP[1], c.qz, a, b, L * D[2], so[1], sn[1]);
+        pml_part<STAGED>(oz + 2 * ZB, p.ZP[2], c.qz, a, b, M * D[2], so[2], sn[2]);
+        if (rigxz != 0.0f || rigyz != 0.0f) {
+            pml_ab(idt, eHz + r * (esum - eIz), a, b);
+            if (rigxz != 0.0f) pml_part<STAGED>(ozs, p.ZP[3], c.qz, a, b, rigxz * D[6], so[4], sn[4]);
+            if (rigyz != 0.0f) pml_part<STAGED>(ozs + ZB, p.ZP[4], c.qz, a, b, rigyz * D[8], so[5], sn[5]);
+        }
+    } else {
+        dr[0] += L * D[2]; dr[1] += L * D[2]; dr[2] += M * D[2]; dr[4] += D[6]; dr[5] += D[8];
     }
+    // the parts of the undamped axes, as one quantity per field
+    pml_ab(idt, r * esum, a, b);
+    s[0] = sn[0] + a * (s[0] - so[0]) + b * dr[0];
+    s[1] = sn[1] + a * (s[1] - so[1]) + b * dr[1];
+    s[2] = sn[2] + a * (s[2] - so[2]) + b * dr[2];
+    if (rigxy != 0.0f) s[3] = sn[3] + a * (s[3] - so[3]) + b * (rigxy * dr[3]);
+    if (rigxz != 0.0f) s[4] = sn[4] + a * (s[4] - so[4]) + b * (rigxz * dr[4]);
+    if (rigyz != 0.0f) s[5] = sn[5] + a * (s[5] - so[5]) + b * (rigyz * dr[5]);
 }
 
 // X[9] = x1 (d+_i Sxx), x2 (d-_j Sxy), x3 (d-_k Sxz), y1 (d-_i Sxy), y2 (d+_j Syy), y3 (d-_k Syz),
@@ -160,28 +192,39 @@ template <bool STAGED>
 __device__ __forceinline__ void particle_pml(const DevParams &p, const PmlCell &c, float bx, float by, float bz, const float *X, float *v,
                                              const float *ox = nullptr, const float *oy = nullptr, const float *oz = nullptr,
                                              int B = 0, int ZB = 0) {
-    const float dt = p.dt;
-    v[0] += dt * bx * ((c.xd ? 0.f : X[0]) + (c.jd ? 0.f : X[1]) + (c.kd ? 0.f : X[2]));
-    v[1] += dt * by * ((c.xd ? 0.f : X[3]) + (c.jd ? 0.f : X[4]) + (c.kd ? 0.f : X[5]));
-    v[2] += dt * bz * ((c.xd ? 0.f : X[6]) + (c.jd ? 0.f : X[7]) + (c.kd ? 0.f : X[8]));
+    const float idt = p.idt, r = p.mpml;
+    float eIx = 0.f, eHx = 0.f, eIy = 0.f, eHy = 0.f, eIz = 0.f, eHz = 0.f;
+    if (c.xd) { eIx = c.cI->eI; eHx = c.cI->eH; }
+    if (c.jd) { eIy = c.cJ->eI; eHy = c.cJ->eH; }
+    if (c.kd) { eIz = c.cK->eI; eHz = c.cK->eH; }
+    const float esum = eIx + eIy + eIz;
+    float so[3] = { 0.f, 0.f, 0.f }, sn[3] = { 0.f, 0.f, 0.f }, dr[3] = { 0.f, 0.f, 0.f };
+    float a, b, ah, bh;
     if (c.xd) {      // Vx sits on a half node of i, Vy and Vz on integer nodes
-        const AxisCoef a = *c.cI;
-        v[0] += pml_part<STAGED>(ox, p.XP[5], c.qx, a.aH, a.bH, bx * X[0]);
-        v[1] += pml_part<STAGED>(ox + B, p.XP[6], c.qx, a.aI, a.bI, by * X[3]);
-        v[2] += pml_part<STAGED>(ox + 2 * B, p.XP[7], c.qx, a.aI, a.bI, bz * X[6]);
-    }
+        pml_ab(idt, eIx + r * (esum - eIx), a, b);
+        pml_ab(idt, eHx + r * (esum - eIx), ah, bh);
+        pml_part<STAGED>(ox, p.XP[5], c.qx, ah, bh, bx * X[0], so[0], sn[0]);
+        pml_part<STAGED>(ox + B, p.XP[6], c.qx, a, b, by * X[3], so[1], sn[1]);
+        pml_part<STAGED>(ox + 2 * B, p.XP[7], c.qx, a, b, bz * X[6], so[2], sn[2]);
+    } else { dr[0] += X[0]; dr[1] += X[3]; dr[2] += X[6]; }
     if (c.jd) {
-        const AxisCoef a = *c.cJ;
-        v[0] += pml_part<STAGED>(oy, p.YP[5], c.qy, a.aI, a.bI, bx * X[1]);
-        v[1] += pml_part<STAGED>(oy + B, p.YP[6], c.qy, a.aH, a.bH, by * X[4]);
-        v[2] += pml_part<STAGED>(oy + 2 * B, p.YP[7], c.qy, a.aI, a.bI, bz * X[7]);
-    }
+        pml_ab(idt, eIy + r * (esum - eIy), a, b);
+        pml_ab(idt, eHy + r * (esum - eIy), ah, bh);
+        pml_part<STAGED>(oy, p.YP[5], c.qy, a, b, bx * X[1], so[0], sn[0]);
+        pml_part<STAGED>(oy + B, p.YP[6], c.qy, ah, bh, by * X[4], so[1], sn[1]);
+        pml_part<STAGED>(oy + 2 * B, p.YP[7], c.qy, a, b, bz * X[7], so[2], sn[2]);
+    } else { dr[0] += X[1]; dr[1] += X[4]; dr[2] += X[7]; }
     if (c.kd) {
-        const AxisCoef a = *c.cK;
-        v[0] += pml_part<STAGED>(oz, p.ZP[5], c.qz, a.aI, a.bI, bx * X[2]);
-        v[1] += pml_part<STAGED>(oz + ZB, p.ZP[6], c.qz, a.aI, a.bI, by * X[5]);
-        v[2] += pml_part<STAGED>(oz + 2 * ZB, p.ZP[7], c.qz, a.aH, a.bH, bz * X[8]);
-    }
+        pml_ab(idt, eIz + r * (esum - eIz), a, b);
+        pml_ab(idt, eHz + r * (esum - eIz), ah, bh);
+        pml_part<STAGED>(oz, p.ZP[5], c.qz, a, b, bx * X[2], so[0], sn[0]);
+        pml_part<STAGED>(oz + ZB, p.ZP[6], c.qz, a, b, by * X[5], so[1], sn[1]);
+        pml_part<STAGED>(oz + 2 * ZB, p.ZP[7], c.qz, ah, bh, bz * X[8], so[2], sn[2]);
+    } else { dr[0] += X[2]; dr[1] += X[5]; dr[2] += X[8]; }
+    pml_ab(idt, r * esum, a, b);
+    v[0] = sn[0] + a * (v[0] - so[0]) + b * (bx * dr[0]);
+    v[1] = sn[1] + a * (v[1] - so[1]) + b * (by * dr[1]);
+    v[2] = sn[2] + a * (v[2] - so[2]) + b * (bz * dr[2]);
 }
 
 // ------------------------------------------------------------------------------------------

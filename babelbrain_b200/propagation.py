@@ -131,7 +131,7 @@ class FdtdSlab:
                            sel_rms_peak=self.sel_rms_peak, sel_maps_rms=hostprep.maps_mask(self.rms_names),
                            sel_maps_sensor=hostprep.maps_mask(self.sensor_names),
                            sensor_subsampling=self.sub, sensor_start=self.sensor_start, device=int(device),
-                           rank=self.rank, nranks=self.nranks, kernel_variant=int(kernel_variant), reserved=0,
+                           rank=self.rank, nranks=self.nranks, kernel_variant=int(kernel_variant), mpml_ratio=hostprep.MPML_RATIO,
                            dt=dt)
         import time
         _t = [time.perf_counter()]

@@ -133,12 +133,14 @@ CONFIGS = {
 }
 
 
-def make_workload(name='ctx500_skull', shape=None, periods=None, seed=1234, pml=12, amplitude=1e5, planes=None, lean=False):
+def make_workload(name='ctx500_skull', shape=None, periods=None, seed=1234, pml=12, amplitude=1e5, planes=None, lean=False,
+                  dense_sources=True):
     """Returns dict(args=tuple of the 8 positional arguments, kwargs=dict of the keyword arguments
     of StaggeredFDTD_3D_with_relaxation as BabelIntegrationBASE.py:2338-2365 passes them, meta=...).
     planes=(lo,hi): materialise only planes [lo,hi) of axis 0 of every volume (a slab with its halo, for
     FdtdSlab(origin=lo, n1_global=shape[0])); the source table then holds this slab's rows only.  lean=True
-    makes Ox/Oy/Oz read-only broadcast views instead of dense float64 volumes (plane sources only)."""
+    makes Ox/Oy/Oz read-only broadcast views instead of dense float64 volumes (plane sources only).  dense_sources=False
+    passes the sources as a sources.CWSourceFunctions object instead of the (Nsrc, Nt) float64 table."""
     cfg = dict(CONFIGS[name])
     if shape is not None:
         cfg['shape'] = tuple(int(s) for s in shape)
@@ -183,7 +185,7 @@ def make_workload(name='ctx500_skull', shape=None, periods=None, seed=1234, pml=
         amp = amplitude * (0.98 * np.exp(-(np.sqrt(r2) / (ap / 2)) ** 8) + 0.02) * focal / dist
         phase = -kwater * (dist - focal)
         cw = cw_source_object(amp.reshape(-1), phase.reshape(-1), f, dt, steps)
-        SF = cw.dense()
+        SF = cw.dense() if dense_sources else cw
         if lean:
             Ox = Oy = np.broadcast_to(np.float64(0.0), lshape)
             Oz = np.broadcast_to(np.float64(1.0 / (1000.0 * 1500.0)), lshape)
@@ -210,7 +212,7 @@ def make_workload(name='ctx500_skull', shape=None, periods=None, seed=1234, pml=
             SourceMap[ci:ci + 2, cj:cj + 2, ck:ck + 2] = e + 1
         dist = np.sqrt(ce[:, 0] ** 2 + ce[:, 1] ** 2 + (ce[:, 2] - zc) ** 2)
         cw = cw_source_object(np.full(nel, amplitude), -kwater * (dist - rad), f, dt, steps)
-        SF = cw.dense()
+        SF = cw.dense() if dense_sources else cw
         MaterialMap[SourceMap > 0] = 0
         kw.update(Ox=np.array([1]), Oy=np.array([1]), Oz=np.array([1]), TypeSource=2)
         kw['SelMapsRMSPeakList'] = ['Pressure']

@@ -67,7 +67,9 @@ typedef struct bb_fdtd_desc {
     int32_t device;              /* CUDA ordinal */
     int32_t rank, nranks;        /* slab rank (0,1 on one GPU) */
     int32_t kernel_variant;      /* 0 = default (fastest); other values select debug variants */
-    int32_t reserved;
+    float mpml_ratio;            /* multi-axial PML: fraction of each axis' damping applied to the split parts of the two
+                                    other axes (Meza-Fajardo & Papageorgiou 2008); 0 = classical split-field layer, which
+                                    is unstable where a fluid-solid interface enters the layer; the host passes 0.1 */
     double dt;                   /* DT */
 } bb_fdtd_desc;
 
@@ -100,7 +102,8 @@ int bb_fdtd_create(const bb_fdtd_desc *desc, bb_fdtd **out);
 void bb_fdtd_destroy(bb_fdtd *h);
 /* optional: run on the caller's CUDA stream (cudaStream_t as void*); NULL = library stream */
 int bb_fdtd_set_stream(bb_fdtd *h, void *cuda_stream);
-/* nmat x BB_NCOEF float table and the 4 x (pml+1) PML table (InvDXDT, DXDT, InvDXDThp, DXDThp) */
+/* nmat x BB_NCOEF float table and the 2 x (pml+1) PML table: damping d at integer depth 0..pml and at half depth
+ * xi + 0.5 (quadratic profile, d0 = ln(1/ReflectionLimit) 3 Vmax / (2 pml h)) */
 int bb_fdtd_set_materials(bb_fdtd *h, const float *table, const float *pml_table);
 /* uint32 label planes [max(i0-2,0), min(i1+2,n1)) ; reflector may be NULL (ReflectorMask=None) */
 int bb_fdtd_set_maps(bb_fdtd *h, const uint32_t *material, const uint32_t *reflector);

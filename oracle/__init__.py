@@ -34,7 +34,7 @@ class _Params(ctypes.Structure):
                 ('sel_rms_peak', ctypes.c_int32), ('sel_maps_rms', ctypes.c_uint32),
                 ('sel_maps_sensor', ctypes.c_uint32), ('sensor_subsampling', ctypes.c_int32),
                 ('sensor_start', ctypes.c_int32), ('nsrc_cells', ctypes.c_int64),
-                ('nsensors', ctypes.c_int64), ('dt', ctypes.c_double)]
+                ('nsensors', ctypes.c_int64), ('dt', ctypes.c_double), ('mpml', ctypes.c_double)]
 
 
 def load(dtype=np.float32):
@@ -71,7 +71,7 @@ def run_c(MaterialMap, MaterialProperties, Frequency, SourceMap, SourceFunctions
           ReflectionLimit=1e-5, AlphaCFL=1.0, TypeSource=0, QfactorCorrection=True, QCorrection=1.0,
           SelRMSorPeak=1, SelMapsRMSPeakList=('Pressure',), SelMapsSensorsList=('Pressure',),
           SensorSubSampling=2, SensorStart=0, ReflectorMask=None, dtype=np.float32, want_last=False,
-          steps_override=None):
+          steps_override=None, MPMLRatio=None):
     """Same arguments / result dict as fdtd_numpy.run, computed by the C/OpenMP oracle."""
     F = fdtd_numpy
     lib = load(dtype)
@@ -85,7 +85,7 @@ def run_c(MaterialMap, MaterialProperties, Frequency, SourceMap, SourceFunctions
     dt = dt_id if DT is None else float(DT)
     steps = F.number_of_steps(DurationSimulation, dt) if steps_override is None else int(steps_override)
     tables = np.ascontiguousarray(np.stack([T[k] for k in ('M', 'G', 'L', 'B', 'tauL', 'tauS', 'ots', 'K')]), dtype=dtype)
-    pmltab = np.ascontiguousarray(np.stack(F.pml_tables(int(NDelta), h, dt, MP[:, 1].max(), ReflectionLimit)), dtype=dtype)
+    pmltab = np.ascontiguousarray(np.stack(F.pml_damping(int(NDelta), h, MP[:, 1].max(), ReflectionLimit)), dtype=dtype)
     SourceMap = np.asarray(SourceMap)
     src_cell = np.flatnonzero(SourceMap.reshape(-1)).astype(np.int64)
     src_id = (SourceMap.reshape(-1)[src_cell].astype(np.int64) - 1).astype(np.int32)
@@ -107,7 +107,7 @@ def run_c(MaterialMap, MaterialProperties, Frequency, SourceMap, SourceFunctions
     sels = [k for k in F.MAP_ORDER if k in SelMapsSensorsList]
     prm = _Params(N1, N2, N3, int(NDelta), MP.shape[0], SF.shape[0], SF.shape[1], steps, int(TypeSource),
                   int(SelRMSorPeak), mask_of(sel), mask_of(sels), sub, int(SensorStart), len(src_cell),
-                  len(sensor_cell), dt)
+                  len(sensor_cell), dt, F.MPML_RATIO if MPMLRatio is None else float(MPMLRatio))
     out_rms = np.zeros((len(sel), N1, N2, N3), dtype) if SelRMSorPeak & 1 else None
     out_peak = np.zeros((len(sel), N1, N2, N3), dtype) if SelRMSorPeak & 2 else None
     out_sensor = np.zeros((len(sels), len(sensor_cell), nsamples), dtype)

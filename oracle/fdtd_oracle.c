@@ -47,6 +47,7 @@ typedef struct {
     int32_t sensor_subsampling, sensor_start;
     int64_t nsrc_cells, nsensors;
     double dt;
+    double mpml;                /* multi-axial damping ratio (oracle/fdtd_numpy.py: MPML_RATIO); 0 = classical layer */
 } oracle_params;
 
 typedef struct {
@@ -55,7 +56,8 @@ typedef struct {
     real dt;
     const uint32_t *mat;
     const real *M, *G, *L, *B, *tauL, *tauS, *ots, *K;
-    const real *inv, *dx, *invhp, *dxhp; /* PML tables, P+1 each */
+    const real *dmp, *dmphp;    /* damping at integer / half depth, P+1 each (oracle/fdtd_numpy.py: pml_damping) */
+    real ratio;                 /* multi-axial damping ratio */
     real *V[3], *S[6], *R[6], *Pr;
     real *sp[24];
 } ctx_t;
@@ -67,16 +69,22 @@ enum { VX_X = 0, VX_Y, VX_Z, VY_X, VY_Y, VY_Z, VZ_X, VZ_Y, VZ_Z,
 
 static inline int in_pml(int n, int N, int P) { return n < P || n >= N - P; }
 
-/* integer-node and half-node PML coefficients along one axis (oracle/fdtd_numpy.py:pml_depth) */
-static inline void coef_int(const ctx_t *c, int n, int N, real *a, real *b) {
+/* integer-node and half-node damping along one axis (oracle/fdtd_numpy.py: pml_depth) */
+static inline real damp_int(const ctx_t *c, int n, int N) {
     int d = 0;
     if (n < c->P) d = c->P - n; else if (n >= N - c->P) d = n - (N - c->P - 1);
-    *a = c->inv[d]; *b = c->dx[d];
+    return c->dmp[d];
 }
-static inline void coef_half(const ctx_t *c, int n, int N, real *a, real *b) {
-    if (n < c->P) { int d = c->P - 1 - n; *a = c->invhp[d]; *b = c->dxhp[d]; }
-    else if (n >= N - c->P) { int d = n - (N - c->P - 1); *a = c->invhp[d]; *b = c->dxhp[d]; }
-    else { *a = c->inv[0]; *b = c->dx[0]; }
+static inline real damp_half(const ctx_t *c, int n, int N) {
+    if (n < c->P) return c->dmphp[c->P - 1 - n];
+    if (n >= N - c->P) return c->dmphp[n - (N - c->P - 1)];
+    return 0;
+}
+/* (InvDXDT, DXDT) of a split part: own damping plus ratio x the integer-node damping of the two other axes
+   (oracle/fdtd_numpy.py: coef) */
+static inline void coef_of(const ctx_t *c, real own, real o1, real o2, real *a, real *b) {
+    const real d = own + c->ratio * (o1 + o2);
+    *a = 1 / (1 / c->dt + d / 2); *b = 1 / c->dt - d / 2;
 }
 
 /* backward / forward staggered differences with the edge rules; st = stride of the axis */
@@ -120,21 +128,24 @@ static void stress_cell(const ctx_t *c, int i, int j, int k, real *out_p_acc) {
     if (pml) {
         real a, b;
         const real M = c->M[m], L = c->L[m];
-        coef_int(c, i, n1, &a, &b);
+        const real di = damp_int(c, i, n1), dj = damp_int(c, j, n2), dk = damp_int(c, k, n3);
+        coef_of(c, di, dj, dk, &a, &b);
         real xx = splitupd(c->sp[SXX_X], p, a, b, M, Dxx);
         real yy = splitupd(c->sp[SYY_X], p, a, b, L, Dxx);
         real zz = splitupd(c->sp[SZZ_X], p, a, b, L, Dxx);
-        coef_int(c, j, n2, &a, &b);
+        coef_of(c, dj, di, dk, &a, &b);
         xx += splitupd(c->sp[SXX_Y], p, a, b, L, Dyy);
         yy += splitupd(c->sp[SYY_Y], p, a, b, M, Dyy);
         zz += splitupd(c->sp[SZZ_Y], p, a, b, L, Dyy);
-        coef_int(c, k, n3, &a, &b);
+        coef_of(c, dk, di, dj, &a, &b);
         xx += splitupd(c->sp[SXX_Z], p, a, b, L, Dzz);
         yy += splitupd(c->sp[SYY_Z], p, a, b, L, Dzz);
         zz += splitupd(c->sp[SZZ_Z], p, a, b, M, Dzz);
         c->S[0][p] = xx; c->S[1][p] = yy; c->S[2][p] = zz;
         real ai, bi, aj, bj, ak, bk;
-        coef_half(c, i, n1, &ai, &bi); coef_half(c, j, n2, &aj, &bj); coef_half(c, k, n3, &ak, &bk);
+        coef_of(c, damp_half(c, i, n1), dj, dk, &ai, &bi);
+        coef_of(c, damp_half(c, j, n2), di, dk, &aj, &bj);
+        coef_of(c, damp_half(c, k, n3), di, dj, &ak, &bk);
         c->S[3][p] = splitupd(c->sp[SXY_X], p, ai, bi, rigxy, dfwd(Vy, p, s1, i, n1))
                    + splitupd(c->sp[SXY_Y], p, aj, bj, rigxy, dfwd(Vx, p, s2, j, n2));
         c->S[4][p] = splitupd(c->sp[SXZ_X], p, ai, bi, rigxz, dfwd(Vz, p, s1, i, n1))
@@ -201,8 +212,11 @@ static void particle_cell(const ctx_t *c, int i, int j, int k) {
     const real z1 = dbwd(Sxz, p, s1, i, n1), z2 = dbwd(Syz, p, s2, j, n2), z3 = dfwd(Szz, p, 1, k, n3);
     if (pml) {
         real ai, bi, aj, bj, ak, bk, hi, gi, hj, gj, hk, gk;
-        coef_int(c, i, n1, &ai, &bi); coef_int(c, j, n2, &aj, &bj); coef_int(c, k, n3, &ak, &bk);
-        coef_half(c, i, n1, &hi, &gi); coef_half(c, j, n2, &hj, &gj); coef_half(c, k, n3, &hk, &gk);
+        const real di = damp_int(c, i, n1), dj = damp_int(c, j, n2), dk = damp_int(c, k, n3);
+        coef_of(c, di, dj, dk, &ai, &bi); coef_of(c, dj, di, dk, &aj, &bj); coef_of(c, dk, di, dj, &ak, &bk);
+        coef_of(c, damp_half(c, i, n1), dj, dk, &hi, &gi);
+        coef_of(c, damp_half(c, j, n2), di, dk, &hj, &gj);
+        coef_of(c, damp_half(c, k, n3), di, dj, &hk, &gk);
         c->V[0][p] = splitupd(c->sp[VX_X], p, hi, gi, bx, x1) + splitupd(c->sp[VX_Y], p, aj, bj, bx, x2)
                    + splitupd(c->sp[VX_Z], p, ak, bk, bx, x3);
         c->V[1][p] = splitupd(c->sp[VY_X], p, ai, bi, by, y1) + splitupd(c->sp[VY_Y], p, hj, gj, by, y2)
@@ -228,7 +242,7 @@ static inline real map_value(const ctx_t *c, int map, int64_t p) {
 static int popcount_below(uint32_t mask, int bit) { return __builtin_popcount(mask & ((1u << bit) - 1)); }
 
 /*
- * tables: 8 arrays of nmat (M,G,L,B,tauL,tauS,ots,K); pmltab: 4 arrays of P+1 (inv,dx,invhp,dxhp);
+ * tables: 8 arrays of nmat (M,G,L,B,tauL,tauS,ots,K); pmltab: 2 arrays of P+1 (damping at integer / half depth);
  * src_cell: C-order linear index of each source cell; src_id 0-based row; o_xyz per source cell;
  * srcfun [nt_src][nsrc]; sensor_cell C-order linear index in the order of IndexSensorMap.
  * out_rms / out_peak: [selected map (ascending MAP_* bit)][N]; out_sensor: [selected map][nsensors][nsamples];
@@ -248,7 +262,7 @@ int oracle_fdtd_run(const oracle_params *prm, const uint32_t *matmap, const real
     const int nm = prm->nmat, P1 = prm->pml + 1;
     c.M = tables; c.G = tables + nm; c.L = tables + 2 * nm; c.B = tables + 3 * nm;
     c.tauL = tables + 4 * nm; c.tauS = tables + 5 * nm; c.ots = tables + 6 * nm; c.K = tables + 7 * nm;
-    c.inv = pmltab; c.dx = pmltab + P1; c.invhp = pmltab + 2 * P1; c.dxhp = pmltab + 3 * P1;
+    c.dmp = pmltab; c.dmphp = pmltab + P1; c.ratio = (real)prm->mpml;
     const int64_t N = (int64_t)c.n1 * c.n2 * c.n3;
     const int narr = 3 + 6 + 6 + 1 + 24;
     real *pool = (real *)calloc((size_t)narr * N, sizeof(real));

@@ -47,10 +47,14 @@ def test_relaxation_fit_meets_q_exactly():
 def test_pml_table_and_steps():
     P, h, dt = 12, 3.675e-4, 4.1667e-8
     t = hostprep.pml_table(P, h, dt, 2476.0, 1e-5)
-    o = np.stack(fdtd_numpy.pml_tables(P, h, dt, 2476.0, 1e-5))
-    assert t.shape == (4, P + 1) and np.allclose(t, o, rtol=1e-14)
-    assert t[0, 0] == pytest.approx(dt) and t[1, 0] == pytest.approx(1 / dt)       # no damping at depth 0
-    assert np.all(np.diff(t[0]) < 0) and np.all(np.diff(t[1]) < 0)                 # monotone profiles
+    o = np.stack(fdtd_numpy.pml_damping(P, h, 2476.0, 1e-5))
+    assert t.shape == (2, P + 1) and np.allclose(t, o, rtol=1e-14)
+    assert t[0, 0] == 0.0 and t[0, P] == pytest.approx(np.log(1e5) * 3 * 2476.0 / (2 * P * h))   # no damping at depth 0, d0 at depth P
+    assert np.all(np.diff(t[0]) > 0) and np.all(np.diff(t[1]) > 0) and np.all(t[1, :-1] > t[0, :-1]) and np.all(t[1, :-1] < t[0, 1:])
+    # the classical coefficients follow from the damping (oracle/fdtd_numpy.py: pml_tables)
+    inv, dx, invh, dxh = fdtd_numpy.pml_tables(P, h, dt, 2476.0, 1e-5)
+    assert np.allclose(inv, 1 / (1 / dt + t[0] / 2)) and np.allclose(dxh, 1 / dt - t[1] / 2)
+    assert hostprep.MPML_RATIO == fdtd_numpy.MPML_RATIO == 0.1
     # TimeSimulation = dt*steps must give back `steps` despite floating point (BabelIntegrationBASE.py:2089)
     for steps in (720, 2544, 5616, 11250):
         assert hostprep.number_of_steps(dt * steps, dt) == steps
