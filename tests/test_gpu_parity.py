@@ -276,3 +276,14 @@ def test_public_call_on_two_gpus_returns_the_single_gpu_arrays(monkeypatch):
     assert len(PM.last_timing['devices']) == 2 and np.array_equal(R3['Pressure'], R2['Pressure'])
     with pytest.raises(ValueError):
         PM.StaggeredFDTD_3D_with_relaxation(*w['args'], NumberGPUs=64, **w['kwargs'])
+
+
+def test_long_run_with_the_skull_inside_the_layer_stays_bounded_and_matches_the_oracle():
+    """100 periods of the case the classical split-field layer cannot survive (tests/test_oracle.py): the CUDA path
+    stays at the steady state and still agrees with the oracle after 4800 steps."""
+    w = workloads.make_workload('ctx500_skull', shape=(40, 36, 56), periods=100, pml=6)
+    (Sensor, RMS, _, _), _ = run_cuda(w)
+    ref = run_oracle(w)
+    assert float(RMS['Pressure'].max()) < 2e6
+    assert rl2(RMS['Pressure'], ref['RMS']['Pressure']) <= TOL and same_peak(RMS['Pressure'], ref['RMS']['Pressure'])
+    assert rl2(Sensor['Pressure'], ref['Sensor']['Pressure']) <= TOL

@@ -145,3 +145,16 @@ def test_rayleigh_c_against_numpy():
         assert rl2(a, b) < 1e-10
         a32 = oracle.rayleigh_c(np.complex64(k), center, ds, u0, rf, dtype=np.float32)
         assert rl2(a32, b) < 1e-4
+
+
+def test_multiaxial_layer_is_stable_where_the_classical_one_blows_up():
+    """A skull label map whose fluid-solid interfaces run into the absorbing layer, 100 periods: the classical
+    split-field layer (ratio 0) grows by many orders of magnitude, the multi-axial one (the default ratio) settles
+    to the steady state it had after 50 periods (profiles/r1_pml_stability.txt)."""
+    def rms_max(periods, ratio):
+        w = workloads.make_workload('ctx500_skull', shape=(40, 36, 56), periods=periods, pml=6)
+        return float(oracle.run_c(*w['args'], MPMLRatio=ratio, **kwargs_of(w))['RMS']['Pressure'].max())
+    steady = rms_max(50, None)
+    late = rms_max(100, None)
+    assert abs(late / steady - 1) < 0.02
+    assert rms_max(100, 0.0) > 1e4 * late
