@@ -308,6 +308,15 @@ extern "C" void bb_fdtd_destroy(bb_fdtd *h) {
     delete h;
 }
 
+extern "C" int bb_host_scatter_rows(void *out, const int64_t *rows, const void *data, int64_t nrows, int64_t row_bytes) {
+    BB_REQUIRE(nrows == 0 || (out && rows && data), "null argument");
+    BB_REQUIRE(nrows >= 0 && row_bytes > 0, "bad sizes");
+    char *o = (char *)out;
+    const char *d = (const char *)data;
+    for (int64_t r = 0; r < nrows; r++) memcpy(o + rows[r] * row_bytes, d + r * row_bytes, (size_t)row_bytes);
+    return BB_OK;
+}
+
 extern "C" int bb_fdtd_set_stream(bb_fdtd *h, void *s) {
     BB_REQUIRE(h, "null handle");
     BB_CUDA(cudaSetDevice(h->d.device));

@@ -381,8 +381,12 @@ def run_slabs_in_process(devices, args, kwargs, timeout=None):
             s.get_map(0, k, out=full[s.i0:s.i1])
         for k, full in shared['peak'].items():
             s.get_map(1, k, out=full[s.i0:s.i1])
+        rows = np.ascontiguousarray(shared['rows'][r], dtype=np.int64)
         for k, full in shared['sensor'].items():
-            full[shared['rows'][r]] = s.get_sensors(k)
+            part = s.get_sensors(k)              # (rows of this slab, samples), page-locked
+            _capi.check(s._L.bb_host_scatter_rows(_capi.ptr(full), _capi.ptr(rows), _capi.ptr(part), rows.size,
+                                                  part.shape[1] * part.itemsize))
+            del part
         gate.wait()
         marks[r].update(setup_upload_s=t1 - t0, time_loop_s=t2 - t1, download_s=time.perf_counter() - t2)
 

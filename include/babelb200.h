@@ -97,6 +97,11 @@ int bb_device_name(int device, char *out, int out_len);
 int bb_host_alloc(int64_t bytes, void **out);
 int bb_host_free(void *ptr);
 
+/* host-side gather of a slab-decomposed run: out[rows[r]] = data[r] for nrows rows of row_bytes bytes each (the rows of
+ * one slab's sensor traces placed into the whole-grid table in IndexSensorMap order).  Plain memcpy loop; exists so
+ * that the per-GPU host threads of the Python layer gather in parallel without holding the interpreter lock. */
+int bb_host_scatter_rows(void *out, const int64_t *rows, const void *data, int64_t nrows, int64_t row_bytes);
+
 /* ---- FDTD handle ---- */
 int bb_fdtd_create(const bb_fdtd_desc *desc, bb_fdtd **out);
 void bb_fdtd_destroy(bb_fdtd *h);

@@ -124,3 +124,20 @@ def test_bhte_without_a_genuine_install_says_so():
         pytest.skip('a genuine BabelViscoFDTD is installed')
     with pytest.raises(NotImplementedError):
         BHTE()
+
+
+def test_host_scatter_rows_places_slab_rows(lib):
+    """The gather helper of the multi-GPU path is plain host code (no device): out[rows[r]] = data[r]."""
+    import ctypes
+    lib.bb_host_scatter_rows.argtypes = [ctypes.c_void_p] * 3 + [ctypes.c_int64] * 2
+    rng = np.random.default_rng(5)
+    rows = np.sort(rng.choice(500, 120, replace=False)).astype(np.int64)
+    data = rng.random((120, 10)).astype(np.float32)
+    out = np.zeros((500, 10), np.float32)
+    p = lambda a: a.ctypes.data_as(ctypes.c_void_p)      # noqa: E731
+    assert lib.bb_host_scatter_rows(p(out), p(rows), p(data), 120, 40) == 0
+    ref = np.zeros_like(out)
+    ref[rows] = data
+    assert np.array_equal(out, ref)
+    assert lib.bb_host_scatter_rows(p(out), p(rows), p(data), 0, 40) == 0
+    assert lib.bb_host_scatter_rows(None, p(rows), p(data), 3, 40) != 0
