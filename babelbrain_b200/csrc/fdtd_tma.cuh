@@ -360,7 +360,7 @@ __global__ void __launch_bounds__(NTB, CTAS_PER_SM) stress_tma(const __grid_cons
     const unsigned MSK = LabelTraits<LT>::MASK;
     // part arrays: index of this cell on plane ic0 and the per-plane strides
     unsigned qy_stride = (unsigned)p.nyrows * p.pitch, qz_stride = (unsigned)p.n2 * p.zpw;
-    keep(qy_stride); keep(qz_stride);
+    // (not pinned: only split-field cells use them, and pinning them made ptxas spill a loop counter to local memory)
     // boundary planes this CTA pushes to the slab neighbours: bit 0 lower, bit 1 upper (0 for almost every CTA)
     int pushsel = has_peer ? ((ic0 < p.i0 + 2 && p.peerS[0] ? 1 : 0) | (ic1 > p.i1 - 2 && p.peerS[1] ? 2 : 0)) : 0;
     keep(pushsel);
