@@ -165,7 +165,10 @@ struct RingPos {
 // class do not need (no Y parts away from the j-PML, no Z parts away from the k-PML) goes to a
 // deeper halo ring, i.e. more planes of prefetch.
 constexpr int SMEM_BYTES = (CTAS_PER_SM == 1 ? 222 : 110) * 1024;
-constexpr int MAX_NSH = 12, MAX_NSP = 8, MIN_NSH = 6;
+#ifndef BB_MIN_NSH
+#define BB_MIN_NSH 6
+#endif
+constexpr int MAX_NSH = 12, MAX_NSP = 8, MIN_NSH = BB_MIN_NSH;
 constexpr int OFF_COEF = 0;                                                      // MatCoef[128] (stress) / float B[128] (particle)
 constexpr int OFF_AXJ = OFF_COEF + BB_MAX_SMEM_MAT * (int)sizeof(MatCoef);
 constexpr int OFF_AXK = OFF_AXJ + TY * (int)sizeof(AxisCoef);

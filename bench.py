@@ -28,7 +28,7 @@ sys.path.insert(0, ROOT)
 WORKLOAD = 'ctx500_skull'
 # dram__bytes_read.sum + dram__bytes_write.sum of one stress_tma launch from the committed ncu --set full capture
 # (profiles/)
-NCU_TRAFFIC_BYTES = 1350.1e6   # profiles/r1_ncu_stress_particle_summary.txt: 878.9 MB read + 471.1 MB written
+NCU_TRAFFIC_BYTES = 1352.5e6   # profiles/r1_ncu_stress_particle_summary.txt: 881.9 MB read + 470.6 MB written
 DROP = ('COMPUTING_BACKEND', 'USE_SINGLE', 'DefaultGPUDeviceName')
 
 
