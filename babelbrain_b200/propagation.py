@@ -9,6 +9,7 @@ include/babelb200.h.  No CPU fallback: without the library or a GPU the call rai
 import collections.abc
 import ctypes
 import os
+import time
 import weakref
 import numpy as np
 
@@ -133,11 +134,10 @@ class FdtdSlab:
                            sensor_subsampling=self.sub, sensor_start=self.sensor_start, device=int(device),
                            rank=self.rank, nranks=self.nranks, kernel_variant=int(kernel_variant), mpml_ratio=hostprep.MPML_RATIO,
                            dt=dt)
-        import time
         _t = [time.perf_counter()]
         _marks = []
 
-        def _mark(name):
+        def _mark(name):          # host-side wall clock of the set-up stages, printed when BB_TIMING is set
             _t.append(time.perf_counter())
             _marks.append('%s %.3f' % (name, _t[-1] - _t[-2]))
         hp = ctypes.c_void_p()
@@ -243,13 +243,14 @@ class FdtdSlab:
         return out
 
     def get_sensors(self, name):
-        import time
+        """(sensors of this slab, samples) float32 traces of one selected sensor map, in table order."""
         t0 = time.perf_counter()
         out = _capi.pinned.empty((self.sensor_rows.size, self.sample_steps.size), np.float32)
         t1 = time.perf_counter()
         _capi.check(self._L.bb_fdtd_get_sensors(self._h, _capi.MAP_ID[name], _capi.ptr(out)))
         if os.environ.get('BB_TIMING'):
-            print('get_sensors: alloc %.3f s copy %.3f s (pool hits %d misses %d)' % (t1 - t0, time.perf_counter() - t1, _capi.pinned.hits, _capi.pinned.misses), flush=True)
+            print('get_sensors: alloc %.3f s copy %.3f s (pool hits %d misses %d)'
+                  % (t1 - t0, time.perf_counter() - t1, _capi.pinned.hits, _capi.pinned.misses), flush=True)
         self.d2h_bytes += out.nbytes
         return out
 
@@ -341,7 +342,6 @@ def run_slabs_in_process(devices, args, kwargs, timeout=None):
     (Sensor, RMS, Peak, InputParam, slabs, timing) with the maps and sensor rows of all slabs gathered into
     whole-grid arrays in the reference's order."""
     import threading
-    import time
     from .slab import merge_sensor_tables
     n = len(devices)
     gate = threading.Barrier(n, timeout=timeout)
@@ -512,7 +512,6 @@ class PropagationModel:
         NumberGPUs (extension; default: environment variable BABELB200_NGPUS, else 1) cuts the domain into that
         many slabs along axis 0, one per GPU of this box, with NVLink halo exchange; the return values are the
         same whole-grid arrays.  An unmodified BabelBrain enables it through the environment variable."""
-        import time
         t0 = time.perf_counter()
         if IntervalSnapshots > 0:
             raise NotImplementedError('IntervalSnapshots is not supported (BabelBrain never passes it)')
@@ -559,7 +558,6 @@ class PropagationModel:
         return Sensor, last, (RMS if SelRMSorPeak == 1 else Peak), InputParam
 
     def _run_multi_gpu(self, ngpu, t0, args, kwargs, name, number):
-        import time
         _capi.require_gpu()
         devices = _select_devices(name, number, ngpu)
         Sensor, RMS, Peak, InputParam, slabs, timing = run_slabs_in_process(devices, args, kwargs)
