@@ -183,6 +183,9 @@ def make_workload(name='ctx500_skull', shape=None, periods=None, seed=1234, pml=
         dist = np.sqrt(r2 + focal ** 2)
         ap = min(cfg['aperture'], 0.8 * (min(n1, n2) - 2 * pml) * h)
         amp = amplitude * (0.98 * np.exp(-(np.sqrt(r2) / (ap / 2)) ** 8) + 0.02) * focal / dist
+        # phase lag growing with the distance to the focal point: with sin(wt + phase) the outer pixels fire late, so the
+        # beam of the benchmark workloads diverges (the cost per cell-update is the same); tests/test_oracle.py flips the
+        # sign for its focusing cross-check against the Rayleigh integral
         phase = -kwater * (dist - focal)
         cw = cw_source_object(amp.reshape(-1), phase.reshape(-1), f, dt, steps)
         SF = cw.dense() if dense_sources else cw
