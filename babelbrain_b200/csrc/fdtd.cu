@@ -317,6 +317,19 @@ extern "C" int bb_host_scatter_rows(void *out, const int64_t *rows, const void *
     return BB_OK;
 }
 
+extern "C" int bb_host_scatter_runs(void *out, const void *data, const int64_t *dst_row, const int64_t *src_row, const int64_t *nrows,
+                                    int64_t nruns, int64_t row_bytes) {
+    BB_REQUIRE(nruns == 0 || (out && data && dst_row && src_row && nrows), "null argument");
+    BB_REQUIRE(nruns >= 0 && row_bytes > 0, "bad sizes");
+    char *o = (char *)out;
+    const char *d = (const char *)data;
+    for (int64_t r = 0; r < nruns; r++) {
+        if (nrows[r] < 0 || dst_row[r] < 0 || src_row[r] < 0) { bb_set_error("negative run %lld", (long long)r); return BB_ERR_ARG; }
+        memcpy(o + dst_row[r] * row_bytes, d + src_row[r] * row_bytes, (size_t)(nrows[r] * row_bytes));
+    }
+    return BB_OK;
+}
+
 extern "C" int bb_fdtd_set_stream(bb_fdtd *h, void *s) {
     BB_REQUIRE(h, "null handle");
     BB_CUDA(cudaSetDevice(h->d.device));

@@ -342,7 +342,7 @@ def run_slabs_in_process(devices, args, kwargs, timeout=None):
     (Sensor, RMS, Peak, InputParam, slabs, timing) with the maps and sensor rows of all slabs gathered into
     whole-grid arrays in the reference's order."""
     import threading
-    from .slab import merge_sensor_tables
+    from .slab import merge_sensor_runs
     n = len(devices)
     gate = threading.Barrier(n, timeout=timeout)
     slabs, exports, errors = [None] * n, [None] * n, []
@@ -371,9 +371,11 @@ def run_slabs_in_process(devices, args, kwargs, timeout=None):
         t2 = time.perf_counter()
         if r == 0:                      # whole-grid result arrays, page-locked, filled by every thread
             N1, N2, N3 = s.shape
-            index, rows = merge_sensor_tables([x.IndexSensorMapLocal for x in slabs], N1, N2 * N3)
-            shared['index'], shared['rows'] = index, rows
-            shared['sensor'] = {k: _capi.pinned.empty((index.size, s.sample_steps.size), np.float32) for k in s.sensor_names}
+            # the slabs' tables merge into the whole-grid IndexSensorMap by runs (one per (j,k) line and slab)
+            ntot, runs = merge_sensor_runs([x.IndexSensorMapLocal for x in slabs], N1, N2 * N3)
+            shared['runs'] = runs
+            shared['index'] = _capi.pinned.empty((ntot,), s._idx_dtype)
+            shared['sensor'] = {k: _capi.pinned.empty((ntot, s.sample_steps.size), np.float32) for k in s.sensor_names}
             shared['rms'] = {k: _capi.pinned.empty(s.shape, np.float32) for k in s.rms_names if s.sel_rms_peak & 1}
             shared['peak'] = {k: _capi.pinned.empty(s.shape, np.float32) for k in s.rms_names if s.sel_rms_peak & 2}
         gate.wait()
@@ -381,12 +383,16 @@ def run_slabs_in_process(devices, args, kwargs, timeout=None):
             s.get_map(0, k, out=full[s.i0:s.i1])
         for k, full in shared['peak'].items():
             s.get_map(1, k, out=full[s.i0:s.i1])
-        rows = np.ascontiguousarray(shared['rows'][r], dtype=np.int64)
+        dst, src, cnt = shared['runs'][r]
+
+        def place(full, part):           # rows of this slab -> their runs in the whole-grid table (memcpy per run, no GIL)
+            part = np.ascontiguousarray(part)
+            row_bytes = part.itemsize * (part.shape[1] if part.ndim > 1 else 1)
+            _capi.check(s._L.bb_host_scatter_runs(_capi.ptr(full), _capi.ptr(part), _capi.ptr(dst), _capi.ptr(src), _capi.ptr(cnt),
+                                                  dst.size, row_bytes))
+        place(shared['index'], s.IndexSensorMapLocal)
         for k, full in shared['sensor'].items():
-            part = s.get_sensors(k)              # (rows of this slab, samples), page-locked
-            _capi.check(s._L.bb_host_scatter_rows(_capi.ptr(full), _capi.ptr(rows), _capi.ptr(part), rows.size,
-                                                  part.shape[1] * part.itemsize))
-            del part
+            place(full, s.get_sensors(k))     # (rows of this slab, samples), page-locked staging
         gate.wait()
         marks[r].update(setup_upload_s=t1 - t0, time_loop_s=t2 - t1, download_s=time.perf_counter() - t2)
 

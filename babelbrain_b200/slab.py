@@ -104,3 +104,35 @@ def merge_sensor_tables(local_tables, n1, n23):
         rows.append(r)
         before = before + c
     return index, rows
+
+
+def merge_sensor_runs(local_tables, n1, n23):
+    """merge_sensor_tables without any per-sensor work: the entries of one (j,k) line are consecutive in a slab's
+    table and consecutive in the global one, so the merge is a list of runs per slab -- (dst_row, src_row, nrows), one
+    run per non-empty line -- found with one binary search per line.  Returns (total number of sensors, runs per slab);
+    bb_host_scatter_runs (or expand_runs + fancy indexing) places table entries and trace rows with them."""
+    n1, n23 = int(n1), int(n23)
+    bounds, counts = [], []
+    for t in local_tables:
+        t = np.asarray(t)
+        edges = np.arange(n23 + 1, dtype=np.int64) * n1 + 1                  # first 1-based index of every line
+        if t.dtype.itemsize < 8 and n1 * n23 + 1 < 2 ** (8 * t.dtype.itemsize):
+            edges = edges.astype(t.dtype)                                     # no up-cast copy of the table
+        b = np.searchsorted(t, edges).astype(np.int64)
+        bounds.append(b)
+        counts.append(np.diff(b))
+    total = np.sum(counts, axis=0) if counts else np.zeros(n23, np.int64)
+    line_start = np.cumsum(total) - total
+    runs, before = [], line_start
+    for b, c in zip(bounds, counts):
+        m = c > 0
+        runs.append((np.ascontiguousarray(before[m]), np.ascontiguousarray(b[:-1][m]), np.ascontiguousarray(c[m])))
+        before = before + c
+    return int(total.sum()), runs
+
+
+def expand_runs(run):
+    """Global row of every entry of a slab's table, from its runs (the rows merge_sensor_tables returns)."""
+    dst, src, n = run
+    total = int(n.sum())
+    return np.arange(total, dtype=np.int64) + np.repeat(dst - src, n)

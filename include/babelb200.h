@@ -101,6 +101,10 @@ int bb_host_free(void *ptr);
  * one slab's sensor traces placed into the whole-grid table in IndexSensorMap order).  Plain memcpy loop; exists so
  * that the per-GPU host threads of the Python layer gather in parallel without holding the interpreter lock. */
 int bb_host_scatter_rows(void *out, const int64_t *rows, const void *data, int64_t nrows, int64_t row_bytes);
+/* the same by runs of consecutive rows: rows [src_row[r], src_row[r] + nrows[r]) of data go to rows
+ * [dst_row[r], dst_row[r] + nrows[r]) of out (one run per (j,k) line of a slab: slab.merge_sensor_runs) */
+int bb_host_scatter_runs(void *out, const void *data, const int64_t *dst_row, const int64_t *src_row, const int64_t *nrows,
+                         int64_t nruns, int64_t row_bytes);
 
 /* ---- FDTD handle ---- */
 int bb_fdtd_create(const bb_fdtd_desc *desc, bb_fdtd **out);

@@ -11,8 +11,8 @@ import torch
 import torch.distributed as dist
 import torch.multiprocessing as mp
 
-from babelbrain_b200.slab import (HALO, SlabPlan, assemble_maps, assemble_sensors, halo_exchange_plan, merge_sensor_tables,
-                                  sensor_rows_of_slab)
+from babelbrain_b200.slab import (HALO, SlabPlan, assemble_maps, assemble_sensors, expand_runs, halo_exchange_plan, merge_sensor_runs,
+                                  merge_sensor_tables, sensor_rows_of_slab)
 
 
 def test_plan_covers_the_grid():
@@ -66,6 +66,24 @@ def test_merge_of_slab_sensor_tables_is_the_global_table(shape, nranks, density)
     for r in range(nranks):
         assert np.array_equal(index[rows[r]], local[r])
         assert np.array_equal(rows[r], sensor_rows_of_slab(expect, shape, *plan.owned(r)))
+    # the same merge as runs of consecutive rows (what the multi-GPU gather uses), placed by the library's host helper
+    import ctypes
+    from babelbrain_b200 import _capi, build
+    build.build()
+    L = _capi.lib()
+    ntot, runs = merge_sensor_runs(local, shape[0], shape[1] * shape[2])
+    assert ntot == expect.size
+    index2 = np.zeros(ntot, np.uint32)
+    traces = [np.arange(t.size * 3, dtype=np.float32).reshape(-1, 3) + 1000 * r for r, t in enumerate(local)]
+    full = np.zeros((ntot, 3), np.float32)
+    for r in range(nranks):
+        dst, src, cnt = runs[r]
+        assert np.array_equal(expand_runs(runs[r]), rows[r]) and int(cnt.sum()) == local[r].size and np.all(cnt > 0)
+        for out, part, nb in ((index2, local[r], 4), (full, traces[r], 12)):
+            assert L.bb_host_scatter_runs(_capi.ptr(out), _capi.ptr(part), _capi.ptr(dst), _capi.ptr(src), _capi.ptr(cnt), dst.size, nb) == 0
+    assert np.array_equal(index2, expect)
+    for r in range(nranks):
+        assert np.array_equal(full[rows[r]], traces[r])
 
 
 def _step(a, forward):
