@@ -164,9 +164,9 @@ struct RingPos {
 };
 
 // ---------------------------------------------------------------- shared-memory layout
-// Every CTA gets the same dynamic allocation (two CTAs per SM); what the point stages of its tile
-// class do not need (no Y parts away from the j-PML, no Z parts away from the k-PML) goes to a
-// deeper halo ring, i.e. more planes of prefetch.
+// Every CTA gets the same dynamic allocation (one CTA per SM); what the stages of a CTA do not need (no Y parts away
+// from the j-PML, no Z parts away from the k-PML, no shear boxes where nothing is solid, no X parts outside the i-PML)
+// becomes deeper rings, see ring_depths().
 constexpr int SMEM_BYTES = (CTAS_PER_SM == 1 ? 222 : 110) * 1024;
 #ifndef BB_MIN_NSH
 #define BB_MIN_NSH 6
