@@ -151,35 +151,43 @@ class PinnedPool:
     array, so a worker that runs several simulations (forward, back-propagation, refocus:
     BabelIntegrationBASE.py:2338-2428) pays the page-locking once."""
 
-    def __init__(self, max_idle_bytes=8 << 30):
+    def __init__(self, max_idle_bytes=8 << 30, block_type=None):
+        import threading
+        self.block_type = block_type or _PinnedBlock     # tests substitute an ordinary-memory block
         self.idle, self.max_idle, self.idle_bytes = [], max_idle_bytes, 0
         self.hits = self.misses = 0
+        # the per-GPU threads of a slab-decomposed run allocate concurrently, and finalizers fire from any thread
+        self._lock = threading.Lock()
 
     def empty(self, shape, dtype):
         import weakref
         dtype = np.dtype(dtype)
         n = int(np.prod(shape, dtype=np.int64)) * dtype.itemsize
-        blk = None
-        for c, b in enumerate(self.idle):     # smallest idle block that fits without wasting more than 2x
-            if n <= b.nbytes <= max(2 * n, 1 << 20) and (blk is None or b.nbytes < blk.nbytes):
-                blk, pos = b, c
-        if blk is not None:
-            self.idle.pop(pos)
-            self.idle_bytes -= blk.nbytes
-            self.hits += 1
-        else:
-            blk = _PinnedBlock(max(n, 16))
-            self.misses += 1
+        with self._lock:
+            blk = None
+            for b in self.idle:               # smallest idle block that fits without wasting more than 2x
+                if n <= b.nbytes <= max(2 * n, 1 << 20) and (blk is None or b.nbytes < blk.nbytes):
+                    blk = b
+            if blk is not None:
+                self.idle.remove(blk)         # by identity (_PinnedBlock defines no __eq__)
+                self.idle_bytes -= blk.nbytes
+                self.hits += 1
+            else:
+                self.misses += 1
+        if blk is None:
+            blk = self.block_type(max(n, 16))
         buf = (ctypes.c_char * blk.nbytes).from_address(blk.ptr)
         arr = np.frombuffer(buf, dtype=dtype, count=int(np.prod(shape, dtype=np.int64))).reshape(shape)
         weakref.finalize(buf, self._give_back, blk)   # buf lives as long as any view of it
         return arr
 
     def _give_back(self, blk):
-        if self.idle_bytes + blk.nbytes <= self.max_idle:
-            self.idle.append(blk)
-            self.idle_bytes += blk.nbytes
-        else:
+        with self._lock:
+            keep = self.idle_bytes + blk.nbytes <= self.max_idle
+            if keep:
+                self.idle.append(blk)
+                self.idle_bytes += blk.nbytes
+        if not keep:
             blk.release()
 
 

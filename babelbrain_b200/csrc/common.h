@@ -113,6 +113,8 @@ struct DevParams {
     unsigned *push_count;                // [2] plane-pushes completed so far in this launch (last CTA publishes)
     unsigned long long seq;              // (epoch << 32) | (half-step index + 1) of this launch
     int publish;                         // 1: the half-step kernel publishes seq itself; 0: a source kernel follows, publish_kernel does
+    unsigned long long peer_timeout_ns;  // longest wait for a neighbour's halo (0: forever); on a timeout *err is set and the run fails
+    int *err;                            // device error word checked by bb_fdtd_run (1, 2: halo wait on the lower / upper side timed out)
     // profiling aid (BB_CTA_TIMING=1): per CTA of the last launch {globaltimer at start, at end, blockIdx packed, planes}
     unsigned long long *dbg;
     // RMS / peak accumulators: [slot][(i-i0)*plane + j*pitch + k]

@@ -7,6 +7,7 @@
 #include <algorithm>
 #include <map>
 #include <mutex>
+#include <thread>
 #include <tuple>
 #include <unistd.h>
 #include "common.h"
@@ -81,6 +82,7 @@ struct bb_fdtd {
     size_t xp_floats = 0, yp_floats = 0, zp_floats = 0;   // per part array
     int nxp = 0;                                          // planes of this slab inside the i-PML
     bool materials_set = false, maps_set = false, prepared = false;
+    int *d_bad = nullptr;                                 // device flag: a label outside the material table was seen
     StressMaps smaps;
     ParticleMaps pmaps;
     int chunk_override = 0, chunk_tail = 1, dbg_kernel = -1;
@@ -110,6 +112,114 @@ static int dev_alloc(bb_fdtd *h, void **ptr, size_t bytes, bool zero = true) {
 }
 
 static int popcount32(uint32_t v) { return __builtin_popcount(v); }
+
+// ------------------------------------------------------------------------------------------
+// Staging: every bulk transfer between the caller's host arrays and the device goes through two fixed-size slots
+// (device scratch + page-locked host buffer + event each), so the host-side copy of chunk c+1 overlaps the transfer and
+// the conversion kernel of chunk c, and no entry point allocates or frees device memory per call.  One stager per
+// device for the life of the process (a worker runs forward, back-propagation and refocus simulations in a row,
+// BabelIntegrationBASE.py:2338-2428); the mutex serialises handles that share a device.
+// ------------------------------------------------------------------------------------------
+constexpr size_t BB_STAGE_BYTES = 32u << 20;
+struct Stager {
+    std::mutex mu;
+    void *dev[2] = {nullptr, nullptr}, *host[2] = {nullptr, nullptr};
+    cudaEvent_t ev[2] = {nullptr, nullptr};
+    bool ready = false;
+};
+static Stager g_stagers[64];
+
+static int stager_get(int device, Stager **out) {
+    BB_REQUIRE(device >= 0 && device < 64, "device ordinal %d", device);
+    Stager &s = g_stagers[device];
+    if (!s.ready) {
+        for (int b = 0; b < 2; b++) {
+            BB_CUDA(cudaMalloc(&s.dev[b], BB_STAGE_BYTES));
+            BB_CUDA(cudaHostAlloc(&s.host[b], BB_STAGE_BYTES, cudaHostAllocDefault));
+            BB_CUDA(cudaEventCreateWithFlags(&s.ev[b], cudaEventDisableTiming));
+        }
+        s.ready = true;
+    }
+    *out = &s;
+    return BB_OK;
+}
+
+static bool host_is_pinned(const void *p) {
+    cudaPointerAttributes a;
+    if (cudaPointerGetAttributes(&a, p) != cudaSuccess) { cudaGetLastError(); return false; }
+    return a.type == cudaMemoryTypeHost;
+}
+
+// host -> host copy on a few threads (a single thread moves ~10 GB/s, PCIe 5 x16 takes 50)
+static void parallel_memcpy(void *dst, const void *src, size_t n) {
+    const size_t piece = 4u << 20;
+    const int nt = (int)std::min<size_t>(4, n / piece);
+    if (nt <= 1) { memcpy(dst, src, n); return; }
+    std::vector<std::thread> th;
+    const size_t per = (n / nt + 63) & ~(size_t)63;
+    for (int t = 0; t < nt; t++) {
+        const size_t o = (size_t)t * per, len = o >= n ? 0 : std::min(per, n - o);
+        if (len) th.emplace_back([=] { memcpy((char *)dst + o, (const char *)src + o, len); });
+    }
+    for (auto &x : th) x.join();
+}
+
+// Upload `total` bytes from `src` in pieces of at most `piece` bytes (<= BB_STAGE_BYTES); consume(dev_ptr, offset, bytes)
+// launches on h->stream whatever turns the staged piece into its final form.
+template <class F>
+static int staged_upload(bb_fdtd *h, const void *src, size_t total, size_t piece, F consume) {
+    Stager *sg;
+    int rc;
+    if ((rc = stager_get(h->d.device, &sg))) return rc;
+    std::lock_guard<std::mutex> lock(sg->mu);
+    const bool pinned = host_is_pinned(src);
+    int b = 0;
+    for (size_t o = 0; o < total; o += piece, b ^= 1) {
+        const size_t n = std::min(piece, total - o);
+        BB_CUDA(cudaEventSynchronize(sg->ev[b]));          // the slot's previous transfer and kernel are done
+        const void *from = (const char *)src + o;
+        if (!pinned) { parallel_memcpy(sg->host[b], from, n); from = sg->host[b]; }
+        BB_CUDA(cudaMemcpyAsync(sg->dev[b], from, n, cudaMemcpyHostToDevice, h->stream));
+        if ((rc = consume(sg->dev[b], o, n))) return rc;
+        BB_CUDA(cudaGetLastError());
+        BB_CUDA(cudaEventRecord(sg->ev[b], h->stream));
+    }
+    BB_CUDA(cudaStreamSynchronize(h->stream));
+    return BB_OK;
+}
+
+// Download `total` bytes to `dst` in pieces: produce(dev_ptr, offset, bytes) launches the kernel that writes the piece.
+template <class F>
+static int staged_download(bb_fdtd *h, void *dst, size_t total, size_t piece, F produce) {
+    Stager *sg;
+    int rc;
+    if ((rc = stager_get(h->d.device, &sg))) return rc;
+    std::lock_guard<std::mutex> lock(sg->mu);
+    const bool pinned = host_is_pinned(dst);
+    size_t pend_o[2] = {0, 0}, pend_n[2] = {0, 0};
+    int b = 0;
+    for (size_t o = 0; o < total; o += piece, b ^= 1) {
+        const size_t n = std::min(piece, total - o);
+        BB_CUDA(cudaEventSynchronize(sg->ev[b]));
+        if (pend_n[b]) { parallel_memcpy((char *)dst + pend_o[b], sg->host[b], pend_n[b]); pend_n[b] = 0; }
+        if ((rc = produce(sg->dev[b], o, n))) return rc;
+        BB_CUDA(cudaGetLastError());
+        if (pinned) BB_CUDA(cudaMemcpyAsync((char *)dst + o, sg->dev[b], n, cudaMemcpyDeviceToHost, h->stream));
+        else { BB_CUDA(cudaMemcpyAsync(sg->host[b], sg->dev[b], n, cudaMemcpyDeviceToHost, h->stream)); pend_o[b] = o; pend_n[b] = n; }
+        BB_CUDA(cudaEventRecord(sg->ev[b], h->stream));
+    }
+    BB_CUDA(cudaStreamSynchronize(h->stream));
+    for (b = 0; b < 2; b++) if (pend_n[b]) parallel_memcpy((char *)dst + pend_o[b], sg->host[b], pend_n[b]);
+    return BB_OK;
+}
+
+// scoped device allocation for the few temporaries that cannot be staged (freed on every return path)
+struct DevTmp {
+    void *p = nullptr;
+    ~DevTmp() { if (p) cudaFree(p); }
+    cudaError_t alloc(size_t bytes) { return cudaMalloc(&p, bytes ? bytes : 16); }
+    template <class T> T *as() const { return reinterpret_cast<T *>(p); }
+};
 
 // ------------------------------------------------------------------------------------------
 // TMA descriptors (driver entry point resolved at run time: the library links only cudart)
@@ -184,6 +294,9 @@ static int make_tensor_maps(bb_fdtd *h) {
     return BB_OK;
 }
 
+static int fdtd_create_body(bb_fdtd *h, const bb_fdtd_desc *d);
+extern "C" void bb_fdtd_destroy(bb_fdtd *h);
+
 extern "C" int bb_fdtd_create(const bb_fdtd_desc *d, bb_fdtd **out) {
     BB_REQUIRE(d && out, "null argument");
     BB_REQUIRE(d->n1 > 0 && d->n2 > 0 && d->n3 > 0, "bad grid %d %d %d", d->n1, d->n2, d->n3);
@@ -203,6 +316,15 @@ extern "C" int bb_fdtd_create(const bb_fdtd_desc *d, bb_fdtd **out) {
     BB_REQUIRE(d->device >= 0 && d->device < ndev, "device %d of %d", d->device, ndev);
     BB_CUDA(cudaSetDevice(d->device));
     bb_fdtd *h = new bb_fdtd();
+    // everything created from here on is owned by the handle: a failure (most likely cudaMalloc on a grid that does not
+    // fit) destroys it, so that the caller can retry with a smaller grid or more GPUs
+    const int rc_create = fdtd_create_body(h, d);
+    if (rc_create) { std::string msg = bb_last_error(); bb_fdtd_destroy(h); bb_set_error("%s", msg.c_str()); return rc_create; }
+    *out = h;
+    return BB_OK;
+}
+
+static int fdtd_create_body(bb_fdtd *h, const bb_fdtd_desc *d) {
     h->d = *d;
     memset(&h->stats, 0, sizeof(h->stats));
     BB_CUDA(cudaStreamCreateWithFlags(&h->stream, cudaStreamNonBlocking));
@@ -285,9 +407,15 @@ extern "C" int bb_fdtd_create(const bb_fdtd_desc *d, bb_fdtd **out) {
     if ((rc = dev_alloc(h, (void **)&h->flags, 64))) return rc;
     p.flag_local = h->flags;
     p.push_count = reinterpret_cast<unsigned *>(h->flags + 2);
+    if ((rc = dev_alloc(h, (void **)&h->d_bad, 16))) return rc;
+    p.err = h->d_bad + 1;
+    {   // BB_PEER_TIMEOUT_S: how long a boundary CTA waits for a neighbour's halo before the run is failed (default 60 s; 0 = forever)
+        const char *e = getenv("BB_PEER_TIMEOUT_S");
+        const double sec = e ? atof(e) : 60.0;
+        p.peer_timeout_ns = sec > 0 ? (unsigned long long)(sec * 1e9) : 0ull;
+    }
     if (d->kernel_variant == 0 && (rc = make_tensor_maps(h))) return rc;
     BB_CUDA(cudaStreamSynchronize(h->stream));
-    *out = h;
     return BB_OK;
 }
 
@@ -394,31 +522,45 @@ extern "C" int bb_fdtd_set_maps(bb_fdtd *h, const uint32_t *material, const uint
     const DevParams &p = h->p;
     const int glo = std::max(p.i0 - 2, 0), ghi = std::min(p.i1 + 2, p.n1);  // planes the host passes
     const long long nrows = (long long)(ghi - glo) * p.n2;
-    const size_t bytes = (size_t)nrows * p.n3 * 4;
-    uint32_t *tmp = nullptr, *tmpr = nullptr;
-    int *bad = nullptr;
-    BB_CUDA(cudaMalloc(&tmp, bytes));
-    BB_CUDA(cudaMalloc(&bad, 4));
-    BB_CUDA(cudaMemsetAsync(bad, 0, 4, h->stream));
-    BB_CUDA(cudaMemcpyAsync(tmp, material, bytes, cudaMemcpyHostToDevice, h->stream));
-    if (reflector) {
-        BB_CUDA(cudaMalloc(&tmpr, bytes));
-        BB_CUDA(cudaMemcpyAsync(tmpr, reflector, bytes, cudaMemcpyHostToDevice, h->stream));
-    }
     const long long first_row = (long long)(glo - (p.i0 - 2)) * p.n2;  // local row where the host data starts
-    const long long total = nrows * p.pitch;
+    BB_CUDA(cudaMemsetAsync(h->d_bad, 0, 4, h->stream));
+    // whole rows per piece; with a reflector mask a piece carries the labels in its first half and the mask behind them
+    const size_t row_bytes = (size_t)p.n3 * 4;
+    const long long rows_per = std::max<long long>(1, (long long)(BB_STAGE_BYTES / (reflector ? 2 : 1) / row_bytes));
+    BB_REQUIRE(row_bytes * (reflector ? 2 : 1) <= BB_STAGE_BYTES, "a row of %d labels does not fit the staging buffer", p.n3);
     const int bs = 256;
-    const unsigned grid = (unsigned)((total + bs - 1) / bs);
-    if (h->label_bytes == 1)
-        label_convert_kernel<uint8_t><<<grid, bs, 0, h->stream>>>(tmp, tmpr, (uint8_t *)p.lab + first_row * p.pitch, nrows, p.n3, p.pitch, h->d.nmat, bad);
-    else
-        label_convert_kernel<uint16_t><<<grid, bs, 0, h->stream>>>(tmp, tmpr, (uint16_t *)p.lab + first_row * p.pitch, nrows, p.n3, p.pitch, h->d.nmat, bad);
-    BB_CUDA(cudaGetLastError());
+    int rc;
+    if (!reflector) {
+        rc = staged_upload(h, material, (size_t)nrows * row_bytes, (size_t)rows_per * row_bytes, [&](void *dev, size_t off, size_t n) {
+            const long long r0 = (long long)(off / row_bytes), nr = (long long)(n / row_bytes);
+            const unsigned grid = (unsigned)((nr * p.pitch + bs - 1) / bs);
+            if (h->label_bytes == 1)
+                label_convert_kernel<uint8_t><<<grid, bs, 0, h->stream>>>((const uint32_t *)dev, nullptr, (uint8_t *)p.lab + (first_row + r0) * p.pitch, nr, p.n3, p.pitch, h->d.nmat, h->d_bad);
+            else
+                label_convert_kernel<uint16_t><<<grid, bs, 0, h->stream>>>((const uint32_t *)dev, nullptr, (uint16_t *)p.lab + (first_row + r0) * p.pitch, nr, p.n3, p.pitch, h->d.nmat, h->d_bad);
+            return BB_OK;
+        });
+        if (rc) return rc;
+    } else {
+        // the mask is rare (CT with air regions, BabelIntegrationBASE.py:2182-2190): upload it whole, then the labels in pieces
+        DevTmp tmpr;
+        BB_CUDA(tmpr.alloc((size_t)nrows * row_bytes));
+        BB_CUDA(cudaMemcpyAsync(tmpr.p, reflector, (size_t)nrows * row_bytes, cudaMemcpyHostToDevice, h->stream));
+        rc = staged_upload(h, material, (size_t)nrows * row_bytes, (size_t)rows_per * row_bytes, [&](void *dev, size_t off, size_t n) {
+            const long long r0 = (long long)(off / row_bytes), nr = (long long)(n / row_bytes);
+            const unsigned grid = (unsigned)((nr * p.pitch + bs - 1) / bs);
+            const uint32_t *rf = tmpr.as<uint32_t>() + r0 * p.n3;
+            if (h->label_bytes == 1)
+                label_convert_kernel<uint8_t><<<grid, bs, 0, h->stream>>>((const uint32_t *)dev, rf, (uint8_t *)p.lab + (first_row + r0) * p.pitch, nr, p.n3, p.pitch, h->d.nmat, h->d_bad);
+            else
+                label_convert_kernel<uint16_t><<<grid, bs, 0, h->stream>>>((const uint32_t *)dev, rf, (uint16_t *)p.lab + (first_row + r0) * p.pitch, nr, p.n3, p.pitch, h->d.nmat, h->d_bad);
+            return BB_OK;
+        });
+        if (rc) return rc;
+    }
     int hbad = 0;
-    BB_CUDA(cudaMemcpyAsync(&hbad, bad, 4, cudaMemcpyDeviceToHost, h->stream));
+    BB_CUDA(cudaMemcpyAsync(&hbad, h->d_bad, 4, cudaMemcpyDeviceToHost, h->stream));
     BB_CUDA(cudaStreamSynchronize(h->stream));
-    cudaFree(tmp); cudaFree(bad);
-    if (tmpr) cudaFree(tmpr);
     BB_REQUIRE(!hbad, "MaterialMap holds a label >= number of materials (%d)", h->d.nmat);
     h->maps_set = true;
     h->prepared = false;
@@ -488,27 +630,21 @@ extern "C" int bb_fdtd_set_source_functions(bb_fdtd *h, const void *data, int is
     BB_REQUIRE(nsrc > 0 && nt > 0 && row_stride >= nt, "bad SourceFunctions shape");
     int rc;
     if (!h->srcfun) if ((rc = dev_alloc(h, (void **)&h->srcfun, (size_t)nsrc * nt * 4, false))) return rc;
-    const size_t esz = is_f64 ? 8 : 4;
+    const size_t esz = is_f64 ? 8 : 4, row_bytes = (size_t)row_stride * esz;
+    BB_REQUIRE(row_bytes <= BB_STAGE_BYTES, "a SourceFunctions row of %lld samples does not fit the staging buffer", (long long)row_stride);
     const dim3 blk(32, 8);
-    // stream the host matrix through a bounded staging buffer (rows of 32-multiples)
-    const int64_t max_stage_bytes = 1ll << 30;
-    int64_t rows_per = std::max<int64_t>(32, (max_stage_bytes / (row_stride * (int64_t)esz)) / 32 * 32);
-    rows_per = std::min<int64_t>(rows_per, (nsrc + 31) / 32 * 32);
-    void *stage = nullptr;
-    BB_CUDA(cudaMalloc(&stage, (size_t)rows_per * row_stride * esz));
-    for (int64_t s0 = 0; s0 < nsrc; s0 += rows_per) {
+    // the caller's (nsrc, nt) float64 matrix (0.95 GB for CTX-500) streams through the two staging slots in groups of
+    // whole rows; each group is converted and transposed into [nt][nsrc] while the next one is being copied
+    const int64_t rows_per = std::max<int64_t>(1, (int64_t)(BB_STAGE_BYTES / row_bytes));
+    const size_t total = ((size_t)(nsrc - 1) * row_stride + nt) * esz;
+    return staged_upload(h, data, total, (size_t)rows_per * row_bytes, [&](void *dev, size_t off, size_t n) {
+        const int64_t s0 = (int64_t)(off / row_bytes);
         const int64_t ns = std::min<int64_t>(rows_per, nsrc - s0);
-        const size_t nbytes = ((size_t)(ns - 1) * row_stride + nt) * esz;
-        BB_CUDA(cudaMemcpyAsync(stage, (const char *)data + (size_t)s0 * row_stride * esz, nbytes, cudaMemcpyHostToDevice, h->stream));
         const dim3 grid((nt + 31) / 32, (unsigned)((ns + 31) / 32));
-        // out rows are full length nsrc: offset columns by s0
-        if (is_f64) srcfun_transpose_kernel<double><<<grid, blk, 0, h->stream>>>((const double *)stage, row_stride, h->srcfun + s0, (int)ns, nt);
-        else srcfun_transpose_kernel<float><<<grid, blk, 0, h->stream>>>((const float *)stage, row_stride, h->srcfun + s0, (int)ns, nt);
-        BB_CUDA(cudaGetLastError());
-        BB_CUDA(cudaStreamSynchronize(h->stream));
-    }
-    cudaFree(stage);
-    return BB_OK;
+        if (is_f64) srcfun_transpose_kernel<double><<<grid, blk, 0, h->stream>>>((const double *)dev, row_stride, h->srcfun + s0, (int)ns, nt, nsrc);
+        else srcfun_transpose_kernel<float><<<grid, blk, 0, h->stream>>>((const float *)dev, row_stride, h->srcfun + s0, (int)ns, nt, nsrc);
+        return BB_OK;
+    });
 }
 
 extern "C" int bb_fdtd_set_source_tones(bb_fdtd *h, const float *a_cos, const float *a_sin, const float *env_sin, const float *env_cos) {
@@ -584,41 +720,44 @@ extern "C" int bb_fdtd_set_sensor_map(bb_fdtd *h, const uint32_t *sensor_map, in
     BB_CUDA(cudaSetDevice(h->d.device));
     const DevParams &p = h->p;
     const long long total = (long long)h->nown * p.n2 * p.n3;
-    uint32_t *dmap = nullptr;
-    long long *dsel = nullptr, *dcount = nullptr;
-    BB_CUDA(cudaMalloc(&dmap, (size_t)total * 4));
-    BB_CUDA(cudaMemcpyAsync(dmap, sensor_map, (size_t)total * 4, cudaMemcpyHostToDevice, h->stream));
-    BB_CUDA(cudaMalloc(&dsel, (size_t)total * 8));   // worst case: every voxel is a sensor
-    BB_CUDA(cudaMalloc(&dcount, 8));
-    const SensorPred pred{dmap, h->nown, p.n2, p.n3};
+    // the selection needs the whole slab of the map on the device (Fortran-order enumeration of a C-order volume);
+    // temporaries are scoped: every return path frees them
+    DevTmp dmap, dsel, dcount, tmp;
+    BB_CUDA(dmap.alloc((size_t)total * 4));
+    {   // upload through the page-locked staging slots (the caller's map is pageable)
+        int rcu = staged_upload(h, sensor_map, (size_t)total * 4, BB_STAGE_BYTES, [&](void *dev, size_t off, size_t n) {
+            BB_CUDA(cudaMemcpyAsync((char *)dmap.p + off, dev, n, cudaMemcpyDeviceToDevice, h->stream));
+            return BB_OK;
+        });
+        if (rcu) return rcu;
+    }
+    BB_CUDA(dsel.alloc((size_t)total * 8));   // worst case: every voxel is a sensor
+    BB_CUDA(dcount.alloc(8));
+    const SensorPred pred{dmap.as<uint32_t>(), h->nown, p.n2, p.n3};
     long long found = 0;
     const long long piece = 1ll << 30;               // keep each selection inside 32-bit item counts
-    void *tmp = nullptr;
     size_t tmp_bytes = 0;
     for (long long t0 = 0; t0 < total; t0 += piece) {
         const int n = (int)std::min(piece, total - t0);
         thrust::counting_iterator<long long> first(t0);
         size_t need = 0;
-        BB_CUDA(cub::DeviceSelect::If(nullptr, need, first, dsel + found, dcount, n, pred, h->stream));
-        if (need > tmp_bytes) { if (tmp) cudaFree(tmp); BB_CUDA(cudaMalloc(&tmp, need)); tmp_bytes = need; }
-        BB_CUDA(cub::DeviceSelect::If(tmp, need, first, dsel + found, dcount, n, pred, h->stream));
+        BB_CUDA(cub::DeviceSelect::If(nullptr, need, first, dsel.as<long long>() + found, dcount.as<long long>(), n, pred, h->stream));
+        if (need > tmp_bytes) { if (tmp.p) { cudaFree(tmp.p); tmp.p = nullptr; } BB_CUDA(tmp.alloc(need)); tmp_bytes = need; }
+        BB_CUDA(cub::DeviceSelect::If(tmp.p, need, first, dsel.as<long long>() + found, dcount.as<long long>(), n, pred, h->stream));
         long long c = 0;
-        BB_CUDA(cudaMemcpyAsync(&c, dcount, 8, cudaMemcpyDeviceToHost, h->stream));
+        BB_CUDA(cudaMemcpyAsync(&c, dcount.p, 8, cudaMemcpyDeviceToHost, h->stream));
         BB_CUDA(cudaStreamSynchronize(h->stream));
         found += c;
     }
-    if (tmp) cudaFree(tmp);
-    cudaFree(dmap); cudaFree(dcount);
     int rc;
     if ((rc = dev_alloc(h, (void **)&h->sensor_cell, (size_t)found * 8, false))) return rc;
     if ((rc = dev_alloc(h, (void **)&h->sensor_findex, (size_t)found * 8, false))) return rc;
     if (found) {
-        sensor_finish_kernel<<<(unsigned)((found + 255) / 256), 256, 0, h->stream>>>(dsel, found, p, h->sensor_cell, h->sensor_findex);
+        sensor_finish_kernel<<<(unsigned)((found + 255) / 256), 256, 0, h->stream>>>(dsel.as<long long>(), found, p, h->sensor_cell, h->sensor_findex);
         BB_CUDA(cudaGetLastError());
     }
     if ((rc = dev_alloc(h, (void **)&h->sensor_out, (size_t)h->n_sensor_maps * h->nsamples * found * 4))) return rc;
     BB_CUDA(cudaStreamSynchronize(h->stream));
-    cudaFree(dsel);
     h->nsensors = found;
     *nsensors = found;
     return BB_OK;
@@ -629,20 +768,14 @@ extern "C" int bb_fdtd_get_sensor_index(bb_fdtd *h, void *out, int elem_bytes) {
     BB_REQUIRE(h->sensor_findex || h->nsensors == 0, "the sensor table was not built with bb_fdtd_set_sensor_map");
     BB_CUDA(cudaSetDevice(h->d.device));
     if (h->nsensors == 0) return BB_OK;
-    if (elem_bytes == 8) {
-        BB_CUDA(cudaMemcpyAsync(out, h->sensor_findex, (size_t)h->nsensors * 8, cudaMemcpyDeviceToHost, h->stream));
-    } else {
-        BB_REQUIRE((long long)h->p.n1 * h->p.n2 * h->p.n3 < (1ll << 32), "grid too large for 32-bit sensor indices");
-        uint32_t *tmp = nullptr;
-        BB_CUDA(cudaMalloc(&tmp, (size_t)h->nsensors * 4));
-        narrow_index_kernel<<<(unsigned)((h->nsensors + 255) / 256), 256, 0, h->stream>>>(h->sensor_findex, tmp, h->nsensors);
-        BB_CUDA(cudaGetLastError());
-        BB_CUDA(cudaMemcpyAsync(out, tmp, (size_t)h->nsensors * 4, cudaMemcpyDeviceToHost, h->stream));
-        BB_CUDA(cudaStreamSynchronize(h->stream));
-        cudaFree(tmp);
-    }
-    BB_CUDA(cudaStreamSynchronize(h->stream));
-    return BB_OK;
+    if (elem_bytes == 4) BB_REQUIRE((long long)h->p.n1 * h->p.n2 * h->p.n3 < (1ll << 32), "grid too large for 32-bit sensor indices");
+    const size_t per = BB_STAGE_BYTES / elem_bytes;
+    return staged_download(h, out, (size_t)h->nsensors * elem_bytes, per * elem_bytes, [&](void *dev, size_t off, size_t n) {
+        const long long s0 = (long long)(off / elem_bytes), ns = (long long)(n / elem_bytes);
+        if (elem_bytes == 8) BB_CUDA(cudaMemcpyAsync(dev, h->sensor_findex + s0, n, cudaMemcpyDeviceToDevice, h->stream));
+        else narrow_index_kernel<<<(unsigned)((ns + 255) / 256), 256, 0, h->stream>>>(h->sensor_findex + s0, (uint32_t *)dev, ns);
+        return BB_OK;
+    });
 }
 
 extern "C" int bb_nccl_unique_id(char *out128) {
@@ -1004,8 +1137,15 @@ extern "C" int bb_fdtd_run(bb_fdtd *h, int64_t nsteps, int profile) {
     if (rc) return rc;
     if (h->d.nranks > 1 && !h->peer_mode) BB_CUDA(cudaStreamWaitEvent(h->stream, h->ev_halo, 0));
     BB_CUDA(cudaEventRecord(h->ev_run1, h->stream));
+    int herr = 0;
+    if (h->peer_mode) BB_CUDA(cudaMemcpyAsync(&herr, h->p.err, 4, cudaMemcpyDeviceToHost, h->stream));
     BB_CUDA(cudaStreamSynchronize(h->stream));
     BB_CUDA(cudaGetLastError());
+    if (herr) {
+        BB_CUDA(cudaMemsetAsync(h->p.err, 0, 4, h->stream));
+        bb_set_error("rank %d: the halo planes of the %s neighbour did not arrive within BB_PEER_TIMEOUT_S; results are invalid", h->d.rank, herr == 1 ? "lower" : "upper");
+        return BB_ERR_STATE;
+    }
     float ms = 0;
     BB_CUDA(cudaEventElapsedTime(&ms, h->ev_run0, h->ev_run1));
     bb_fdtd_stats &st = h->stats;
@@ -1053,33 +1193,37 @@ extern "C" int bb_fdtd_get_map(bb_fdtd *h, int which, int map_id, float *out) {
     BB_CUDA(cudaSetDevice(h->d.device));
     const DevParams &p = h->p;
     const long long nrows = (long long)h->nown * p.n2;
-    const long long total = nrows * p.n3;
-    float *tmp = nullptr;
-    BB_CUDA(cudaMalloc(&tmp, (size_t)total * 4));
-    const unsigned grid = (unsigned)((total + 255) / 256);
+    const float *src = nullptr;
+    int mode = 0;
+    float inv_nacc = 0.f;
     if (which == 2) {
         BB_REQUIRE(map_id != BB_MAP_ALLV, "no last map for ALLV");
-        if (map_id == BB_MAP_PRESSURE) {
-            if (h->label_bytes == 1) finalize_pressure_kernel<uint8_t><<<grid, 256, 0, h->stream>>>(p, tmp, nrows);
-            else finalize_pressure_kernel<uint16_t><<<grid, 256, 0, h->stream>>>(p, tmp, nrows);
-        } else {
-            const float *src = map_id <= BB_MAP_VZ ? p.V[map_id - BB_MAP_VX] : p.S[map_id - BB_MAP_SXX];
-            finalize_map_kernel<<<grid, 256, 0, h->stream>>>(src + 2 * p.plane, tmp, nrows, p.n3, p.pitch, 0, 0.f);
-        }
+        if (map_id != BB_MAP_PRESSURE) src = (map_id <= BB_MAP_VZ ? p.V[map_id - BB_MAP_VX] : p.S[map_id - BB_MAP_SXX]) + 2 * p.plane;
     } else {
         const float *base = which == 0 ? p.acc_rms : p.acc_peak;
-        if (!base || !(h->d.sel_maps_rms & (1u << map_id))) { cudaFree(tmp); bb_set_error("map %d was not selected", map_id); return BB_ERR_ARG; }
+        if (!base || !(h->d.sel_maps_rms & (1u << map_id))) { bb_set_error("map %d was not selected", map_id); return BB_ERR_ARG; }
         const int slot = popcount32(h->d.sel_maps_rms & ((1u << map_id) - 1u));
         const int n0 = h->d.sensor_start * h->d.sensor_subsampling;
         const long long nacc = std::max<long long>(1, h->d.steps - n0);
-        const int mode = which == 0 ? 1 : (map_id == BB_MAP_ALLV ? 2 : 0);
-        finalize_map_kernel<<<grid, 256, 0, h->stream>>>(base + (size_t)slot * p.acc_stride, tmp, nrows, p.n3, p.pitch, mode, 1.0f / (float)nacc);
+        mode = which == 0 ? 1 : (map_id == BB_MAP_ALLV ? 2 : 0);
+        inv_nacc = 1.0f / (float)nacc;
+        src = base + (size_t)slot * p.acc_stride;
     }
-    BB_CUDA(cudaGetLastError());
-    BB_CUDA(cudaMemcpyAsync(out, tmp, (size_t)total * 4, cudaMemcpyDeviceToHost, h->stream));
-    BB_CUDA(cudaStreamSynchronize(h->stream));
-    cudaFree(tmp);
-    return BB_OK;
+    // dense rows leave through the staging slots, a group of whole rows at a time (no per-call device allocation)
+    const size_t row_bytes = (size_t)p.n3 * 4;
+    const long long rows_per = std::max<long long>(1, (long long)(BB_STAGE_BYTES / row_bytes));
+    BB_REQUIRE(row_bytes <= BB_STAGE_BYTES, "a row of %d values does not fit the staging buffer", p.n3);
+    return staged_download(h, out, (size_t)nrows * row_bytes, (size_t)rows_per * row_bytes, [&](void *dev, size_t off, size_t n) {
+        const long long r0 = (long long)(off / row_bytes), nr = (long long)(n / row_bytes);
+        const unsigned grid = (unsigned)((nr * p.n3 + 255) / 256);
+        if (!src) {
+            if (h->label_bytes == 1) finalize_pressure_kernel<uint8_t><<<grid, 256, 0, h->stream>>>(p, (float *)dev, r0, nr);
+            else finalize_pressure_kernel<uint16_t><<<grid, 256, 0, h->stream>>>(p, (float *)dev, r0, nr);
+        } else {
+            finalize_map_kernel<<<grid, 256, 0, h->stream>>>(src + r0 * p.pitch, (float *)dev, nr, p.n3, p.pitch, mode, inv_nacc);
+        }
+        return BB_OK;
+    });
 }
 
 extern "C" int bb_fdtd_get_sensors(bb_fdtd *h, int map_id, float *out) {
@@ -1088,15 +1232,19 @@ extern "C" int bb_fdtd_get_sensors(bb_fdtd *h, int map_id, float *out) {
     BB_CUDA(cudaSetDevice(h->d.device));
     if (h->nsensors == 0 || h->nsamples == 0) return BB_OK;
     const int slot = popcount32(h->d.sel_maps_sensor & ((1u << map_id) - 1u));
-    const size_t n = (size_t)h->nsensors * h->nsamples;
-    float *tmp = nullptr;
-    BB_CUDA(cudaMalloc(&tmp, n * 4));
-    sensor_transpose_kernel<<<(unsigned)((h->nsensors + 255) / 256), 256, 0, h->stream>>>(h->sensor_out + (size_t)slot * n, tmp, h->nsensors, (int)h->nsamples);
-    BB_CUDA(cudaGetLastError());
-    BB_CUDA(cudaMemcpyAsync(out, tmp, n * 4, cudaMemcpyDeviceToHost, h->stream));
-    BB_CUDA(cudaStreamSynchronize(h->stream));
-    cudaFree(tmp);
-    return BB_OK;
+    const int nsam = (int)h->nsamples;
+    const size_t smem = (size_t)nsam * (BB_ST_SENSORS + 1) * 4;
+    BB_REQUIRE(smem <= 200u * 1024u, "%d samples per sensor exceed the transpose tile", nsam);
+    if (smem > 48u * 1024u) BB_CUDA(cudaFuncSetAttribute(sensor_transpose_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    const float *in = h->sensor_out + (size_t)slot * h->nsensors * h->nsamples;
+    const size_t row_bytes = (size_t)nsam * 4;
+    const long long per = std::max<long long>(BB_ST_SENSORS, (long long)(BB_STAGE_BYTES / row_bytes) / BB_ST_SENSORS * BB_ST_SENSORS);
+    BB_REQUIRE((size_t)per * row_bytes <= BB_STAGE_BYTES, "%d samples per sensor do not fit the staging buffer", nsam);
+    return staged_download(h, out, (size_t)h->nsensors * row_bytes, (size_t)per * row_bytes, [&](void *dev, size_t off, size_t n) {
+        const long long s0 = (long long)(off / row_bytes), ns = (long long)(n / row_bytes);
+        sensor_transpose_kernel<<<(unsigned)((ns + BB_ST_SENSORS - 1) / BB_ST_SENSORS), BB_ST_SENSORS, smem, h->stream>>>(in, (float *)dev, h->nsensors, nsam, s0, ns);
+        return BB_OK;
+    });
 }
 
 extern "C" int bb_fdtd_get_phase_data(bb_fdtd *h, int map_id, int bin, int nsamples_used, float scale,

@@ -92,11 +92,23 @@ __global__ void sensor_kernel(const DevParams p, unsigned sel_maps, long long ns
     }
 }
 
-// (sample, sensor) -> (sensor, sample)
-__global__ void sensor_transpose_kernel(const float *__restrict__ in, float *__restrict__ out, long long nsensors, int nsamples) {
-    const long long s = (long long)blockIdx.x * blockDim.x + threadIdx.x;
-    if (s >= nsensors) return;
-    for (int t = 0; t < nsamples; t++) out[s * nsamples + t] = in[(long long)t * nsensors + s];
+// (sample, sensor) -> (sensor, sample) for the sensors [s0, s0 + ns): a CTA stages 256 sensors x nsamples through shared
+// memory, so both the reads (consecutive sensors of one sample) and the writes (the 256 x nsamples floats of the CTA's
+// sensors are one contiguous run of the output) are coalesced.  out points at the row of sensor s0.
+constexpr int BB_ST_SENSORS = 256;
+__global__ void __launch_bounds__(BB_ST_SENSORS) sensor_transpose_kernel(const float *__restrict__ in, float *__restrict__ out, long long nsensors,
+                                                                          int nsamples, long long s0, long long ns) {
+    extern __shared__ float st_tile[];              // [nsamples][BB_ST_SENSORS + 1]
+    const long long base = (long long)blockIdx.x * BB_ST_SENSORS;
+    const int nhere = (int)min((long long)BB_ST_SENSORS, ns - base);
+    for (int t = 0; t < nsamples; t++)
+        if ((int)threadIdx.x < nhere) st_tile[t * (BB_ST_SENSORS + 1) + threadIdx.x] = in[(long long)t * nsensors + s0 + base + threadIdx.x];
+    __syncthreads();
+    float *o = out + base * nsamples;
+    for (int e = threadIdx.x; e < nhere * nsamples; e += BB_ST_SENSORS) {
+        const int sl = e / nsamples, t = e - sl * nsamples;
+        o[e] = st_tile[t * (BB_ST_SENSORS + 1) + sl];
+    }
 }
 
 // Single-bin DFT of each sensor's trace (in: [sample][sensor]), its angle and the largest sample, scattered to the dense
@@ -140,9 +152,10 @@ __global__ void label_convert_kernel(const uint32_t *__restrict__ in, const uint
     out[r * pitch + k] = (LT)v;
 }
 
-// SourceFunctions (nsrc, nt) with row stride -> float32 [nt][nsrc]; 32x32 smem tile transpose
+// `nsrc` rows of SourceFunctions (nsrc, nt) with row stride -> float32 columns of out[nt][out_stride]; 32x32 smem tile transpose
 template <typename T>
-__global__ void srcfun_transpose_kernel(const T *__restrict__ in, long long row_stride, float *__restrict__ out, int nsrc, int nt) {
+__global__ void srcfun_transpose_kernel(const T *__restrict__ in, long long row_stride, float *__restrict__ out, int nsrc, int nt,
+                                        int out_stride) {
     __shared__ float tile[32][33];
     const int t0 = blockIdx.x * 32, s0 = blockIdx.y * 32;
     for (int r = threadIdx.y; r < 32; r += blockDim.y) {
@@ -152,7 +165,7 @@ __global__ void srcfun_transpose_kernel(const T *__restrict__ in, long long row_
     __syncthreads();
     for (int r = threadIdx.y; r < 32; r += blockDim.y) {
         const int t = t0 + r, s = s0 + threadIdx.x;
-        if (t < nt && s < nsrc) out[(long long)t * nsrc + s] = tile[threadIdx.x][r];
+        if (t < nt && s < nsrc) out[(long long)t * out_stride + s] = tile[threadIdx.x][r];
     }
 }
 
@@ -169,12 +182,13 @@ __global__ void finalize_map_kernel(const float *__restrict__ in, float *__restr
     out[t] = v;
 }
 
+// rows [r0, r0 + nrows) of the owned planes
 template <typename LT>
-__global__ void finalize_pressure_kernel(const DevParams p, float *__restrict__ out, long long nrows) {
+__global__ void finalize_pressure_kernel(const DevParams p, float *__restrict__ out, long long r0, long long nrows) {
     const long long t = (long long)blockIdx.x * blockDim.x + threadIdx.x;
     const long long r = t / p.n3;
     const int k = (int)(t - r * p.n3);
     if (r >= nrows) return;
-    const long long q = 2 * p.plane + r * p.pitch + k;
+    const long long q = 2 * p.plane + (r0 + r) * p.pitch + k;
     out[t] = field_value<LT>(p, BB_MAP_PRESSURE, q);
 }

@@ -90,12 +90,25 @@ __device__ __forceinline__ void mbar_arrive(uint32_t bar) {
 __device__ __forceinline__ void peer_wait(const DevParams &p, int side) {
     const unsigned long long want = p.seq - 1;                   // the neighbour's previous half-step of this epoch
     const volatile unsigned long long *f = p.flag_local + side;
+    // a neighbour can be arbitrarily late (profiler replay, sanitizer, a shared GPU): wait on the wall clock, and on a
+    // timeout flag the run as failed (bb_fdtd_run reports it) instead of trapping the context
+    unsigned long long t0 = 0;
     unsigned spins = 0;
-    while (*f < want) { if (++spins > (1u << 24)) __trap(); __nanosleep(64); }
+    while (*f < want) {
+        __nanosleep(64);
+        if ((++spins & 1023u) == 0 && p.peer_timeout_ns) {
+            unsigned long long t;
+            asm volatile("mov.u64 %0, %globaltimer;" : "=l"(t));
+            if (!t0) t0 = t;
+            else if (t - t0 > p.peer_timeout_ns) { atomicExch(p.err, 1 + side); break; }
+        }
+    }
     __threadfence();
     asm volatile("fence.proxy.async;" ::: "memory");             // the TMA unit reads what the neighbour wrote
 }
-// called by one thread of a CTA whose consumers have all finished (and fenced) their peer stores
+// Called by one thread of a CTA after a barrier of the consumer warps that stored the pushed planes.  The barrier
+// orders their peer stores before this thread; its system-scope fence then makes them visible to the neighbour GPU
+// before the count / flag writes (the "last block" pattern: fence, count, and the CTA completing the count publishes).
 __device__ __forceinline__ void peer_publish(const DevParams &p, int side, unsigned planes_pushed, unsigned expected) {
     const unsigned before = atomicAdd(p.push_count + side, planes_pushed);
     if (before + planes_pushed == expected) {
@@ -537,6 +550,22 @@ __global__ void __launch_bounds__(NTB, CTAS_PER_SM) stress_tma(const __grid_cons
         if (cellpml ? (upd_pml && !(f & TF_ILAST)) : active) {
             if (f & TF_SOLID) cell_update(std::true_type{}); else cell_update(std::false_type{});
         }
+        // ---------------- a slab-boundary plane pair of this CTA is complete: count it in right away (not at the end of
+        // the chunk -- the neighbour's next half-step waits for it); the CTA completing the count publishes the sequence
+        // number in the neighbour's flag word.  With sources injected behind this kernel the host's publish_kernel does it.
+        if (pushsel) {
+            const bool last_lo = (pushsel & 1) && i == min(ic1, p.i0 + 2) - 1;
+            const bool last_hi = (pushsel & 2) && i == ic1 - 1;
+            if ((last_lo || last_hi) && p.publish) {
+                consumer_bar();
+                if (tid == 0) {
+                    __threadfence_system();
+                    const unsigned expected = 2u * gridDim.x * gridDim.y;
+                    if (last_lo) peer_publish(p, 0, (unsigned)(min(ic1, p.i0 + 2) - ic0), expected);
+                    if (last_hi) peer_publish(p, 1, (unsigned)(ic1 - max(ic0, p.i1 - 2)), expected);
+                }
+            }
+        }
         // ---------------- this warp is done with the slots of plane i
         __syncwarp();
         if (lane0) { mbar_arrive(hb0 + MAX_NSH * 8); mbar_arrive(pbar + MAX_NSP * 8); }
@@ -545,20 +574,6 @@ __global__ void __launch_bounds__(NTB, CTAS_PER_SM) stress_tma(const __grid_cons
         if (ho2 == hend) { ho2 = 0; hb2 = fullH; hpar ^= 1u; }
         po += pstage; pbar += 8;
         if (po == pend) { po = 0; pbar = fullP; ppar ^= 1u; }
-    }
-    // ---- boundary planes pushed by this CTA: fence them system-wide, then one thread counts them in; the CTA that
-    // completes the count publishes the sequence number in the neighbour's flag word
-    // (when sources are injected after this kernel, the host launches publish_kernel behind them instead)
-    const int push_lo = p.peerS[0] ? max(0, min(ic1, p.i0 + 2) - ic0) : 0;
-    const int push_hi = p.peerS[1] ? max(0, ic1 - max(ic0, p.i1 - 2)) : 0;
-    if ((push_lo || push_hi) && p.publish) {
-        __threadfence_system();
-        consumer_bar();
-        if (tid == 0) {
-            const unsigned expected = 2u * gridDim.x * gridDim.y;
-            if (push_lo) peer_publish(p, 0, push_lo, expected);
-            if (push_hi) peer_publish(p, 1, push_hi, expected);
-        }
     }
     if (p.dbg && tid == 0) {    // tid 0 is a consumer thread: it leaves the loop when the CTA's last plane is done
         unsigned long long *d = p.dbg + 4ull * ((blockIdx.z * gridDim.y + blockIdx.y) * gridDim.x + blockIdx.x);
@@ -835,6 +850,22 @@ __global__ void __launch_bounds__(NTB, CTAS_PER_SM) particle_tma(const __grid_co
         if (cellpml ? (upd_pml && !(f & TF_ILAST)) : active) {
             if (fsh) cell_update(std::true_type{}); else cell_update(std::false_type{});
         }
+        // ---------------- a slab-boundary plane pair of this CTA is complete: count it in right away (not at the end of
+        // the chunk -- the neighbour's next half-step waits for it); the CTA completing the count publishes the sequence
+        // number in the neighbour's flag word.  With sources injected behind this kernel the host's publish_kernel does it.
+        if (pushsel) {
+            const bool last_lo = (pushsel & 1) && i == min(ic1, p.i0 + 2) - 1;
+            const bool last_hi = (pushsel & 2) && i == ic1 - 1;
+            if ((last_lo || last_hi) && p.publish) {
+                consumer_bar();
+                if (tid == 0) {
+                    __threadfence_system();
+                    const unsigned expected = 2u * gridDim.x * gridDim.y;
+                    if (last_lo) peer_publish(p, 0, (unsigned)(min(ic1, p.i0 + 2) - ic0), expected);
+                    if (last_hi) peer_publish(p, 1, (unsigned)(ic1 - max(ic0, p.i1 - 2)), expected);
+                }
+            }
+        }
         __syncwarp();
         if (lane0) { mbar_arrive(hb0 + MAX_NSH * 8); mbar_arrive(pbar + MAX_NSP * 8); }
         ho = ho1; hb0 = hb1; ho1 = ho2; hb1 = hb2;
@@ -842,19 +873,6 @@ __global__ void __launch_bounds__(NTB, CTAS_PER_SM) particle_tma(const __grid_co
         if (ho2 == hend) { ho2 = 0; hb2 = fullH; hpar ^= 1u; }
         po += pstage; pbar += 8;
         if (po == pend) { po = 0; pbar = fullP; ppar ^= 1u; }
-    }
-    // ---- boundary planes pushed by this CTA: fence them system-wide, then one thread counts them in; the CTA that
-    // completes the count publishes the sequence number in the neighbour's flag word
-    const int push_lo = p.peerV[0] ? max(0, min(ic1, p.i0 + 2) - ic0) : 0;
-    const int push_hi = p.peerV[1] ? max(0, ic1 - max(ic0, p.i1 - 2)) : 0;
-    if ((push_lo || push_hi) && p.publish) {
-        __threadfence_system();
-        consumer_bar();
-        if (tid == 0) {
-            const unsigned expected = 2u * gridDim.x * gridDim.y;
-            if (push_lo) peer_publish(p, 0, push_lo, expected);
-            if (push_hi) peer_publish(p, 1, push_hi, expected);
-        }
     }
     if (p.dbg && tid == 0) {    // tid 0 is a consumer thread: it leaves the loop when the CTA's last plane is done
         unsigned long long *d = p.dbg + 4ull * ((blockIdx.z * gridDim.y + blockIdx.y) * gridDim.x + blockIdx.x);

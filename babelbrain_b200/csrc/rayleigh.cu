@@ -80,6 +80,32 @@ __global__ void __launch_bounds__(RB) rayleigh_kernel(float k_re, float k_im, lo
 }
 }  // namespace
 
+// Device buffers, stream and events of the Rayleigh path live per device for the life of the process: the transducer
+// models call ForwardSimple many times in a row (phase programming point by point, then the whole grid;
+// BabelIntegrationANNULAR_ARRAY.py:376-420), and nothing is allocated or freed per call unless a buffer has to grow.
+#include <mutex>
+namespace {
+struct GrowBuf {
+    void *p = nullptr;
+    size_t cap = 0;
+    cudaError_t need(size_t bytes) {
+        if (bytes <= cap) return cudaSuccess;
+        if (p) { cudaFree(p); p = nullptr; cap = 0; }
+        const size_t want = bytes + bytes / 4 + 256;
+        cudaError_t e = cudaMalloc(&p, want);
+        if (e == cudaSuccess) cap = want;
+        return e;
+    }
+};
+struct RayleighCtx {
+    std::mutex mu;
+    cudaStream_t st = nullptr;
+    cudaEvent_t e0 = nullptr, e1 = nullptr;
+    GrowBuf center, ds, u0, rf, out;
+};
+RayleighCtx g_rl[64];
+}  // namespace
+
 extern "C" int bb_rayleigh_forward(float k_re, float k_im, int64_t nsrc, const float *center, const float *ds,
                                    const float *u0_reim, int64_t npts, const float *rf, float *out_reim,
                                    float max_distance, int64_t u0_step, int device, double *kernel_ms) {
@@ -87,41 +113,41 @@ extern "C" int bb_rayleigh_forward(float k_re, float k_im, int64_t nsrc, const f
     BB_REQUIRE(u0_step == 0 || u0_step == nsrc, "u0step must equal the number of sources");
     int ndev = bb_device_count();
     if (ndev <= 0) { if (ndev == 0) bb_set_error("no CUDA device (this library has no CPU fallback)"); return BB_ERR_CUDA; }
-    BB_REQUIRE(device >= 0 && device < ndev, "device %d of %d", device, ndev);
+    BB_REQUIRE(device >= 0 && device < ndev && device < 64, "device %d of %d", device, ndev);
     BB_CUDA(cudaSetDevice(device));
-    float *d_center = nullptr, *d_ds = nullptr, *d_rf = nullptr;
-    float2 *d_u0 = nullptr, *d_out = nullptr;
+    RayleighCtx &c = g_rl[device];
+    std::lock_guard<std::mutex> lock(c.mu);
+    if (!c.st) {
+        BB_CUDA(cudaStreamCreateWithFlags(&c.st, cudaStreamNonBlocking));
+        BB_CUDA(cudaEventCreate(&c.e0));
+        BB_CUDA(cudaEventCreate(&c.e1));
+    }
+    cudaStream_t st = c.st;
     const size_t nu = u0_step ? (size_t)npts * nsrc : (size_t)nsrc;
-    cudaStream_t st;
-    BB_CUDA(cudaStreamCreateWithFlags(&st, cudaStreamNonBlocking));
-    BB_CUDA(cudaMalloc(&d_center, (size_t)nsrc * 12));
-    BB_CUDA(cudaMalloc(&d_ds, (size_t)nsrc * 4));
-    BB_CUDA(cudaMalloc(&d_u0, nu * 8));
-    BB_CUDA(cudaMalloc(&d_rf, (size_t)npts * 12));
-    BB_CUDA(cudaMalloc(&d_out, (size_t)npts * 8));
+    BB_CUDA(c.center.need((size_t)nsrc * 12));
+    BB_CUDA(c.ds.need((size_t)nsrc * 4));
+    BB_CUDA(c.u0.need(nu * 8));
+    BB_CUDA(c.rf.need((size_t)npts * 12));
+    BB_CUDA(c.out.need((size_t)npts * 8));
+    float *d_center = (float *)c.center.p, *d_ds = (float *)c.ds.p, *d_rf = (float *)c.rf.p;
+    float2 *d_u0 = (float2 *)c.u0.p, *d_out = (float2 *)c.out.p;
     BB_CUDA(cudaMemcpyAsync(d_center, center, (size_t)nsrc * 12, cudaMemcpyHostToDevice, st));
     BB_CUDA(cudaMemcpyAsync(d_ds, ds, (size_t)nsrc * 4, cudaMemcpyHostToDevice, st));
     BB_CUDA(cudaMemcpyAsync(d_u0, u0_reim, nu * 8, cudaMemcpyHostToDevice, st));
     BB_CUDA(cudaMemcpyAsync(d_rf, rf, (size_t)npts * 12, cudaMemcpyHostToDevice, st));
-    cudaEvent_t e0, e1;
-    BB_CUDA(cudaEventCreate(&e0));
-    BB_CUDA(cudaEventCreate(&e1));
     const unsigned grid = (unsigned)((npts + (long long)RB * PPT - 1) / ((long long)RB * PPT));
     const bool att = k_im != 0.f, maxd = max_distance > 0.f, pp = u0_step != 0;
-    BB_CUDA(cudaEventRecord(e0, st));
+    BB_CUDA(cudaEventRecord(c.e0, st));
 #define BB_RL(A, M, Q) rayleigh_kernel<A, M, Q><<<grid, RB, 0, st>>>(k_re, k_im, nsrc, d_center, d_ds, d_u0, npts, d_rf, d_out, max_distance)
     if (pp) { if (att) { if (maxd) BB_RL(true, true, true); else BB_RL(true, false, true); } else { if (maxd) BB_RL(false, true, true); else BB_RL(false, false, true); } }
     else { if (att) { if (maxd) BB_RL(true, true, false); else BB_RL(true, false, false); } else { if (maxd) BB_RL(false, true, false); else BB_RL(false, false, false); } }
 #undef BB_RL
     BB_CUDA(cudaGetLastError());
-    BB_CUDA(cudaEventRecord(e1, st));
+    BB_CUDA(cudaEventRecord(c.e1, st));
     BB_CUDA(cudaMemcpyAsync(out_reim, d_out, (size_t)npts * 8, cudaMemcpyDeviceToHost, st));
     BB_CUDA(cudaStreamSynchronize(st));
     float ms = 0;
-    cudaEventElapsedTime(&ms, e0, e1);
+    BB_CUDA(cudaEventElapsedTime(&ms, c.e0, c.e1));
     if (kernel_ms) *kernel_ms = ms;
-    cudaEventDestroy(e0); cudaEventDestroy(e1);
-    cudaFree(d_center); cudaFree(d_ds); cudaFree(d_u0); cudaFree(d_rf); cudaFree(d_out);
-    cudaStreamDestroy(st);
     return BB_OK;
 }

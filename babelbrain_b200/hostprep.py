@@ -86,11 +86,14 @@ def stable_dt(MaterialProperties, SpatialStep, AlphaCFL):
     return float(AlphaCFL) * np.sqrt(3.0) / 3.0 * float(SpatialStep) / MP[:, 1].max()
 
 
-# Multi-axial PML (Meza-Fajardo & Papageorgiou, BSSA 2008): every split part is also damped by this fraction of the
-# damping of the two other axes.  The classical split-field layer (ratio 0) grows without bound where a fluid-solid
-# interface enters the layer -- on the CTX-500 label map RMS 1e6 -> 1e13 between 2544 and 5088 steps, in the CPU
-# oracle as much as on the GPU (profiles/r1_pml_stability.txt); 0.05 and 0.1 are stable over 9600 steps.
-MPML_RATIO = 0.1
+# Damping of the split parts of the absorbing layer.  0 = the classical split-field layer (every part damped along its
+# own axis only), which is what the restated scheme uses and the default.  BabelBrain always hands the solver a water
+# shell (UpdateConditions writes the tissue mask only inside the PML offsets, BabelIntegrationBASE.py:1853-1862,
+# :2154-2159), and there the classical layer is stable (9600 steps, profiles/r2_pml_stability.txt).  A label map with
+# fluid-solid interfaces *inside* the shell makes it grow without bound (profiles/r1_pml_stability.txt); for such maps
+# the public call takes MPMLRatio > 0 (0.05-0.1): the multi-axial layer of Meza-Fajardo & Papageorgiou (BSSA 2008),
+# every part also damped by that fraction of the damping of the two other axes.
+MPML_RATIO = 0.0
 
 
 def pml_table(NDelta, SpatialStep, dt, Vmax, ReflectionLimit):

@@ -29,7 +29,7 @@ class FdtdSlab:
                  QCorrection=1.0, TypeSource=0, SelRMSorPeak=1, SelMapsRMSPeakList=('ALLV',),
                  SelMapsSensorsList=('Vx', 'Vy', 'Vz'), SensorSubSampling=2, SensorStart=0,
                  ReflectorMask=None, device=0, rank=0, nranks=1, kernel_variant=0, steps=None,
-                 origin=None, n1_global=None, global_sensor_table=True):
+                 origin=None, n1_global=None, global_sensor_table=True, MPMLRatio=None):
         self._h = None
         if not isinstance(MaterialMap, np.ndarray) or MaterialMap.ndim != 3:
             raise ValueError('MaterialMap must be a 3-D numpy array')
@@ -64,6 +64,9 @@ class FdtdSlab:
         self.rms_names = [n for n in hostprep.MAP_NAMES if n in SelMapsRMSPeakList]
         self.sensor_names = [n for n in hostprep.MAP_NAMES if n in SelMapsSensorsList]
         hostprep.maps_mask(SelMapsRMSPeakList), hostprep.maps_mask(SelMapsSensorsList)
+        self.mpml_ratio = float(hostprep.MPML_RATIO if MPMLRatio is None else MPMLRatio)
+        if not 0.0 <= self.mpml_ratio <= 1.0:
+            raise ValueError('MPMLRatio must lie in [0, 1] (0 = classical split-field layer)')
         self.sel_rms_peak = int(SelRMSorPeak)
         if self.sel_rms_peak not in (1, 2, 3):
             raise ValueError('SelRMSorPeak must be 1 (RMS), 2 (peak) or 3 (both)')
@@ -132,7 +135,7 @@ class FdtdSlab:
                            sel_rms_peak=self.sel_rms_peak, sel_maps_rms=hostprep.maps_mask(self.rms_names),
                            sel_maps_sensor=hostprep.maps_mask(self.sensor_names),
                            sensor_subsampling=self.sub, sensor_start=self.sensor_start, device=int(device),
-                           rank=self.rank, nranks=self.nranks, kernel_variant=int(kernel_variant), mpml_ratio=hostprep.MPML_RATIO,
+                           rank=self.rank, nranks=self.nranks, kernel_variant=int(kernel_variant), mpml_ratio=self.mpml_ratio,
                            dt=dt)
         _t = [time.perf_counter()]
         _marks = []
@@ -435,11 +438,20 @@ def collect_results(slab):
     return Sensor, RMS, Peak, InputParam
 
 
+def release_device_state():
+    """Free the device memory the most recent simulation still holds for LastMap / CalculatePhaseDataOnDevice (it is
+    otherwise released when the next simulation starts or the process ends)."""
+    for v in _live_lastmaps:
+        v._release()
+    del _live_lastmaps[:]
+
+
 class PropagationModel:
     """Drop-in for BabelViscoFDTD.PropagationModel.PropagationModel (the two methods BabelBrain uses), plus
     CalculatePhaseDataOnDevice."""
 
     _last_slabs = ()
+    ReleaseDeviceState = staticmethod(release_device_state)
 
     def CalculatePhaseDataOnDevice(self, Frequency, MapName='Pressure'):
         """What the caller's CalculatePhaseData (BabelIntegrationBASE.py:2460-2518, forward branch) derives on the
@@ -510,22 +522,23 @@ class PropagationModel:
                                          SelMapsSensorsList=['Vx', 'Vy', 'Vz'], SensorSubSampling=2,
                                          SensorStart=0, DefaultGPUDeviceName='B200', DefaultGPUDeviceNumber=0,
                                          ReflectorMask=None, SILENT=0, ManualGroupSize=None, ManualLocalSize=None,
-                                         NumberGPUs=None, **_ignored):
+                                         NumberGPUs=None, MPMLRatio=None, **_ignored):
         """Same call as the reference.  COMPUTING_BACKEND, DefaultGPUDeviceName, USE_SINGLE and the
         manual work-group sizes are accepted for compatibility; every backend value runs the
         sm_100a CUDA path in float32 (there is no multi-backend dispatch).
 
         NumberGPUs (extension; default: environment variable BABELB200_NGPUS, else 1) cuts the domain into that
         many slabs along axis 0, one per GPU of this box, with NVLink halo exchange; the return values are the
-        same whole-grid arrays.  An unmodified BabelBrain enables it through the environment variable."""
+        same whole-grid arrays.  An unmodified BabelBrain enables it through the environment variable.
+
+        MPMLRatio (extension; default 0 = the classical split-field layer of the reference scheme): > 0 selects the
+        multi-axial layer for label maps that carry fluid-solid interfaces into the absorbing shell (hostprep.py)."""
         t0 = time.perf_counter()
         if IntervalSnapshots > 0:
             raise NotImplementedError('IntervalSnapshots is not supported (BabelBrain never passes it)')
         if SPP_ZONES != 1:
             raise NotImplementedError('superposition zones (SPP_ZONES>1) are not supported')
-        for v in _live_lastmaps:
-            v._release()
-        del _live_lastmaps[:]
+        release_device_state()
         ngpu = int(NumberGPUs if NumberGPUs is not None else os.environ.get('BABELB200_NGPUS', 1))
         if ngpu < 1:
             raise ValueError('NumberGPUs must be >= 1')
@@ -537,14 +550,14 @@ class PropagationModel:
                                             TypeSource=TypeSource, SelRMSorPeak=SelRMSorPeak,
                                             SelMapsRMSPeakList=SelMapsRMSPeakList, SelMapsSensorsList=SelMapsSensorsList,
                                             SensorSubSampling=SensorSubSampling, SensorStart=SensorStart,
-                                            ReflectorMask=ReflectorMask), DefaultGPUDeviceName, DefaultGPUDeviceNumber)
+                                            ReflectorMask=ReflectorMask, MPMLRatio=MPMLRatio), DefaultGPUDeviceName, DefaultGPUDeviceNumber)
         slab = FdtdSlab(MaterialMap, MaterialProperties, Frequency, SourceMap, SourceFunctions, SpatialStep,
                         DurationSimulation, SensorMap, Ox=Ox, Oy=Oy, Oz=Oz, AlphaCFL=AlphaCFL, NDelta=NDelta,
                         ReflectionLimit=ReflectionLimit, DT=DT, QfactorCorrection=QfactorCorrection,
                         QCorrection=QCorrection, TypeSource=TypeSource, SelRMSorPeak=SelRMSorPeak,
                         SelMapsRMSPeakList=SelMapsRMSPeakList, SelMapsSensorsList=SelMapsSensorsList,
                         SensorSubSampling=SensorSubSampling, SensorStart=SensorStart, ReflectorMask=ReflectorMask,
-                        device=(DefaultGPUDeviceName, DefaultGPUDeviceNumber))
+                        MPMLRatio=MPMLRatio, device=(DefaultGPUDeviceName, DefaultGPUDeviceNumber))
         if CheckOnlyParams:
             slab.close()
             return None
@@ -577,22 +590,37 @@ class PropagationModel:
         return Sensor, last, (RMS if kwargs['SelRMSorPeak'] == 1 else Peak), InputParam
 
 
-def _select_devices(name, number, count):
-    """`count` device ordinals for a slab-decomposed run: the devices whose name holds `name`
-    (all devices if none does), starting at the `number`-th of them."""
+def _matching_devices(name):
+    """Ordinals of the CUDA devices whose name contains `name`, like the reference's InitCuda / device selection
+    (a substring such as 'A6000' or 'B200').  An empty name or None means "any device".  A non-empty name that matches
+    nothing raises, as the reference does, unless BABELB200_ANY_DEVICE=1 asks for the old advisory behaviour (configs
+    written for another GPU, e.g. BabelBrain/default.yaml)."""
     names = _capi.device_names()
-    hits = [n for n, s in enumerate(names) if isinstance(name, str) and name and name in s] or list(range(len(names)))
-    hits = hits[min(int(number), max(len(hits) - 1, 0)):] + hits[:min(int(number), max(len(hits) - 1, 0))]
+    if not (isinstance(name, str) and name):
+        return list(range(len(names)))
+    hits = [n for n, s in enumerate(names) if name in s]
+    if not hits:
+        if os.environ.get('BABELB200_ANY_DEVICE') == '1':
+            return list(range(len(names)))
+        raise ValueError('no CUDA device whose name contains %r (visible: %s); set BABELB200_ANY_DEVICE=1 to run on any device'
+                         % (name, names))
+    return hits
+
+
+def _select_devices(name, number, count):
+    """`count` device ordinals for a slab-decomposed run: the devices whose name holds `name`, starting at the
+    `number`-th of them."""
+    hits = _matching_devices(name)
+    first = min(int(number), max(len(hits) - 1, 0))
+    hits = hits[first:] + hits[:first]
     if len(hits) < count:
-        raise ValueError('NumberGPUs=%d but only %d CUDA device(s) are visible' % (count, len(hits)))
+        raise ValueError('NumberGPUs=%d but only %d matching CUDA device(s) are visible' % (count, len(hits)))
     return hits[:count]
 
 
 def _select_device(name, number=0):
-    """Device-name substring selection like the reference's InitCuda; falls back to ordinal
-    `number` (or 0) when nothing matches -- the name is advisory on a B200 box."""
-    names = _capi.device_names()
-    hits = [n for n, s in enumerate(names) if isinstance(name, str) and name and name in s]
-    if hits:
-        return hits[min(int(number), len(hits) - 1)]
-    return min(int(number), len(names) - 1) if names else 0
+    """The `number`-th CUDA device whose name contains `name` (the last one if there are fewer)."""
+    hits = _matching_devices(name)
+    if not hits:
+        raise _capi.BabelB200Error('no CUDA device visible: babelbrain_b200 has no CPU fallback')
+    return hits[min(int(number), len(hits) - 1)]

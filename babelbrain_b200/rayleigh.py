@@ -9,15 +9,19 @@ import numpy as np
 
 from . import _capi
 
-_state = {'device': 0, 'last_kernel_ms': None}
+_state = {'device': 0, 'devices': [0], 'last_kernel_ms': None}
 
 
 def _init(deviceName='B200', **_kw):
-    """Select the CUDA device whose name contains deviceName (advisory: falls back to device 0)."""
-    names = _capi.device_names()
-    hits = [n for n, s in enumerate(names) if isinstance(deviceName, str) and deviceName in s]
-    _state['device'] = hits[0] if hits else 0
-    return names[_state['device']] if names else None
+    """Select the CUDA device(s) whose name contains deviceName, like the reference's InitCuda (an unknown name raises;
+    BABELB200_ANY_DEVICE=1 makes the name advisory).  All matching devices are remembered: ForwardSimple shards its
+    field points over the first BABELB200_NGPUS of them."""
+    from .propagation import _matching_devices
+    hits = _matching_devices(deviceName)
+    if not hits:
+        raise _capi.BabelB200Error('no CUDA device visible: babelbrain_b200 has no CPU fallback')
+    _state['device'], _state['devices'] = hits[0], hits
+    return _capi.device_names()[hits[0]]
 
 
 InitCuda = _init
@@ -26,10 +30,16 @@ InitMetal = _init
 InitMLX = _init
 
 
-def ForwardSimple(cwvnb, center, ds, u0, rf, MaxDistance=-1.0, u0step=0, MacOsPlatform='Metal', deviceMetal='B200'):
+def ForwardSimple(cwvnb, center, ds, u0, rf, MaxDistance=-1.0, u0step=0, MacOsPlatform='Metal', deviceMetal='B200',
+                  NumberGPUs=None):
     """Rayleigh integral from N_src sub-elements to N_pts field points; returns complex64 (N_pts,).
     cwvnb complex wavenumber; center (N_src,3); ds (N_src,) or (N_src,1); u0 (N_src,) complex;
-    rf (N_pts,3).  With u0step != 0, u0 holds one amplitude set per field point (N_pts*N_src)."""
+    rf (N_pts,3).  With u0step != 0, u0 holds one amplitude set per field point (N_pts*N_src).
+
+    NumberGPUs (extension; default: environment variable BABELB200_NGPUS, else 1): the field points are independent, so
+    they are cut into that many contiguous shares, one per GPU selected by InitCuda, computed concurrently (no
+    exchange step: every GPU needs all sources and only its own points)."""
+    import os
     _capi.require_gpu()
     k = complex(np.asarray(cwvnb).reshape(-1)[0])
     center = np.ascontiguousarray(center, dtype=np.float32)
@@ -45,11 +55,39 @@ def ForwardSimple(cwvnb, center, ds, u0, rf, MaxDistance=-1.0, u0step=0, MacOsPl
     elif not (ds.shape[0] == nsrc and u0.shape[0] == nsrc):
         raise ValueError('center, ds and u0 must describe the same number of sources')
     out = np.empty(npts, np.complex64)
-    ms = ctypes.c_double(0.0)
-    _capi.check(_capi.lib().bb_rayleigh_forward(k.real, k.imag, nsrc, _capi.ptr(center), _capi.ptr(ds), _capi.ptr(u0),
-                                                npts, _capi.ptr(rf), _capi.ptr(out), float(MaxDistance), int(u0step),
-                                                _state['device'], ctypes.byref(ms)))
-    _state['last_kernel_ms'] = ms.value
+    ngpu = int(NumberGPUs if NumberGPUs is not None else os.environ.get('BABELB200_NGPUS', 1))
+    devices = (_state['devices'] or [_state['device']])[:max(1, ngpu)]
+    if ngpu > len(devices):
+        raise ValueError('NumberGPUs=%d but only %d selected CUDA device(s)' % (ngpu, len(devices)))
+    L = _capi.lib()
+
+    def share(dev, lo, hi):
+        ms = ctypes.c_double(0.0)
+        u = u0 if u0step == 0 else u0[lo * nsrc:hi * nsrc]
+        _capi.check(L.bb_rayleigh_forward(k.real, k.imag, nsrc, _capi.ptr(center), _capi.ptr(ds), _capi.ptr(u),
+                                          hi - lo, _capi.ptr(rf[lo:hi]), _capi.ptr(out[lo:hi]), float(MaxDistance), int(u0step),
+                                          dev, ctypes.byref(ms)))
+        return ms.value
+    if len(devices) == 1 or npts < 4096 * len(devices):
+        _state['last_kernel_ms'] = share(devices[0], 0, npts)
+        return out
+    import threading
+    cuts = [npts * r // len(devices) for r in range(len(devices) + 1)]
+    times, errors = [0.0] * len(devices), []
+
+    def work(r):
+        try:
+            times[r] = share(devices[r], cuts[r], cuts[r + 1])
+        except BaseException as e:  # noqa: BLE001 -- re-raised in the calling thread
+            errors.append(e)
+    th = [threading.Thread(target=work, args=(r,)) for r in range(len(devices))]
+    for t in th:
+        t.start()
+    for t in th:
+        t.join()
+    if errors:
+        raise errors[0]
+    _state['last_kernel_ms'] = max(times)
     return out
 
 

@@ -77,10 +77,15 @@ def _smooth_field(rng, n1, n2, amp):
     return amp * f / max(np.abs(f).max(), 1e-9)
 
 
-def skull_labels(shape, h, pml, seed=1234, skin_depth_frac=0.14, planes=None):
+def skull_labels(shape, h, pml, seed=1234, skin_depth_frac=0.14, planes=None, tissue_in_shell=False):
     """Labels 0 water, 1 skin, 2 cortical, 3 trabecular, 4 brain: spherical shell (outer radius
     85 mm; 1.5 mm skin; 2/2/2 mm cortical/trabecular/cortical) centred below the domain, radius
-    perturbed by a smooth +-1 mm field so interfaces are not grid aligned."""
+    perturbed by a smooth +-1 mm field so interfaces are not grid aligned.
+
+    As in the caller, the absorbing shell itself is water: UpdateConditions starts from an all-zero map and writes
+    the tissue mask only into [XLOffset:-XROffset, YLOffset:-YROffset, ZLOffset:-ZROffset] with every offset >= the PML
+    thickness (BabelIntegrationBASE.py:1853-1862, :2110, :2154-2159).  tissue_in_shell=True keeps the labels in the
+    shell (a map BabelBrain never builds; used to exercise the multi-axial layer, MPMLRatio)."""
     n1, n2, n3 = shape
     rng = np.random.default_rng(seed)
     x = (np.arange(n1) - n1 / 2 + 0.5) * h
@@ -103,6 +108,13 @@ def skull_labels(shape, h, pml, seed=1234, skin_depth_frac=0.14, planes=None):
         l[r < r_out - 5.5e-3] = 2
         l[r < r_out - 7.5e-3] = 4
         lab[:, :, k0:k0 + 64] = l
+    if not tissue_in_shell:
+        glo = 0 if planes is None else planes[0]
+        gi = np.arange(glo, glo + x.size)
+        lab[(gi < pml) | (gi >= n1 - pml)] = 0
+        lab[:, :pml] = 0
+        lab[:, n2 - pml:] = 0
+        lab[:, :, n3 - pml:] = 0
     lab[:, :, :pml + 1] = 0  # BabelIntegrationBASE.py:2201
     return lab
 
@@ -134,7 +146,7 @@ CONFIGS = {
 
 
 def make_workload(name='ctx500_skull', shape=None, periods=None, seed=1234, pml=12, amplitude=1e5, planes=None, lean=False,
-                  dense_sources=True):
+                  dense_sources=True, tissue_in_shell=False):
     """Returns dict(args=tuple of the 8 positional arguments, kwargs=dict of the keyword arguments
     of StaggeredFDTD_3D_with_relaxation as BabelIntegrationBASE.py:2338-2365 passes them, meta=...).
     planes=(lo,hi): materialise only planes [lo,hi) of axis 0 of every volume (a slab with its halo, for
@@ -163,7 +175,7 @@ def make_workload(name='ctx500_skull', shape=None, periods=None, seed=1234, pml=
     if planes is not None and cfg['source'] != 'plane':
         raise ValueError('planes= is implemented for plane sources')
     lshape = (hi - lo, n2, n3)
-    MaterialMap = np.zeros(lshape, np.uint32) if cfg['medium'] == 'water' else skull_labels(cfg['shape'], h, pml, seed, planes=planes)
+    MaterialMap = np.zeros(lshape, np.uint32) if cfg['medium'] == 'water' else skull_labels(cfg['shape'], h, pml, seed, planes=planes, tissue_in_shell=tissue_in_shell)
     SourceMap = np.zeros(lshape, np.uint32)
     kw = dict(NDelta=pml, DT=dt, ReflectionLimit=1e-5, COMPUTING_BACKEND=1, USE_SINGLE=True,
               SelMapsRMSPeakList=list(cfg.get('rms_maps', ['Pressure'])), SelMapsSensorsList=['Pressure'],

@@ -137,14 +137,14 @@ def pml_tables(P, h, dt, Vmax, ReflectionLimit):
     return 1.0 / (1.0 / dt + d / 2), (1.0 / dt - d / 2), 1.0 / (1.0 / dt + dhp / 2), (1.0 / dt - dhp / 2)
 
 
-# (g') multi-axial damping.  The classical split-field layer above (each part damped along its own axis only) is
-# unstable where a fluid-solid interface runs into the layer: on the CTX-500 label map the oracle itself grows without
-# bound (e-folding ~130 steps, RMS 1e6 -> 1e13 between 2544 and 5088 steps), while the same run with the solid kept out
-# of the layer, or with the damping switched off, stays bounded.  Meza-Fajardo & Papageorgiou
-# (BSSA 2008) cure exactly this by adding a fraction of each axis' damping to the parts of the other two axes:
-#     d_eff(part of axis a) = d_a(own staggering) + MPML_RATIO * (d_b + d_c)     (d_b, d_c at integer nodes)
-# 0 gives back the classical layer.  Whether BabelViscoFDTD does the same is unknown (PARITY UNPINNED).
-MPML_RATIO = 0.1
+# (g') multi-axial damping (optional, MPMLRatio > 0).  The classical split-field layer above (each part damped along
+# its own axis only) is the default: BabelBrain's label maps are water inside the shell (BabelIntegrationBASE.py:2110,
+# :2154-2159) and there it is stable.  Where a fluid-solid interface runs INTO the layer it grows without bound
+# (e-folding ~130 steps; same map with the solid kept out of the layer, or damping off: bounded).
+# Meza-Fajardo & Papageorgiou (BSSA 2008) cure that by adding a fraction of each axis' damping to the parts of the
+# other two axes:
+#     d_eff(part of axis a) = d_a(own staggering) + ratio * (d_b + d_c)     (d_b, d_c at integer nodes)
+MPML_RATIO = 0.0
 
 
 def pml_damping(P, h, Vmax, ReflectionLimit):

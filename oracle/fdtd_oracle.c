@@ -372,3 +372,11 @@ int oracle_num_threads(void) {
     return 1;
 #endif
 }
+/* torch.distributed.run exports OMP_NUM_THREADS=1 to its children; the CPU baseline asks for the host's cores explicitly */
+void oracle_set_threads(int n) {
+#ifdef _OPENMP
+    if (n > 0) omp_set_num_threads(n);
+#else
+    (void)n;
+#endif
+}

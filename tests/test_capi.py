@@ -141,3 +141,46 @@ def test_host_scatter_rows_places_slab_rows(lib):
     assert np.array_equal(out, ref)
     assert lib.bb_host_scatter_rows(p(out), p(rows), p(data), 0, 40) == 0
     assert lib.bb_host_scatter_rows(None, p(rows), p(data), 3, 40) != 0
+
+
+def test_pinned_pool_is_thread_safe():
+    """The per-GPU threads of a slab-decomposed run allocate result buffers concurrently and finalizers give blocks back
+    from any thread: no block may ever back two live arrays.  Ordinary memory stands in for page-locked
+    memory, so this runs without a device."""
+    import gc
+    import threading
+
+    class Block:
+        def __init__(self, nbytes):
+            self.buf = (ctypes.c_char * nbytes)()
+            self.ptr, self.nbytes = ctypes.addressof(self.buf), nbytes
+
+        def release(self):
+            self.ptr = None
+
+    pool = _capi.PinnedPool(max_idle_bytes=64 << 20, block_type=Block)
+    errors = []
+
+    def hammer(seed):
+        rng = np.random.default_rng(seed)
+        try:
+            for it in range(300):
+                sizes = rng.integers(1, 5000, 4)
+                arrs = [pool.empty((int(n),), np.int64) for n in sizes]
+                for t, a in enumerate(arrs):
+                    a[:] = seed * 1000003 + it * 7 + t
+                for t, a in enumerate(arrs):
+                    if not (a == seed * 1000003 + it * 7 + t).all():
+                        errors.append('two live arrays share a block')
+                del arrs
+        except Exception as e:  # noqa: BLE001
+            errors.append(repr(e))
+    th = [threading.Thread(target=hammer, args=(s,)) for s in range(8)]
+    for t in th:
+        t.start()
+    for t in th:
+        t.join()
+    gc.collect()
+    assert not errors, errors[:3]
+    assert pool.hits > 0 and len(set(id(b) for b in pool.idle)) == len(pool.idle)
+    assert pool.idle_bytes == sum(b.nbytes for b in pool.idle)

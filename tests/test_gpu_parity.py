@@ -278,12 +278,130 @@ def test_public_call_on_two_gpus_returns_the_single_gpu_arrays(monkeypatch):
         PM.StaggeredFDTD_3D_with_relaxation(*w['args'], NumberGPUs=64, **w['kwargs'])
 
 
-def test_long_run_with_the_skull_inside_the_layer_stays_bounded_and_matches_the_oracle():
-    """100 periods of the case the classical split-field layer cannot survive (tests/test_oracle.py): the CUDA path
-    stays at the steady state and still agrees with the oracle after 4800 steps."""
-    w = workloads.make_workload('ctx500_skull', shape=(40, 36, 56), periods=100, pml=6)
-    (Sensor, RMS, _, _), _ = run_cuda(w)
-    ref = run_oracle(w)
-    assert float(RMS['Pressure'].max()) < 2e6
+@pytest.mark.parametrize('ratio,tissue_in_shell', [(0.0, False), (0.1, True), (0.05, False)])
+def test_long_run_stays_bounded_and_matches_the_oracle_for_both_layers(ratio, tissue_in_shell):
+    """100 periods (4800 steps).  MPMLRatio 0 -- the classical split-field layer, the default -- on the caller's kind
+    of map (water inside the shell, BabelIntegrationBASE.py:2154-2159); the multi-axial layer on the map the classical
+    one cannot survive (tissue inside the shell, tests/test_oracle.py).  Both stay at the steady state and agree with
+    the oracle run at the same ratio."""
+    w = workloads.make_workload('ctx500_skull', shape=(40, 36, 56), periods=100, pml=6, tissue_in_shell=tissue_in_shell)
+    (Sensor, RMS, _, _), _ = run_cuda(w, MPMLRatio=ratio)
+    ref = run_oracle(w, MPMLRatio=ratio)
+    assert float(RMS['Pressure'].max()) < 3e6
     assert rl2(RMS['Pressure'], ref['RMS']['Pressure']) <= TOL and same_peak(RMS['Pressure'], ref['RMS']['Pressure'])
     assert rl2(Sensor['Pressure'], ref['Sensor']['Pressure']) <= TOL
+
+
+def test_mpml_ratio_through_the_public_call():
+    """MPMLRatio is a keyword of the public call (default 0 = classical layer); both layers against the oracle on a
+    short run of a map with tissue inside the shell, where they differ at the 1e-2 level."""
+    w = workloads.make_workload('ctx500_skull', shape=(48, 40, 64), periods=8, pml=8, tissue_in_shell=True)
+    PM = PropagationModel()
+    maps = {}
+    for ratio in (None, 0.0, 0.1):
+        kw = dict(w['kwargs']) if ratio is None else dict(w['kwargs'], MPMLRatio=ratio)
+        _, _, RMS, _ = PM.StaggeredFDTD_3D_with_relaxation(*w['args'], **kw)
+        ref = run_oracle(w, MPMLRatio=0.0 if ratio is None else ratio)
+        assert rl2(RMS['Pressure'], ref['RMS']['Pressure']) <= TOL, ratio
+        maps[ratio] = np.array(RMS['Pressure'])
+    assert np.array_equal(maps[None], maps[0.0])
+    assert rl2(maps[0.1], maps[0.0]) > 1e-3
+    with pytest.raises(ValueError):
+        PM.StaggeredFDTD_3D_with_relaxation(*w['args'], **dict(w['kwargs'], MPMLRatio=-0.5))
+
+
+def test_full_size_ctx500_properties():
+    """BASELINE configs[1] at full size (240x240x320, 2544 steps), where the oracle is too slow to be the
+    checker: size-independent properties instead.  Linear in the source amplitude, zero RMS inside the PML
+    shell, sensor table = every voxel of the sensor box in IndexSensorMap order, p == -Sigmaxx wherever the
+    wave has only crossed lossless water, finite everywhere."""
+    w = workloads.make_workload('ctx500_skull')
+    over = dict(SelMapsRMSPeakList=['Pressure', 'Sigmaxx'])
+    (S1, R1, _, IP), _ = run_cuda(w, 0, **over)
+    p = R1['Pressure']
+    assert p.shape == (240, 240, 320) and np.isfinite(p).all() and np.isfinite(S1['Pressure']).all()
+    pml = w['meta']['pml']
+    assert not p[:pml].any() and not p[-pml:].any() and not p[:, :pml].any() and not p[:, :, -pml:].any()
+    assert p[pml:-pml, pml:-pml, pml + 1:-pml].min() > 0
+    n1, n2, n3 = p.shape
+    assert IP['IndexSensorMap'].size == (n1 - 2 * pml) * (n2 - 2 * pml) * (n3 - 2 * pml - 1)
+    assert S1['Pressure'].shape == (IP['IndexSensorMap'].size, 2 * w['meta']['ppp'] // w['meta']['sub'])
+    assert np.all(np.diff(IP['IndexSensorMap'].astype(np.int64)) > 0)
+    # in front of the skull the medium is lossless water: pressure and -Sigmaxx coincide there
+    water = (w['args'][0][pml:-pml, pml:-pml, pml + 1:pml + 24] == 0).all()
+    assert water
+    assert rl2(R1['Pressure'][pml:-pml, pml:-pml, pml + 1:pml + 20], R1['Sigmaxx'][pml:-pml, pml:-pml, pml + 1:pml + 20]) <= 1e-4
+    args = list(w['args'])
+    args[4] = args[4] * 0.5
+    (S2, R2, _, _), _ = run_cuda(dict(args=tuple(args), kwargs=w['kwargs']), 0, **over)
+    assert rl2(R2['Pressure'], 0.5 * p.astype(np.float64)) <= 1e-5
+    assert rl2(S2['Pressure'], 0.5 * S1['Pressure'].astype(np.float64)) <= 1e-5
+
+
+def test_rayleigh_variants_against_oracle():
+    """ForwardSimple as the transducer files call it: whole-grid fields, single points (phase programming,
+    BabelIntegrationANNULAR_ARRAY.py:383), attenuating wavenumber, MaxDistance, per-point amplitudes (u0step)."""
+    from BabelViscoFDTD.tools.RayleighAndBHTE import ForwardSimple, InitCuda
+    InitCuda('B200')
+    rng = np.random.default_rng(21)
+    nsrc = 700
+    center = (rng.random((nsrc, 3)).astype(np.float32) - 0.5) * 0.05
+    center[:, 2] = -0.04 - 0.01 * rng.random(nsrc).astype(np.float32)
+    ds = np.full((nsrc, 1), 3e-6, np.float32)
+    u0 = (rng.random(nsrc) + 1j * rng.random(nsrc)).astype(np.complex64)
+    k0 = 2 * np.pi * 7e5 / 1500
+    for npts in (1, 128, 5000):
+        rf = (rng.random((npts, 3)).astype(np.float32) - 0.5) * 0.06
+        rf[:, 2] = rng.random(npts).astype(np.float32) * 0.08
+        for k in (k0 + 0j, k0 - 4.0j):
+            got = ForwardSimple(np.array(k).astype(np.complex64), center, ds, u0, rf)
+            ref = oracle.rayleigh_numpy(np.complex64(k), center, ds, u0, rf)
+            assert got.dtype == np.complex64 and got.shape == (npts,)
+            # a single point is an ill-conditioned sum (700 random phases cancel): float32 itself is at 3e-5 there
+            assert rl2(got, ref) <= (TOL if npts > 1 else 2 * TOL), (npts, k, rl2(got, ref))
+        got = ForwardSimple(np.array(k0 + 0j).astype(np.complex64), center, ds, u0, rf, MaxDistance=0.07)
+        ref = oracle.rayleigh_numpy(np.complex64(k0), center, ds, u0, rf, MaxDistance=0.07)
+        assert rl2(got, ref) <= TOL
+    # per-point source amplitudes
+    npts = 64
+    rf = (rng.random((npts, 3)).astype(np.float32) - 0.5) * 0.06
+    u0pp = (rng.random((npts, nsrc)) + 1j * rng.random((npts, nsrc))).astype(np.complex64)
+    got = ForwardSimple(np.array(k0 + 0j).astype(np.complex64), center, ds, u0pp.reshape(-1), rf, u0step=nsrc)
+    ref = np.array([oracle.rayleigh_numpy(np.complex64(k0), center, ds, u0pp[n], rf[n:n + 1])[0] for n in range(npts)])
+    assert rl2(got, ref) <= TOL
+    with pytest.raises(ValueError):
+        ForwardSimple(np.array(k0 + 0j).astype(np.complex64), center, ds[:-1], u0, rf)
+
+
+def test_edge_cases_empty_sources_sensors_peak_only_short_pulse():
+    """Empty and ragged inputs: no source voxel, no sensor voxel, peak-only maps, a pulse table shorter than
+    the run (the source stops, BabelIntegrationSingle.py:315-316), DT=None (stable step), odd sizes that are
+    not multiples of the 8 x 64 tile, CheckOnlyParams."""
+    w = workloads.make_workload('ctx500_skull', shape=(37, 43, 67), periods=4, pml=5)
+    MM, ML, f, SM, SF, h, T, SEN = w['args']
+    kw = {k: v for k, v in w['kwargs'].items() if k not in DROP}
+    # no sources: everything stays exactly zero
+    s = FdtdSlab(MM, ML, f, np.zeros_like(SM), SF, h, T, SEN, **kw)
+    s.run()
+    Sensor, RMS, Peak, IP = collect_results(s)
+    s.close()
+    assert not RMS['Pressure'].any() and not Sensor['Pressure'].any()
+    # no sensors: empty table with the right number of columns
+    (S0, R0, _, IP0), _ = run_cuda(dict(args=(MM, ML, f, SM, SF, h, T, np.zeros_like(SEN)), kwargs=w['kwargs']), 0)
+    assert S0['Pressure'].shape == (0, S0['time'].size) and IP0['IndexSensorMap'].size == 0
+    ref = run_oracle(w)
+    assert rl2(R0['Pressure'], ref['RMS']['Pressure']) <= TOL
+    # peak only
+    (S2, _, P2, _), _ = run_cuda(w, 0, SelRMSorPeak=2)
+    refp = run_oracle(w, SelRMSorPeak=2)
+    assert rl2(P2['Pressure'], refp['Peak']['Pressure']) <= TOL
+    r4 = PropagationModel().StaggeredFDTD_3D_with_relaxation(*w['args'], **dict(w['kwargs'], SelRMSorPeak=2))
+    assert len(r4) == 4 and rl2(r4[2]['Pressure'], refp['Peak']['Pressure']) <= TOL
+    # pulse shorter than the run, and the solver's own stable step
+    short = SF[:, :SF.shape[1] // 2]
+    w3 = dict(args=(MM, ML, f, SM, short, h, T, SEN), kwargs=dict(w['kwargs'], DT=None, AlphaCFL=0.8, SensorStart=4))   # 0.8: inside the O(2,4) stability limit 6/7
+    (S3, R3, _, _), _ = run_cuda(w3, 0)
+    ref3 = run_oracle(w3)
+    assert S3['time'].size == ref3['Sensor']['time'].size
+    assert rl2(R3['Pressure'], ref3['RMS']['Pressure']) <= TOL and rl2(S3['Pressure'], ref3['Sensor']['Pressure']) <= TOL
+    assert PropagationModel().StaggeredFDTD_3D_with_relaxation(*w['args'], **dict(w['kwargs'], CheckOnlyParams=True)) is None

@@ -54,7 +54,7 @@ def test_pml_table_and_steps():
     # the classical coefficients follow from the damping (oracle/fdtd_numpy.py: pml_tables)
     inv, dx, invh, dxh = fdtd_numpy.pml_tables(P, h, dt, 2476.0, 1e-5)
     assert np.allclose(inv, 1 / (1 / dt + t[0] / 2)) and np.allclose(dxh, 1 / dt - t[1] / 2)
-    assert hostprep.MPML_RATIO == fdtd_numpy.MPML_RATIO == 0.1
+    assert hostprep.MPML_RATIO == fdtd_numpy.MPML_RATIO == 0.0      # classical split-field layer by default
     # TimeSimulation = dt*steps must give back `steps` despite floating point (BabelIntegrationBASE.py:2089)
     for steps in (720, 2544, 5616, 11250):
         assert hostprep.number_of_steps(dt * steps, dt) == steps
