@@ -81,9 +81,29 @@ def material_table(MaterialProperties, Frequency, QfactorCorrection, SpatialStep
     return T, dict(QL=QL, QS=QS, cLr=cLr, cSr=cSr)
 
 
+# Courant number of the O(2,4) staggered scheme at its stability limit in 3-D, relative to h/(sqrt(3) c):
+# 1/(9/8 + 1/24) = 6/7.
+CFL_LIMIT_O24 = 6.0 / 7.0
+
+
 def stable_dt(MaterialProperties, SpatialStep, AlphaCFL):
+    """Stable time step: min(AlphaCFL, 6/7) * (sqrt(3)/3) * h / max c_L.
+
+    The linear part is pinned by the caller: with AlphaCFL = 0.5 (BabelIntegrationBASE.py:934) it reproduces the awkward
+    points-per-period the caller special-cases (47 for cortical bone at 500 kHz and 6 PPW, 71 at 9 PPW, :1811-1824).
+    The limit at 6/7 -- the largest Courant fraction at which the fourth-order scheme is stable at all -- is pinned by
+    the caller's second use of this function, the water-only step at AlphaCFL = 1.0 (:1801) that normalises its
+    dispersion-correction polynomial (:1674, :2433-2440): only with (6/7) h/(sqrt(3) c) there does the corrected FDTD
+    amplitude agree with the Rayleigh integral in water as the reference's own 309-case comparison records it
+    (OfflineBatchExamples/CompareRayleightWithFDTD/SummaryAnalysis.xlsx: +0.1 ... +0.9 % at the peak; an uncapped
+    step gives -14 %, tests/test_reference_caller.py).  [Recalled scheme corrected by in-tree evidence; DESIGN.md 2.]"""
     MP = np.atleast_2d(np.asarray(MaterialProperties, dtype=np.float64))
-    return float(AlphaCFL) * np.sqrt(3.0) / 3.0 * float(SpatialStep) / MP[:, 1].max()
+    return min(float(AlphaCFL), CFL_LIMIT_O24) * np.sqrt(3.0) / 3.0 * float(SpatialStep) / MP[:, 1].max()
+
+
+def hard_limit_dt(MaterialProperties, SpatialStep):
+    """The step above which the scheme is certainly unstable (the O(2,4) limit for the fastest material)."""
+    return stable_dt(MaterialProperties, SpatialStep, CFL_LIMIT_O24)
 
 
 # Damping of the split parts of the absorbing layer.  0 = the classical split-field layer (every part damped along its

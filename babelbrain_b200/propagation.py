@@ -54,8 +54,15 @@ class FdtdSlab:
             dt = dt_ideal
         else:
             dt = float(DT)
+            # the reference only warns when the manual step exceeds the one it would choose; beyond the stability
+            # limit of the scheme itself the run can only diverge, which is reported before any device work
+            if dt > hostprep.hard_limit_dt(MP, h) * (1.0 + 1e-9):
+                raise ValueError('Staggered:DT_INVALID: DT %g is above the stability limit %g of the O(2,4) scheme'
+                                 % (dt, hostprep.hard_limit_dt(MP, h)))
             if dt > dt_ideal * (1.0 + 1e-9):
-                raise ValueError('Staggered:DT_INVALID: DT %g is larger than the stable step %g' % (dt, dt_ideal))
+                import warnings
+                warnings.warn('Staggered:DT_INVALID The specified manual step is larger than the minimal optimal size, '
+                              'there is a risk of unstable calculation %g,%g' % (dt, dt_ideal))
         self.dt = dt
         self.steps = hostprep.number_of_steps(DurationSimulation, dt) if steps is None else int(steps)
         self.sub = int(SensorSubSampling)

@@ -109,8 +109,12 @@ def material_tables(MaterialProperties, Frequency, QfactorCorrection, h, QCorrec
 
 
 def ideal_dt(MaterialProperties, h, AlphaCFL):
-    """(c) dt_ideal = AlphaCFL * (sqrt(3)/3) * h / max cL."""
-    return AlphaCFL * np.sqrt(3.0) / 3.0 * h / np.max(np.asarray(MaterialProperties, float)[:, 1])
+    """(c) dt_ideal = min(AlphaCFL, 6/7) * (sqrt(3)/3) * h / max cL.  The linear part reproduces the caller's special-cased
+    points-per-period (BabelIntegrationBASE.py:1811-1824); the cap at the O(2,4) stability limit 6/7 = 1/(9/8 + 1/24) is
+    what makes the caller's water-only normalisation step (AlphaCFL = 1.0, :1801) and its dispersion-correction
+    polynomial (:1674) reproduce the FDTD-vs-Rayleigh agreement recorded in SummaryAnalysis.xlsx
+    (tests/test_reference_caller.py)."""
+    return min(float(AlphaCFL), 6.0 / 7.0) * np.sqrt(3.0) / 3.0 * h / np.max(np.asarray(MaterialProperties, float)[:, 1])
 
 
 def calculate_matrices_for_propagation(MaterialMap, MaterialProperties, Frequency,

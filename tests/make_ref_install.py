@@ -1,0 +1,30 @@
+"""Places an unmodified copy of the reference's TranscranialModeling package under baseline/_ref/ (git-ignored, so it never
+enters the repository history; not gpurun-ignored, so it travels to the GPU box, where /root/reference does not exist).
+tests/test_reference_caller.py imports the reference caller from there.  __graft_entry__.build() runs this whenever
+/root/reference is present.
+
+    python tests/make_ref_install.py
+"""
+import os
+import shutil
+import sys
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+SRC = '/root/reference/TranscranialModeling'
+DST = os.path.join(ROOT, 'baseline', '_ref', 'TranscranialModeling')
+
+
+def install():
+    if not os.path.isdir(SRC):
+        return None
+    os.makedirs(os.path.dirname(DST), exist_ok=True)
+    if os.path.isdir(DST):
+        shutil.rmtree(DST)
+    # the Python sources of the caller only: geometry tables (.mat/.csv/.h5) are not touched by the harness
+    shutil.copytree(SRC, DST, ignore=shutil.ignore_patterns('__pycache__', '*.mat', '*.h5', '*.csv', '*.stl', '*.npz'))
+    return DST
+
+
+if __name__ == '__main__':
+    print(install() or ('no reference tree at %s' % SRC))
+    sys.exit(0)

@@ -22,7 +22,7 @@ CANDIDATES = ('/root/reference', os.path.join(ROOT, 'baseline', '_ref'))
 
 
 def reference_root():
-    for c in CANDIDATES:
+    for c in ((os.environ['BB_REF_ROOT'],) if os.environ.get('BB_REF_ROOT') else CANDIDATES):
         if os.path.isfile(os.path.join(c, 'TranscranialModeling', 'BabelIntegrationBASE.py')):
             return c
     return None
@@ -143,10 +143,13 @@ def load_reference(mask, transducer='BabelIntegrationSingle'):
     return base, tx, old
 
 
-def run_cases(mask, captured, transducer='BabelIntegrationSingle', **kargs):
+def run_cases(mask, captured, transducer='BabelIntegrationSingle', patch=None, **kargs):
     """RUN_SIM().RunCases(**kargs) of the unmodified reference.  Steps 9-10 are replaced by a capture of the reference's
-    own ReturnResults(); `captured` receives 'sim' (the SimulationConditions object) and 'results'."""
+    own ReturnResults(); `captured` receives 'sim' (the SimulationConditions object) and 'results'.  patch(base, tx) may
+    replace names inside the freshly imported reference modules (the CPU test answers the solver calls with the oracle)."""
     base, tx, old_err = load_reference(mask, transducer)
+    if patch is not None:
+        patch(base, tx)
 
     def step9(self):
         return None

@@ -405,3 +405,28 @@ def test_edge_cases_empty_sources_sensors_peak_only_short_pulse():
     assert S3['time'].size == ref3['Sensor']['time'].size
     assert rl2(R3['Pressure'], ref3['RMS']['Pressure']) <= TOL and rl2(S3['Pressure'], ref3['Sensor']['Pressure']) <= TOL
     assert PropagationModel().StaggeredFDTD_3D_with_relaxation(*w['args'], **dict(w['kwargs'], CheckOnlyParams=True)) is None
+
+
+def test_full_size_ctx500_against_the_committed_oracle_reduction():
+    """BASELINE configs[1] (the benchmark workload) at FULL size, 240x240x320 and all 2544 steps, against the float64
+    C oracle's run of the same inputs (tests/golden/make_ctx500_full_golden.py, ~17 min of CPU, committed as a
+    reduction): identical peak voxel, the three RMS planes and the line through it, the norm of the whole map, every
+    97th sensor trace and index, all within the north-star tolerance."""
+    import os
+    from tests.golden import make_ctx500_full_golden as G
+    g = np.load(os.path.join(os.path.dirname(os.path.abspath(__file__)), 'golden', 'ctx500_full.npz'))
+    w = G.build_case()
+    assert str(g['digest']) == G.digest(w), 'the seeded workload generator drifted: regenerate tests/golden/ctx500_full.npz'
+    (Sensor, RMS, _, IP), _ = run_cuda(w, 0)
+    p = RMS['Pressure']
+    pk = tuple(int(x) for x in g['peak_voxel'])
+    assert tuple(int(x) for x in np.unravel_index(int(np.argmax(p)), p.shape)) == pk
+    assert abs(float(p[pk]) / float(g['peak_value']) - 1) <= TOL
+    assert rl2(p[pk[0]], g['plane_i']) <= TOL and rl2(p[:, pk[1]], g['plane_j']) <= TOL and rl2(p[:, :, pk[2]], g['plane_k']) <= TOL
+    assert rl2(p[pk[0], pk[1]], g['line_k']) <= TOL
+    assert abs(float(np.linalg.norm(p.astype(np.float64))) / float(g['rms_norm']) - 1) <= TOL
+    assert IP['IndexSensorMap'].size == int(g['nsensors'])
+    assert np.array_equal(IP['IndexSensorMap'][::G.ROW_STRIDE], g['index_rows'])
+    assert rl2(Sensor['Pressure'][::G.ROW_STRIDE], g['sensor_rows']) <= TOL
+    assert abs(float(np.linalg.norm(Sensor['Pressure'].astype(np.float64))) / float(g['sensor_norm']) - 1) <= TOL
+    assert np.allclose(Sensor['time'], g['time'], rtol=1e-12) and int(g['steps']) == w['meta']['steps']

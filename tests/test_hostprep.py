@@ -25,6 +25,11 @@ def test_material_table_matches_oracle(f, qfc):
     assert T[0, 1] == 0 and T[0, 4] == 0 and T[0, 5] == 0 and T[0, 6] == 0
     assert np.all(T[[1, 4], 1] == 0) and np.all(T[[1, 4], 4] > 0)
     assert hostprep.stable_dt(ML, h, 0.5) == pytest.approx(fdtd_numpy.ideal_dt(ML, h, 0.5), rel=1e-15)
+    # linear in AlphaCFL up to the stability limit of the O(2,4) scheme, 6/7, and capped there (the caller's water-only
+    # normalisation step asks for AlphaCFL = 1.0, BabelIntegrationBASE.py:1801)
+    assert hostprep.stable_dt(ML, h, 0.5) == pytest.approx(0.5 * np.sqrt(3) / 3 * h / ML[:, 1].max(), rel=1e-15)
+    assert hostprep.stable_dt(ML, h, 1.0) == pytest.approx(6 / 7 * np.sqrt(3) / 3 * h / ML[:, 1].max(), rel=1e-15)
+    assert hostprep.stable_dt(ML, h, 1.0) == fdtd_numpy.ideal_dt(ML, h, 0.99) == hostprep.hard_limit_dt(ML, h)
 
 
 def test_relaxation_fit_meets_q_exactly():

@@ -49,9 +49,11 @@ def band(captured):
 
 
 def check(b):
-    assert -0.03 <= b['peak_diff'] <= 0.05, b          # reference data: -0.56 % ... +3.86 %
-    assert b['l2'] <= 0.12, b                          # reference data: mean 5 %, max 24 % over whole fields
-    assert b['focal_distance_mm'] <= 1.5, b            # two voxels
+    # reference data for this transducer / frequency / resolution (27 cases "Single_250kHz_6PPW" of SummaryAnalysis.xlsx):
+    # peak difference +0.18 ... +2.53 % (mean +0.91 %), L2 1.9 ... 5 % (mean 3.2 %), focal maximum at the same voxel
+    assert -0.006 <= b['peak_diff'] <= 0.026, b
+    assert b['l2'] <= 0.05, b
+    assert b['focal_distance_mm'] <= 0.8, b            # one voxel
 
 
 @needs_ref
@@ -73,18 +75,11 @@ def test_unmodified_caller_with_the_oracle_behind_the_solver_call():
         return oracle.rayleigh_c(cwvnb, center, ds, u0, rf)
 
     cap = {}
-    mask = refcaller.water_mask()
-    base, tx, old = refcaller.load_reference(mask)
-    np.seterr(**old)
-    import babelbrain_b200.propagation as prop
-    orig = prop.PropagationModel.StaggeredFDTD_3D_with_relaxation
-    prop.PropagationModel.StaggeredFDTD_3D_with_relaxation = lambda self, *a, **k: solver(*a, **k)
-    try:
-        import TranscranialModeling.BabelIntegrationSingle as single
-        single.ForwardSimple = forward_simple
-        refcaller.run_cases(mask, cap, reload=False, COMPUTING_BACKEND=0, **KARGS)
-    finally:
-        prop.PropagationModel.StaggeredFDTD_3D_with_relaxation = orig
+
+    def patch(base, tx):
+        base.PModel.StaggeredFDTD_3D_with_relaxation = solver        # instance attribute: CalculateMatricesForPropagation stays the product's
+        tx.ForwardSimple = forward_simple
+    refcaller.run_cases(refcaller.water_mask(), cap, patch=patch, COMPUTING_BACKEND=0, **KARGS)
     # what the caller handed over: the contract of SURVEY.md 8(a) F0
     s = calls['solver']
     assert s['dtypes'] == (np.uint32, np.uint32, np.uint32) and s['NDelta'] == 12 and s['SelRMSorPeak'] == 1
