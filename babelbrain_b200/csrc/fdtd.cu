@@ -14,6 +14,7 @@
 #include "fdtd_kernels.cuh"
 #include "fdtd_direct.cuh"
 #include "fdtd_tma.cuh"
+#include "fdtd_tma2.cuh"
 #include "nccl_dyn.h"
 #include <cub/device/device_select.cuh>
 #include <thrust/iterator/counting_iterator.h>
@@ -84,7 +85,7 @@ struct bb_fdtd {
     bool materials_set = false, maps_set = false, prepared = false;
     int *d_bad = nullptr;                                 // device flag: a label outside the material table was seen
     StressMaps smaps;
-    ParticleMaps pmaps;
+    ParticleMaps pmaps, pmaps16;                           // pmaps16: boxes of the 16-row particle tiles (fdtd_tma2.cuh)
     int chunk_override = 0, chunk_tail = 1, dbg_kernel = -1;
     // NVLink halo push
     bool peer_mode = false;
@@ -250,8 +251,16 @@ static int make_map4(CUtensorMap *m, const void *base, CUtensorMapDataType dt, i
     const cuuint64_t strides[3] = { (cuuint64_t)rowpitch * esz, (cuuint64_t)planepitch * esz, (cuuint64_t)comppitch * esz };
     const cuuint32_t box[4] = { (cuuint32_t)bw, (cuuint32_t)bh, 1, (cuuint32_t)depth };
     const cuuint32_t estr[4] = { 1, 1, 1, 1 };
+    static const CUtensorMapL2promotion promo = [] {      // BB_L2PROMO=none|64|128|256 (experiments; default 128)
+        const char *e = getenv("BB_L2PROMO");
+        if (!e) return CU_TENSOR_MAP_L2_PROMOTION_L2_128B;
+        if (!strcmp(e, "none")) return CU_TENSOR_MAP_L2_PROMOTION_NONE;
+        if (!strcmp(e, "64")) return CU_TENSOR_MAP_L2_PROMOTION_L2_64B;
+        if (!strcmp(e, "256")) return CU_TENSOR_MAP_L2_PROMOTION_L2_256B;
+        return CU_TENSOR_MAP_L2_PROMOTION_L2_128B;
+    }();
     CUresult r = enc(m, dt, ncomp > 1 ? 4 : 3, const_cast<void *>(base), dims, strides, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_NONE,
-                     CU_TENSOR_MAP_L2_PROMOTION_L2_128B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+                     promo, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
     if (r != CUDA_SUCCESS) { bb_set_error("cuTensorMapEncodeTiled failed (%d) for box %dx%dx1x%d", (int)r, bw, bh, depth); return BB_ERR_CUDA; }
     return BB_OK;
 }
@@ -289,6 +298,19 @@ static int make_tensor_maps(bb_fdtd *h) {
         if ((rc = make_map4(mz, p.ZP[0], F, 4, p.zpw, p.n2, h->nown, BB_NPART, p.zpw, zpl, (long long)h->zp_floats, p.zbw, TY, depth))) return rc;
     }
     h->pmaps.xp3 = h->smaps.xp3; h->pmaps.yp3 = h->smaps.yp3; h->pmaps.zp3 = h->smaps.zp3;
+    {   // the particle kernel on 16-row tiles: same tensors, taller boxes
+        constexpr int R = 16, RH = R + 2 * HALO;
+        ParticleMaps &m = h->pmaps16;
+        if ((rc = field(&m.v3, p.V[0], 3, TX, R, 3))) return rc;
+        if ((rc = field(&m.sxx, p.S[0], 6, TX, R, 1))) return rc;
+        if ((rc = field(&m.sh2, p.S[0], 6, SW, RH, 2))) return rc;
+        if ((rc = field(&m.sh3, p.S[0], 6, SW, RH, 3))) return rc;
+        if ((rc = make_map4(&m.lab, p.lab, u8 ? CU_TENSOR_MAP_DATA_TYPE_UINT8 : CU_TENSOR_MAP_DATA_TYPE_UINT16, h->label_bytes,
+                            p.n3, p.n2, p.nloc + 1, 1, p.pitch, p.plane, 0, lw, R + 1, 1))) return rc;
+        if ((rc = make_map4(&m.xp3, p.XP[0], F, 4, p.n3, p.n2, h->nxp, BB_NPART, p.pitch, p.plane, (long long)h->xp_floats, TX, R, 3))) return rc;
+        if ((rc = make_map4(&m.yp3, p.YP[0], F, 4, p.n3, p.nyrows, h->nown, BB_NPART, p.pitch, ypl, (long long)h->yp_floats, TX, R, 3))) return rc;
+        if ((rc = make_map4(&m.zp3, p.ZP[0], F, 4, p.zpw, p.n2, h->nown, BB_NPART, p.zpw, zpl, (long long)h->zp_floats, p.zbw, R, 3))) return rc;
+    }
     if (p.acc_rms) { if ((rc = make_map4(&h->smaps.acc, p.acc_rms, F, 4, p.n3, p.n2, h->nown, 1, p.pitch, p.plane, 0, TX, TY, 1))) return rc; }
     else h->smaps.acc = h->smaps.pr;
     return BB_OK;
@@ -414,7 +436,7 @@ static int fdtd_create_body(bb_fdtd *h, const bb_fdtd_desc *d) {
         const double sec = e ? atof(e) : 60.0;
         p.peer_timeout_ns = sec > 0 ? (unsigned long long)(sec * 1e9) : 0ull;
     }
-    if (d->kernel_variant == 0 && (rc = make_tensor_maps(h))) return rc;
+    if (d->kernel_variant != 1 && (rc = make_tensor_maps(h))) return rc;
     BB_CUDA(cudaStreamSynchronize(h->stream));
     return BB_OK;
 }
@@ -876,7 +898,7 @@ static int map_peer(bb_fdtd *h, const bb_peer_info *nb, int side) {
 
 extern "C" int bb_fdtd_peer_attach(bb_fdtd *h, const bb_peer_info *lower, const bb_peer_info *upper) {
     BB_REQUIRE(h, "null handle");
-    BB_REQUIRE(h->d.kernel_variant == 0, "the NVLink halo push needs the default kernels");
+    BB_REQUIRE(h->d.kernel_variant != 1, "the NVLink halo push needs the TMA kernels (variant 0 or 2)");
     BB_REQUIRE((lower != nullptr) == (h->d.rank > 0) && (upper != nullptr) == (h->d.rank < h->d.nranks - 1),
                "rank %d of %d needs exactly its existing neighbours", h->d.rank, h->d.nranks);
     BB_CUDA(cudaSetDevice(h->d.device));
@@ -910,10 +932,10 @@ struct Timer {
 // Plane ranges of the CTAs of one launch over the planes [ib, ie).  One CTA per SM is resident; chunks are as long
 // as the flag table allows (64 planes), and the last one is split into pieces of halving length (>= 6 planes) so
 // that the final, partially filled wave costs a few planes instead of a whole chunk.
-static ChunkPlan make_chunk_plan(const bb_fdtd *h, int ib, int ie) {
+static ChunkPlan make_chunk_plan(const bb_fdtd *h, int ib, int ie, int tile_rows = tma::TY) {
     ChunkPlan pl;
     const int nplanes = ie - ib;
-    const int tiles = h->p.ntk * h->p.ntj;
+    const int tiles = h->p.ntk * ((h->p.n2 + tile_rows - 1) / tile_rows);
     int chunk;
     if (h->chunk_override > 0) chunk = h->chunk_override;
     else {
@@ -962,6 +984,13 @@ static int prepare_kernels() {
     if ((rc = set_smem(tma::stress_tma<LT, 2>, tma::SMEM_BYTES))) return rc;
     if ((rc = set_smem(tma::particle_tma<LT, 0>, tma::SMEM_BYTES))) return rc;
     if ((rc = set_smem(tma::particle_tma<LT, 2>, tma::SMEM_BYTES))) return rc;
+    if ((rc = set_smem(tma::stress_tma2<LT, 0>, tma::SMEM_BYTES))) return rc;
+    if ((rc = set_smem(tma::stress_tma2<LT, 1>, tma::SMEM_BYTES))) return rc;
+    if ((rc = set_smem(tma::stress_tma2<LT, 2>, tma::SMEM_BYTES))) return rc;
+    if ((rc = set_smem(tma::particle_tma2<LT, 0, 8>, tma::SMEM_BYTES))) return rc;
+    if ((rc = set_smem(tma::particle_tma2<LT, 2, 8>, tma::SMEM_BYTES))) return rc;
+    if ((rc = set_smem(tma::particle_tma2<LT, 0, 16>, tma::SMEM_BYTES))) return rc;
+    if ((rc = set_smem(tma::particle_tma2<LT, 2, 16>, tma::SMEM_BYTES))) return rc;
     return BB_OK;
 }
 
@@ -982,21 +1011,38 @@ static int launch_half_step(bb_fdtd *h, bool stress, int acc_mode, int ib, int i
             else direct::particle_direct<LT, false><<<grid, blk, 0, h->stream>>>(p, ib);
         }
     } else {
-        const ChunkPlan plan = given ? *given : make_chunk_plan(h, ib, ie);
+        const int variant = h->d.kernel_variant;
+        const bool p16 = !stress && variant == 3;                 // particle half-step on 16-row tiles, two cells per thread
+        const ChunkPlan plan = given ? *given : make_chunk_plan(h, ib, ie, p16 ? 16 : tma::TY);
         DevParams p = h->p;       // per-launch copy: the sequence number of this half-step for the NVLink halo push
         p.seq = half_step_seq(h, stress);
         p.publish = publish_in_kernel ? 1 : 0;
         if (h->dbg_kernel >= 0 && h->dbg_kernel != (stress ? 0 : 1)) p.dbg = nullptr;   // BB_CTA_TIMING=stress|particle
-        const dim3 blk(tma::NTB, 1, 1), grid(p.ntk, p.ntj, plan.n);
-        if (stress) {
-            const int sm = tma::SMEM_BYTES;
-            if (acc_mode == 1) tma::stress_tma<LT, 1><<<grid, blk, sm, h->stream>>>(h->smaps, p, plan);
-            else if (acc_mode == 2) tma::stress_tma<LT, 2><<<grid, blk, sm, h->stream>>>(h->smaps, p, plan);
-            else tma::stress_tma<LT, 0><<<grid, blk, sm, h->stream>>>(h->smaps, p, plan);
+        const int sm = tma::SMEM_BYTES;
+        if (p16) {
+            const dim3 grid(p.ntk, (p.n2 + 15) / 16, plan.n), blk(tma::PT<16>::NTB, 1, 1);
+            if (acc_mode) tma::particle_tma2<LT, 2, 16><<<grid, blk, sm, h->stream>>>(h->pmaps16, p, plan);
+            else tma::particle_tma2<LT, 0, 16><<<grid, blk, sm, h->stream>>>(h->pmaps16, p, plan);
+        } else if (variant == 2) {      // two cells per thread on the 8-row tiles (fdtd_tma2.cuh)
+            const dim3 grid(p.ntk, p.ntj, plan.n), blk(tma::NTB2, 1, 1);
+            if (stress) {
+                if (acc_mode == 1) tma::stress_tma2<LT, 1><<<grid, blk, sm, h->stream>>>(h->smaps, p, plan);
+                else if (acc_mode == 2) tma::stress_tma2<LT, 2><<<grid, blk, sm, h->stream>>>(h->smaps, p, plan);
+                else tma::stress_tma2<LT, 0><<<grid, blk, sm, h->stream>>>(h->smaps, p, plan);
+            } else {
+                if (acc_mode) tma::particle_tma2<LT, 2, 8><<<grid, blk, sm, h->stream>>>(h->pmaps, p, plan);
+                else tma::particle_tma2<LT, 0, 8><<<grid, blk, sm, h->stream>>>(h->pmaps, p, plan);
+            }
         } else {
-            const int sm = tma::SMEM_BYTES;
-            if (acc_mode) tma::particle_tma<LT, 2><<<grid, blk, sm, h->stream>>>(h->pmaps, p, plan);
-            else tma::particle_tma<LT, 0><<<grid, blk, sm, h->stream>>>(h->pmaps, p, plan);
+            const dim3 grid(p.ntk, p.ntj, plan.n), blk(tma::NTB, 1, 1);
+            if (stress) {
+                if (acc_mode == 1) tma::stress_tma<LT, 1><<<grid, blk, sm, h->stream>>>(h->smaps, p, plan);
+                else if (acc_mode == 2) tma::stress_tma<LT, 2><<<grid, blk, sm, h->stream>>>(h->smaps, p, plan);
+                else tma::stress_tma<LT, 0><<<grid, blk, sm, h->stream>>>(h->smaps, p, plan);
+            } else {
+                if (acc_mode) tma::particle_tma<LT, 2><<<grid, blk, sm, h->stream>>>(h->pmaps, p, plan);
+                else tma::particle_tma<LT, 0><<<grid, blk, sm, h->stream>>>(h->pmaps, p, plan);
+            }
         }
     }
     tm.end();
@@ -1063,7 +1109,7 @@ static int half_step(bb_fdtd *h, bool stress, int n, int acc, Timer &tm) {
         // inputs of this half-step: halos sent during the previous half-step
         BB_CUDA(cudaStreamWaitEvent(h->stream, h->ev_halo, 0));
         // the two boundary plane pairs in one launch (variant 0), so their results can leave while the interior runs
-        if (h->d.kernel_variant == 0) {
+        if (h->d.kernel_variant != 1) {
             ChunkPlan edge;
             edge.n = 2;
             edge.start[0] = p.i0; edge.end[0] = p.i0 + 2; edge.start[1] = p.i1 - 2; edge.end[1] = p.i1;

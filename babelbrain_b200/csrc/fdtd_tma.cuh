@@ -34,7 +34,7 @@ namespace tma {
 constexpr int TX = 64, TY = BB_TY, HALO = 2;
 // other tile heights (BB_TILE_ROWS 9, 10: +3 % when last measured) have not been re-validated since the compact ring stages
 // and the k-PML thread remap went in -- builds with 10 and 12 rows faulted on a B200 -- so they do not compile for now
-static_assert(TY == 8, "only 8-row tiles are validated");
+static_assert(TY == 8 || TY == 12, "tile heights other than 8 and 12 rows are not validated");
 // the innermost TMA coordinate must be a multiple of 16 bytes (measured: a box starting at k0-2
 // raises an illegal-instruction fault), so halo boxes start at k0-4 and are TX+8 floats wide
 constexpr int HK = 4;
@@ -64,10 +64,24 @@ __device__ __forceinline__ void mbar_init(uint32_t bar, int count) {
 __device__ __forceinline__ void mbar_expect_tx(uint32_t bar, uint32_t bytes) {
     asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(bar), "r"(bytes) : "memory");
 }
+// BB_WAIT_HINT_NS > 0: the try_wait may park the thread in hardware for up to that many nanoseconds before it reports
+// "not yet", instead of the default (shorter) limit -- fewer trips round the spin loop for a warp that is ahead of its data
+// BB_SKELETON (profiling builds only): 1 = waits and arrives without the cell update, 2 = + the loads / stores of a fluid cell
+#ifndef BB_SKELETON
+#define BB_SKELETON 0
+#endif
+#ifndef BB_WAIT_HINT_NS
+#define BB_WAIT_HINT_NS 0
+#endif
 __device__ __forceinline__ bool mbar_try_wait(uint32_t bar, uint32_t parity) {
     uint32_t ok;
+#if BB_WAIT_HINT_NS > 0
+    asm volatile("{\n\t.reg .pred p;\n\tmbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2, %3;\n\tselp.u32 %0, 1, 0, p;\n\t}"
+                 : "=r"(ok) : "r"(bar), "r"(parity), "r"((uint32_t)BB_WAIT_HINT_NS) : "memory");
+#else
     asm volatile("{\n\t.reg .pred p;\n\tmbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\tselp.u32 %0, 1, 0, p;\n\t}"
                  : "=r"(ok) : "r"(bar), "r"(parity) : "memory");
+#endif
     return ok != 0;
 }
 // a TMA that never lands (bad descriptor, wrong byte count) must not hang the GPU: trap after ~seconds
@@ -199,6 +213,9 @@ __device__ __forceinline__ void ring_depths(int pstage, int hstage, int &nsp, in
     constexpr int avail = SMEM_BYTES - OFF_RINGS;
     nsp = max(3, min(MAX_NSP, (avail - MIN_NSH * hstage) / pstage));
     nsh = min(MAX_NSH, (avail - nsp * pstage) / hstage);
+    // the largest stages (solid tile inside two PML slabs, tall tiles): double-buffer the point ring rather than starve
+    // the halo ring, of which the consumers hold three slots at a time
+    if (nsh < 5) { nsp = 2; nsh = min(MAX_NSH, (avail - nsp * pstage) / hstage); }
 }
 
 // =========================================================================================
@@ -547,9 +564,20 @@ __global__ void __launch_bounds__(NTB, CTAS_PER_SM) stress_tma(const __grid_cons
             }
             }
         };
+#if BB_SKELETON == 0
         if (cellpml ? (upd_pml && !(f & TF_ILAST)) : active) {
             if (f & TF_SOLID) cell_update(std::true_type{}); else cell_update(std::false_type{});
         }
+#elif BB_SKELETON == 2      // profiling aid: the data movement of an attenuating-fluid cell without its arithmetic
+        if (active) {
+            const float *pb = reinterpret_cast<const float *>(psc + po);
+            const float e = hbox(ho, 1)[0] + hbox(ho, 2)[1] + vx_0;
+            p.S[0][q] = pb[PB_SXX * NT] + e; p.S[1][q] = pb[PB_SYY * NT]; p.S[2][q] = pb[PB_SZZ * NT];
+            if (!cellpml) { p.R[0][q] = pb[PB_RXX * NT]; p.R[1][q] = pb[PB_RYY * NT]; p.R[2][q] = pb[PB_RZZ * NT]; p.Pr[q] = pb[PB_PR * NT]; }
+        }
+#else
+        (void)cell_update;
+#endif
         // ---------------- a slab-boundary plane pair of this CTA is complete: count it in right away (not at the end of
         // the chunk -- the neighbour's next half-step waits for it); the CTA completing the count publishes the sequence
         // number in the neighbour's flag word.  With sources injected behind this kernel the host's publish_kernel does it.
@@ -847,9 +875,19 @@ __global__ void __launch_bounds__(NTB, CTAS_PER_SM) particle_tma(const __grid_co
                 accumulate(p, BB_MAP_ALLV, qa, v[0] * v[0] + v[1] * v[1] + v[2] * v[2], true);
             }
         };
+#if BB_SKELETON == 0
         if (cellpml ? (upd_pml && !(f & TF_ILAST)) : active) {
             if (fsh) cell_update(std::true_type{}); else cell_update(std::false_type{});
         }
+#elif BB_SKELETON == 2
+        if (active) {
+            const float *pb = reinterpret_cast<const float *>(psc + po);
+            const float e = hbox(ho, HB_SYY)[0] + hbox(ho, HB_SZZ)[1] + xx_0;
+            p.V[0][q] = pb[(QB_V + 0) * NT] + e; p.V[1][q] = pb[(QB_V + 1) * NT]; p.V[2][q] = pb[(QB_V + 2) * NT];
+        }
+#else
+        (void)cell_update;
+#endif
         // ---------------- a slab-boundary plane pair of this CTA is complete: count it in right away (not at the end of
         // the chunk -- the neighbour's next half-step waits for it); the CTA completing the count publishes the sequence
         // number in the neighbour's flag word.  With sources injected behind this kernel the host's publish_kernel does it.

@@ -607,8 +607,9 @@ def main():
             guarded('strong', lambda: strong_record(R, args.strong_periods, args.strong_n))
         if world in (2, 4):
             guarded('dome', lambda: dome_record(R))
+        R.host_barrier()              # rank 0 shards the Rayleigh points over all GPUs: the others wait on the host, not in a spinning NCCL kernel
         guarded('rayleigh', lambda: rayleigh_record(R))
-        R.barrier()
+        R.host_barrier()
     if rank == 0:
         if not args.no_cpu_baseline and world == 1:
             try:

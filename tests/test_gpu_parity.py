@@ -54,7 +54,7 @@ CASES = [('single_water', (40, 44, 56), 5, 8), ('ctx500_skull', (56, 48, 72), 6,
          ('dome_stress', (64, 64, 48), 4, 8), ('hires_1mhz', (44, 40, 70), 3, 12)]
 
 
-@pytest.mark.parametrize('variant', [0, 1])
+@pytest.mark.parametrize('variant', [0, 1, 2, 3])
 @pytest.mark.parametrize('name,shape,periods,pml', CASES)
 def test_parity_small(name, shape, periods, pml, variant):
     w = workloads.make_workload(name, shape=shape, periods=periods, pml=pml)
