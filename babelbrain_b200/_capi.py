@@ -48,7 +48,7 @@ SYMBOLS = ['bb_last_error', 'bb_version', 'bb_device_count', 'bb_device_name', '
            'bb_fdtd_set_source_cells', 'bb_fdtd_set_source_functions', 'bb_fdtd_set_source_tones', 'bb_fdtd_set_sensors',
            'bb_fdtd_set_sensor_map', 'bb_fdtd_get_sensor_index',
            'bb_nccl_unique_id', 'bb_fdtd_comm_init', 'bb_fdtd_peer_export', 'bb_fdtd_peer_attach', 'bb_fdtd_run', 'bb_fdtd_reset', 'bb_fdtd_get_map',
-           'bb_fdtd_get_sensors', 'bb_fdtd_get_phase_data', 'bb_fdtd_get_stats', 'bb_fdtd_debug_cta_times', 'bb_rayleigh_forward']
+           'bb_fdtd_get_sensors', 'bb_fdtd_get_phase_data', 'bb_fdtd_get_stats', 'bb_fdtd_debug_cta_times', 'bb_rayleigh_forward', 'bb_bhte_run']
 
 _lib = None
 
@@ -94,6 +94,8 @@ def lib():
         L.bb_fdtd_debug_cta_times.argtypes = [vp, vp, i64]
         L.bb_rayleigh_forward.argtypes = [ctypes.c_float, ctypes.c_float, i64, vp, vp, vp, i64, vp, vp,
                                           ctypes.c_float, i64, i32, ctypes.POINTER(ctypes.c_double)]
+        L.bb_bhte_run.argtypes = [i32, i32, i32, i32, i32, vp, vp, vp, vp, vp, vp, vp, i64, ctypes.c_float, ctypes.c_float, i32, i32, vp, vp,
+                                  i64, vp, i32, ctypes.POINTER(ctypes.c_double)]
         _lib = L
     return _lib
 

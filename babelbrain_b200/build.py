@@ -7,8 +7,8 @@ import sys
 HERE = os.path.dirname(os.path.abspath(__file__))
 CSRC = os.path.join(HERE, 'csrc')
 LIB = os.environ.get('BB_LIB', os.path.join(HERE, 'libbabelb200.so'))   # BB_LIB / BB_NVCC_FLAGS: build experiment variants
-SOURCES = ['fdtd.cu', 'rayleigh.cu']
-HEADERS = ['common.h', 'fdtd_cell.cuh', 'fdtd_kernels.cuh', 'fdtd_direct.cuh', 'fdtd_tma.cuh', 'nccl_dyn.h',
+SOURCES = ['fdtd.cu', 'rayleigh.cu', 'bhte.cu']
+HEADERS = ['common.h', 'fdtd_cell.cuh', 'fdtd_kernels.cuh', 'fdtd_direct.cuh', 'fdtd_tma.cuh', 'fdtd_tma2.cuh', 'nccl_dyn.h',
            os.path.join('..', '..', 'include', 'babelb200.h')]
 
 

@@ -135,13 +135,5 @@ def GenerateFocusTx(f, Foc, Diam, c, PPWSurface=4):
     return Tx
 
 
-def _not_on_hot_path(name):
-    def f(*a, **k):
-        raise NotImplementedError('%s (bio-heat step) is outside the FDTD/Rayleigh hot path this package implements; '
-                                  'see DESIGN.md "out of scope"' % name)
-    f.__name__ = name
-    return f
-
-
-BHTE = _not_on_hot_path('BHTE')
-BHTEMultiplePressureFields = _not_on_hot_path('BHTEMultiplePressureFields')
+# the bio-heat functions of the same upstream module (thermal step)
+from .thermal import BHTE, BHTEMultiplePressureFields  # noqa: E402,F401

@@ -13,6 +13,8 @@
  *                        TranscranialModeling/BabelIntegrationSingle.py:295,
  *                        BabelIntegrationANNULAR_ARRAY.py:383,411,
  *                        BabelIntegrationCONCAVE_PHASEDARRAY.py:307,328,425,446
+ *   bb_bhte_run          BHTE / BHTEMultiplePressureFields(...)
+ *                        ThermalModeling/CalculateTemperatureEffects.py:365-395, :406, :439, :960-990
  *   bb_device_count/name InitCuda(deviceName) (BabelIntegrationBASE.py:918-925) and
  *                        StaggeredFDTD_3D_With_Relaxation_CUDA.ListDevices()
  *                        (BabelBrain/SelFiles/SelFiles.py:254-258)
@@ -185,6 +187,20 @@ int bb_fdtd_debug_cta_times(bb_fdtd *h, unsigned long long *out, int64_t n);
 int bb_rayleigh_forward(float k_re, float k_im, int64_t nsrc, const float *center, const float *ds,
                         const float *u0_reim, int64_t npts, const float *rf, float *out_reim,
                         float max_distance, int64_t u0_step, int device, double *kernel_ms);
+
+/* ---- bio-heat transfer (thermal step) ---- */
+/* Pennes equation + CEM43 dose, explicit 7-point stencil; replaces BHTE / BHTEMultiplePressureFields
+ * (ThermalModeling/CalculateTemperatureEffects.py:14, :365-395, :406, :439, :960-990).  Host pointers.
+ * q: nfields x (n1,n2,n3) heat added per step where that field's beam is on (already scaled by dt and the duty cycle);
+ * labels: (n1,n2,n3) uint32 material map; bh / perf: nmat conduction and perfusion coefficients per step;
+ * temp / dose: (n1,n2,n3) in = initial state, out = state after total_steps; field_at_step[n] = index of the pressure field
+ * heating during step n, -1 = beam off; monitor_slice (n1, n3, total_steps / nfactor_monitoring) receives the plane
+ * j = sel_j every nfactor_monitoring-th step (NULL: none); monitor_points: (n1,n2,n3) map of 1-based point ids (NULL: none),
+ * temp_points (npoints, total_steps) their temperature histories. */
+int bb_bhte_run(int n1, int n2, int n3, int nmat, int nfields, const float *q, const uint32_t *labels, const float *bh,
+                const float *perf, float *temp, float *dose, const int16_t *field_at_step, int64_t total_steps, float dt,
+                float core_temp, int sel_j, int nfactor_monitoring, float *monitor_slice, const uint32_t *monitor_points,
+                int64_t npoints, float *temp_points, int device, double *kernel_ms);
 
 #ifdef __cplusplus
 }
