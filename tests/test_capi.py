@@ -94,9 +94,9 @@ def test_drop_in_import_surface():
     assert 1480 < SpeedofSoundWater(20.0) < 1485
 
 
-def test_shim_delegates_non_hot_path_names_to_a_genuine_install(tmp_path):
-    """With a genuine BabelViscoFDTD further down sys.path, the shim keeps the hot path (ForwardSimple,
-    PropagationModel) and hands out the genuine bio-heat functions / H5pySimple (thermal step unmodified)."""
+def test_shim_keeps_the_solvers_and_delegates_file_io_to_a_genuine_install(tmp_path):
+    """With a genuine BabelViscoFDTD further down sys.path, the shim keeps everything that computes (ForwardSimple,
+    PropagationModel, BHTE / BHTEMultiplePressureFields) and hands out the genuine H5pySimple (same on-disk format)."""
     import subprocess
     import sys
     up = tmp_path / 'site' / 'BabelViscoFDTD'
@@ -104,26 +104,25 @@ def test_shim_delegates_non_hot_path_names_to_a_genuine_install(tmp_path):
     (up / '__init__.py').write_text('__version__ = "1.2.4"\n')
     (up / 'tools' / '__init__.py').write_text('')
     (up / 'tools' / 'RayleighAndBHTE.py').write_text('def BHTE(*a, **k):\n    return "genuine BHTE"\n'
-                                                    'def BHTEMultiplePressureFields(*a, **k):\n    return "genuine multi"\n'
                                                     'def ForwardSimple(*a, **k):\n    return "genuine FS"\n')
     (up / 'H5pySimple.py').write_text('def ReadFromH5py(f):\n    return "genuine read"\ndef SaveToH5py(d, f):\n    return "genuine save"\n')
     code = ('import sys; sys.path.insert(0, %r); sys.path.append(%r)\n'
             'from BabelViscoFDTD.tools.RayleighAndBHTE import BHTE, BHTEMultiplePressureFields, ForwardSimple\n'
             'from BabelViscoFDTD.H5pySimple import ReadFromH5py\n'
             'from BabelViscoFDTD.PropagationModel import PropagationModel\n'
-            'print(BHTE(), BHTEMultiplePressureFields(), ForwardSimple.__module__, ReadFromH5py(None), PropagationModel.__module__)\n'
+            'print(BHTE.__module__, BHTEMultiplePressureFields.__module__, ForwardSimple.__module__, ReadFromH5py(None), PropagationModel.__module__)\n'
             % (ROOT, str(tmp_path / 'site')))
     out = subprocess.run([sys.executable, '-c', code], capture_output=True, text=True, check=True).stdout.split('\n')[0]
-    assert out == 'genuine BHTE genuine multi babelbrain_b200.rayleigh genuine read babelbrain_b200.propagation'
+    assert out == 'babelbrain_b200.thermal babelbrain_b200.thermal babelbrain_b200.rayleigh genuine read babelbrain_b200.propagation'
 
 
-def test_bhte_without_a_genuine_install_says_so():
+def test_bhte_has_no_cpu_fallback(lib):
     from BabelViscoFDTD.tools.RayleighAndBHTE import BHTE
-    import BabelViscoFDTD
-    if BabelViscoFDTD.upstream() is not None:
-        pytest.skip('a genuine BabelViscoFDTD is installed')
-    with pytest.raises(NotImplementedError):
-        BHTE()
+    if not _no_gpu(lib):
+        pytest.skip('a CUDA device is present')
+    ML = {k: np.ones(1) for k in ('Density', 'SoS', 'Attenuation', 'SpecificHeat', 'Conductivity', 'Perfusion', 'Absorption', 'InitTemperature')}
+    with pytest.raises(_capi.BabelB200Error):
+        BHTE(np.zeros((4, 4, 4), np.float32), np.zeros((4, 4, 4), np.uint32), ML, 1e-3, 2, 1, -1, dt=0.01)
 
 
 def test_host_scatter_rows_places_slab_rows(lib):
