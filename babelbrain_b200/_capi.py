@@ -43,7 +43,7 @@ class FdtdStats(ctypes.Structure):
 
 
 # every symbol include/babelb200.h declares (checked by tests/test_capi.py)
-SYMBOLS = ['bb_last_error', 'bb_version', 'bb_device_count', 'bb_device_name', 'bb_host_alloc', 'bb_host_free', 'bb_host_scatter_rows', 'bb_host_scatter_runs', 'bb_fdtd_create',
+SYMBOLS = ['bb_last_error', 'bb_version', 'bb_device_count', 'bb_device_name', 'bb_host_alloc', 'bb_host_free', 'bb_host_scatter_rows', 'bb_host_scatter_runs', 'bb_release_cached_memory', 'bb_fdtd_create',
            'bb_fdtd_destroy', 'bb_fdtd_set_stream', 'bb_fdtd_set_materials', 'bb_fdtd_set_maps',
            'bb_fdtd_set_source_cells', 'bb_fdtd_set_source_functions', 'bb_fdtd_set_source_tones', 'bb_fdtd_set_sensors',
            'bb_fdtd_set_sensor_map', 'bb_fdtd_get_sensor_index',

@@ -63,6 +63,7 @@ struct bb_fdtd {
     cudaStream_t stream = nullptr, comm_stream = nullptr;
     bool own_stream = false;
     std::vector<void *> allocs;
+    std::vector<size_t> alloc_bytes;
     int64_t device_bytes = 0;
     // sources
     int64_t nsrc_cells = 0, nsrc_boundary = 0;
@@ -103,10 +104,62 @@ struct bb_fdtd {
     bb_fdtd_stats stats;
 };
 
+// ------------------------------------------------------------------------------------------
+// Device-memory cache.  A worker runs several simulations of the same grid in a row (forward, back-propagation, refocus:
+// BabelIntegrationBASE.py:2338-2428), and cudaMalloc / cudaFree of the ~20 field arrays cost 0.2-0.5 s per simulation.
+// Allocations of a destroyed handle therefore return to a per-device free list (exact-size reuse, at most
+// BB_DEVICE_POOL_GB gigabytes, default 32) instead of to the driver; an allocation the driver cannot satisfy purges the
+// list and retries.  bb_release_cached_memory() empties it.
+// ------------------------------------------------------------------------------------------
+struct DevPool { std::mutex mu; std::multimap<size_t, void *> free; size_t bytes = 0; };
+static DevPool g_pool[64];
+static size_t pool_cap() {
+    static const size_t cap = [] { const char *e = getenv("BB_DEVICE_POOL_GB"); return (size_t)((e ? atof(e) : 32.0) * 1e9); }();
+    return cap;
+}
+static void pool_purge(int dev) {
+    DevPool &pl = g_pool[dev];
+    std::lock_guard<std::mutex> lock(pl.mu);
+    for (auto &kv : pl.free) cudaFree(kv.second);
+    pl.free.clear();
+    pl.bytes = 0;
+}
+static cudaError_t pool_alloc(int dev, void **ptr, size_t bytes) {
+    DevPool &pl = g_pool[dev];
+    {
+        std::lock_guard<std::mutex> lock(pl.mu);
+        auto it = pl.free.find(bytes);
+        if (it != pl.free.end()) { *ptr = it->second; pl.free.erase(it); pl.bytes -= bytes; return cudaSuccess; }
+    }
+    cudaError_t e = cudaMalloc(ptr, bytes);
+    if (e == cudaErrorMemoryAllocation) { cudaGetLastError(); pool_purge(dev); e = cudaMalloc(ptr, bytes); }
+    return e;
+}
+static void pool_free(int dev, void *ptr, size_t bytes) {
+    if (!ptr) return;
+    DevPool &pl = g_pool[dev];
+    {
+        std::lock_guard<std::mutex> lock(pl.mu);
+        if (pl.bytes + bytes <= pool_cap()) { pl.free.emplace(bytes, ptr); pl.bytes += bytes; return; }
+    }
+    cudaFree(ptr);
+}
+extern "C" int bb_release_cached_memory(int device) {
+    int ndev = bb_device_count();
+    if (ndev < 0) return BB_ERR_CUDA;
+    for (int d = 0; d < ndev && d < 64; d++) {
+        if (device >= 0 && d != device) continue;
+        BB_CUDA(cudaSetDevice(d));
+        pool_purge(d);
+    }
+    return BB_OK;
+}
+
 static int dev_alloc(bb_fdtd *h, void **ptr, size_t bytes, bool zero = true) {
     if (bytes == 0) bytes = 16;
-    BB_CUDA(cudaMalloc(ptr, bytes));
+    BB_CUDA(pool_alloc(h->d.device, ptr, bytes));
     h->allocs.push_back(*ptr);
+    h->alloc_bytes.push_back(bytes);
     h->device_bytes += (int64_t)bytes;
     if (zero) BB_CUDA(cudaMemsetAsync(*ptr, 0, bytes, h->stream));
     return BB_OK;
@@ -217,8 +270,12 @@ static int staged_download(bb_fdtd *h, void *dst, size_t total, size_t piece, F 
 // scoped device allocation for the few temporaries that cannot be staged (freed on every return path)
 struct DevTmp {
     void *p = nullptr;
-    ~DevTmp() { if (p) cudaFree(p); }
-    cudaError_t alloc(size_t bytes) { return cudaMalloc(&p, bytes ? bytes : 16); }
+    size_t n = 0;
+    int dev = 0;
+    explicit DevTmp(int device = 0) : dev(device) {}
+    ~DevTmp() { release(); }
+    void release() { if (p) pool_free(dev, p, n); p = nullptr; n = 0; }
+    cudaError_t alloc(size_t bytes) { release(); n = bytes ? bytes : 16; return pool_alloc(dev, &p, n); }
     template <class T> T *as() const { return reinterpret_cast<T *>(p); }
 };
 
@@ -447,7 +504,7 @@ extern "C" void bb_fdtd_destroy(bb_fdtd *h) {
     cudaDeviceSynchronize();
     // h->comm belongs to the process-wide cache (bb_fdtd_comm_init)
     for (void *m : h->ipc_opened) if (m) cudaIpcCloseMemHandle(m);
-    for (void *a : h->allocs) cudaFree(a);
+    for (size_t n = 0; n < h->allocs.size(); n++) pool_free(h->d.device, h->allocs[n], h->alloc_bytes[n]);
     for (cudaEvent_t e : h->ev_pool) cudaEventDestroy(e);
     if (h->ev_run0) cudaEventDestroy(h->ev_run0);
     if (h->ev_run1) cudaEventDestroy(h->ev_run1);
@@ -565,7 +622,7 @@ extern "C" int bb_fdtd_set_maps(bb_fdtd *h, const uint32_t *material, const uint
         if (rc) return rc;
     } else {
         // the mask is rare (CT with air regions, BabelIntegrationBASE.py:2182-2190): upload it whole, then the labels in pieces
-        DevTmp tmpr;
+        DevTmp tmpr(h->d.device);
         BB_CUDA(tmpr.alloc((size_t)nrows * row_bytes));
         BB_CUDA(cudaMemcpyAsync(tmpr.p, reflector, (size_t)nrows * row_bytes, cudaMemcpyHostToDevice, h->stream));
         rc = staged_upload(h, material, (size_t)nrows * row_bytes, (size_t)rows_per * row_bytes, [&](void *dev, size_t off, size_t n) {
@@ -744,7 +801,7 @@ extern "C" int bb_fdtd_set_sensor_map(bb_fdtd *h, const uint32_t *sensor_map, in
     const long long total = (long long)h->nown * p.n2 * p.n3;
     // the selection needs the whole slab of the map on the device (Fortran-order enumeration of a C-order volume);
     // temporaries are scoped: every return path frees them
-    DevTmp dmap, dsel, dcount, tmp;
+    DevTmp dmap(h->d.device), dsel(h->d.device), dcount(h->d.device), tmp(h->d.device);
     BB_CUDA(dmap.alloc((size_t)total * 4));
     {   // upload through the page-locked staging slots (the caller's map is pageable)
         int rcu = staged_upload(h, sensor_map, (size_t)total * 4, BB_STAGE_BYTES, [&](void *dev, size_t off, size_t n) {
@@ -764,7 +821,7 @@ extern "C" int bb_fdtd_set_sensor_map(bb_fdtd *h, const uint32_t *sensor_map, in
         thrust::counting_iterator<long long> first(t0);
         size_t need = 0;
         BB_CUDA(cub::DeviceSelect::If(nullptr, need, first, dsel.as<long long>() + found, dcount.as<long long>(), n, pred, h->stream));
-        if (need > tmp_bytes) { if (tmp.p) { cudaFree(tmp.p); tmp.p = nullptr; } BB_CUDA(tmp.alloc(need)); tmp_bytes = need; }
+        if (need > tmp_bytes) { BB_CUDA(tmp.alloc(need)); tmp_bytes = need; }
         BB_CUDA(cub::DeviceSelect::If(tmp.p, need, first, dsel.as<long long>() + found, dcount.as<long long>(), n, pred, h->stream));
         long long c = 0;
         BB_CUDA(cudaMemcpyAsync(&c, dcount.p, 8, cudaMemcpyDeviceToHost, h->stream));
@@ -1307,13 +1364,13 @@ extern "C" int bb_fdtd_get_phase_data(bb_fdtd *h, int map_id, int bin, int nsamp
         const double a = -2.0 * M_PI * (double)(((long long)bin * n) % nsamples_used) / (double)nsamples_used;
         tw[n] = make_float2((float)cos(a), (float)sin(a));
     }
-    float2 *dtw = nullptr, *dfou = nullptr;
-    float *dph = nullptr, *dpk = nullptr;
-    auto cleanup = [&]() { if (dtw) cudaFree(dtw); if (dfou) cudaFree(dfou); if (dph) cudaFree(dph); if (dpk) cudaFree(dpk); };
-    cudaError_t e = cudaMalloc(&dtw, tw.size() * sizeof(float2));
-    if (e == cudaSuccess) e = cudaMalloc(&dfou, cells * sizeof(float2));
-    if (e == cudaSuccess && phase) e = cudaMalloc(&dph, cells * 4);
-    if (e == cudaSuccess && peak) e = cudaMalloc(&dpk, cells * 4);
+    DevTmp ttw(h->d.device), tfou(h->d.device), tph(h->d.device), tpk(h->d.device);      // cached between calls, freed on every path
+    cudaError_t e = ttw.alloc(tw.size() * sizeof(float2));
+    if (e == cudaSuccess) e = tfou.alloc(cells * sizeof(float2));
+    if (e == cudaSuccess && phase) e = tph.alloc(cells * 4);
+    if (e == cudaSuccess && peak) e = tpk.alloc(cells * 4);
+    float2 *dtw = ttw.as<float2>(), *dfou = tfou.as<float2>();
+    float *dph = phase ? tph.as<float>() : nullptr, *dpk = peak ? tpk.as<float>() : nullptr;
     if (e == cudaSuccess) e = cudaMemcpyAsync(dtw, tw.data(), tw.size() * sizeof(float2), cudaMemcpyHostToDevice, h->stream);
     if (e == cudaSuccess) e = cudaMemsetAsync(dfou, 0, cells * sizeof(float2), h->stream);
     if (e == cudaSuccess && dph) e = cudaMemsetAsync(dph, 0, cells * 4, h->stream);
@@ -1327,7 +1384,6 @@ extern "C" int bb_fdtd_get_phase_data(bb_fdtd *h, int map_id, int bin, int nsamp
     if (e == cudaSuccess && dph) e = cudaMemcpyAsync(phase, dph, cells * 4, cudaMemcpyDeviceToHost, h->stream);
     if (e == cudaSuccess && dpk) e = cudaMemcpyAsync(peak, dpk, cells * 4, cudaMemcpyDeviceToHost, h->stream);
     if (e == cudaSuccess) e = cudaStreamSynchronize(h->stream);
-    cleanup();
     if (e != cudaSuccess) { bb_set_error("bb_fdtd_get_phase_data: %s", cudaGetErrorString(e)); return BB_ERR_CUDA; }
     return BB_OK;
 }

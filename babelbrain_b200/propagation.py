@@ -445,12 +445,15 @@ def collect_results(slab):
     return Sensor, RMS, Peak, InputParam
 
 
-def release_device_state():
+def release_device_state(purge_cache=False):
     """Free the device memory the most recent simulation still holds for LastMap / CalculatePhaseDataOnDevice (it is
-    otherwise released when the next simulation starts or the process ends)."""
+    otherwise released when the next simulation starts or the process ends).  The arrays go back to the library's
+    per-device cache for the next simulation of the same grid; purge_cache=True returns them to the driver."""
     for v in _live_lastmaps:
         v._release()
     del _live_lastmaps[:]
+    if purge_cache:
+        _capi.check(_capi.lib().bb_release_cached_memory(-1))
 
 
 class PropagationModel:

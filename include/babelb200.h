@@ -108,6 +108,11 @@ int bb_host_scatter_rows(void *out, const int64_t *rows, const void *data, int64
 int bb_host_scatter_runs(void *out, const void *data, const int64_t *dst_row, const int64_t *src_row, const int64_t *nrows,
                          int64_t nruns, int64_t row_bytes);
 
+/* device memory of destroyed handles is kept per device for the next simulation of the same grid (a worker runs the forward,
+ * back-propagation and refocus simulations in a row, BabelIntegrationBASE.py:2338-2428; at most BB_DEVICE_POOL_GB gigabytes,
+ * default 32); this returns it to the driver.  device < 0: every device. */
+int bb_release_cached_memory(int device);
+
 /* ---- FDTD handle ---- */
 int bb_fdtd_create(const bb_fdtd_desc *desc, bb_fdtd **out);
 void bb_fdtd_destroy(bb_fdtd *h);
