@@ -153,7 +153,7 @@ class PinnedPool:
     array, so a worker that runs several simulations (forward, back-propagation, refocus:
     BabelIntegrationBASE.py:2338-2428) pays the page-locking once."""
 
-    def __init__(self, max_idle_bytes=8 << 30, block_type=None):
+    def __init__(self, max_idle_bytes=int(float(os.environ.get('BB_PINNED_POOL_GB', 32)) * (1 << 30)), block_type=None):
         import threading
         self.block_type = block_type or _PinnedBlock     # tests substitute an ordinary-memory block
         self.idle, self.max_idle, self.idle_bytes = [], max_idle_bytes, 0

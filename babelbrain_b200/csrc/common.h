@@ -112,9 +112,20 @@ struct DevParams {
     unsigned long long *flag_peer[2];    // where this slab publishes: lower neighbour's [1], upper neighbour's [0]
     unsigned *push_count;                // [2] plane-pushes completed so far in this launch (last CTA publishes)
     unsigned long long seq;              // (epoch << 32) | (half-step index + 1) of this launch
-    int publish;                         // 1: the half-step kernel publishes seq itself; 0: a source kernel follows, publish_kernel does
+    int publish;                         // 1: the half-step kernel publishes seq itself (always, since the boundary-plane sources moved into it)
     unsigned long long peer_timeout_ns;  // longest wait for a neighbour's halo (0: forever); on a timeout *err is set and the run fails
     int *err;                            // device error word checked by bb_fdtd_run (1, 2: halo wait on the lower / upper side timed out)
+    // Sources that sit in the slab's boundary planes (the two planes next to each existing neighbour) are injected by the
+    // half-step kernel itself, so that those planes can be pushed and published without waiting for the source kernel
+    // that follows: bsrc_map[b * plane + j * pitch + k] = index into the (boundary-first) source-cell arrays or -1, for
+    // b = 0, 1 (planes i0, i0+1) and 2, 3 (planes i1-2, i1-1).  nullptr when the launch injects no sources of its kind.
+    const int *bsrc_map;
+    const int *bsrc_row;                 // source row of each source cell
+    const float *bsrc_o[3];              // Ox / Oy / Oz weights of each source cell
+    const float *sf_row;                 // SourceFunctions row of this time step (nullptr: continuous-wave tones)
+    const float *tone_ac, *tone_as;      // per source A cos(phi), A sin(phi)
+    float env_sin, env_cos;              // ramp(n) sin(w t_n), ramp(n) cos(w t_n)
+    int src_hard;                        // 0 soft (additive), 1 hard (replaces the field)
     // profiling aid (BB_CTA_TIMING=1): per CTA of the last launch {globaltimer at start, at end, blockIdx packed, planes}
     unsigned long long *dbg;
     // RMS / peak accumulators: [slot][(i-i0)*plane + j*pitch + k]

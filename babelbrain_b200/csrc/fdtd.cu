@@ -71,6 +71,7 @@ struct bb_fdtd {
     int *src_row = nullptr;
     float *src_o[3] = {nullptr, nullptr, nullptr};
     float *srcfun = nullptr;  // [nt_src][nsrc]
+    int *bsrc_map = nullptr;  // [4][plane] boundary-plane source index map (multi-rank handles)
     // continuous-wave sources synthesised in the source kernel instead of read from srcfun (bb_fdtd_set_source_tones)
     float *tone_ac = nullptr, *tone_as = nullptr;     // [nsrc] A cos(phi), A sin(phi)
     std::vector<float> tone_es, tone_ec;              // [nt_src] ramp(n) sin(w t_n), ramp(n) cos(w t_n)
@@ -676,7 +677,8 @@ extern "C" int bb_fdtd_set_source_cells(bb_fdtd *h, int64_t ncells, const int64_
                 BB_REQUIRE(row[s] >= 0 && row[s] < h->d.nsrc, "source row %d out of range", row[s]);
             }
             const int ip = (int)(loc[s] / p.plane) - 2;
-            const bool boundary = multi && (ip < 2 || ip >= h->nown - 2);
+            // boundary = in one of the two planes next to a neighbour that exists (those planes are pushed to it)
+            const bool boundary = multi && ((ip < 2 && h->d.rank > 0) || (ip >= h->nown - 2 && h->d.rank < h->d.nranks - 1));
             if ((pass == 0) == boundary) order.push_back(s);
             if (pass == 0 && boundary) nb++;
         }
@@ -699,6 +701,17 @@ extern "C" int bb_fdtd_set_source_cells(bb_fdtd *h, int64_t ncells, const int64_
     }
     h->nsrc_cells = ncells;
     h->nsrc_boundary = nb;
+    if (multi) {
+        // where the boundary-plane sources sit, for the half-step kernels that inject them themselves (DevParams::bsrc_map)
+        std::vector<int> map((size_t)4 * p.plane, -1);
+        for (int64_t t = 0; t < nb; t++) {
+            const int ip = (int)(c2[t] / p.plane) - 2;
+            const int b = ip < 2 ? ip : 2 + ip - (h->nown - 2);
+            map[(size_t)b * p.plane + (size_t)(c2[t] % p.plane)] = (int)t;
+        }
+        if ((rc = dev_alloc(h, (void **)&h->bsrc_map, map.size() * 4, false))) return rc;
+        BB_CUDA(cudaMemcpy(h->bsrc_map, map.data(), map.size() * 4, cudaMemcpyHostToDevice));
+    }
     return BB_OK;
 }
 
@@ -1054,7 +1067,7 @@ static int prepare_kernels() {
 // one half-step over the owned planes [ib, ie): a single fused launch (interior + PML shell)
 template <typename LT>
 static int launch_half_step(bb_fdtd *h, bool stress, int acc_mode, int ib, int ie, Timer &tm, const ChunkPlan *given = nullptr,
-                            bool publish_in_kernel = true) {
+                            bool publish_in_kernel = true, int src_step = -1) {
     if (ie <= ib) return BB_OK;
     const DevParams &p = h->p;
     tm.begin(stress ? CAT_STRESS : CAT_PARTICLE);
@@ -1074,6 +1087,15 @@ static int launch_half_step(bb_fdtd *h, bool stress, int acc_mode, int ib, int i
         DevParams p = h->p;       // per-launch copy: the sequence number of this half-step for the NVLink halo push
         p.seq = half_step_seq(h, stress);
         p.publish = publish_in_kernel ? 1 : 0;
+        p.bsrc_map = nullptr;
+        if (src_step >= 0 && h->bsrc_map && h->nsrc_boundary > 0) {     // this launch injects the boundary-plane sources of time step src_step
+            p.bsrc_map = h->bsrc_map; p.bsrc_row = h->src_row;
+            p.bsrc_o[0] = h->src_o[0]; p.bsrc_o[1] = h->src_o[1]; p.bsrc_o[2] = h->src_o[2];
+            p.sf_row = h->tone_ac ? nullptr : h->srcfun + (size_t)src_step * h->d.nsrc;
+            p.tone_ac = h->tone_ac; p.tone_as = h->tone_as;
+            p.env_sin = h->tone_ac ? h->tone_es[src_step] : 0.f; p.env_cos = h->tone_ac ? h->tone_ec[src_step] : 0.f;
+            p.src_hard = (h->d.type_source & 1);
+        }
         if (h->dbg_kernel >= 0 && h->dbg_kernel != (stress ? 0 : 1)) p.dbg = nullptr;   // BB_CTA_TIMING=stress|particle
         const int sm = tma::SMEM_BYTES;
         if (p16) {
@@ -1110,7 +1132,12 @@ static int launch_half_step(bb_fdtd *h, bool stress, int acc_mode, int ib, int i
 static int launch_sources(bb_fdtd *h, int n, int64_t first, int64_t count, Timer &tm) {
     if (count <= 0 || n >= h->d.nt_src || !(h->srcfun || h->tone_ac)) return BB_OK;
     tm.begin(CAT_OTHER);
-    source_kernel<<<(unsigned)((count + 127) / 128), 128, 0, h->stream>>>(h->p, h->d.type_source, count, h->src_cell + first, h->src_row + first,
+    DevParams sp = h->p;
+    // NVLink halo push: the source cells of the pushed planes are injected by the half-step kernels (DevParams::bsrc_map);
+    // the cells handled here lie in no pushed plane, so this kernel neither stores to a neighbour nor fences system-wide
+    // (one fence.sys per source thread made this 15 us kernel cost 45 us of every time step at N = 2)
+    if (h->peer_mode) { sp.peerV[0] = sp.peerV[1] = sp.peerS[0] = sp.peerS[1] = nullptr; }
+    source_kernel<<<(unsigned)((count + 127) / 128), 128, 0, h->stream>>>(sp, h->d.type_source, count, h->src_cell + first, h->src_row + first,
                                                                          h->src_o[0] + first, h->src_o[1] + first, h->src_o[2] + first,
                                                                          h->tone_ac ? nullptr : h->srcfun + (size_t)n * h->d.nsrc,
                                                                          h->tone_ac, h->tone_as, h->tone_ac ? h->tone_es[n] : 0.f,
@@ -1149,17 +1176,14 @@ static int half_step(bb_fdtd *h, bool stress, int n, int acc, Timer &tm) {
     const bool src_here = stress ? (h->d.type_source >= 2) : (h->d.type_source < 2);
     int rc;
     if (h->peer_mode) {
-        // NVLink halo push: one launch; the boundary CTAs store into the neighbours' halo planes.  When sources are
-        // injected behind the kernel they push their cells too and a one-thread kernel publishes the half-step.
-        const bool src_now = src_here && h->nsrc_cells > 0 && n < h->d.nt_src && (h->srcfun || h->tone_ac);
-        if ((rc = launch_half_step<LT>(h, stress, acc, p.i0, p.i1, tm, nullptr, !src_now))) return rc;
-        if (src_now) {
-            if ((rc = launch_sources(h, n, 0, h->nsrc_cells, tm))) return rc;
-            DevParams pp = h->p;
-            pp.seq = half_step_seq(h, stress);
-            publish_kernel<<<1, 1, 0, h->stream>>>(pp);
-            BB_CUDA(cudaGetLastError());
-        }
+        // NVLink halo push: one launch; the boundary CTAs store into the neighbours' halo planes, inject the sources that sit
+        // in those planes themselves and publish the half-step as soon as the planes are complete.  The source kernel behind
+        // it handles the other source cells (measured before this: publishing behind the source kernel cost 5 % at N = 2,
+        // profiles/r2_scaling_experiments.txt).
+        static const bool nosrc = getenv("BB_EXPERIMENT_NOSRC") != nullptr;     // scaling experiments only
+        const bool src_now = !nosrc && src_here && h->nsrc_cells > 0 && n < h->d.nt_src && (h->srcfun || h->tone_ac);
+        if ((rc = launch_half_step<LT>(h, stress, acc, p.i0, p.i1, tm, nullptr, true, src_now ? n : -1))) return rc;
+        if (src_now && (rc = launch_sources(h, n, h->nsrc_boundary, h->nsrc_cells - h->nsrc_boundary, tm))) return rc;
         return BB_OK;
     }
     if (h->d.nranks > 1) {

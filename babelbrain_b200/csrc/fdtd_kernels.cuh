@@ -54,13 +54,6 @@ __global__ void source_kernel(const DevParams p, int type_source, long long ncel
     }
 }
 
-// publishes the sequence number of a half-step whose pushes were completed by earlier kernels of the stream
-__global__ void publish_kernel(const DevParams p) {
-    __threadfence_system();
-    if (p.flag_peer[0]) *reinterpret_cast<volatile unsigned long long *>(p.flag_peer[0]) = p.seq;
-    if (p.flag_peer[1]) *reinterpret_cast<volatile unsigned long long *>(p.flag_peer[1]) = p.seq;
-}
-
 template <typename LT>
 __device__ __forceinline__ float field_value(const DevParams &p, int map, long long q) {
     switch (map) {

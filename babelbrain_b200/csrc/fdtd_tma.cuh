@@ -131,6 +131,21 @@ __device__ __forceinline__ void peer_publish(const DevParams &p, int side, unsig
         *reinterpret_cast<volatile unsigned long long *>(p.flag_peer[side]) = p.seq;
     }
 }
+// value and weights of the source (if any) sitting at cell `col` of boundary plane b of the slab (DevParams::bsrc_map)
+__device__ __forceinline__ bool boundary_source(const DevParams &p, int b, unsigned col, float &value, float &ox, float &oy, float &oz) {
+    const int sidx = p.bsrc_map[(long long)b * p.plane + col];
+    if (sidx < 0) return false;
+    const int row = p.bsrc_row[sidx];
+    value = p.sf_row ? p.sf_row[row] : fmaf(p.env_sin, p.tone_ac[row], p.env_cos * p.tone_as[row]);
+    ox = p.bsrc_o[0][sidx]; oy = p.bsrc_o[1][sidx]; oz = p.bsrc_o[2][sidx];
+    return true;
+}
+// boundary plane index of plane i for the sides this CTA pushes (pushsel bit 0: lower, bit 1: upper), or -1
+__device__ __forceinline__ int boundary_plane(const DevParams &p, int pushsel, int i) {
+    if ((pushsel & 1) && i < p.i0 + 2) return i - p.i0;
+    if ((pushsel & 2) && i >= p.i1 - 2) return 2 + i - (p.i1 - 2);
+    return -1;
+}
 // keep a loop-invariant value in a register: the compiler otherwise re-derives it from the constant bank / special
 // registers in every iteration of the plane loop (S2R + LDC + IMAD chains seen in the SASS)
 // (ptxas does the re-deriving, so the value has to pass through an instruction it cannot see through: a shuffle from
@@ -550,6 +565,15 @@ __global__ void __launch_bounds__(NTB, CTAS_PER_SM) stress_tma(const __grid_cons
             }
             // ---------------- boundary planes also go to the slab neighbour (the stresses its particle update differentiates along i)
             if (pushsel) {
+            if (p.bsrc_map) {      // stress sources of the boundary planes are injected here (the source kernel skips them)
+                const int bp = boundary_plane(p, pushsel, i);
+                float val, ox, oy, oz;
+                if (bp >= 0 && boundary_source(p, bp, col, val, ox, oy, oz)) {
+                    const float w = val * ox;
+                    if (p.src_hard) { s[0] = w; s[1] = w; s[2] = w; } else { s[0] += w; s[1] += w; s[2] += w; }
+                    p.S[0][q] = s[0]; p.S[1][q] = s[1]; p.S[2][q] = s[2];
+                }
+            }
             if ((pushsel & 1) && i < p.i0 + 2) {
                 float *b = p.peerS[0];
                 const unsigned qn = (p.peer_plane[0] + (unsigned)(i - p.i0)) * s1 + col;
@@ -856,15 +880,24 @@ __global__ void __launch_bounds__(NTB, CTAS_PER_SM) particle_tma(const __grid_co
             if (l0 & LabelTraits<LT>::REFL) { v[0] = v[1] = v[2] = 0.f; }
             p.V[0][q] = v[0]; p.V[1][q] = v[1]; p.V[2][q] = v[2];
             if (pushsel) {
+            float w0 = v[0], w1 = v[1], w2 = v[2];      // what the arrays hold after this half-step (the RMS maps below see v)
+            if (p.bsrc_map) {      // particle sources of the boundary planes are injected here (the source kernel skips them)
+                const int bp = boundary_plane(p, pushsel, i);
+                float val, ox, oy, oz;
+                if (bp >= 0 && boundary_source(p, bp, col, val, ox, oy, oz)) {
+                    if (p.src_hard) { w0 = val * ox; w1 = val * oy; w2 = val * oz; } else { w0 += val * ox; w1 += val * oy; w2 += val * oz; }
+                    p.V[0][q] = w0; p.V[1][q] = w1; p.V[2][q] = w2;
+                }
+            }
             if ((pushsel & 1) && i < p.i0 + 2) {
                 float *b = p.peerV[0];
                 const unsigned qn = (p.peer_plane[0] + (unsigned)(i - p.i0)) * s1 + col;
-                b[qn] = v[0]; b[p.peer_vol[0] + qn] = v[1]; b[2 * p.peer_vol[0] + qn] = v[2];
+                b[qn] = w0; b[p.peer_vol[0] + qn] = w1; b[2 * p.peer_vol[0] + qn] = w2;
             }
             if ((pushsel & 2) && i >= p.i1 - 2) {
                 float *b = p.peerV[1];
                 const unsigned qn = (p.peer_plane[1] + (unsigned)(i - (p.i1 - 2))) * s1 + col;
-                b[qn] = v[0]; b[p.peer_vol[1] + qn] = v[1]; b[2 * p.peer_vol[1] + qn] = v[2];
+                b[qn] = w0; b[p.peer_vol[1] + qn] = w1; b[2 * p.peer_vol[1] + qn] = w2;
             }
             }
             if (ACC && !cellpml) {

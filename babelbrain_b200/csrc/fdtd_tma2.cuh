@@ -412,6 +412,20 @@ __global__ void __launch_bounds__(NTB2, 1) stress_tma2(const __grid_constant__ S
             }
             // ---------------- boundary planes also go to the slab neighbour (the stresses its particle update differentiates along i)
             if (pushsel) {
+                if (p.bsrc_map) {      // stress sources of the boundary planes are injected here (the source kernel skips them)
+                    const int bp = boundary_plane(p, pushsel, i);
+                    bool any = false;
+#pragma unroll
+                    for (int c = 0; c < 2; c++) {
+                        float val, ox, oy, oz;
+                        if (bp >= 0 && active[c] && boundary_source(p, bp, col + c, val, ox, oy, oz)) {
+                            const float w = val * ox;
+                            if (p.src_hard) { s[c][0] = w; s[c][1] = w; s[c][2] = w; } else { s[c][0] += w; s[c][1] += w; s[c][2] += w; }
+                            any = true;
+                        }
+                    }
+                    if (any) { st2(p.S[0] + q, s[0][0], s[1][0]); st2(p.S[1] + q, s[0][1], s[1][1]); st2(p.S[2] + q, s[0][2], s[1][2]); }
+                }
                 if ((pushsel & 1) && i < p.i0 + 2) {
                     float *b = p.peerS[0];
                     const unsigned qn = (p.peer_plane[0] + (unsigned)(i - p.i0)) * s1 + col;
@@ -804,6 +818,20 @@ __global__ void __launch_bounds__(PT<ROWS>::NTB, 1) particle_tma2(const __grid_c
             }
             st2(p.V[0] + q, v[0][0], v[1][0]); st2(p.V[1] + q, v[0][1], v[1][1]); st2(p.V[2] + q, v[0][2], v[1][2]);
             if (pushsel) {
+                if (p.bsrc_map) {      // particle sources of the boundary planes are injected here (the source kernel skips them)
+                    const int bp = boundary_plane(p, pushsel, i);
+                    bool any = false;
+#pragma unroll
+                    for (int c = 0; c < 2; c++) {
+                        float val, ox, oy, oz;
+                        if (bp >= 0 && active[c] && boundary_source(p, bp, col + c, val, ox, oy, oz)) {
+                            if (p.src_hard) { v[c][0] = val * ox; v[c][1] = val * oy; v[c][2] = val * oz; }
+                            else { v[c][0] += val * ox; v[c][1] += val * oy; v[c][2] += val * oz; }
+                            any = true;
+                        }
+                    }
+                    if (any) { st2(p.V[0] + q, v[0][0], v[1][0]); st2(p.V[1] + q, v[0][1], v[1][1]); st2(p.V[2] + q, v[0][2], v[1][2]); }
+                }
                 if ((pushsel & 1) && i < p.i0 + 2) {
                     float *b = p.peerV[0];
                     const unsigned qn = (p.peer_plane[0] + (unsigned)(i - p.i0)) * s1 + col;
