@@ -604,7 +604,7 @@ __global__ void __launch_bounds__(NTB, CTAS_PER_SM) stress_tma(const __grid_cons
 #endif
         // ---------------- a slab-boundary plane pair of this CTA is complete: count it in right away (not at the end of
         // the chunk -- the neighbour's next half-step waits for it); the CTA completing the count publishes the sequence
-        // number in the neighbour's flag word.  With sources injected behind this kernel the host's publish_kernel does it.
+        // number in the neighbour's flag word (sources of these planes were injected above, DevParams::bsrc_map).
         if (pushsel) {
             const bool last_lo = (pushsel & 1) && i == min(ic1, p.i0 + 2) - 1;
             const bool last_hi = (pushsel & 2) && i == ic1 - 1;
@@ -923,7 +923,7 @@ __global__ void __launch_bounds__(NTB, CTAS_PER_SM) particle_tma(const __grid_co
 #endif
         // ---------------- a slab-boundary plane pair of this CTA is complete: count it in right away (not at the end of
         // the chunk -- the neighbour's next half-step waits for it); the CTA completing the count publishes the sequence
-        // number in the neighbour's flag word.  With sources injected behind this kernel the host's publish_kernel does it.
+        // number in the neighbour's flag word (sources of these planes were injected above, DevParams::bsrc_map).
         if (pushsel) {
             const bool last_lo = (pushsel & 1) && i == min(ic1, p.i0 + 2) - 1;
             const bool last_hi = (pushsel & 2) && i == ic1 - 1;
