@@ -309,16 +309,30 @@ __global__ void __launch_bounds__(NTB, CTAS_PER_SM) stress_tma(const __grid_cons
     if (warp == NCW) {          // halo ring: the three V boxes (one 4-D TMA) + labels of plane ic0 + r
         if (lane != 0) return;
         RingPos rh(nsh, 0, 1);
-        for (int r = 0; r < np + 2; r++) {
+        // This thread also publishes the slab-boundary planes the CTA pushes to a neighbour: the wait for a halo slot to come
+        // back tells it that every consumer warp has finished (stored, pushed, released) the plane that used the slot, so
+        // the system-scope fence and the flag write cost the consumer warps nothing (they were 150-300 us per launch on the
+        // 1 MHz slabs when consumer thread 0 did them: ~30 boundary CTAs per SM).
+        const int lo_last = (ic0 < p.i0 + 2 && p.peerS[0]) ? min(ic1, p.i0 + 2) - 1 - ic0 : -1;
+        const int hi_last = (ic1 > p.i1 - 2 && p.peerS[1]) ? np - 1 : -1;
+        const int rend = p.publish ? max(np + 2, max(lo_last, hi_last) + nsh + 1) : np + 2;
+        for (int r = 0; r < rend; r++) {
             const int slot = rh.slot;
             mbar_wait(emptyH + slot * 8, rh.par);
+            if (p.publish && r >= nsh && (r - nsh == lo_last || r - nsh == hi_last)) {
+                __threadfence_system();
+                const unsigned expected = 2u * gridDim.x * gridDim.y;
+                if (r - nsh == lo_last) peer_publish(p, 0, (unsigned)(min(ic1, p.i0 + 2) - ic0), expected);
+                if (r - nsh == hi_last) peer_publish(p, 1, (unsigned)(ic1 - max(ic0, p.i1 - 2)), expected);
+            }
+            rh.advance();
+            if (r >= np + 2) continue;
             const uint32_t st = sm32 + offH + slot * ST_HSTAGE;
             const uint32_t bar = fullH + slot * 8;
             mbar_expect_tx(bar, 3 * HBOX + LW * LH * (int)sizeof(LT));
             const int ipl = ipl0 + r;
             tma_load_4d(st, &tm.v3, bar, k0 - HK, j0 - HALO, ipl, 0);
             tma_load_3d(st + ST_LOFF, &tm.lab, bar, k0, j0, ipl);
-            rh.advance();
         }
         return;
     }
@@ -602,22 +616,6 @@ __global__ void __launch_bounds__(NTB, CTAS_PER_SM) stress_tma(const __grid_cons
 #else
         (void)cell_update;
 #endif
-        // ---------------- a slab-boundary plane pair of this CTA is complete: count it in right away (not at the end of
-        // the chunk -- the neighbour's next half-step waits for it); the CTA completing the count publishes the sequence
-        // number in the neighbour's flag word (sources of these planes were injected above, DevParams::bsrc_map).
-        if (pushsel) {
-            const bool last_lo = (pushsel & 1) && i == min(ic1, p.i0 + 2) - 1;
-            const bool last_hi = (pushsel & 2) && i == ic1 - 1;
-            if ((last_lo || last_hi) && p.publish) {
-                consumer_bar();
-                if (tid == 0) {
-                    __threadfence_system();
-                    const unsigned expected = 2u * gridDim.x * gridDim.y;
-                    if (last_lo) peer_publish(p, 0, (unsigned)(min(ic1, p.i0 + 2) - ic0), expected);
-                    if (last_hi) peer_publish(p, 1, (unsigned)(ic1 - max(ic0, p.i1 - 2)), expected);
-                }
-            }
-        }
         // ---------------- this warp is done with the slots of plane i
         __syncwarp();
         if (lane0) { mbar_arrive(hb0 + MAX_NSH * 8); mbar_arrive(pbar + MAX_NSP * 8); }
@@ -709,9 +707,21 @@ __global__ void __launch_bounds__(NTB, CTAS_PER_SM) particle_tma(const __grid_co
     if (warp == NCW) {          // halo ring: stresses with halo + Sxx + labels of plane ic0 + r
         if (lane != 0) return;
         RingPos rh(nsh, 0, 1);
-        for (int r = 0; r < np + 2; r++) {
+        // publishes the pushed boundary planes once every consumer warp has released them (see stress_tma)
+        const int lo_last = (ic0 < p.i0 + 2 && p.peerV[0]) ? min(ic1, p.i0 + 2) - 1 - ic0 : -1;
+        const int hi_last = (ic1 > p.i1 - 2 && p.peerV[1]) ? np - 1 : -1;
+        const int rend = p.publish ? max(np + 2, max(lo_last, hi_last) + nsh + 1) : np + 2;
+        for (int r = 0; r < rend; r++) {
             const int slot = rh.slot;
             mbar_wait(emptyH + slot * 8, rh.par);
+            if (p.publish && r >= nsh && (r - nsh == lo_last || r - nsh == hi_last)) {
+                __threadfence_system();
+                const unsigned expected = 2u * gridDim.x * gridDim.y;
+                if (r - nsh == lo_last) peer_publish(p, 0, (unsigned)(min(ic1, p.i0 + 2) - ic0), expected);
+                if (r - nsh == hi_last) peer_publish(p, 1, (unsigned)(ic1 - max(ic0, p.i1 - 2)), expected);
+            }
+            rh.advance();
+            if (r >= np + 2) continue;
             const uint32_t st = sm32 + offH + slot * hstage;
             const uint32_t bar = fullH + slot * 8;
             const bool fsh = sF[r] & TF_SHEAR;
@@ -721,7 +731,6 @@ __global__ void __launch_bounds__(NTB, CTAS_PER_SM) particle_tma(const __grid_co
             if (fsh) tma_load_4d(st + PT_S3OFF, &tm.sh3, bar, k0 - HK, j0 - HALO, ipl, 3);
             tma_load_4d(st + PT_XOFF, &tm.sxx, bar, k0, j0, ipl, 0);
             tma_load_3d(st + PT_LOFF, &tm.lab, bar, k0, j0, ipl);
-            rh.advance();
         }
         return;
     }
@@ -921,22 +930,6 @@ __global__ void __launch_bounds__(NTB, CTAS_PER_SM) particle_tma(const __grid_co
 #else
         (void)cell_update;
 #endif
-        // ---------------- a slab-boundary plane pair of this CTA is complete: count it in right away (not at the end of
-        // the chunk -- the neighbour's next half-step waits for it); the CTA completing the count publishes the sequence
-        // number in the neighbour's flag word (sources of these planes were injected above, DevParams::bsrc_map).
-        if (pushsel) {
-            const bool last_lo = (pushsel & 1) && i == min(ic1, p.i0 + 2) - 1;
-            const bool last_hi = (pushsel & 2) && i == ic1 - 1;
-            if ((last_lo || last_hi) && p.publish) {
-                consumer_bar();
-                if (tid == 0) {
-                    __threadfence_system();
-                    const unsigned expected = 2u * gridDim.x * gridDim.y;
-                    if (last_lo) peer_publish(p, 0, (unsigned)(min(ic1, p.i0 + 2) - ic0), expected);
-                    if (last_hi) peer_publish(p, 1, (unsigned)(ic1 - max(ic0, p.i1 - 2)), expected);
-                }
-            }
-        }
         __syncwarp();
         if (lane0) { mbar_arrive(hb0 + MAX_NSH * 8); mbar_arrive(pbar + MAX_NSP * 8); }
         ho = ho1; hb0 = hb1; ho1 = ho2; hb1 = hb2;

@@ -104,3 +104,28 @@ def test_unmodified_caller_through_the_cuda_path():
     refcaller.run_cases(refcaller.water_mask(), cap2, COMPUTING_BACKEND=1, **dict(KARGS, bWaterOnly=False, bForceHomogenousMedium=True))
     full = np.asarray(cap2['results'][2])
     assert np.isfinite(full).all() and full.max() > 0 and full.max() < np.asarray(cap['results'][2]).max()      # 5 Np/m of attenuation lowers the focus
+
+
+CTX500 = dict(targets=['T'], ID='S', basedir='/nonexistent/', deviceName='B200', Frequencies=[500e3], basePPW=[6],
+              bTightNarrowBeamDomain=True, bDoRefocusing=False, bWaterOnly=True, bMinimalSaving=True, bForceRecalc=True, bDisplay=False,
+              ZSteering=0.0, Aperture=64.0e-3, FocalLength=62.94e-3,                                   # BabelBrain/Babel_CTX500/default.yaml
+              InDiameters=np.array([0.0, 31.6988e-3, 44.2688e-3, 53.6688e-3]), OutDiameters=np.array([31.14e-3, 43.71e-3, 53.11e-3, 60.83e-3]))
+
+
+@needs_ref
+@pytest.mark.gpu
+def test_unmodified_annular_array_caller_ctx500_through_the_cuda_path():
+    """BASELINE configs[1]'s own caller: BabelIntegrationANNULAR_ARRAY.py (CTX-500: four rings, 500 kHz, 6 PPW) unmodified --
+    per-ring phase programming with ForwardSimple on a single point (:376-395), the whole-grid Rayleigh field (:403-420),
+    sources, the solver call, the dispersion correction -- on the CUDA path, water only.  Reference data for this
+    configuration (12 cases "CTX_500_500kHz_6PPW" of SummaryAnalysis.xlsx): peak difference -0.15 ... +1.18 % (mean
+    +0.56 %), L2 mean 3.2 %."""
+    cap = {}
+    refcaller.run_cases(refcaller.water_mask(shape=(150, 150, 190), h_mm=0.3675, skin_z=90, focus=(75, 75, 120)), cap,
+                        transducer='BabelIntegrationANNULAR_ARRAY', COMPUTING_BACKEND=1, **CTX500)
+    b = band(cap)
+    print('unmodified CTX-500 caller + CUDA path:', b)
+    assert b['ppp'] == 30
+    assert -0.01 <= b['peak_diff'] <= 0.02, b
+    assert b['l2'] <= 0.05, b
+    assert b['focal_distance_mm'] <= 0.4, b            # one voxel
