@@ -113,6 +113,7 @@ struct DevParams {
     unsigned *push_count;                // [2] plane-pushes completed so far in this launch (last CTA publishes)
     unsigned long long seq;              // (epoch << 32) | (half-step index + 1) of this launch
     int publish;                         // 1: the half-step kernel publishes seq itself (always, since the boundary-plane sources moved into it)
+    int exp;                             // timing experiments only (BB_EXPERIMENT_HALO): 1 no fence before the count, 4 no flag wait, 16 system-scope fence after the flag wait, 32 system-scope fence before every count
     unsigned long long peer_timeout_ns;  // longest wait for a neighbour's halo (0: forever); on a timeout *err is set and the run fails
     int *err;                            // device error word checked by bb_fdtd_run (1, 2: halo wait on the lower / upper side timed out)
     // Sources that sit in the slab's boundary planes (the two planes next to each existing neighbour) are injected by the

@@ -493,6 +493,7 @@ static int fdtd_create_body(bb_fdtd *h, const bb_fdtd_desc *d) {
         const char *e = getenv("BB_PEER_TIMEOUT_S");
         const double sec = e ? atof(e) : 60.0;
         p.peer_timeout_ns = sec > 0 ? (unsigned long long)(sec * 1e9) : 0ull;
+        p.exp = getenv("BB_EXPERIMENT_HALO") ? atoi(getenv("BB_EXPERIMENT_HALO")) : 0;
     }
     if (d->kernel_variant != 1 && (rc = make_tensor_maps(h))) return rc;
     BB_CUDA(cudaStreamSynchronize(h->stream));
@@ -1243,6 +1244,8 @@ static int run_steps(bb_fdtd *h, int64_t nsteps, Timer &tm) {
 extern "C" int bb_fdtd_run(bb_fdtd *h, int64_t nsteps, int profile) {
     BB_REQUIRE(h, "null handle");
     if (!h->materials_set || !h->maps_set) { bb_set_error("set_materials / set_maps must be called before run"); return BB_ERR_STATE; }
+    // timing experiments only (profiles/run_slab_cost.py): run one slab of a decomposed grid alone, halos left as uploaded
+    if (h->d.nranks > 1 && !h->comm && !h->peer_mode && getenv("BB_EXPERIMENT_NOHALO")) h->peer_mode = true;
     if (h->d.nranks > 1 && !h->comm && !h->peer_mode) { bb_set_error("multi-rank handle without comm_init / peer_attach"); return BB_ERR_STATE; }
     BB_CUDA(cudaSetDevice(h->d.device));
     if (nsteps < 0 || h->step + nsteps > h->d.steps) nsteps = h->d.steps - h->step;

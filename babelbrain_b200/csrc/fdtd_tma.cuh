@@ -117,7 +117,7 @@ __device__ __forceinline__ void peer_wait(const DevParams &p, int side) {
             else if (t - t0 > p.peer_timeout_ns) { atomicExch(p.err, 1 + side); break; }
         }
     }
-    __threadfence();
+    if (p.exp & 16) __threadfence_system(); else __threadfence();
     asm volatile("fence.proxy.async;" ::: "memory");             // the TMA unit reads what the neighbour wrote
 }
 // Called by one thread of a CTA after a barrier of the consumer warps that stored the pushed planes.  The barrier
@@ -297,8 +297,8 @@ __global__ void __launch_bounds__(NTB, CTAS_PER_SM) stress_tma(const __grid_cons
     const bool near_lo = ic0 < p.i0 + 2 && p.peerV[0] != nullptr, near_hi = ic1 > p.i1 - 2 && p.peerV[1] != nullptr;
     const bool has_peer = (ic0 < p.i0 + 2 || ic1 > p.i1 - 2) && (p.peerV[0] != nullptr || p.peerV[1] != nullptr);   // this CTA may push planes
     if (tid == 0) {
-        if (!first_hs && near_lo) peer_wait(p, 0);
-        if (!first_hs && near_hi) peer_wait(p, 1);
+        if (!first_hs && near_lo && !(p.exp & 4)) peer_wait(p, 0);
+        if (!first_hs && near_hi && !(p.exp & 4)) peer_wait(p, 1);
         for (int s = 0; s < nsh; s++) { mbar_init(fullH + s * 8, 1); mbar_init(emptyH + s * 8, NCW); }
         for (int s = 0; s < nsp; s++) { mbar_init(fullP + s * 8, 1); mbar_init(emptyP + s * 8, NCW); }
         fence_barrier_init();
@@ -320,7 +320,7 @@ __global__ void __launch_bounds__(NTB, CTAS_PER_SM) stress_tma(const __grid_cons
             const int slot = rh.slot;
             mbar_wait(emptyH + slot * 8, rh.par);
             if (p.publish && r >= nsh && (r - nsh == lo_last || r - nsh == hi_last)) {
-                __threadfence_system();
+                if (p.exp & 32) __threadfence_system(); else if (!(p.exp & 1)) __threadfence();
                 const unsigned expected = 2u * gridDim.x * gridDim.y;
                 if (r - nsh == lo_last) peer_publish(p, 0, (unsigned)(min(ic1, p.i0 + 2) - ic0), expected);
                 if (r - nsh == hi_last) peer_publish(p, 1, (unsigned)(ic1 - max(ic0, p.i1 - 2)), expected);
@@ -695,8 +695,8 @@ __global__ void __launch_bounds__(NTB, CTAS_PER_SM) particle_tma(const __grid_co
     const bool near_lo = ic0 < p.i0 + 2 && p.peerS[0] != nullptr, near_hi = ic1 > p.i1 - 2 && p.peerS[1] != nullptr;
     const bool has_peer = (ic0 < p.i0 + 2 || ic1 > p.i1 - 2) && (p.peerV[0] != nullptr || p.peerV[1] != nullptr);   // this CTA may push planes
     if (tid == 0) {
-        if (!first_hs && near_lo) peer_wait(p, 0);
-        if (!first_hs && near_hi) peer_wait(p, 1);
+        if (!first_hs && near_lo && !(p.exp & 4)) peer_wait(p, 0);
+        if (!first_hs && near_hi && !(p.exp & 4)) peer_wait(p, 1);
         for (int s = 0; s < nsh; s++) { mbar_init(fullH + s * 8, 1); mbar_init(emptyH + s * 8, NCW); }
         for (int s = 0; s < nsp; s++) { mbar_init(fullP + s * 8, 1); mbar_init(emptyP + s * 8, NCW); }
         fence_barrier_init();
@@ -715,7 +715,7 @@ __global__ void __launch_bounds__(NTB, CTAS_PER_SM) particle_tma(const __grid_co
             const int slot = rh.slot;
             mbar_wait(emptyH + slot * 8, rh.par);
             if (p.publish && r >= nsh && (r - nsh == lo_last || r - nsh == hi_last)) {
-                __threadfence_system();
+                if (p.exp & 32) __threadfence_system(); else if (!(p.exp & 1)) __threadfence();
                 const unsigned expected = 2u * gridDim.x * gridDim.y;
                 if (r - nsh == lo_last) peer_publish(p, 0, (unsigned)(min(ic1, p.i0 + 2) - ic0), expected);
                 if (r - nsh == hi_last) peer_publish(p, 1, (unsigned)(ic1 - max(ic0, p.i1 - 2)), expected);

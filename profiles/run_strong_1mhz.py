@@ -1,7 +1,7 @@
 """Strong scaling of the 1 MHz high-resolution domain (BASELINE configs[4]: 1080^3, 1.26 G cells) over the GPUs of one box,
 a few periods of the real run (11250 steps) with the RMS window and the sensor sampling active in the second half:
 
-   python profiles/run_strong_1mhz.py [periods] [n]                                   one GPU, whole domain (n = grid size, default 1080)
+   python profiles/run_strong_1mhz.py [periods] [n] [n1]                              one GPU, whole domain (n = grid size, default 1080)
    python -m torch.distributed.run --nnodes=1 --nproc-per-node N --master-addr 127.0.0.1 --master-port 29511 \
           profiles/run_strong_1mhz.py [periods] [n]                                   N slabs, NVLink halo push
 
@@ -19,6 +19,7 @@ from babelbrain_b200.slab import SlabPlan
 
 periods = int(sys.argv[1]) if len(sys.argv) > 1 else 4
 n = int(sys.argv[2]) if len(sys.argv) > 2 else 1080
+n1 = int(sys.argv[3]) if len(sys.argv) > 3 else n          # planes along the decomposed axis (default: cube)
 world, rank, local_rank = (int(os.environ.get(k, d)) for k, d in (('WORLD_SIZE', 1), ('RANK', 0), ('LOCAL_RANK', 0)))
 torch.cuda.set_device(local_rank)
 if world > 1:
@@ -31,21 +32,21 @@ def barrier():
     torch.cuda.synchronize()
 
 
-shape = (n, n, n)
-plan = SlabPlan(n, world)
+shape = (n1, n, n)
+plan = SlabPlan(n1, world)
 glo, ghi = plan.with_halo(rank)
 t0 = time.time()
-w = workloads.make_workload('hires_1mhz', shape=shape, periods=periods, planes=(glo, ghi), lean=True)
+w = workloads.make_workload('hires_1mhz', shape=shape, periods=periods, planes=(glo, ghi), lean=True, dense_sources=False)
 t_build = time.time() - t0
 kw = {k: v for k, v in w['kwargs'].items() if k not in bench.DROP}
-s = FdtdSlab(*w['args'], device=local_rank, rank=rank, nranks=world, origin=glo, n1_global=n, **kw)
+s = FdtdSlab(*w['args'], device=local_rank, rank=rank, nranks=world, origin=glo, n1_global=n1, **kw)
 t_setup = time.time() - t0 - t_build
 if world > 1:
     exports = [None] * world
     dist.all_gather_object(exports, s.peer_export())
     s.peer_attach(exports[rank - 1] if rank > 0 else None, exports[rank + 1] if rank < world - 1 else None)
     dist.barrier()
-cls, alg = bench.traffic_model(w['args'][0], w['args'][1], 12, s.i0, s.i1, glo, n)
+cls, alg = bench.traffic_model(w['args'][0], w['args'][1], 12, s.i0, s.i1, glo, n1)
 barrier()
 s.run(5)
 barrier()
@@ -60,9 +61,9 @@ run_ms, stress_ms, particle_ms = (float(x) for x in t.tolist())
 steps = w['meta']['steps']
 if rank == 0:
     peak = bench.measured_peak()[0]
-    cells = n ** 3
+    cells = n1 * n * n
     line = {'workload': '1 MHz PPW 9 high-resolution domain %dx%dx%d, %d of 11250 time steps (%d periods), RMS window and sensors in the last 2 periods'
-                        % (n, n, n, steps, periods),
+                        % (n1, n, n, steps, periods),
             'n_gpus': world, 'planes_per_gpu': s.i1 - s.i0, 'run_ms': run_ms, 'ms_per_time_step': run_ms / steps,
             'gcell_updates_per_s': cells * steps / run_ms / 1e6, 'per_gpu': cells * steps / run_ms / 1e6 / world,
             'nominal_158B_frac_of_peak_per_gpu': 158.0 * cells * steps / run_ms / 1e6 / world / peak,
