@@ -1050,11 +1050,16 @@ static int set_smem(K kernel, int bytes) {
 template <typename LT>
 static int prepare_kernels() {
     int rc;
-    if ((rc = set_smem(tma::stress_tma<LT, 0>, tma::SMEM_BYTES))) return rc;
-    if ((rc = set_smem(tma::stress_tma<LT, 1>, tma::SMEM_BYTES))) return rc;
-    if ((rc = set_smem(tma::stress_tma<LT, 2>, tma::SMEM_BYTES))) return rc;
-    if ((rc = set_smem(tma::particle_tma<LT, 0>, tma::SMEM_BYTES))) return rc;
-    if ((rc = set_smem(tma::particle_tma<LT, 2>, tma::SMEM_BYTES))) return rc;
+    if ((rc = set_smem(tma::stress_tma<LT, 0, false>, tma::SMEM_BYTES))) return rc;
+    if ((rc = set_smem(tma::stress_tma<LT, 1, false>, tma::SMEM_BYTES))) return rc;
+    if ((rc = set_smem(tma::stress_tma<LT, 2, false>, tma::SMEM_BYTES))) return rc;
+    if ((rc = set_smem(tma::particle_tma<LT, 0, false>, tma::SMEM_BYTES))) return rc;
+    if ((rc = set_smem(tma::particle_tma<LT, 2, false>, tma::SMEM_BYTES))) return rc;
+    if ((rc = set_smem(tma::stress_tma<LT, 0, true>, tma::SMEM_BYTES))) return rc;
+    if ((rc = set_smem(tma::stress_tma<LT, 1, true>, tma::SMEM_BYTES))) return rc;
+    if ((rc = set_smem(tma::stress_tma<LT, 2, true>, tma::SMEM_BYTES))) return rc;
+    if ((rc = set_smem(tma::particle_tma<LT, 0, true>, tma::SMEM_BYTES))) return rc;
+    if ((rc = set_smem(tma::particle_tma<LT, 2, true>, tma::SMEM_BYTES))) return rc;
     if ((rc = set_smem(tma::stress_tma2<LT, 0>, tma::SMEM_BYTES))) return rc;
     if ((rc = set_smem(tma::stress_tma2<LT, 1>, tma::SMEM_BYTES))) return rc;
     if ((rc = set_smem(tma::stress_tma2<LT, 2>, tma::SMEM_BYTES))) return rc;
@@ -1115,13 +1120,17 @@ static int launch_half_step(bb_fdtd *h, bool stress, int acc_mode, int ib, int i
             }
         } else {
             const dim3 grid(p.ntk, p.ntj, plan.n), blk(tma::NTB, 1, 1);
+            // the kernels are compiled twice: for a slab with a neighbour on some side (halo wait, push, publish) and without
+            const bool peer = p.peerV[0] || p.peerV[1] || p.peerS[0] || p.peerS[1];
             if (stress) {
-                if (acc_mode == 1) tma::stress_tma<LT, 1><<<grid, blk, sm, h->stream>>>(h->smaps, p, plan);
-                else if (acc_mode == 2) tma::stress_tma<LT, 2><<<grid, blk, sm, h->stream>>>(h->smaps, p, plan);
-                else tma::stress_tma<LT, 0><<<grid, blk, sm, h->stream>>>(h->smaps, p, plan);
+                auto k = acc_mode == 1 ? (peer ? tma::stress_tma<LT, 1, true> : tma::stress_tma<LT, 1, false>)
+                       : acc_mode == 2 ? (peer ? tma::stress_tma<LT, 2, true> : tma::stress_tma<LT, 2, false>)
+                                       : (peer ? tma::stress_tma<LT, 0, true> : tma::stress_tma<LT, 0, false>);
+                k<<<grid, blk, sm, h->stream>>>(h->smaps, p, plan);
             } else {
-                if (acc_mode) tma::particle_tma<LT, 2><<<grid, blk, sm, h->stream>>>(h->pmaps, p, plan);
-                else tma::particle_tma<LT, 0><<<grid, blk, sm, h->stream>>>(h->pmaps, p, plan);
+                auto k = acc_mode ? (peer ? tma::particle_tma<LT, 2, true> : tma::particle_tma<LT, 2, false>)
+                                  : (peer ? tma::particle_tma<LT, 0, true> : tma::particle_tma<LT, 0, false>);
+                k<<<grid, blk, sm, h->stream>>>(h->pmaps, p, plan);
             }
         }
     }

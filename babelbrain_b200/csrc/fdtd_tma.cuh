@@ -245,7 +245,7 @@ enum { PB_SXX = 0, PB_SYY, PB_SZZ, PB_RXX, PB_RYY, PB_RZZ, PB_PR, PB_ACC, PB_FLU
 constexpr int ST_LOFF = align128(3 * HBOX_STRIDE);         // label box behind the three V boxes
 constexpr int ST_HSTAGE = ST_LOFF + LBOX_STRIDE;
 
-template <typename LT, int ACC>
+template <typename LT, int ACC, bool PEER>
 __global__ void __launch_bounds__(NTB, CTAS_PER_SM) stress_tma(const __grid_constant__ StressMaps tm, const DevParams p, const ChunkPlan plan) {
     constexpr bool SMC = sizeof(LT) == 1;
     constexpr int LW = LabBox<LT>::W;
@@ -294,8 +294,8 @@ __global__ void __launch_bounds__(NTB, CTAS_PER_SM) stress_tma(const __grid_cons
     // halo planes received through NVLink: the neighbour's previous half-step must have landed before this CTA
     // (its TMA loads and its queue prologue) reads them
     const bool first_hs = (unsigned)(p.seq & 0xffffffffu) <= 1u;
-    const bool near_lo = ic0 < p.i0 + 2 && p.peerV[0] != nullptr, near_hi = ic1 > p.i1 - 2 && p.peerV[1] != nullptr;
-    const bool has_peer = (ic0 < p.i0 + 2 || ic1 > p.i1 - 2) && (p.peerV[0] != nullptr || p.peerV[1] != nullptr);   // this CTA may push planes
+    const bool near_lo = PEER && ic0 < p.i0 + 2 && p.peerV[0] != nullptr, near_hi = PEER && ic1 > p.i1 - 2 && p.peerV[1] != nullptr;
+    const bool has_peer = PEER && (ic0 < p.i0 + 2 || ic1 > p.i1 - 2) && (p.peerV[0] != nullptr || p.peerV[1] != nullptr);   // this CTA may push planes
     if (tid == 0) {
         if (!first_hs && near_lo && !(p.exp & 4)) peer_wait(p, 0);
         if (!first_hs && near_hi && !(p.exp & 4)) peer_wait(p, 1);
@@ -315,11 +315,11 @@ __global__ void __launch_bounds__(NTB, CTAS_PER_SM) stress_tma(const __grid_cons
         // 1 MHz slabs when consumer thread 0 did them: ~30 boundary CTAs per SM).
         const int lo_last = (ic0 < p.i0 + 2 && p.peerS[0]) ? min(ic1, p.i0 + 2) - 1 - ic0 : -1;
         const int hi_last = (ic1 > p.i1 - 2 && p.peerS[1]) ? np - 1 : -1;
-        const int rend = p.publish ? max(np + 2, max(lo_last, hi_last) + nsh + 1) : np + 2;
+        const int rend = (PEER && p.publish) ? max(np + 2, max(lo_last, hi_last) + nsh + 1) : np + 2;
         for (int r = 0; r < rend; r++) {
             const int slot = rh.slot;
             mbar_wait(emptyH + slot * 8, rh.par);
-            if (p.publish && r >= nsh && (r - nsh == lo_last || r - nsh == hi_last)) {
+            if (PEER && p.publish && r >= nsh && (r - nsh == lo_last || r - nsh == hi_last)) {
                 if (p.exp & 32) __threadfence_system(); else if (!(p.exp & 1)) __threadfence();
                 const unsigned expected = 2u * gridDim.x * gridDim.y;
                 if (r - nsh == lo_last) peer_publish(p, 0, (unsigned)(min(ic1, p.i0 + 2) - ic0), expected);
@@ -427,8 +427,9 @@ __global__ void __launch_bounds__(NTB, CTAS_PER_SM) stress_tma(const __grid_cons
     unsigned qy_stride = (unsigned)p.nyrows * p.pitch, qz_stride = (unsigned)p.n2 * p.zpw;
     // (not pinned: only split-field cells use them, and pinning them made ptxas spill a loop counter to local memory)
     // boundary planes this CTA pushes to the slab neighbours: bit 0 lower, bit 1 upper (0 for almost every CTA)
-    int pushsel = has_peer ? ((ic0 < p.i0 + 2 && p.peerS[0] ? 1 : 0) | (ic1 > p.i1 - 2 && p.peerS[1] ? 2 : 0)) : 0;
-    keep(pushsel);
+    // (PEER = false, a slab without neighbours: a constant, and every block it guards leaves the instruction stream)
+    int pushsel = 0;
+    if constexpr (PEER) { pushsel = has_peer ? ((ic0 < p.i0 + 2 && p.peerS[0] ? 1 : 0) | (ic1 > p.i1 - 2 && p.peerS[1] ? 2 : 0)) : 0; keep(pushsel); }
     int nplanes = np, lane0 = lane == 0;
     keep(nplanes); keep(lane0);
     unsigned qy = ((unsigned)(ic0 - p.i0) * p.nyrows + yt + ty) * p.pitch + k;
@@ -645,7 +646,7 @@ constexpr int PT_LOFF = PT_XOFF + PBOX;
 constexpr int PT_S3OFF = align128(PT_LOFF + LBOX_STRIDE);  // the three shear boxes (own TMA)
 constexpr int PT_HSTAGE = PT_S3OFF + align128(3 * HBOX_STRIDE);
 
-template <typename LT, int ACC>
+template <typename LT, int ACC, bool PEER>
 __global__ void __launch_bounds__(NTB, CTAS_PER_SM) particle_tma(const __grid_constant__ ParticleMaps tm, const DevParams p, const ChunkPlan plan) {
     constexpr bool SMC = sizeof(LT) == 1;
     constexpr int LW = LabBox<LT>::W;
@@ -692,8 +693,8 @@ __global__ void __launch_bounds__(NTB, CTAS_PER_SM) particle_tma(const __grid_co
     // halo planes received through NVLink: the neighbour's previous half-step must have landed before this CTA
     // (its TMA loads and its queue prologue) reads them
     const bool first_hs = (unsigned)(p.seq & 0xffffffffu) <= 1u;
-    const bool near_lo = ic0 < p.i0 + 2 && p.peerS[0] != nullptr, near_hi = ic1 > p.i1 - 2 && p.peerS[1] != nullptr;
-    const bool has_peer = (ic0 < p.i0 + 2 || ic1 > p.i1 - 2) && (p.peerV[0] != nullptr || p.peerV[1] != nullptr);   // this CTA may push planes
+    const bool near_lo = PEER && ic0 < p.i0 + 2 && p.peerS[0] != nullptr, near_hi = PEER && ic1 > p.i1 - 2 && p.peerS[1] != nullptr;
+    const bool has_peer = PEER && (ic0 < p.i0 + 2 || ic1 > p.i1 - 2) && (p.peerV[0] != nullptr || p.peerV[1] != nullptr);   // this CTA may push planes
     if (tid == 0) {
         if (!first_hs && near_lo && !(p.exp & 4)) peer_wait(p, 0);
         if (!first_hs && near_hi && !(p.exp & 4)) peer_wait(p, 1);
@@ -710,11 +711,11 @@ __global__ void __launch_bounds__(NTB, CTAS_PER_SM) particle_tma(const __grid_co
         // publishes the pushed boundary planes once every consumer warp has released them (see stress_tma)
         const int lo_last = (ic0 < p.i0 + 2 && p.peerV[0]) ? min(ic1, p.i0 + 2) - 1 - ic0 : -1;
         const int hi_last = (ic1 > p.i1 - 2 && p.peerV[1]) ? np - 1 : -1;
-        const int rend = p.publish ? max(np + 2, max(lo_last, hi_last) + nsh + 1) : np + 2;
+        const int rend = (PEER && p.publish) ? max(np + 2, max(lo_last, hi_last) + nsh + 1) : np + 2;
         for (int r = 0; r < rend; r++) {
             const int slot = rh.slot;
             mbar_wait(emptyH + slot * 8, rh.par);
-            if (p.publish && r >= nsh && (r - nsh == lo_last || r - nsh == hi_last)) {
+            if (PEER && p.publish && r >= nsh && (r - nsh == lo_last || r - nsh == hi_last)) {
                 if (p.exp & 32) __threadfence_system(); else if (!(p.exp & 1)) __threadfence();
                 const unsigned expected = 2u * gridDim.x * gridDim.y;
                 if (r - nsh == lo_last) peer_publish(p, 0, (unsigned)(min(ic1, p.i0 + 2) - ic0), expected);
@@ -799,8 +800,9 @@ __global__ void __launch_bounds__(NTB, CTAS_PER_SM) particle_tma(const __grid_co
     unsigned qy_stride = (unsigned)p.nyrows * p.pitch, qz_stride = (unsigned)p.n2 * p.zpw;
     keep(qy_stride); keep(qz_stride);
     // boundary planes this CTA pushes to the slab neighbours: bit 0 lower, bit 1 upper (0 for almost every CTA)
-    int pushsel = has_peer ? ((ic0 < p.i0 + 2 && p.peerV[0] ? 1 : 0) | (ic1 > p.i1 - 2 && p.peerV[1] ? 2 : 0)) : 0;
-    keep(pushsel);
+    // (PEER = false, a slab without neighbours: a constant, and every block it guards leaves the instruction stream)
+    int pushsel = 0;
+    if constexpr (PEER) { pushsel = has_peer ? ((ic0 < p.i0 + 2 && p.peerV[0] ? 1 : 0) | (ic1 > p.i1 - 2 && p.peerV[1] ? 2 : 0)) : 0; keep(pushsel); }
     int nplanes = np, lane0 = lane == 0;
     keep(nplanes); keep(lane0);
     unsigned qy = ((unsigned)(ic0 - p.i0) * p.nyrows + yt + ty) * p.pitch + k;
