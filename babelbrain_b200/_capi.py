@@ -48,7 +48,7 @@ SYMBOLS = ['bb_last_error', 'bb_version', 'bb_device_count', 'bb_device_name', '
            'bb_fdtd_set_source_cells', 'bb_fdtd_set_source_functions', 'bb_fdtd_set_source_tones', 'bb_fdtd_set_sensors',
            'bb_fdtd_set_sensor_map', 'bb_fdtd_get_sensor_index',
            'bb_nccl_unique_id', 'bb_fdtd_comm_init', 'bb_fdtd_peer_export', 'bb_fdtd_peer_attach', 'bb_fdtd_run', 'bb_fdtd_reset', 'bb_fdtd_get_map',
-           'bb_fdtd_get_sensors', 'bb_fdtd_get_phase_data', 'bb_fdtd_get_stats', 'bb_fdtd_debug_cta_times', 'bb_rayleigh_forward', 'bb_bhte_run']
+           'bb_fdtd_get_sensors', 'bb_fdtd_get_sensors_runs', 'bb_fdtd_get_phase_data', 'bb_fdtd_get_stats', 'bb_fdtd_debug_cta_times', 'bb_rayleigh_forward', 'bb_bhte_run']
 
 _lib = None
 
@@ -89,6 +89,7 @@ def lib():
         L.bb_fdtd_reset.argtypes = [vp]
         L.bb_fdtd_get_map.argtypes = [vp, i32, i32, vp]
         L.bb_fdtd_get_sensors.argtypes = [vp, i32, vp]
+        L.bb_fdtd_get_sensors_runs.argtypes = [vp, i32, vp, i64, vp, vp, vp, i64, vp]
         L.bb_fdtd_get_phase_data.argtypes = [vp, i32, i32, i32, ctypes.c_float, vp, vp, vp]
         L.bb_fdtd_get_stats.argtypes = [vp, ctypes.POINTER(FdtdStats)]
         L.bb_fdtd_debug_cta_times.argtypes = [vp, vp, i64]

@@ -1386,6 +1386,51 @@ extern "C" int bb_fdtd_get_sensors(bb_fdtd *h, int map_id, float *out) {
     });
 }
 
+extern "C" int bb_fdtd_get_sensors_runs(bb_fdtd *h, int map_id, float *table, int64_t table_rows, const int64_t *dst_row,
+                                        const int64_t *src_row, const int64_t *nrows, int64_t nruns, int *done) {
+    BB_REQUIRE(h && table && done, "null argument");
+    BB_REQUIRE(map_id >= 0 && map_id < BB_MAP_COUNT && (h->d.sel_maps_sensor & (1u << map_id)), "sensor map %d not selected", map_id);
+    BB_REQUIRE(nruns >= 0 && (nruns == 0 || (dst_row && src_row && nrows)), "bad run tables");
+    *done = 0;
+    BB_CUDA(cudaSetDevice(h->d.device));
+    if (!host_is_pinned(table)) return BB_OK;                // the caller falls back to bb_fdtd_get_sensors + bb_host_scatter_runs
+    *done = 1;
+    if (h->nsensors == 0 || h->nsamples == 0 || nruns == 0) return BB_OK;
+    int64_t at = 0;                                          // the runs must tile the slab's rows in order and stay inside the table
+    for (int64_t u = 0; u < nruns; u++) {
+        if (nrows[u] <= 0 || src_row[u] != at || dst_row[u] < 0 || dst_row[u] + nrows[u] > table_rows) {
+            bb_set_error("run %lld (rows %lld..+%lld -> %lld) does not continue the slab's rows or leaves the table of %lld rows",
+                         (long long)u, (long long)src_row[u], (long long)nrows[u], (long long)dst_row[u], (long long)table_rows);
+            return BB_ERR_ARG;
+        }
+        at += nrows[u];
+    }
+    BB_REQUIRE(at == h->nsensors, "the runs cover %lld rows, the slab has %lld sensors", (long long)at, (long long)h->nsensors);
+    const int slot = popcount32(h->d.sel_maps_sensor & ((1u << map_id) - 1u));
+    const int nsam = (int)h->nsamples;
+    const size_t smem = (size_t)nsam * (BB_ST_SENSORS + 1) * 4;
+    BB_REQUIRE(smem <= 200u * 1024u, "%d samples per sensor exceed the transpose tile", nsam);
+    if (smem > 40u * 1024u) BB_CUDA(cudaFuncSetAttribute(sensor_transpose_scatter_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    DevTmp tsrc(h->d.device), tdst(h->d.device);
+    cudaError_t e = tsrc.alloc((size_t)nruns * 8);
+    if (e == cudaSuccess) e = tdst.alloc((size_t)nruns * 8);
+    if (e == cudaSuccess) e = cudaMemcpyAsync(tsrc.as<long long>(), src_row, (size_t)nruns * 8, cudaMemcpyHostToDevice, h->stream);
+    if (e == cudaSuccess) e = cudaMemcpyAsync(tdst.as<long long>(), dst_row, (size_t)nruns * 8, cudaMemcpyHostToDevice, h->stream);
+    if (e == cudaSuccess) {
+        const float *in = h->sensor_out + (size_t)slot * h->nsensors * h->nsamples;
+        float *dtab = nullptr;
+        e = cudaHostGetDevicePointer((void **)&dtab, table, 0);
+        if (e == cudaSuccess) {
+            sensor_transpose_scatter_kernel<<<(unsigned)((h->nsensors + BB_ST_SENSORS - 1) / BB_ST_SENSORS), BB_ST_SENSORS, smem, h->stream>>>(
+                in, dtab, h->nsensors, nsam, tsrc.as<long long>(), tdst.as<long long>(), nruns);
+            e = cudaGetLastError();
+        }
+    }
+    if (e == cudaSuccess) e = cudaStreamSynchronize(h->stream);
+    if (e != cudaSuccess) { bb_set_error("get_sensors_runs: %s", cudaGetErrorString(e)); cudaGetLastError(); return BB_ERR_CUDA; }
+    return BB_OK;
+}
+
 extern "C" int bb_fdtd_get_phase_data(bb_fdtd *h, int map_id, int bin, int nsamples_used, float scale,
                                       float *fourier_reim, float *phase, float *peak) {
     BB_REQUIRE(h && fourier_reim, "null argument");

@@ -104,6 +104,32 @@ __global__ void __launch_bounds__(BB_ST_SENSORS) sensor_transpose_kernel(const f
     }
 }
 
+// The same for one slab of a multi-GPU run, written straight into the whole-grid table in page-locked host memory: the
+// slab's rows form runs of consecutive rows (one per (j,k) line, slab.merge_sensor_runs); run u holds the slab's rows
+// [src_row[u], src_row[u+1]) and starts at row dst_row[u] of the table.  Rows of one run stay contiguous, so the PCIe
+// writes are as coalesced as the device-memory ones above.
+__global__ void __launch_bounds__(BB_ST_SENSORS) sensor_transpose_scatter_kernel(const float *__restrict__ in, float *__restrict__ table, long long nsensors,
+                                                                                  int nsamples, const long long *__restrict__ src_row,
+                                                                                  const long long *__restrict__ dst_row, long long nruns) {
+    extern __shared__ float st_tile[];              // [nsamples][BB_ST_SENSORS + 1]
+    __shared__ long long grow[BB_ST_SENSORS];
+    const long long base = (long long)blockIdx.x * BB_ST_SENSORS;
+    const int nhere = (int)min((long long)BB_ST_SENSORS, nsensors - base);
+    if ((int)threadIdx.x < nhere) {
+        const long long s = base + threadIdx.x;
+        long long lo = 0, hi = nruns;               // last run with src_row <= s
+        while (hi - lo > 1) { const long long mid = (lo + hi) >> 1; if (src_row[mid] <= s) lo = mid; else hi = mid; }
+        grow[threadIdx.x] = dst_row[lo] + (s - src_row[lo]);
+    }
+    for (int t = 0; t < nsamples; t++)
+        if ((int)threadIdx.x < nhere) st_tile[t * (BB_ST_SENSORS + 1) + threadIdx.x] = in[(long long)t * nsensors + base + threadIdx.x];
+    __syncthreads();
+    for (int e = threadIdx.x; e < nhere * nsamples; e += BB_ST_SENSORS) {
+        const int sl = e / nsamples, t = e - sl * nsamples;
+        table[grow[sl] * nsamples + t] = st_tile[t * (BB_ST_SENSORS + 1) + sl];
+    }
+}
+
 // Single-bin DFT of each sensor's trace (in: [sample][sensor]), its angle and the largest sample, scattered to the dense
 // (nown, n2, n3) volumes of the slab.  tw = nsamples (cos, -sin) pairs of the bin, rounded from double on the host.
 __global__ void phase_data_kernel(const DevParams p, const float *__restrict__ in, const long long *__restrict__ cell, long long nsensors,

@@ -171,6 +171,13 @@ int bb_fdtd_reset(bb_fdtd *h);                               /* zero state, step
 int bb_fdtd_get_map(bb_fdtd *h, int which, int map_id, float *out);
 /* out = (nsensors, nsamples) float32 for one selected sensor map */
 int bb_fdtd_get_sensors(bb_fdtd *h, int map_id, float *out);
+/* one slab of a multi-GPU run: the slab's rows go straight into the whole-grid (table_rows, nsamples) table `table` in
+ * page-locked host memory, run by run (run u = the slab's rows [src_row[u], src_row[u] + nrows[u]) -> table rows from
+ * dst_row[u]; the runs tile the slab's rows in order: slab.merge_sensor_runs).  *done = 0 and nothing written when `table`
+ * is not page-locked: use bb_fdtd_get_sensors + bb_host_scatter_runs then.  Replaces the per-sensor placement the caller
+ * would otherwise do on the host after gathering slabs (the reference has one GPU and no such step). */
+int bb_fdtd_get_sensors_runs(bb_fdtd *h, int map_id, float *table, int64_t table_rows, const int64_t *dst_row,
+                             const int64_t *src_row, const int64_t *nrows, int64_t nruns, int *done);
 /* Phase / amplitude extraction of the sampled traces on the device -- what the caller's CalculatePhaseData does on the
  * host with an FFT over Sensor['Pressure'] (BabelIntegrationBASE.py:2498-2518): for every sensor of this slab, bin `bin`
  * of the DFT of its first nsamples_used samples (sum_n x[n] exp(-2 pi j bin n / nsamples_used)) times `scale`

@@ -254,6 +254,42 @@ def test_two_gpu_slabs_match_single_gpu(halo):
     assert rl2(sens, S1['Pressure']) <= 1e-6
 
 
+def test_sensor_rows_placed_by_runs_on_the_device():
+    """bb_fdtd_get_sensors_runs (the gather of a multi-GPU run through the public call): a slab's rows, cut into runs,
+    land in their places of a larger page-locked table; everything else in the table stays untouched."""
+    import ctypes
+    from babelbrain_b200 import _capi
+    w = workloads.make_workload('ctx500_skull', shape=(30, 26, 36), periods=3, pml=4)
+    kw = {k: v for k, v in w['kwargs'].items() if k not in DROP}
+    s = FdtdSlab(*w['args'], **kw)
+    s.run()
+    ref = s.get_sensors('Pressure')
+    n, nsam = ref.shape
+    cuts = np.array([0, n // 3, n // 2, n], np.int64)
+    src, cnt = np.ascontiguousarray(cuts[:-1]), np.ascontiguousarray(np.diff(cuts))
+    dst = np.array([cnt[2] + 3 + cnt[1] + 2, cnt[2] + 3, 0], np.int64)           # the three runs in reverse order, with gaps
+    rows = int(n + 7)
+    table = _capi.pinned.empty((rows, nsam), np.float32)
+    table[:] = -7.0
+    done = ctypes.c_int(0)
+    call = lambda t, d, sr, c: _capi.lib().bb_fdtd_get_sensors_runs(s._h, _capi.MAP_ID['Pressure'], _capi.ptr(t), t.shape[0], _capi.ptr(d),
+                                                                    _capi.ptr(sr), _capi.ptr(c), d.size, ctypes.byref(done))
+    _capi.check(call(table, dst, src, cnt))
+    assert done.value == 1
+    expect = np.full((rows, nsam), -7.0, np.float32)
+    for d, a, c in zip(dst, src, cnt):
+        expect[d:d + c] = ref[a:a + c]
+    assert np.array_equal(table, expect)
+    pageable = np.zeros((rows, nsam), np.float32)                                  # not page-locked: nothing written, the caller falls back
+    _capi.check(call(pageable, dst, src, cnt))
+    assert done.value == 0 and not pageable.any()
+    bad = src.copy(); bad[1] += 1                                                  # runs that do not tile the slab's rows
+    assert call(table, dst, bad, cnt) != 0
+    too_far = dst.copy(); too_far[0] += 10                                         # a run that leaves the table
+    assert call(table, too_far, src, cnt) != 0
+    s.close()
+
+
 def test_public_call_on_two_gpus_returns_the_single_gpu_arrays(monkeypatch):
     """NumberGPUs=2 (or BABELB200_NGPUS=2 for an unmodified caller) through the reference-shaped call: same
     tuple, whole-grid arrays, IndexSensorMap bit-exact, maps and sensor traces equal to the one-GPU run."""
