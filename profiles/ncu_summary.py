@@ -1,6 +1,13 @@
-"""Summarise an ncu report: python profiles/ncu_summary.py <file.ncu-rep> [kernel-regex]
-Prints the headline metrics per captured launch and the top stall locations (needs -lineinfo)."""
-import csv, io, subprocess, sys
+"""Summarise an ncu report: python profiles/ncu_summary.py <file.ncu-rep> [kernel-regex] [--traffic-json "<how it was captured>"]
+Prints the headline metrics per captured launch and the top stall locations (needs -lineinfo).  With --traffic-json the DRAM
+bytes of the first stress_tma / particle_tma launch go to profiles/ncu_traffic.json together with the hash of the kernel sources
+of this tree (bench.py reports them as roofline.traffic and says whether they still belong to the current kernels)."""
+import csv, io, json, os, subprocess, sys
+traffic_note = None
+if '--traffic-json' in sys.argv:
+    i = sys.argv.index('--traffic-json')
+    traffic_note = sys.argv[i + 1]
+    del sys.argv[i:i + 2]
 rep = sys.argv[1]
 raw = subprocess.run(['ncu', '-i', rep, '--page', 'raw', '--csv'], capture_output=True, text=True).stdout
 rows = list(csv.reader(io.StringIO(raw)))
@@ -18,6 +25,24 @@ for r in rows[2:]:
     st = sorted(((float(r[i]), h) for i, h in enumerate(hdr) if 'issue_stalled' in h and h.endswith('per_issue_active.ratio') and r[i]), reverse=True)
     for v, h in st[:6]:
         print('   stall %-40s %.2f' % (h.replace('smsp__average_warps_issue_stalled_', '').replace('_per_issue_active.ratio', ''), v))
+if traffic_note is not None:
+    sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
+    import bench
+    out = {'source': traffic_note, 'kernel_sha16': bench.kernel_sha16()}
+    for key in ('stress_tma', 'particle_tma'):
+        for r in rows[2:]:
+            name = r[hdr.index('Kernel Name')]
+            if key + '<' in name or name.startswith(key):
+                def val(metric):        # ncu prints Mbyte / Gbyte / usecond ...: normalise to bytes and microseconds
+                    v, u = float(r[hdr.index(metric)].replace(',', '')), units[hdr.index(metric)]
+                    return v * {'byte': 1.0, 'Kbyte': 1e3, 'Mbyte': 1e6, 'Gbyte': 1e9, 'nsecond': 1e-3, 'usecond': 1.0, 'msecond': 1e3, 'ns': 1e-3, 'us': 1.0, 'ms': 1e3}[u]
+                rd, wr = val('dram__bytes_read.sum'), val('dram__bytes_write.sum')
+                out[key] = {'kernel': name, 'dram_bytes_read': rd, 'dram_bytes_write': wr, 'dram_bytes_per_launch': rd + wr,
+                            'duration_us': val('gpu__time_duration.sum')}
+                break
+    with open(os.path.join(os.path.dirname(os.path.abspath(__file__)), 'ncu_traffic.json'), 'w') as f:
+        json.dump(out, f, indent=1)
+    print('wrote profiles/ncu_traffic.json:', json.dumps(out)[:300])
 pat = sys.argv[2] if len(sys.argv) > 2 else None
 if pat:
     src = subprocess.run(['ncu', '-i', rep, '--page', 'source', '--csv', '--kernel-name', 'regex:' + pat], capture_output=True, text=True).stdout
