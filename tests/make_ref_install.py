@@ -1,4 +1,4 @@
-"""Places an unmodified copy of the reference's TranscranialModeling package under baseline/_ref/ (git-ignored, so it never
+"""Places an unmodified copy of the reference's TranscranialModeling and ThermalModeling packages under baseline/_ref/ (git-ignored, so it never
 enters the repository history; not gpurun-ignored, so it travels to the GPU box, where /root/reference does not exist).
 tests/test_reference_caller.py imports the reference caller from there.  __graft_entry__.build() runs this whenever
 /root/reference is present.
@@ -21,7 +21,13 @@ def install():
     if os.path.isdir(DST):
         shutil.rmtree(DST)
     # the Python sources of the caller only: geometry tables (.mat/.csv/.h5) are not touched by the harness
-    shutil.copytree(SRC, DST, ignore=shutil.ignore_patterns('__pycache__', '*.mat', '*.h5', '*.csv', '*.stl', '*.npz'))
+    ignore = shutil.ignore_patterns('__pycache__', '*.mat', '*.h5', '*.csv', '*.stl', '*.npz')
+    shutil.copytree(SRC, DST, ignore=ignore)
+    thermal_src, thermal_dst = os.path.join(os.path.dirname(SRC), 'ThermalModeling'), os.path.join(os.path.dirname(DST), 'ThermalModeling')
+    if os.path.isdir(thermal_src):         # the driver of the thermal step (tests/test_reference_thermal_caller.py)
+        if os.path.isdir(thermal_dst):
+            shutil.rmtree(thermal_dst)
+        shutil.copytree(thermal_src, thermal_dst, ignore=ignore)
     return DST
 
 

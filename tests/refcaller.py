@@ -165,3 +165,22 @@ def run_cases(mask, captured, transducer='BabelIntegrationSingle', patch=None, *
         return tx.RUN_SIM().RunCases(**kargs)
     finally:
         np.seterr(**old_err)                   # the reference sets np.seterr(divide='raise') at import (BASE.py:11)
+
+
+def load_thermal():
+    """Import the unmodified ThermalModeling/CalculateTemperatureEffects.py (the driver of the thermal step) with the shim
+    first on sys.path and the stand-ins above for matplotlib / linetimer."""
+    ref = reference_root()
+    if ref is None or not os.path.isfile(os.path.join(ref, 'ThermalModeling', 'CalculateTemperatureEffects.py')):
+        raise FileNotFoundError('no reference ThermalModeling: neither /root/reference nor baseline/_ref (python tests/make_ref_install.py)')
+    if ROOT not in sys.path:
+        sys.path.insert(0, ROOT)
+    install_stubs(None)
+    for k in [k for k in sys.modules if k == 'ThermalModeling' or k.startswith('ThermalModeling.')]:
+        del sys.modules[k]
+    if ref not in sys.path:
+        sys.path.append(ref)
+    pkg = types.ModuleType('ThermalModeling')
+    pkg.__path__ = [os.path.join(ref, 'ThermalModeling')]
+    sys.modules['ThermalModeling'] = pkg
+    return importlib.import_module('ThermalModeling.CalculateTemperatureEffects')
