@@ -43,9 +43,9 @@ class FdtdStats(ctypes.Structure):
 
 
 # every symbol include/babelb200.h declares (checked by tests/test_capi.py)
-SYMBOLS = ['bb_last_error', 'bb_version', 'bb_device_count', 'bb_device_name', 'bb_host_alloc', 'bb_host_free', 'bb_host_scatter_rows', 'bb_host_scatter_runs', 'bb_release_cached_memory', 'bb_fdtd_create',
+SYMBOLS = ['bb_last_error', 'bb_version', 'bb_device_count', 'bb_device_name', 'bb_host_alloc', 'bb_host_free', 'bb_host_scatter_rows', 'bb_host_scatter_runs', 'bb_host_nonzero_u32', 'bb_release_cached_memory', 'bb_fdtd_create',
            'bb_fdtd_destroy', 'bb_fdtd_set_stream', 'bb_fdtd_set_materials', 'bb_fdtd_set_maps',
-           'bb_fdtd_set_source_cells', 'bb_fdtd_set_source_functions', 'bb_fdtd_set_source_tones', 'bb_fdtd_set_sensors',
+           'bb_fdtd_set_source_cells', 'bb_fdtd_set_source_functions', 'bb_fdtd_set_source_functions_streamed', 'bb_fdtd_set_source_tones', 'bb_fdtd_set_sensors',
            'bb_fdtd_set_sensor_map', 'bb_fdtd_get_sensor_index',
            'bb_nccl_unique_id', 'bb_fdtd_comm_init', 'bb_fdtd_peer_export', 'bb_fdtd_peer_attach', 'bb_fdtd_run', 'bb_fdtd_reset', 'bb_fdtd_get_map',
            'bb_fdtd_get_sensors', 'bb_fdtd_get_sensors_runs', 'bb_fdtd_get_phase_data', 'bb_fdtd_get_stats', 'bb_fdtd_debug_cta_times', 'bb_rayleigh_forward', 'bb_bhte_run']
@@ -69,6 +69,7 @@ def lib():
         L.bb_host_free.argtypes = [vp]
         L.bb_host_scatter_rows.argtypes = [vp, vp, vp, i64, i64]
         L.bb_host_scatter_runs.argtypes = [vp, vp, vp, vp, vp, i64, i64]
+        L.bb_host_nonzero_u32.argtypes = [vp, i64, vp, vp, i64, vp]
         L.bb_fdtd_create.argtypes = [ctypes.POINTER(FdtdDesc), ctypes.POINTER(vp)]
         L.bb_fdtd_destroy.argtypes = [vp]
         L.bb_fdtd_destroy.restype = None
@@ -77,6 +78,7 @@ def lib():
         L.bb_fdtd_set_maps.argtypes = [vp, vp, vp]
         L.bb_fdtd_set_source_cells.argtypes = [vp, i64, vp, vp, vp, vp, vp]
         L.bb_fdtd_set_source_functions.argtypes = [vp, vp, i32, i64]
+        L.bb_fdtd_set_source_functions_streamed.argtypes = [vp, vp, i32, i64]
         L.bb_fdtd_set_source_tones.argtypes = [vp, vp, vp, vp, vp]
         L.bb_fdtd_set_sensors.argtypes = [vp, i64, vp]
         L.bb_fdtd_set_sensor_map.argtypes = [vp, vp, ctypes.POINTER(ctypes.c_int64)]

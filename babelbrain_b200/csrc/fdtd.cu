@@ -71,6 +71,13 @@ struct bb_fdtd {
     int *src_row = nullptr;
     float *src_o[3] = {nullptr, nullptr, nullptr};
     float *srcfun = nullptr;  // [nt_src][nsrc]
+    // SourceFunctions streamed during the run (bb_fdtd_set_source_functions_streamed): the caller's table, how much of it
+    // (time samples) is on the device, and the copy stream / events that order each chunk before the step that reads it
+    const void *sf_host = nullptr;
+    int sf_f64 = 0, sf_chunk = 0, sf_uploaded = 0, sf_waited = 0;
+    int64_t sf_stride = 0;
+    cudaStream_t sf_stream = nullptr;
+    cudaEvent_t sf_ev[2] = {nullptr, nullptr};
     int *bsrc_map = nullptr;  // [4][plane] boundary-plane source index map (multi-rank handles)
     // continuous-wave sources synthesised in the source kernel instead of read from srcfun (bb_fdtd_set_source_tones)
     float *tone_ac = nullptr, *tone_as = nullptr;     // [nsrc] A cos(phi), A sin(phi)
@@ -514,6 +521,8 @@ extern "C" void bb_fdtd_destroy(bb_fdtd *h) {
     if (h->ev_halo) cudaEventDestroy(h->ev_halo);
     if (h->own_stream && h->stream) cudaStreamDestroy(h->stream);
     if (h->comm_stream) cudaStreamDestroy(h->comm_stream);
+    if (h->sf_stream) cudaStreamDestroy(h->sf_stream);
+    for (cudaEvent_t e : h->sf_ev) if (e) cudaEventDestroy(e);
     delete h;
 }
 
@@ -536,6 +545,43 @@ extern "C" int bb_host_scatter_runs(void *out, const void *data, const int64_t *
         if (nrows[r] < 0 || dst_row[r] < 0 || src_row[r] < 0) { bb_set_error("negative run %lld", (long long)r); return BB_ERR_ARG; }
         memcpy(o + dst_row[r] * row_bytes, d + src_row[r] * row_bytes, (size_t)(nrows[r] * row_bytes));
     }
+    return BB_OK;
+}
+
+// Nonzero entries of a uint32 volume (the caller's SourceMap: 46 656 of 18.4 M cells for CTX-500) on a few host threads:
+// flat index and value of every nonzero entry, in order.  np.flatnonzero takes 40-60 ms for that volume, a third of the
+// set-up phase of a simulation; this takes 3.  *count receives the number of nonzero entries; nothing is written when it
+// exceeds `capacity` (call again with larger arrays).
+extern "C" int bb_host_nonzero_u32(const uint32_t *a, int64_t n, int64_t *index, uint32_t *value, int64_t capacity, int64_t *count) {
+    BB_REQUIRE(count && n >= 0 && (n == 0 || a) && capacity >= 0 && (capacity == 0 || (index && value)), "bad argument");
+    const int nth = (int)std::max<int64_t>(1, std::min<int64_t>(8, n / (1 << 20)));
+    const int64_t per = ((n + nth - 1) / nth + 7) & ~(int64_t)7;
+    std::vector<std::vector<int64_t>> found(nth);
+    auto body = [&](int t) {
+        const int64_t b = std::min<int64_t>(n, t * per), e = std::min<int64_t>(n, b + per);
+        std::vector<int64_t> &f = found[t];
+        int64_t i = b;
+        for (; i < e && (((uintptr_t)(a + i)) & 31); i++) if (a[i]) f.push_back(i);     // up to a 32-byte boundary
+        for (; i + 8 <= e; i += 8) {                                                     // the volume is almost all zeros: 8 cells per test
+            uint64_t w[4];
+            memcpy(w, a + i, 32);
+            if ((w[0] | w[1] | w[2] | w[3]) == 0) continue;
+            for (int k = 0; k < 8; k++) if (a[i + k]) f.push_back(i + k);
+        }
+        for (; i < e; i++) if (a[i]) f.push_back(i);
+    };
+    if (nth == 1) body(0);
+    else {
+        std::vector<std::thread> th;
+        for (int t = 0; t < nth; t++) th.emplace_back(body, t);
+        for (auto &x : th) x.join();
+    }
+    int64_t total = 0;
+    for (const auto &f : found) total += (int64_t)f.size();
+    *count = total;
+    if (total > capacity) return BB_OK;
+    int64_t o = 0;
+    for (const auto &f : found) for (int64_t i : f) { index[o] = i; value[o] = a[i]; o++; }
     return BB_OK;
 }
 
@@ -738,6 +784,86 @@ extern "C" int bb_fdtd_set_source_functions(bb_fdtd *h, const void *data, int is
         else srcfun_transpose_kernel<float><<<grid, blk, 0, h->stream>>>((const float *)dev, row_stride, h->srcfun + s0, (int)ns, nt, nsrc);
         return BB_OK;
     });
+}
+
+// ---- SourceFunctions streamed in time chunks while the time loop runs
+// The dense table is 0.95 GB of float64 for CTX-500 and the time loop only ever needs the samples of the step it is at, so
+// the upload does not have to finish before the first step: chunk c (sf_chunk consecutive samples of every row) is gathered
+// into a page-locked staging slot by the host thread that launches the time loop (it runs hundreds of launches ahead of
+// the GPU), copied and transposed on a second stream, and the time loop waits on the chunk's event at the first step
+// that reads it.  One chunk is kept in flight ahead of the one in use.
+static int upload_source_chunk(bb_fdtd *h) {
+    const int nsrc = h->d.nsrc, nt = h->d.nt_src;
+    const int t0 = h->sf_uploaded, T = std::min(h->sf_chunk, nt - t0);
+    if (T <= 0) return BB_OK;
+    const size_t esz = h->sf_f64 ? 8 : 4, seg = (size_t)T * esz;
+    Stager *sg;
+    int rc;
+    if ((rc = stager_get(h->d.device, &sg))) return rc;
+    std::lock_guard<std::mutex> lock(sg->mu);
+    const int b = (t0 / h->sf_chunk) & 1;
+    BB_CUDA(cudaEventSynchronize(sg->ev[b]));          // the slot's previous transfer and kernel are done
+    {   // rows' segments [t0, t0 + T) -> dense (nsrc, T) block in the staging slot, on a few threads
+        const char *src = (const char *)h->sf_host + (size_t)t0 * esz;
+        char *dst = (char *)sg->host[b];
+        const size_t rstride = (size_t)h->sf_stride * esz;
+        const int nth = (size_t)nsrc * seg >= (8u << 20) ? 4 : 1;
+        auto part = [=](int r0, int r1) { for (int r = r0; r < r1; r++) memcpy(dst + (size_t)r * seg, src + (size_t)r * rstride, seg); };
+        if (nth == 1) part(0, nsrc);
+        else {
+            std::vector<std::thread> th;
+            const int per = (nsrc + nth - 1) / nth;
+            for (int t = 0; t < nth; t++) th.emplace_back(part, std::min(nsrc, t * per), std::min(nsrc, (t + 1) * per));
+            for (auto &x : th) x.join();
+        }
+    }
+    BB_CUDA(cudaMemcpyAsync(sg->dev[b], sg->host[b], (size_t)nsrc * seg, cudaMemcpyHostToDevice, h->sf_stream));
+    const dim3 blk(32, 8), grid((T + 31) / 32, (unsigned)((nsrc + 31) / 32));
+    float *out = h->srcfun + (size_t)t0 * nsrc;
+    if (h->sf_f64) srcfun_transpose_kernel<double><<<grid, blk, 0, h->sf_stream>>>((const double *)sg->dev[b], T, out, nsrc, T, nsrc);
+    else srcfun_transpose_kernel<float><<<grid, blk, 0, h->sf_stream>>>((const float *)sg->dev[b], T, out, nsrc, T, nsrc);
+    BB_CUDA(cudaGetLastError());
+    BB_CUDA(cudaEventRecord(sg->ev[b], h->sf_stream));
+    BB_CUDA(cudaEventRecord(h->sf_ev[b], h->sf_stream));
+    h->sf_uploaded = t0 + T;
+    return BB_OK;
+}
+
+// before the kernels of time step n are launched: its chunk is on its way, the next one too, and the time loop's stream
+// waits for the chunk of n if it has not yet
+static int ensure_source_samples(bb_fdtd *h, int n) {
+    if (!h->sf_host || n >= h->d.nt_src) return BB_OK;
+    int rc;
+    const int want = std::min(h->d.nt_src, (n / h->sf_chunk + 2) * h->sf_chunk);
+    while (h->sf_uploaded < want) if ((rc = upload_source_chunk(h))) return rc;
+    const int c = n / h->sf_chunk;
+    if (c >= h->sf_waited) {
+        BB_CUDA(cudaStreamWaitEvent(h->stream, h->sf_ev[c & 1], 0));
+        h->sf_waited = c + 1;
+    }
+    return BB_OK;
+}
+
+extern "C" int bb_fdtd_set_source_functions_streamed(bb_fdtd *h, const void *data, int is_f64, int64_t row_stride) {
+    BB_REQUIRE(h && data, "null argument");
+    const int nsrc = h->d.nsrc, nt = h->d.nt_src;
+    BB_REQUIRE(nsrc > 0 && nt > 0 && row_stride >= nt, "bad SourceFunctions shape");
+    const size_t esz = is_f64 ? 8 : 4;
+    const int64_t chunk = (int64_t)(BB_STAGE_BYTES / ((size_t)nsrc * esz));
+    // many short rows (H317: 331 776 sources) would make chunks of a few samples: the whole-row upload serves those
+    if (chunk < 64 || getenv("BB_SOURCES_UPFRONT")) return bb_fdtd_set_source_functions(h, data, is_f64, row_stride);
+    BB_CUDA(cudaSetDevice(h->d.device));
+    int rc;
+    if (!h->srcfun) if ((rc = dev_alloc(h, (void **)&h->srcfun, (size_t)nsrc * nt * 4, false))) return rc;
+    if (!h->sf_stream) {
+        BB_CUDA(cudaStreamCreateWithFlags(&h->sf_stream, cudaStreamNonBlocking));
+        for (cudaEvent_t &e : h->sf_ev) BB_CUDA(cudaEventCreateWithFlags(&e, cudaEventDisableTiming));
+    }
+    BB_CUDA(cudaStreamSynchronize(h->stream));          // srcfun may still be read by an earlier run of this handle
+    h->sf_host = data; h->sf_f64 = is_f64; h->sf_stride = row_stride;
+    h->sf_chunk = (int)std::min<int64_t>(chunk, 512);
+    h->sf_uploaded = 0; h->sf_waited = 0;
+    return BB_OK;
 }
 
 extern "C" int bb_fdtd_set_source_tones(bb_fdtd *h, const float *a_cos, const float *a_sin, const float *env_sin, const float *env_cos) {
@@ -1233,6 +1359,7 @@ static int run_steps(bb_fdtd *h, int64_t nsteps, Timer &tm) {
     int rc;
     for (int64_t t = 0; t < nsteps; t++) {
         const int n = (int)h->step;
+        if ((rc = ensure_source_samples(h, n))) return rc;
         const bool window = d.sel_rms_peak != 0 && n >= n0;
         const bool only_p_rms = d.sel_rms_peak == 1 && d.sel_maps_rms == (1u << BB_MAP_PRESSURE);
         if ((rc = half_step<LT>(h, true, n, (window && stress_maps) ? (only_p_rms ? 1 : 2) : 0, tm))) return rc;

@@ -29,8 +29,10 @@ class FdtdSlab:
                  QCorrection=1.0, TypeSource=0, SelRMSorPeak=1, SelMapsRMSPeakList=('ALLV',),
                  SelMapsSensorsList=('Vx', 'Vy', 'Vz'), SensorSubSampling=2, SensorStart=0,
                  ReflectorMask=None, device=0, rank=0, nranks=1, kernel_variant=0, steps=None,
-                 origin=None, n1_global=None, global_sensor_table=True, MPMLRatio=None):
+                 origin=None, n1_global=None, global_sensor_table=True, MPMLRatio=None, stream_sources=False):
         self._h = None
+        self._sf_keepalive = None
+        _t_init = time.perf_counter()
         if not isinstance(MaterialMap, np.ndarray) or MaterialMap.ndim != 3:
             raise ValueError('MaterialMap must be a 3-D numpy array')
         for name, arr in (('MaterialMap', MaterialMap), ('SourceMap', SourceMap), ('SensorMap', SensorMap)):
@@ -94,8 +96,8 @@ class FdtdSlab:
 
         # ---- sources owned by this slab (global C-order cell index; ids are 1-based rows)
         sm_slab = SourceMap[i0 - org:i1 - org]
-        flat = np.flatnonzero(sm_slab.reshape(-1))
-        rows = sm_slab.reshape(-1)[flat].astype(np.int64) - 1
+        flat, ids = _nonzero_u32(sm_slab)
+        rows = ids.astype(np.int64) - 1
         if flat.size and rows.max() >= SF.shape[0]:
             raise ValueError('SourceMap refers to source %d but SourceFunctions has %d rows' % (rows.max() + 1, SF.shape[0]))
         cells = flat.astype(np.int64) + np.int64(i0) * N2 * N3
@@ -146,7 +148,7 @@ class FdtdSlab:
                            rank=self.rank, nranks=self.nranks, kernel_variant=int(kernel_variant), mpml_ratio=self.mpml_ratio,
                            dt=dt)
         _t = [time.perf_counter()]
-        _marks = []
+        _marks = ['host prep %.3f' % (_t[0] - _t_init)]
 
         def _mark(name):          # host-side wall clock of the set-up stages, printed when BB_TIMING is set
             _t.append(time.perf_counter())
@@ -177,8 +179,11 @@ class FdtdSlab:
             _capi.check(L.bb_fdtd_set_source_tones(hp, *[_capi.ptr(a) for a in tones]))
             sf_bytes = sum(a.nbytes for a in tones)
         elif cells.size:
-            _capi.check(L.bb_fdtd_set_source_functions(hp, _capi.ptr(SF), int(SF.dtype == np.float64),
-                                                       SF.strides[0] // SF.itemsize))
+            # stream_sources: the table goes up in chunks of time samples while the time loop runs (the public call; SF is
+            # kept alive here until the slab is closed); otherwise at once, so that a timed run() starts with its inputs resident
+            setter = L.bb_fdtd_set_source_functions_streamed if stream_sources else L.bb_fdtd_set_source_functions
+            _capi.check(setter(hp, _capi.ptr(SF), int(SF.dtype == np.float64), SF.strides[0] // SF.itemsize))
+            self._sf_keepalive = SF if stream_sources else None
             sf_bytes = SF.nbytes
         _mark('sources')
         self.d2h_bytes = 0
@@ -233,6 +238,8 @@ class FdtdSlab:
 
     def run(self, nsteps=-1, profile=False):
         _capi.check(self._L.bb_fdtd_run(self._h, int(nsteps), int(bool(profile))))
+        if int(nsteps) < 0:
+            self._sf_keepalive = None        # a run to the last step has streamed the whole source table
         return self.stats()
 
     def reset(self):
@@ -344,6 +351,21 @@ class _LastMapSlabs(_LastMap):
         for s in self._slabs:
             s.close()
         self._slabs = []
+
+
+def _nonzero_u32(volume):
+    """(flat indices, values) of the nonzero entries of a C-contiguous uint32 volume, in order: np.flatnonzero takes 40-60 ms
+    on the CTX-500 SourceMap (18.4 M cells, 46 656 sources), bb_host_nonzero_u32 scans it on a few threads in ~3."""
+    a = np.ascontiguousarray(volume).reshape(-1)
+    L = _capi.lib()
+    cap = max(1024, a.size // 256)
+    while True:
+        idx, val = np.empty(cap, np.int64), np.empty(cap, np.uint32)
+        n = ctypes.c_int64(0)
+        _capi.check(L.bb_host_nonzero_u32(_capi.ptr(a), a.size, _capi.ptr(idx), _capi.ptr(val), cap, ctypes.byref(n)))
+        if n.value <= cap:
+            return idx[:n.value], val[:n.value]
+        cap = n.value
 
 
 def run_slabs_in_process(devices, args, kwargs, timeout=None):
@@ -570,6 +592,8 @@ class PropagationModel:
         if SPP_ZONES != 1:
             raise NotImplementedError('superposition zones (SPP_ZONES>1) are not supported')
         release_device_state()
+        if os.environ.get('BB_TIMING'):
+            print('release of the previous simulation: %.3f s' % (time.perf_counter() - t0), flush=True)
         ngpu = int(NumberGPUs if NumberGPUs is not None else os.environ.get('BABELB200_NGPUS', 1))
         if ngpu < 1:
             raise ValueError('NumberGPUs must be >= 1')
@@ -581,14 +605,14 @@ class PropagationModel:
                                             TypeSource=TypeSource, SelRMSorPeak=SelRMSorPeak,
                                             SelMapsRMSPeakList=SelMapsRMSPeakList, SelMapsSensorsList=SelMapsSensorsList,
                                             SensorSubSampling=SensorSubSampling, SensorStart=SensorStart,
-                                            ReflectorMask=ReflectorMask, MPMLRatio=MPMLRatio), DefaultGPUDeviceName, DefaultGPUDeviceNumber)
+                                            ReflectorMask=ReflectorMask, MPMLRatio=MPMLRatio, stream_sources=True), DefaultGPUDeviceName, DefaultGPUDeviceNumber)
         slab = FdtdSlab(MaterialMap, MaterialProperties, Frequency, SourceMap, SourceFunctions, SpatialStep,
                         DurationSimulation, SensorMap, Ox=Ox, Oy=Oy, Oz=Oz, AlphaCFL=AlphaCFL, NDelta=NDelta,
                         ReflectionLimit=ReflectionLimit, DT=DT, QfactorCorrection=QfactorCorrection,
                         QCorrection=QCorrection, TypeSource=TypeSource, SelRMSorPeak=SelRMSorPeak,
                         SelMapsRMSPeakList=SelMapsRMSPeakList, SelMapsSensorsList=SelMapsSensorsList,
                         SensorSubSampling=SensorSubSampling, SensorStart=SensorStart, ReflectorMask=ReflectorMask,
-                        MPMLRatio=MPMLRatio, device=(DefaultGPUDeviceName, DefaultGPUDeviceNumber))
+                        MPMLRatio=MPMLRatio, stream_sources=True, device=(DefaultGPUDeviceName, DefaultGPUDeviceNumber))
         if CheckOnlyParams:
             slab.close()
             return None

@@ -108,6 +108,11 @@ int bb_host_scatter_rows(void *out, const int64_t *rows, const void *data, int64
 int bb_host_scatter_runs(void *out, const void *data, const int64_t *dst_row, const int64_t *src_row, const int64_t *nrows,
                          int64_t nruns, int64_t row_bytes);
 
+/* flat index and value of every nonzero entry of a uint32 volume, in order, on a few host threads (the caller's SourceMap;
+ * replaces np.flatnonzero in the host side of BabelIntegrationBASE.py:2338's call).  *count = number of nonzero entries;
+ * nothing is written when it exceeds capacity. */
+int bb_host_nonzero_u32(const uint32_t *a, int64_t n, int64_t *index, uint32_t *value, int64_t capacity, int64_t *count);
+
 /* device memory of destroyed handles is kept per device for the next simulation of the same grid (a worker runs the forward,
  * back-propagation and refocus simulations in a row, BabelIntegrationBASE.py:2338-2428; at most BB_DEVICE_POOL_GB gigabytes,
  * default 32); this returns it to the driver.  device < 0: every device. */
@@ -130,6 +135,11 @@ int bb_fdtd_set_source_cells(bb_fdtd *h, int64_t ncells, const int64_t *cell, co
 /* SourceFunctions as the caller holds it: (nsrc, nt_src), float64 or float32, row stride in
  * elements (BabelIntegrationSingle.py:335).  Converted and transposed on the device. */
 int bb_fdtd_set_source_functions(bb_fdtd *h, const void *data, int is_f64, int64_t row_stride);
+/* the same table, uploaded in chunks of time samples while bb_fdtd_run advances (each chunk is on the device before the
+ * step that reads it; the first two before the first step).  `data` must stay valid and unchanged until bb_fdtd_run has
+ * passed time step nt_src - 1 -- the caller of StaggeredFDTD_3D_with_relaxation holds it for the whole call anyway
+ * (BabelIntegrationBASE.py:2338-2365).  Tables with so many rows that a chunk would hold < 64 samples are uploaded at once. */
+int bb_fdtd_set_source_functions_streamed(bb_fdtd *h, const void *data, int is_f64, int64_t row_stride);
 /* Alternative to bb_fdtd_set_source_functions for the continuous-wave sources every transducer model builds
  * (CreateSources, BabelIntegrationSingle.py:313-346: row s = |u0_s| sin(2 pi f t + angle(u0_s)), the first ramp samples
  * scaled by a raised cosine): the rows are evaluated in the source kernel from a_cos[s] = |u0_s| cos(angle), a_sin[s] =

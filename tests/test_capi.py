@@ -125,6 +125,21 @@ def test_bhte_has_no_cpu_fallback(lib):
         BHTE(np.zeros((4, 4, 4), np.float32), np.zeros((4, 4, 4), np.uint32), ML, 1e-3, 2, 1, -1, dt=0.01)
 
 
+def test_host_nonzero_matches_numpy(lib):
+    """bb_host_nonzero_u32 (source cells of the caller's SourceMap, host threads only): indices and values of np.flatnonzero,
+    for empty, sparse, dense, unaligned and multi-threaded (> 1 M cells per thread) volumes."""
+    from babelbrain_b200.propagation import _nonzero_u32
+    rng = np.random.default_rng(5)
+    for shape in ((3, 4, 5), (50, 40, 30), (129, 65, 33), (160, 160, 130)):
+        for density in (0.0, 0.002, 0.4, 1.0):
+            a = ((rng.random(shape) < density) * rng.integers(1, 2 ** 31, shape)).astype(np.uint32)
+            for view in (a, a[1:]):                              # the second starts off a 32-byte boundary for odd plane sizes
+                idx, val = _nonzero_u32(view)
+                ref = np.flatnonzero(view.reshape(-1))
+                assert idx.dtype == np.int64 and val.dtype == np.uint32
+                assert np.array_equal(idx, ref) and np.array_equal(val, view.reshape(-1)[ref])
+
+
 def test_host_scatter_rows_places_slab_rows(lib):
     """The gather helper of the multi-GPU path is plain host code (no device): out[rows[r]] = data[r]."""
     import ctypes

@@ -254,6 +254,31 @@ def test_two_gpu_slabs_match_single_gpu(halo):
     assert rl2(sens, S1['Pressure']) <= 1e-6
 
 
+def test_sources_streamed_during_the_run_match_the_upfront_upload():
+    """bb_fdtd_set_source_functions_streamed (what the public call uses): the table goes up in chunks of time samples while
+    the time loop runs; results must be those of the upload-at-once path bit for bit, for a float64 table and for a float32
+    view with a row stride, over several chunks (512 samples each for a small source count) and a partial run + rest."""
+    w = workloads.make_workload('ctx500_skull', shape=(30, 26, 36), periods=30, pml=4)
+    kw = {k: v for k, v in w['kwargs'].items() if k not in DROP}
+    args = list(w['args'])
+    SF = np.asarray(args[4])
+    assert SF.shape[1] > 1100                                   # at least three chunks
+    wide = np.zeros((SF.shape[0], SF.shape[1] + 7), np.float32)
+    wide[:, :SF.shape[1]] = SF
+    for table in (SF, wide[:, :SF.shape[1]]):
+        args[4] = table
+        out = []
+        for streamed in (False, True):
+            s = FdtdSlab(*args, stream_sources=streamed, **kw)
+            if streamed:
+                s.run(700)                                      # stop inside the second chunk, then finish
+            s.run()
+            out.append((s.get_map(0, 'Pressure').copy(), s.get_sensors('Pressure').copy()))
+            s.close()
+        assert np.array_equal(out[0][0], out[1][0]) and np.array_equal(out[0][1], out[1][1])
+        assert out[0][0].max() > 0
+
+
 def test_sensor_rows_placed_by_runs_on_the_device():
     """bb_fdtd_get_sensors_runs (the gather of a multi-GPU run through the public call): a slab's rows, cut into runs,
     land in their places of a larger page-locked table; everything else in the table stays untouched."""
