@@ -43,7 +43,7 @@ class FdtdStats(ctypes.Structure):
 
 
 # every symbol include/babelb200.h declares (checked by tests/test_capi.py)
-SYMBOLS = ['bb_last_error', 'bb_version', 'bb_device_count', 'bb_device_name', 'bb_host_alloc', 'bb_host_free', 'bb_host_scatter_rows', 'bb_host_scatter_runs', 'bb_host_nonzero_u32', 'bb_release_cached_memory', 'bb_fdtd_create',
+SYMBOLS = ['bb_last_error', 'bb_version', 'bb_device_count', 'bb_device_name', 'bb_host_alloc', 'bb_host_free', 'bb_host_scatter_rows', 'bb_host_scatter_runs', 'bb_host_nonzero_u32', 'bb_host_lz4_decompress', 'bb_release_cached_memory', 'bb_fdtd_create',
            'bb_fdtd_destroy', 'bb_fdtd_set_stream', 'bb_fdtd_set_materials', 'bb_fdtd_set_maps',
            'bb_fdtd_set_source_cells', 'bb_fdtd_set_source_functions', 'bb_fdtd_set_source_functions_streamed', 'bb_fdtd_set_source_tones', 'bb_fdtd_set_sensors',
            'bb_fdtd_set_sensor_map', 'bb_fdtd_get_sensor_index',
@@ -70,6 +70,8 @@ def lib():
         L.bb_host_scatter_rows.argtypes = [vp, vp, vp, i64, i64]
         L.bb_host_scatter_runs.argtypes = [vp, vp, vp, vp, vp, i64, i64]
         L.bb_host_nonzero_u32.argtypes = [vp, i64, vp, vp, i64, vp]
+        L.bb_host_lz4_decompress.argtypes = [vp, i64, vp, i64]
+        L.bb_host_lz4_decompress.restype = ctypes.c_longlong
         L.bb_fdtd_create.argtypes = [ctypes.POINTER(FdtdDesc), ctypes.POINTER(vp)]
         L.bb_fdtd_destroy.argtypes = [vp]
         L.bb_fdtd_destroy.restype = None

@@ -585,6 +585,32 @@ extern "C" int bb_host_nonzero_u32(const uint32_t *a, int64_t n, int64_t *index,
     return BB_OK;
 }
 
+// LZ4 block decoder for babelbrain_b200/h5mini.py (the genuine H5pySimple writes its datasets as Blosc-LZ4 chunks; the
+// pure-Python decoder manages a few MB/s).  Returns the number of bytes written, or -1 for a corrupt block.
+extern "C" long long bb_host_lz4_decompress(const unsigned char *src, long long n, unsigned char *dst, long long cap) {
+    if (!src || !dst || n < 0 || cap < 0) return -1;
+    long long i = 0, o = 0;
+    while (i < n) {
+        const unsigned tok = src[i++];
+        long long ll = tok >> 4;
+        if (ll == 15) { unsigned b; do { if (i >= n) return -1; b = src[i++]; ll += b; } while (b == 255); }
+        if (i + ll > n || o + ll > cap) return -1;
+        memcpy(dst + o, src + i, (size_t)ll);
+        i += ll; o += ll;
+        if (i >= n) break;                          // the last sequence has no match
+        if (i + 2 > n) return -1;
+        const long long off = src[i] | (src[i + 1] << 8);
+        i += 2;
+        long long ml = tok & 15;
+        if (ml == 15) { unsigned b; do { if (i >= n) return -1; b = src[i++]; ml += b; } while (b == 255); }
+        ml += 4;
+        if (off == 0 || off > o || o + ml > cap) return -1;
+        for (long long k = 0; k < ml; k++) dst[o + k] = dst[o - off + k];     // may overlap: byte by byte
+        o += ml;
+    }
+    return o;
+}
+
 extern "C" int bb_fdtd_set_stream(bb_fdtd *h, void *s) {
     BB_REQUIRE(h, "null handle");
     BB_CUDA(cudaSetDevice(h->d.device));

@@ -113,6 +113,10 @@ int bb_host_scatter_runs(void *out, const void *data, const int64_t *dst_row, co
  * nothing is written when it exceeds capacity. */
 int bb_host_nonzero_u32(const uint32_t *a, int64_t n, int64_t *index, uint32_t *value, int64_t capacity, int64_t *count);
 
+/* LZ4 block decoder (host) for the Blosc-LZ4 chunks of the HDF5 files the genuine H5pySimple writes (read here by
+ * babelbrain_b200/h5mini.py when h5py is absent).  Returns the bytes written to dst, -1 for a corrupt block. */
+long long bb_host_lz4_decompress(const unsigned char *src, long long n, unsigned char *dst, long long cap);
+
 /* device memory of destroyed handles is kept per device for the next simulation of the same grid (a worker runs the forward,
  * back-propagation and refocus simulations in a row, BabelIntegrationBASE.py:2338-2428; at most BB_DEVICE_POOL_GB gigabytes,
  * default 32); this returns it to the driver.  device < 0: every device. */

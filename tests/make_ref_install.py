@@ -20,8 +20,9 @@ def install():
     os.makedirs(os.path.dirname(DST), exist_ok=True)
     if os.path.isdir(DST):
         shutil.rmtree(DST)
-    # the Python sources of the caller only: geometry tables (.mat/.csv/.h5) are not touched by the harness
-    ignore = shutil.ignore_patterns('__pycache__', '*.mat', '*.h5', '*.csv', '*.stl', '*.npz')
+    # the Python sources of the caller only: geometry tables (.mat/.csv) are not touched by the harness
+    # (the two small HDF5 files travel too: MapPichardo.h5 is read at import time, and both pin babelbrain_b200/h5mini.py)
+    ignore = shutil.ignore_patterns('__pycache__', '*.mat', '*.csv', '*.stl', '*.npz')
     shutil.copytree(SRC, DST, ignore=ignore)
     thermal_src, thermal_dst = os.path.join(os.path.dirname(SRC), 'ThermalModeling'), os.path.join(os.path.dirname(DST), 'ThermalModeling')
     if os.path.isdir(thermal_src):         # the driver of the thermal step (tests/test_reference_thermal_caller.py)
