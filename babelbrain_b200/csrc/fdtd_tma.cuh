@@ -120,9 +120,12 @@ __device__ __forceinline__ void peer_wait(const DevParams &p, int side) {
     if (p.exp & 16) __threadfence_system(); else __threadfence();
     asm volatile("fence.proxy.async;" ::: "memory");             // the TMA unit reads what the neighbour wrote
 }
-// Called by one thread of a CTA after a barrier of the consumer warps that stored the pushed planes.  The barrier
-// orders their peer stores before this thread; its system-scope fence then makes them visible to the neighbour GPU
-// before the count / flag writes (the "last block" pattern: fence, count, and the CTA completing the count publishes).
+// Called by one thread of a CTA (the halo-ring producer) once every consumer warp has released the side's last pushed
+// plane: the mbarrier arrive / wait pair orders the warps' peer stores before this thread, its gpu-scope fence (issued by
+// the caller) and the atomic count release them to the CTA that completes the count, and that CTA's system-scope fence --
+// one per side and launch, cumulative over everything the counts released -- makes them visible to the neighbour GPU
+// before the flag write.  (A system-scope fence in every boundary CTA cost 0.06-0.3 ms per half-step on the 1 MHz slabs:
+// profiles/r2_scaling_experiments.txt.)
 __device__ __forceinline__ void peer_publish(const DevParams &p, int side, unsigned planes_pushed, unsigned expected) {
     const unsigned before = atomicAdd(p.push_count + side, planes_pushed);
     if (before + planes_pushed == expected) {
@@ -311,8 +314,8 @@ __global__ void __launch_bounds__(NTB, CTAS_PER_SM) stress_tma(const __grid_cons
         RingPos rh(nsh, 0, 1);
         // This thread also publishes the slab-boundary planes the CTA pushes to a neighbour: the wait for a halo slot to come
         // back tells it that every consumer warp has finished (stored, pushed, released) the plane that used the slot, so
-        // the system-scope fence and the flag write cost the consumer warps nothing (they were 150-300 us per launch on the
-        // 1 MHz slabs when consumer thread 0 did them: ~30 boundary CTAs per SM).
+        // the fence, the count and the flag write cost the consumer warps nothing (150-300 us per launch on the 1 MHz
+        // slabs when consumer thread 0 did them behind a barrier: ~30 boundary CTAs per SM).
         const int lo_last = (ic0 < p.i0 + 2 && p.peerS[0]) ? min(ic1, p.i0 + 2) - 1 - ic0 : -1;
         const int hi_last = (ic1 > p.i1 - 2 && p.peerS[1]) ? np - 1 : -1;
         const int rend = (PEER && p.publish) ? max(np + 2, max(lo_last, hi_last) + nsh + 1) : np + 2;
