@@ -89,6 +89,20 @@ def test_unmodified_caller_with_the_oracle_behind_the_solver_call():
     print('unmodified caller + oracle:', b)
     assert b['ppp'] == 30 and b['steps'] % b['ppp'] == 0
     check(b)
+    # the dictionary the caller would write as *_DataForSim.h5 (ReturnResults' DataForSim, BASE.py:2815-2884; Step10 saves it
+    # with SaveToH5py, the thermal step reads it back with ReadFromH5py): through the shim's HDF5 path of this image
+    import os, tempfile
+    from BabelViscoFDTD.H5pySimple import SaveToH5py, ReadFromH5py
+    data = cap['results'][4]
+    assert isinstance(data, dict) and 'p_amp' in data and 'MaterialMap' in data
+    with tempfile.TemporaryDirectory() as d:
+        path = os.path.join(d, 'Single_DataForSim.h5')
+        SaveToH5py(data, path)
+        back = ReadFromH5py(path)
+    assert sorted(back) == sorted(str(k) for k in data)
+    for k, v in data.items():
+        if isinstance(v, np.ndarray) and v.dtype.kind != 'O':
+            assert np.array_equal(back[str(k)], v), k
 
 
 @needs_ref
