@@ -105,3 +105,25 @@ def test_plane_wave_speeds_in_a_solid(polarisation, speed):
     v_group = dist / (delay(np.abs(hilbert(a)), np.abs(hilbert(b))) * dt)
     assert v_phase > speed > v_group, (v_phase, v_group)
     assert np.sqrt(v_phase * v_group) == pytest.approx(speed, rel=0.01), (v_phase, v_group, speed)
+
+
+@pytest.mark.parametrize('polarisation,speed,column', [('shear', 1500.0, 4), ('compressional', 2800.0, 3)])
+def test_attenuation_of_shear_and_compressional_waves_in_a_solid(polarisation, speed, column):
+    """The same channel once with lossless and once with attenuating bone (alpha_L = 60 Np/m, alpha_S = 120 Np/m at the drive
+    frequency): walls and diffraction act on both bursts alike, so the amplitude ratio between two depths differs by
+    exp(-alpha dz).  The fitted alpha must be within 15 % of the MaterialList value of that wave type -- the relaxation fit of
+    the shear modulus is a separate code path from the compressional one (memory variables of the shear stresses)."""
+    n12, n3, ppw = 40, 160, 12
+    h = speed / F0 / ppw
+    dt = 0.4 * h / 2800.0 / np.sqrt(3.0)
+    k_src, k1, k2 = 12, 40, 120
+    steps = int(1.1 * ((k2 - k_src) * h / speed + 5 / F0) / dt)
+    MM = np.zeros((n12, n12, n3), np.uint32)
+    O, comp = ((1.0, 0.0, 0.0), 'Vx') if polarisation == 'shear' else ((0.0, 0.0, 1.0), 'Vz')
+    lossy = [1850.0, 2800.0, 1500.0, 60.0, 120.0]
+    drop = []
+    for row in (BONE, lossy):
+        tr, _ = run(MM, [row], h, dt, steps, k_src, O, (comp,), [k1, k2], n12=n12)
+        drop.append(np.log(np.abs(tr[comp][k2]).max() / np.abs(tr[comp][k1]).max()))
+    alpha = -(drop[1] - drop[0]) / ((k2 - k1) * h)
+    assert alpha == pytest.approx(lossy[column], rel=0.15), (alpha, lossy[column])
